@@ -1,0 +1,153 @@
+/*
+ * troute_b200.h -- C ABI of the B200 channel-routing engine (libtroute_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path
+ *     compute_nhd_routing_v02 (src/troute-routing/troute/routing/compute.py:507-1738)
+ *       -> compute_network_structured (src/troute-routing/troute/routing/fast_reach/mc_reach.pyx:164-845)
+ *         -> c_muskingcungenwm (src/kernel/muskingum/pyMCsingleSegStime_NoLoop.f90:8-21)
+ *         -> run_lp           (src/kernel/reservoir/bind_lp.f90:52-90)
+ * (paths relative to /root/reference).  The reference's own FFI for this path is the per-segment
+ * `c_muskingcungenwm(float* x21)` / `run_lp(handle, float* x5)` pair declared in
+ * fast_reach/fortran_wrappers.pxd:19-40 and reservoirs/levelpool/levelpool_structs.c:8-18; one call
+ * per segment per timestep is meaningless for a GPU, so the boundary moves up one level: a network
+ * handle holds the flattened river network on the device and one call routes every segment for
+ * every timestep.  INTEGRATION.md shows the ctypes stub a maintainer registers in
+ * compute.py:_compute_func_map (:21-26).
+ *
+ * Conventions: plain C, pointers + sizes, no torch types.  Every function returns 0 on success or a
+ * negative trt_status; trt_last_error() returns the message of the last failure on the calling
+ * thread.  The caller owns every host buffer.  "rows" are positions in the caller's sorted segment
+ * index (data_idx of mc_reach.pyx:170); the engine keeps its own level-sorted device order and
+ * converts at the boundary.  A handle owns one CUDA stream and is not re-entrant.
+ */
+#ifndef TROUTE_B200_H
+#define TROUTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct trt_network trt_network;
+
+typedef enum {
+    TRT_OK = 0,
+    TRT_ERR_INVALID = -1,     /* bad argument / shape mismatch (ValueError in mc_reach.pyx:243-250) */
+    TRT_ERR_CYCLE = -2,       /* the upstream graph is not a DAG */
+    TRT_ERR_CUDA = -3,        /* CUDA runtime failure; message holds cudaGetErrorString */
+    TRT_ERR_NOMEM = -4,
+    TRT_ERR_STATE = -5        /* call order violated (e.g. download before run) */
+} trt_status;
+
+/* segment kinds (reach types of mc_reach.pyx:291 / compute.py:41-47, plus prescribed rows) */
+#define TRT_KIND_MC        0  /* Muskingum-Cunge segment */
+#define TRT_KIND_LEVELPOOL 1  /* level-pool reservoir (RESERVOIR_LP, plain level pool) */
+#define TRT_KIND_BOUNDARY  2  /* flow series prescribed by the caller (upstream_results, mc_reach.pyx:458-469) */
+
+const char* trt_last_error(void);
+int trt_version(void);
+/* number of visible CUDA devices, or a negative trt_status */
+int trt_device_count(void);
+
+/*
+ * Build a network on `device`.
+ *   n_rows            rows of the caller's segment index
+ *   up_ptr, up_rows   CSR: rows whose outflow enters row r are up_rows[up_ptr[r] .. up_ptr[r+1]), in the
+ *                     order the reference sums them (mc_reach.pyx:499-502; inside a reach the single
+ *                     upstream is the previous segment, mc_reach.pyx:133-138)
+ *   kind              [n_rows] TRT_KIND_*
+ *   data_values       [n_rows, ncols] float32 parameter table (param_df_sub.values, compute.py:1538)
+ *   scols             [9] columns of dt, dx, bw, tw, twcc, n, ncc, cs, s0 in data_values
+ *                     (column_mapper, mc_reach.pyx:150-162)
+ * The graph is levelled (longest path from the headwaters), segments are renumbered level by level
+ * and all arrays are uploaded as structure-of-arrays.
+ */
+int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
+                       const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
+                       trt_network** out);
+int trt_network_destroy(trt_network* net);
+
+/* topology queries: number of wavefront levels; level of every row; engine position of every row */
+int trt_network_num_levels(const trt_network* net, int32_t* out);
+int trt_network_get_levels(const trt_network* net, int32_t* level_of_row /* [n_rows] */);
+int trt_network_get_positions(const trt_network* net, int32_t* pos_of_row /* [n_rows] */);
+
+/*
+ * Level-pool reservoirs.  wbody_cols rows are (LkArea, LkMxE, OrificeA, OrificeC, OrificeE, WeirC,
+ * WeirE, WeirL, ifd, qd0, h0) as in compute.py:1416-1430 / levelpool.pyx:48-57; dam length is 10 m
+ * (levelpool.pyx:66); h0 < -9e8 selects the cold-start elevation (levelpool_structs.c:97-103).
+ * May be called before every trt_upload_forcing (the reference passes the table on every call).
+ */
+int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols);
+
+/*
+ * One routing call = upload, run, download.  Shapes follow compute_network_structured:
+ *   qlat       [n_rows, nqcols] float32, nqcols >= nsteps/qts_subdivisions   (mc_reach.pyx:243-247)
+ *   q0         [n_rows, 3] float32 (qu0, qd0, h0): column 0 seeds flow, column 2 seeds depth (:361)
+ *   bnd_rows   [n_bnd] rows of kind TRT_KIND_BOUNDARY;  bnd_fvd [n_bnd, nsteps*3] their prescribed
+ *              (q, v, d) series for steps 1..nsteps (tmp["results"], mc_reach.pyx:462-463)
+ *   fvd_out    [n_rows, nsteps*3] float32 (q, v, d interleaved per step)      (:807-813)
+ *   upstream_out [n_rows, nsteps] float32 or NULL: reservoir inflow on level-pool rows, 0 elsewhere
+ *              (the reference leaves np.empty garbage on non-reservoir rows, mc_reach.pyx:487)
+ * Host pointers may be pageable or pinned; pinned buffers make the copies asynchronous-capable.
+ */
+int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, const float* qlat,
+                       int32_t nqcols, const float* q0, int64_t n_bnd, const int64_t* bnd_rows,
+                       const float* bnd_fvd);
+/* kernels only; everything is already resident in HBM.  Blocks until the device is done. */
+int trt_run(trt_network* net, int32_t assume_short_ts);
+/* trt_run without the final wait: enqueue on the handle's stream and return; trt_sync waits and
+ * collects the run statistics.  Used with the "stream" option to time on the caller's stream. */
+int trt_run_async(trt_network* net, int32_t assume_short_ts);
+int trt_sync(trt_network* net);
+int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out);
+/* the three calls above in sequence */
+int trt_route(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, int32_t assume_short_ts,
+              const float* qlat, int32_t nqcols, const float* q0, int64_t n_bnd, const int64_t* bnd_rows,
+              const float* bnd_fvd, float* fvd_out, float* upstream_out);
+
+/*
+ * Device-side access for multi-GPU hand-off and for checks without a host round trip.
+ *   trt_export_flow_series   gathers q[rows, 0..nsteps] into dst (DEVICE pointer, [n, nsteps+1] float32)
+ *   trt_import_boundary_flow writes prescribed q[rows, 1..nsteps] from src (DEVICE pointer,
+ *                            [n, nsteps+1] float32, column 0 ignored); v and d of those rows stay 0
+ *   trt_device_results       device pointer of the [n_rows, nsteps*3] result after trt_run
+ *                            (valid until the next upload)
+ */
+int trt_export_flow_series(trt_network* net, int64_t n, const int64_t* rows, void* dst_device);
+int trt_import_boundary_flow(trt_network* net, int64_t n, const int64_t* rows, const void* src_device);
+int trt_device_results(trt_network* net, void** fvd_device);
+
+/* run-time knobs:
+ *   "mode"        0 = one launch per wavefront stage, 1 = persistent cooperative kernel (default)
+ *   "grid_blocks" CTAs of the persistent kernel (0 = as many as are co-resident)
+ *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
+int trt_set_option(trt_network* net, const char* key, int64_t value);
+/* statistics of the last trt_run: device milliseconds of the wavefront kernels, number of kernel
+ * launches, wavefront stages, lane-steps executed */
+int trt_last_run_stats(const trt_network* net, double* kernel_ms, int64_t* launches, int64_t* stages,
+                       int64_t* lane_steps);
+
+/*
+ * Batch of independent single-segment solves on the device: the GPU twin of
+ * reach.compute_reach_kernel (fast_reach/reach.pyx:66-103) for known-answer tests.
+ *   in15  [count, 15] rows (dt,qup,quc,qdp,ql,dx,bw,tw,twcc,n,ncc,cs,s0,velp,depthp)
+ *   out6  [count, 6]  rows (qdc, velc, depthc, ck, cn, X)       iters [count] or NULL
+ */
+int trt_mc_segment_batch(int device, int64_t count, const float* in15, float* out6, int32_t* iters);
+/* level pool over an inflow series on the device (reservoir KATs); out = {outflow, elevation} per step */
+int trt_levelpool_series(int device, const double* wbody_row, int64_t nsteps, const float* inflow,
+                         float lateral_inflow, float routing_period, float* outflow_series,
+                         float* elevation_series);
+/* elementwise trt_powf_det on the device (numerics-contract test) */
+int trt_powf_batch(int device, int64_t count, const float* x, const float* y, float* out);
+
+/* pinned host memory helpers for callers that want asynchronous-capable buffers */
+int trt_host_alloc(void** ptr, uint64_t bytes);
+int trt_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TROUTE_B200_H */

@@ -1,0 +1,649 @@
+/*
+ * engine.cu -- host side of libtroute_b200.so: the C ABI of include/troute_b200.h.
+ *
+ * Owns what compute_network_structured sets up per call in Python/Cython objects
+ * (/root/reference/src/troute-routing/troute/routing/fast_reach/mc_reach.pyx:287-378: binary_find per
+ * reach, MC_Segment / MC_Reach / MC_Levelpool objects, the _Reach struct array :476-481) -- but builds it
+ * ONCE per network as flat level-sorted arrays resident in HBM, and per routing call only moves the
+ * forcing (qlat, q0) in and the (n_rows, 3*nsteps) result out.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/troute_b200.h"
+#include "kernels.cuh"
+
+using namespace trt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(TRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t count)
+    {
+        if (count <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+};
+
+}  // namespace
+
+struct trt_network {
+    int device = 0;
+    int64_t n = 0;                 // rows == segments
+    int nlevels = 0;
+    std::vector<int32_t> level_of_row, pos_of_row, row_of_pos, lvl_ptr;
+    std::vector<uint8_t> kind_of_row;
+
+    // device topology / parameters
+    DevBuf<int> d_lvl_ptr, d_level, d_up_ptr, d_up_idx, d_row_of_pos;
+    DevBuf<unsigned char> d_kind;
+    DevBuf<float> d_par;
+
+    // level pools
+    int64_t n_lp = 0;
+    DevBuf<int> d_lp_pos;
+    DevBuf<float> d_lp_qd0, d_lp_h0;
+
+    // per-call state
+    int T = 0, qts = 1, nq = 0;
+    bool uploaded = false, ran = false;
+    DevBuf<float> d_qlat_in, d_q0_in, d_qlat_t, d_q, d_v, d_d, d_fvd, d_up_out, d_bnd_fvd;
+    DevBuf<int> d_bnd_pos, d_tmp_pos;
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // options / stats
+    int mode = 1;                  // 0 stage-per-launch, 1 persistent cooperative
+    int grid_blocks = 0;           // 0 = max co-resident
+    double kernel_ms = 0.0;
+    int64_t launches = 0, stages = 0, lane_steps = 0;
+
+    NetDev netdev() const
+    {
+        NetDev d;
+        d.n = (int)n; d.nlevels = nlevels; d.lvl_ptr = d_lvl_ptr.p; d.level = d_level.p; d.up_ptr = d_up_ptr.p;
+        d.up_idx = d_up_idx.p; d.kind = d_kind.p; d.par = d_par.p; d.row_of_pos = d_row_of_pos.p;
+        return d;
+    }
+    RunDev rundev(int short_ts) const
+    {
+        RunDev r;
+        r.T = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.q = d_q.p; r.v = d_v.p;
+        r.d = d_d.p;
+        return r;
+    }
+};
+
+extern "C" {
+
+const char* trt_last_error(void) { return g_err.c_str(); }
+int trt_version(void) { return 100; }
+
+int trt_device_count(void)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) return fail(TRT_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return c;
+}
+
+int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows, const uint8_t* kind,
+                       const float* data_values, int32_t ncols, const int32_t* scols, trt_network** out)
+{
+    if (!out) return fail(TRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_rows < 0 || n_rows > 2000000000LL) return fail(TRT_ERR_INVALID, "n_rows out of range: %lld", (long long)n_rows);
+    if (n_rows > 0 && (!up_ptr || !kind || !data_values || !scols))
+        return fail(TRT_ERR_INVALID, "NULL array argument");
+    if (ncols < 9) return fail(TRT_ERR_INVALID, "data_values needs at least 9 columns, got %d", ncols);
+    for (int c = 0; c < 9; ++c)
+        if (scols[c] < 0 || scols[c] >= ncols) return fail(TRT_ERR_INVALID, "scols[%d]=%d out of range", c, scols[c]);
+    const int64_t n = n_rows;
+    const int64_t E = n ? up_ptr[n] : 0;
+    if (n && up_ptr[0] != 0) return fail(TRT_ERR_INVALID, "up_ptr[0] must be 0");
+    if (E < 0 || E > 2000000000LL) return fail(TRT_ERR_INVALID, "edge count out of range");
+    for (int64_t r = 0; r < n; ++r)
+        if (up_ptr[r + 1] < up_ptr[r]) return fail(TRT_ERR_INVALID, "up_ptr not monotone at row %lld", (long long)r);
+    for (int64_t e = 0; e < E; ++e)
+        if (up_rows[e] < 0 || up_rows[e] >= n)
+            return fail(TRT_ERR_INVALID, "upstream row %lld out of range (edge %lld)", (long long)up_rows[e], (long long)e);
+    for (int64_t r = 0; r < n; ++r) {
+        if (kind[r] > TRT_KIND_BOUNDARY) return fail(TRT_ERR_INVALID, "kind[%lld]=%d unknown", (long long)r, kind[r]);
+        if (kind[r] == TRT_KIND_BOUNDARY && up_ptr[r + 1] != up_ptr[r])
+            return fail(TRT_ERR_INVALID, "boundary row %lld must not have upstream rows", (long long)r);
+    }
+
+    trt_network* net = new (std::nothrow) trt_network();
+    if (!net) return fail(TRT_ERR_NOMEM, "out of host memory");
+    net->device = device;
+    net->n = n;
+
+    // ---- levels: longest path from a headwater (Kahn sweep over the downstream adjacency) ----
+    std::vector<int32_t>& level = net->level_of_row;
+    level.assign((size_t)n, 0);
+    {
+        std::vector<int64_t> down_ptr((size_t)n + 1, 0);
+        for (int64_t e = 0; e < E; ++e) down_ptr[(size_t)up_rows[e] + 1]++;
+        for (int64_t r = 0; r < n; ++r) down_ptr[(size_t)r + 1] += down_ptr[(size_t)r];
+        std::vector<int64_t> down((size_t)E), fill(down_ptr.begin(), down_ptr.end() - 1);
+        for (int64_t r = 0; r < n; ++r)
+            for (int64_t e = up_ptr[r]; e < up_ptr[r + 1]; ++e) down[(size_t)fill[(size_t)up_rows[e]]++] = r;
+        std::vector<int64_t> indeg((size_t)n), queue;
+        queue.reserve((size_t)n);
+        for (int64_t r = 0; r < n; ++r) {
+            indeg[(size_t)r] = up_ptr[r + 1] - up_ptr[r];
+            if (indeg[(size_t)r] == 0) queue.push_back(r);
+        }
+        size_t head = 0;
+        while (head < queue.size()) {
+            const int64_t r = queue[head++];
+            for (int64_t e = down_ptr[(size_t)r]; e < down_ptr[(size_t)r + 1]; ++e) {
+                const int64_t dn = down[(size_t)e];
+                level[(size_t)dn] = std::max(level[(size_t)dn], level[(size_t)r] + 1);
+                if (--indeg[(size_t)dn] == 0) queue.push_back(dn);
+            }
+        }
+        if ((int64_t)queue.size() != n) {
+            delete net;
+            return fail(TRT_ERR_CYCLE, "upstream graph has a cycle (%lld of %lld rows reachable)",
+                        (long long)queue.size(), (long long)n);
+        }
+    }
+    int nlev = 0;
+    for (int64_t r = 0; r < n; ++r) nlev = std::max(nlev, level[(size_t)r] + 1);
+    net->nlevels = nlev;
+
+    // ---- counting sort by level: engine position order ----
+    net->lvl_ptr.assign((size_t)nlev + 1, 0);
+    for (int64_t r = 0; r < n; ++r) net->lvl_ptr[(size_t)level[(size_t)r] + 1]++;
+    for (int l = 0; l < nlev; ++l) net->lvl_ptr[(size_t)l + 1] += net->lvl_ptr[(size_t)l];
+    net->pos_of_row.resize((size_t)n);
+    net->row_of_pos.resize((size_t)n);
+    {
+        std::vector<int32_t> cursor(net->lvl_ptr.begin(), net->lvl_ptr.end() - (nlev ? 1 : 0));
+        for (int64_t r = 0; r < n; ++r) {
+            const int32_t p = cursor[(size_t)level[(size_t)r]]++;
+            net->pos_of_row[(size_t)r] = p;
+            net->row_of_pos[(size_t)p] = (int32_t)r;
+        }
+    }
+    net->kind_of_row.assign(kind, kind + n);
+
+    // ---- position-space arrays ----
+    std::vector<int32_t> h_level((size_t)n), h_up_ptr((size_t)n + 1, 0), h_up_idx((size_t)E);
+    std::vector<unsigned char> h_kind((size_t)n);
+    std::vector<float> h_par((size_t)9 * (size_t)std::max<int64_t>(n, 1));
+    for (int64_t p = 0; p < n; ++p) {
+        const int64_t r = net->row_of_pos[(size_t)p];
+        h_level[(size_t)p] = level[(size_t)r];
+        h_kind[(size_t)p] = kind[r];
+        h_up_ptr[(size_t)p + 1] = h_up_ptr[(size_t)p] + (int32_t)(up_ptr[r + 1] - up_ptr[r]);
+        int32_t o = h_up_ptr[(size_t)p];
+        for (int64_t e = up_ptr[r]; e < up_ptr[r + 1]; ++e) h_up_idx[(size_t)o++] = net->pos_of_row[(size_t)up_rows[e]];
+        const float* dv = data_values + (size_t)r * ncols;
+        for (int c = 0; c < 9; ++c) h_par[(size_t)c * n + p] = dv[scols[c]];
+    }
+
+    // ---- upload ----
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&net->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&net->ev1);
+    if (e == cudaSuccess) e = net->d_lvl_ptr.reserve((size_t)nlev + 1);
+    if (e == cudaSuccess) e = net->d_level.reserve((size_t)n);
+    if (e == cudaSuccess) e = net->d_up_ptr.reserve((size_t)n + 1);
+    if (e == cudaSuccess) e = net->d_up_idx.reserve((size_t)E);
+    if (e == cudaSuccess) e = net->d_row_of_pos.reserve((size_t)n);
+    if (e == cudaSuccess) e = net->d_kind.reserve((size_t)n);
+    if (e == cudaSuccess) e = net->d_par.reserve((size_t)9 * n);
+#define UP(dst, src, count) \
+    if (e == cudaSuccess && (count) > 0) e = cudaMemcpy(dst, src, (size_t)(count) * sizeof(*(src)), cudaMemcpyHostToDevice)
+    UP(net->d_lvl_ptr.p, net->lvl_ptr.data(), nlev + 1);
+    UP(net->d_level.p, h_level.data(), n);
+    UP(net->d_up_ptr.p, h_up_ptr.data(), n + 1);
+    UP(net->d_up_idx.p, h_up_idx.data(), E);
+    UP(net->d_row_of_pos.p, net->row_of_pos.data(), n);
+    UP(net->d_kind.p, h_kind.data(), n);
+    UP(net->d_par.p, h_par.data(), 9 * n);
+#undef UP
+    if (e != cudaSuccess) {
+        const int rc = fail(TRT_ERR_CUDA, "network upload failed: %s", cudaGetErrorString(e));
+        trt_network_destroy(net);
+        return rc;
+    }
+    *out = net;
+    return TRT_OK;
+}
+
+int trt_network_destroy(trt_network* net)
+{
+    if (!net) return TRT_OK;
+    cudaSetDevice(net->device);
+    if (net->ev0) cudaEventDestroy(net->ev0);
+    if (net->ev1) cudaEventDestroy(net->ev1);
+    if (net->stream && net->own_stream) cudaStreamDestroy(net->stream);
+    delete net;
+    return TRT_OK;
+}
+
+int trt_network_num_levels(const trt_network* net, int32_t* out)
+{
+    if (!net || !out) return fail(TRT_ERR_INVALID, "NULL argument");
+    *out = net->nlevels;
+    return TRT_OK;
+}
+int trt_network_get_levels(const trt_network* net, int32_t* level_of_row)
+{
+    if (!net || !level_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::copy(net->level_of_row.begin(), net->level_of_row.end(), level_of_row);
+    return TRT_OK;
+}
+int trt_network_get_positions(const trt_network* net, int32_t* pos_of_row)
+{
+    if (!net || !pos_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::copy(net->pos_of_row.begin(), net->pos_of_row.end(), pos_of_row);
+    return TRT_OK;
+}
+
+int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (n_lp < 0 || (n_lp > 0 && (!lp_rows || !wbody_cols))) return fail(TRT_ERR_INVALID, "bad level-pool arguments");
+    CU(cudaSetDevice(net->device));
+    const int64_t n = net->n;
+    std::vector<int32_t> pos((size_t)n_lp);
+    std::vector<float> qd0((size_t)n_lp), h0((size_t)n_lp), par((size_t)n_lp * 8);
+    for (int64_t i = 0; i < n_lp; ++i) {
+        const int64_t r = lp_rows[i];
+        if (r < 0 || r >= n) return fail(TRT_ERR_INVALID, "level-pool row %lld out of range", (long long)r);
+        if (net->kind_of_row[(size_t)r] != TRT_KIND_LEVELPOOL)
+            return fail(TRT_ERR_INVALID, "row %lld is not of kind TRT_KIND_LEVELPOOL", (long long)r);
+        const double* a = wbody_cols + 11 * i;
+        pos[(size_t)i] = net->pos_of_row[(size_t)r];
+        // MC_Levelpool.__init__ argument order, levelpool.pyx:48-57 (double -> C float)
+        const float area = (float)a[0], max_depth = (float)a[1], oa = (float)a[2], oc = (float)a[3], oe = (float)a[4],
+                    wc = (float)a[5], we = (float)a[6], wl = (float)a[7], ifd = (float)a[8];
+        const float we0 = (float)a[10];
+        float H = we0;
+        if (we0 < -900000000.0f) H = oe + ((max_depth - oe) * ifd);   // levelpool_structs.c:97-103
+        qd0[(size_t)i] = (float)a[9];                                  // mc_reach.pyx:298
+        h0[(size_t)i] = H;
+        float* p = &par[(size_t)i * 8];
+        p[0] = area; p[1] = max_depth; p[2] = oa; p[3] = oc; p[4] = oe; p[5] = wc; p[6] = we; p[7] = wl;
+    }
+    CU(net->d_lp_pos.reserve((size_t)n_lp));
+    CU(net->d_lp_qd0.reserve((size_t)n_lp));
+    CU(net->d_lp_h0.reserve((size_t)n_lp));
+    if (n_lp > 0) {
+        CU(cudaMemcpy(net->d_lp_pos.p, pos.data(), (size_t)n_lp * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_lp_qd0.p, qd0.data(), (size_t)n_lp * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_lp_h0.p, h0.data(), (size_t)n_lp * sizeof(float), cudaMemcpyHostToDevice));
+        DevBuf<float> d_par8;
+        CU(d_par8.reserve((size_t)n_lp * 8));
+        CU(cudaMemcpy(d_par8.p, par.data(), (size_t)n_lp * 8 * sizeof(float), cudaMemcpyHostToDevice));
+        CU(launch_scatter_lp_params(net->d_lp_pos.p, d_par8.p, net->d_par.p, (int)n, (int)n_lp, net->stream));
+        CU(cudaStreamSynchronize(net->stream));
+    }
+    net->n_lp = n_lp;
+    return TRT_OK;
+}
+
+int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, const float* q0,
+                       int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (nsteps < 0) return fail(TRT_ERR_INVALID, "nsteps < 0");
+    if (qts < 1) return fail(TRT_ERR_INVALID, "qts_subdivisions must be >= 1");
+    // mc_reach.pyx:246-247
+    if ((double)nqcols < (double)nsteps / (double)qts)
+        return fail(TRT_ERR_INVALID,
+                    "Number of columns (timesteps) in Qlat is incorrect: expected at least (%g), got (%d)",
+                    (double)nsteps / (double)qts, nqcols);
+    const int64_t n = net->n;
+    if (n > 0 && (!qlat || !q0)) return fail(TRT_ERR_INVALID, "NULL qlat / q0");
+    if (n_bnd < 0 || (n_bnd > 0 && (!bnd_rows || !bnd_fvd))) return fail(TRT_ERR_INVALID, "bad boundary arguments");
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = net->stream;
+    net->T = nsteps; net->qts = qts; net->nq = nqcols;
+    net->uploaded = false; net->ran = false;
+
+    const size_t rows_t = (size_t)(nsteps + 1) * (size_t)n;
+    CU(net->d_qlat_in.reserve((size_t)n * nqcols));
+    CU(net->d_q0_in.reserve((size_t)n * 3));
+    CU(net->d_qlat_t.reserve((size_t)n * nqcols));
+    CU(net->d_q.reserve(rows_t));
+    CU(net->d_v.reserve(rows_t));
+    CU(net->d_d.reserve(rows_t));
+    CU(net->d_fvd.reserve((size_t)n * 3 * (size_t)nsteps));
+
+    if (n > 0) {
+        CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(launch_gather_qlat(net->d_qlat_in.p, net->d_row_of_pos.p, net->d_qlat_t.p, (int)n, nqcols, st));
+        CU(launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, st));
+        CU(launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_q.p, net->d_v.p, net->d_d.p,
+                                 (int)net->n_lp, st));
+    }
+    if (n_bnd > 0) {
+        std::vector<int32_t> pos((size_t)n_bnd);
+        for (int64_t i = 0; i < n_bnd; ++i) {
+            const int64_t r = bnd_rows[i];
+            if (r < 0 || r >= n) return fail(TRT_ERR_INVALID, "boundary row %lld out of range", (long long)r);
+            if (net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY)
+                return fail(TRT_ERR_INVALID, "row %lld is not of kind TRT_KIND_BOUNDARY", (long long)r);
+            pos[(size_t)i] = net->pos_of_row[(size_t)r];
+        }
+        CU(net->d_bnd_pos.reserve((size_t)n_bnd));
+        CU(net->d_bnd_fvd.reserve((size_t)n_bnd * 3 * (size_t)nsteps));
+        CU(cudaMemcpyAsync(net->d_bnd_pos.p, pos.data(), (size_t)n_bnd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(net->d_bnd_fvd.p, bnd_fvd, (size_t)n_bnd * 3 * (size_t)nsteps * sizeof(float),
+                           cudaMemcpyHostToDevice, st));
+        CU(launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n,
+                                (int)n_bnd, nsteps, st));
+        CU(cudaStreamSynchronize(st));   // `pos` is a stack-owned staging vector
+    }
+    net->uploaded = true;
+    return TRT_OK;
+}
+
+static int run_async(trt_network* net, int32_t assume_short_ts)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run called before trt_upload_forcing");
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = net->stream;
+    const NetDev nd = net->netdev();
+    const RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
+    const int T = net->T;
+    const int L = assume_short_ts ? 1 : net->nlevels;
+    net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0;
+
+    CU(cudaEventRecord(net->ev0, st));
+    if (net->n > 0 && T > 0 && L > 0) {
+        const int k_begin = 1, k_end = L + T;   // stages k = level + t, level in [0, L), t in [1, T]
+        net->stages = k_end - k_begin;
+        int64_t routed = 0;
+        for (int64_t r = 0; r < net->n; ++r) routed += net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY;
+        net->lane_steps = routed * T;
+        if (net->mode == 1) {
+            int grid = net->grid_blocks;
+            int max_grid = 0;
+            CU(persistent_max_grid(&max_grid));
+            if (max_grid <= 0) return fail(TRT_ERR_CUDA, "persistent kernel cannot be made resident");
+            if (grid <= 0 || grid > max_grid) grid = max_grid;
+            CU(launch_persistent(nd, rd, k_begin, k_end, grid, st));
+            net->launches = 1;
+        } else {
+            for (int k = k_begin; k < k_end; ++k) {
+                int lo, hi;
+                if (assume_short_ts) { lo = 0; hi = (int)net->n; }
+                else {
+                    lo = net->lvl_ptr[(size_t)std::max(0, k - T)];
+                    hi = net->lvl_ptr[(size_t)std::min(L, k)];
+                }
+                if (hi > lo) {
+                    CU(launch_stage(nd, rd, k, lo, hi, st));
+                    net->launches++;
+                }
+            }
+        }
+    }
+    CU(cudaEventRecord(net->ev1, st));
+    CU(launch_finalize(nd, rd, net->d_fvd.p, st));
+    net->launches += (net->n > 0 && T > 0) ? 1 : 0;
+    net->ran = true;
+    return TRT_OK;
+}
+
+int trt_run_async(trt_network* net, int32_t assume_short_ts) { return run_async(net, assume_short_ts); }
+
+int trt_sync(trt_network* net)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    CU(cudaSetDevice(net->device));
+    CU(cudaStreamSynchronize(net->stream));
+    if (net->ran) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, net->ev0, net->ev1) == cudaSuccess) net->kernel_ms = ms;
+    }
+    return TRT_OK;
+}
+
+int trt_run(trt_network* net, int32_t assume_short_ts)
+{
+    const int rc = run_async(net, assume_short_ts);
+    if (rc != TRT_OK) return rc;
+    return trt_sync(net);
+}
+
+int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_download_results called before trt_run");
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = net->stream;
+    const size_t n = (size_t)net->n, T = (size_t)net->T;
+    if (fvd_out && n * T > 0)
+        CU(cudaMemcpyAsync(fvd_out, net->d_fvd.p, n * 3 * T * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (upstream_out && n * T > 0) {
+        CU(net->d_up_out.reserve(n * T));
+        CU(cudaMemsetAsync(net->d_up_out.p, 0, n * T * sizeof(float), st));
+        CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_v.p, net->d_up_out.p, (int)n, (int)net->n_lp,
+                               (int)T, st));
+        CU(cudaMemcpyAsync(upstream_out, net->d_up_out.p, n * T * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return TRT_OK;
+}
+
+int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_short_ts, const float* qlat, int32_t nqcols,
+              const float* q0, int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd, float* fvd_out,
+              float* upstream_out)
+{
+    int rc = trt_upload_forcing(net, nsteps, qts, qlat, nqcols, q0, n_bnd, bnd_rows, bnd_fvd);
+    if (rc != TRT_OK) return rc;
+    rc = run_async(net, assume_short_ts);
+    if (rc != TRT_OK) return rc;
+    rc = trt_download_results(net, fvd_out, upstream_out);
+    if (rc != TRT_OK) return rc;
+    return trt_sync(net);
+}
+
+static int rows_to_device_pos(trt_network* net, int64_t count, const int64_t* rows)
+{
+    std::vector<int32_t> pos((size_t)count);
+    for (int64_t i = 0; i < count; ++i) {
+        if (rows[i] < 0 || rows[i] >= net->n) return fail(TRT_ERR_INVALID, "row %lld out of range", (long long)rows[i]);
+        pos[(size_t)i] = net->pos_of_row[(size_t)rows[i]];
+    }
+    CU(net->d_tmp_pos.reserve((size_t)count));
+    if (count > 0)
+        CU(cudaMemcpyAsync(net->d_tmp_pos.p, pos.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, net->stream));
+    CU(cudaStreamSynchronize(net->stream));
+    return TRT_OK;
+}
+
+int trt_export_flow_series(trt_network* net, int64_t count, const int64_t* rows, void* dst_device)
+{
+    if (!net || (count > 0 && (!rows || !dst_device))) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "no forcing uploaded");
+    CU(cudaSetDevice(net->device));
+    int rc = rows_to_device_pos(net, count, rows);
+    if (rc != TRT_OK) return rc;
+    CU(launch_export_series(net->d_tmp_pos.p, net->d_q.p, (float*)dst_device, (int)net->n, (int)count, net->T, net->stream));
+    CU(cudaStreamSynchronize(net->stream));
+    return TRT_OK;
+}
+
+int trt_import_boundary_flow(trt_network* net, int64_t count, const int64_t* rows, const void* src_device)
+{
+    if (!net || (count > 0 && (!rows || !src_device))) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "no forcing uploaded");
+    for (int64_t i = 0; i < count; ++i)
+        if (rows[i] >= 0 && rows[i] < net->n && net->kind_of_row[(size_t)rows[i]] != TRT_KIND_BOUNDARY)
+            return fail(TRT_ERR_INVALID, "row %lld is not of kind TRT_KIND_BOUNDARY", (long long)rows[i]);
+    CU(cudaSetDevice(net->device));
+    int rc = rows_to_device_pos(net, count, rows);
+    if (rc != TRT_OK) return rc;
+    CU(launch_import_series(net->d_tmp_pos.p, (const float*)src_device, net->d_q.p, (int)net->n, (int)count, net->T,
+                            net->stream));
+    CU(cudaStreamSynchronize(net->stream));
+    return TRT_OK;
+}
+
+int trt_device_results(trt_network* net, void** fvd_device)
+{
+    if (!net || !fvd_device) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_device_results called before trt_run");
+    *fvd_device = net->d_fvd.p;
+    return TRT_OK;
+}
+
+int trt_set_option(trt_network* net, const char* key, int64_t value)
+{
+    if (!net || !key) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "mode")) {
+        if (value != 0 && value != 1) return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches) or 1 (persistent)");
+        net->mode = (int)value;
+    } else if (!strcmp(key, "grid_blocks")) {
+        if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
+        net->grid_blocks = (int)value;
+    } else if (!strcmp(key, "stream")) {
+        // adopt a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so that the
+        // caller's CUDA events bracket this handle's kernels; 0 restores the private stream
+        CU(cudaSetDevice(net->device));
+        CU(cudaStreamSynchronize(net->stream));
+        if (value == 0) {
+            if (!net->own_stream) {
+                CU(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
+                net->own_stream = true;
+            }
+        } else {
+            if (net->own_stream && net->stream) cudaStreamDestroy(net->stream);
+            net->stream = (cudaStream_t)(uintptr_t)value;
+            net->own_stream = false;
+        }
+    } else {
+        return fail(TRT_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return TRT_OK;
+}
+
+int trt_last_run_stats(const trt_network* net, double* kernel_ms, int64_t* launches, int64_t* stages, int64_t* lane_steps)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (kernel_ms) *kernel_ms = net->kernel_ms;
+    if (launches) *launches = net->launches;
+    if (stages) *stages = net->stages;
+    if (lane_steps) *lane_steps = net->lane_steps;
+    return TRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// known-answer entry points
+// ---------------------------------------------------------------------------------------------------
+int trt_mc_segment_batch(int device, int64_t count, const float* in15, float* out6, int32_t* iters)
+{
+    if (count < 0 || (count > 0 && (!in15 || !out6))) return fail(TRT_ERR_INVALID, "bad arguments");
+    if (count == 0) return TRT_OK;
+    CU(cudaSetDevice(device));
+    DevBuf<float> d_in, d_out;
+    DevBuf<int> d_it;
+    CU(d_in.reserve((size_t)count * 15));
+    CU(d_out.reserve((size_t)count * 6));
+    CU(d_it.reserve((size_t)count));
+    CU(cudaMemcpy(d_in.p, in15, (size_t)count * 15 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_mc_batch(d_in.p, d_out.p, d_it.p, count, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out6, d_out.p, (size_t)count * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, d_it.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
+    return TRT_OK;
+}
+
+int trt_levelpool_series(int device, const double* a, int64_t nsteps, const float* inflow, float lateral_inflow,
+                         float routing_period, float* outflow_series, float* elevation_series)
+{
+    if (!a || nsteps < 0 || (nsteps > 0 && (!inflow || !outflow_series || !elevation_series)))
+        return fail(TRT_ERR_INVALID, "bad arguments");
+    if (nsteps == 0) return TRT_OK;
+    CU(cudaSetDevice(device));
+    float lp9[9] = {(float)a[0], (float)a[1], (float)a[2], (float)a[3], (float)a[4], (float)a[5], (float)a[6], (float)a[7], 10.0f};
+    const float ifd = (float)a[8], we0 = (float)a[10];
+    float H = we0;
+    if (we0 < -900000000.0f) H = lp9[4] + ((lp9[1] - lp9[4]) * ifd);
+    DevBuf<float> d_lp, d_in, d_q, d_h;
+    CU(d_lp.reserve(9)); CU(d_in.reserve((size_t)nsteps)); CU(d_q.reserve((size_t)nsteps)); CU(d_h.reserve((size_t)nsteps));
+    CU(cudaMemcpy(d_lp.p, lp9, sizeof(lp9), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_in.p, inflow, (size_t)nsteps * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_levelpool_series(d_lp.p, H, d_in.p, lateral_inflow, routing_period, d_q.p, d_h.p, nsteps, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(outflow_series, d_q.p, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(elevation_series, d_h.p, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost));
+    return TRT_OK;
+}
+
+int trt_powf_batch(int device, int64_t count, const float* x, const float* y, float* out)
+{
+    if (count < 0 || (count > 0 && (!x || !y || !out))) return fail(TRT_ERR_INVALID, "bad arguments");
+    if (count == 0) return TRT_OK;
+    CU(cudaSetDevice(device));
+    DevBuf<float> d_x, d_y, d_o;
+    CU(d_x.reserve((size_t)count)); CU(d_y.reserve((size_t)count)); CU(d_o.reserve((size_t)count));
+    CU(cudaMemcpy(d_x.p, x, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_y.p, y, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_powf_batch(d_x.p, d_y.p, d_o.p, count, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, d_o.p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+    return TRT_OK;
+}
+
+int trt_host_alloc(void** ptr, uint64_t bytes)
+{
+    if (!ptr) return fail(TRT_ERR_INVALID, "NULL argument");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return TRT_OK;
+}
+int trt_host_free(void* ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return TRT_OK;
+}
+
+}  // extern "C"

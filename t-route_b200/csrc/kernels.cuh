@@ -1,0 +1,75 @@
+/*
+ * kernels.cuh -- device-side view of a routing network and the launchers of routing_kernels.cu.
+ *
+ * HBM layout (all float32 unless noted; `pos` = level-sorted engine position, n = segments):
+ *   par      [9][n]      structure-of-arrays channel geometry: dt, dx, bw, tw, twcc, n, ncc, cs, s0
+ *                        (for level-pool rows the same 9 slots hold dt, LkArea, LkMxE, OrificeA, OrificeC,
+ *                         OrificeE, WeirC, WeirE, WeirL -- a reservoir has no channel geometry)
+ *   kind     [n] u8      TRT_KIND_*
+ *   level    [n] i32     wavefront level; positions are sorted by it, lvl_ptr[L+1] delimits the levels
+ *   up_ptr   [n+1] i32, up_idx [E] i32   CSR of upstream positions, reference summation order
+ *   qlat_t   [nq][n]     lateral inflow, time-major
+ *   q, v, d  [T+1][n]    flow / velocity / depth, time-major; row 0 = initial state.  Rows are the only
+ *                        state of the model: step t reads row t-1 (own) and rows t, t-1 (upstream).
+ *   fvd      [n_rows][3T] the reference's result layout (mc_reach.pyx:807-813), caller row order
+ */
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace trt {
+
+struct NetDev {
+    int n;                     // segments
+    int nlevels;               // wavefront levels of the dependent (assume_short_ts = false) schedule
+    const int* lvl_ptr;        // [nlevels + 1]
+    const int* level;          // [n]
+    const int* up_ptr;         // [n + 1]
+    const int* up_idx;         // [E]
+    const unsigned char* kind; // [n]
+    const float* par;          // [9][n]
+    const int* row_of_pos;     // [n]
+};
+
+struct RunDev {
+    int T;          // timesteps
+    int qts;        // qts_subdivisions
+    int nq;         // qlat columns
+    int short_ts;   // assume_short_ts
+    const float* qlat_t;
+    float* q;
+    float* v;
+    float* d;
+};
+
+// wavefront: stage k routes every (segment s, step t) with level(s) + t == k
+cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st);
+// persistent cooperative kernel over stages [k_begin, k_end)
+cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin, int k_end, int grid_blocks,
+                              cudaStream_t st);
+// largest co-resident grid (blocks) of the persistent kernel on the current device
+cudaError_t persistent_max_grid(int* blocks);
+
+cudaError_t launch_gather_qlat(const float* qlat_rows, const int* row_of_pos, float* qlat_t, int n, int nq,
+                               cudaStream_t st);
+cudaError_t launch_init_state(const float* q0_rows, const int* row_of_pos, float* q, float* v, float* d, int n,
+                              cudaStream_t st);
+cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const float* lp_h0, float* q, float* v,
+                                  float* d, int n_lp, cudaStream_t st);
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par8, float* par, int n, int n_lp, cudaStream_t st);
+cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,
+                                 int n_bnd, int T, cudaStream_t st);
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st);
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* v, float* up_rows, int n,
+                                int n_lp, int T, cudaStream_t st);
+cudaError_t launch_export_series(const int* pos, const float* q, float* dst, int n, int count, int T,
+                                 cudaStream_t st);
+cudaError_t launch_import_series(const int* pos, const float* src, float* q, int n, int count, int T,
+                                 cudaStream_t st);
+
+cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long long count, cudaStream_t st);
+cudaError_t launch_levelpool_series(const float* lp9, float h0, const float* inflow, float ql, float dt,
+                                    float* outflow, float* elev, long long nsteps, cudaStream_t st);
+cudaError_t launch_powf_batch(const float* x, const float* y, float* out, long long count, cudaStream_t st);
+
+}  // namespace trt

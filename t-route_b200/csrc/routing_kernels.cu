@@ -1,0 +1,416 @@
+/*
+ * routing_kernels.cu -- sm_100a kernels of the routing path.
+ *
+ * Replaces the time-outer / reach-inner double loop of compute_network_structured
+ * (/root/reference/src/troute-routing/troute/routing/fast_reach/mc_reach.pyx:492-800) and the
+ * per-reach segment walk of compute_reach_kernel (:70-138).
+ *
+ * Schedule.  Segment s at step t needs q[u, t], q[u, t-1] of its upstream neighbours u and its own
+ * q[s, t-1], depth[s, t-1] (mc_reach.pyx:499-502, :721-735), nothing else.  With level(s) = longest
+ * path from a headwater, all pairs (s, t) with level(s) + t == k are mutually independent, so the
+ * network is routed as a wavefront over k = 1 .. L + T - 1 instead of T * L dependent level-steps.
+ * Positions are sorted by level, hence the active set of stage k is ONE contiguous position range
+ * [lvl_ptr[max(0, k-T)], lvl_ptr[min(L, k)]) and every load below is a unit-stride sweep of an SoA
+ * array (the upstream gather is the only indexed access).  With assume_short_ts every segment of a
+ * step is independent (quc := qup) and the same kernel runs with L = 1.
+ *
+ * One lane = one segment-step; 32 consecutive positions per warp.  No tensor cores: the work is
+ * ~2k dependent scalar FP32/FP64 instructions per lane, not a contraction.
+ *
+ * Compile with -fmad=false (see mc_device.cuh).
+ */
+#include <cooperative_groups.h>
+#include "kernels.cuh"
+#include "mc_device.cuh"
+#include "../../include/troute_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace trt {
+
+__device__ const trt_u64 g_log2_tab[2 * TRT_LOG2_TAB_N] = TRT_LOG2_TAB_INIT;
+__device__ const trt_u64 g_exp2_tab[TRT_EXP2_TAB_N] = TRT_EXP2_TAB_INIT;
+
+constexpr int kBlock = 256;
+
+struct SmemTabs {
+    __align__(16) trt_u64 tl[2 * TRT_LOG2_TAB_N];
+    trt_u64 te[TRT_EXP2_TAB_N];
+};
+
+__device__ __forceinline__ PowTabs stage_tables(SmemTabs& s)
+{
+    for (int i = threadIdx.x; i < 2 * TRT_LOG2_TAB_N; i += blockDim.x) s.tl[i] = g_log2_tab[i];
+    for (int i = threadIdx.x; i < TRT_EXP2_TAB_N; i += blockDim.x) s.te[i] = g_exp2_tab[i];
+    __syncthreads();
+    PowTabs t; t.tl = s.tl; t.te = s.te;
+    return t;
+}
+
+// route segment `s` (engine position) at step `t`
+__device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs)
+{
+    const unsigned kind = net.kind[s];
+    if (kind == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
+
+    const size_t n = (size_t)net.n;
+    const float* qc = run.q + (size_t)t * n;          // row t
+    const float* qp = qc - n;                         // row t-1
+
+    // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
+    float quc = 0.0f, qup = 0.0f;
+    const int e0 = __ldg(net.up_ptr + s), e1 = __ldg(net.up_ptr + s + 1);
+    if (run.short_ts) {
+        for (int e = e0; e < e1; ++e) qup += __ldcg(qp + __ldg(net.up_idx + e));
+        quc = qup;
+    } else {
+        for (int e = e0; e < e1; ++e) {
+            const int u = __ldg(net.up_idx + e);
+            quc += __ldcg(qc + u);
+            qup += __ldcg(qp + u);
+        }
+    }
+
+    const float* par = net.par + s;
+    const float p0 = __ldg(par + 0 * n), p1 = __ldg(par + 1 * n), p2 = __ldg(par + 2 * n), p3 = __ldg(par + 3 * n),
+                p4 = __ldg(par + 4 * n), p5 = __ldg(par + 5 * n), p6 = __ldg(par + 6 * n), p7 = __ldg(par + 7 * n),
+                p8 = __ldg(par + 8 * n);
+    const float statep = __ldcg(run.d + (size_t)(t - 1) * n + s);   // depth (MC) / water elevation (level pool) at t-1
+
+    float o_q, o_v, o_d;
+    if (kind == TRT_KIND_LEVELPOOL) {
+        // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
+        LpParams lp;
+        lp.area = p1; lp.max_depth = p2; lp.orifice_area = p3; lp.orifice_coefficient = p4; lp.orifice_elevation = p5;
+        lp.weir_coefficient = p6; lp.weir_elevation = p7; lp.weir_length = p8; lp.dam_length = 10.0f;
+        float H = statep, outflow;
+        trt_levelpool_step(lp, quc, 0.0f, p0, H, outflow, tabs);
+        o_q = outflow;
+        o_v = quc;      // velocity slot carries the reservoir inflow (upstream_array, :710); finalize writes 0 for v
+        o_d = H;
+    } else {
+        const float ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);   // :723
+        const float qdp = __ldcg(qp + s);                                            // :733
+        const McResult r = trt_mc_segment<false>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
+        o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
+    }
+    run.q[(size_t)t * n + s] = o_q;
+    run.v[(size_t)t * n + s] = o_v;
+    run.d[(size_t)t * n + s] = o_d;
+}
+
+__device__ __forceinline__ int lane_step(const NetDev& net, const RunDev& run, int k, int s)
+{
+    return run.short_ts ? k : k - __ldg(net.level + s);
+}
+
+__global__ void __launch_bounds__(kBlock) stage_kernel(NetDev net, RunDev run, int k, int lo, int hi)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    const int s = lo + blockIdx.x * kBlock + threadIdx.x;
+    if (s >= hi) return;
+    const int t = lane_step(net, run, k, s);
+    if (t < 1 || t > run.T) return;
+    route_lane(net, run, s, t, tabs);
+}
+
+__global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev run, int k_begin, int k_end)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    cg::grid_group grid = cg::this_grid();
+    const int L = run.short_ts ? 1 : net.nlevels;
+    const int gstride = gridDim.x * kBlock;
+    const int gtid = blockIdx.x * kBlock + threadIdx.x;
+    for (int k = k_begin; k < k_end; ++k) {
+        int lo, hi;
+        if (run.short_ts) { lo = 0; hi = net.n; }
+        else {
+            lo = __ldg(net.lvl_ptr + max(0, k - run.T));
+            hi = __ldg(net.lvl_ptr + min(L, k));
+        }
+        for (int s = lo + gtid; s < hi; s += gstride) {
+            const int t = lane_step(net, run, k, s);
+            if (t >= 1 && t <= run.T) route_lane(net, run, s, t, tabs);
+        }
+        grid.sync();
+    }
+}
+
+cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st)
+{
+    if (hi <= lo) return cudaSuccess;
+    const int blocks = (hi - lo + kBlock - 1) / kBlock;
+    stage_kernel<<<blocks, kBlock, 0, st>>>(net, run, k, lo, hi);
+    return cudaGetLastError();
+}
+
+cudaError_t persistent_max_grid(int* blocks)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    *blocks = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin, int k_end, int grid_blocks,
+                              cudaStream_t st)
+{
+    NetDev n = net; RunDev r = run;
+    void* args[] = {&n, &r, &k_begin, &k_end};
+    return cudaLaunchCooperativeKernel((void*)persistent_kernel, dim3(grid_blocks), dim3(kBlock), args, 0, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary conversions between the caller's row-major tables and the time-major engine arrays
+// ------------------------------------------------------------------------------------------------
+
+// qlat_t[c][pos] = qlat_rows[row_of_pos[pos]][c]
+__global__ void gather_qlat_kernel(const float* __restrict__ in, const int* __restrict__ row_of_pos,
+                                   float* __restrict__ out, int n, int nq)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const float* src = in + (size_t)row_of_pos[pos] * nq;
+    for (int c = 0; c < nq; ++c) out[(size_t)c * n + pos] = __ldg(src + c);
+}
+
+// row 0 of q, v, d = initial_conditions columns (flowveldepth_nd[ids, 0] = init_array[ids], mc_reach.pyx:361)
+__global__ void init_state_kernel(const float* __restrict__ q0, const int* __restrict__ row_of_pos,
+                                  float* __restrict__ q, float* __restrict__ v, float* __restrict__ d, int n)
+{
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const float* src = q0 + (size_t)row_of_pos[pos] * 3;
+    q[pos] = src[0]; v[pos] = src[1]; d[pos] = src[2];
+}
+
+// reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth row
+__global__ void init_levelpool_kernel(const int* __restrict__ lp_pos, const float* __restrict__ qd0,
+                                      const float* __restrict__ h0, float* q, float* v, float* d, int n_lp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lp) return;
+    const int pos = lp_pos[i];
+    q[pos] = qd0[i]; v[pos] = 0.0f; d[pos] = h0[i];
+}
+
+// overlay the 8 reservoir parameters on the channel-geometry slots 1..8 of the level-pool positions
+__global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const float* __restrict__ par8, float* par, int n,
+                                         int n_lp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lp * 8) return;
+    const int l = i / 8, c = i % 8;
+    par[(size_t)(c + 1) * n + lp_pos[l]] = par8[i];
+}
+
+// prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463)
+__global__ void fill_boundary_kernel(const int* __restrict__ bnd_pos, const float* __restrict__ bnd_fvd, float* q,
+                                     float* v, float* d, int n, int n_bnd, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_bnd * T) return;
+    const int b = (int)(i / T), t = (int)(i % T) + 1;
+    const float* src = bnd_fvd + ((size_t)b * T + (t - 1)) * 3;
+    const size_t o = (size_t)t * n + bnd_pos[b];
+    q[o] = src[0]; v[o] = src[1]; d[o] = src[2];
+}
+
+// fvd[row][3*(t-1) + c] = {q, v, d}[t][pos]: 32 positions x 32 steps per block through shared memory so that
+// both the time-major reads and the row-major writes are coalesced.
+__global__ void __launch_bounds__(256) finalize_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
+{
+    __shared__ float sq[32][33], sv[32][33], sd[32][33];
+    const int p0 = blockIdx.x * 32, t0 = blockIdx.y * 32 + 1;     // steps t0 .. t0+31
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const size_t n = (size_t)net.n;
+    for (int j = ty; j < 32; j += 8) {
+        const int t = t0 + j, p = p0 + tx;
+        if (t <= run.T && p < net.n) {
+            const size_t o = (size_t)t * n + p;
+            sq[j][tx] = run.q[o]; sv[j][tx] = run.v[o]; sd[j][tx] = run.d[o];
+        }
+    }
+    __syncthreads();
+    const int nt = min(32, run.T - t0 + 1);                       // valid steps in this tile
+    const int width = 3 * nt;
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+        const int pl = idx / 96, c = idx % 96;
+        const int p = p0 + pl;
+        if (p >= net.n || c >= width) continue;
+        const int j = c / 3, comp = c % 3;
+        float val = comp == 0 ? sq[j][pl] : (comp == 1 ? sv[j][pl] : sd[j][pl]);
+        if (comp == 1 && net.kind[p] == TRT_KIND_LEVELPOOL) val = 0.0f;   // flowveldepth[r.id, t, 1] = 0.0  (:708)
+        fvd[(size_t)net.row_of_pos[p] * (3 * (size_t)run.T) + 3 * (size_t)(t0 - 1) + c] = val;
+    }
+}
+
+// upstream_array[row, t] = reservoir inflow (mc_reach.pyx:710), carried in the velocity slot of level-pool rows
+__global__ void upstream_out_kernel(const int* __restrict__ lp_pos, const int* __restrict__ row_of_pos,
+                                    const float* __restrict__ v, float* __restrict__ up, int n, int n_lp, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_lp * T) return;
+    const int l = (int)(i / T), t = (int)(i % T) + 1;
+    const int pos = lp_pos[l];
+    up[(size_t)row_of_pos[pos] * T + (t - 1)] = v[(size_t)t * n + pos];
+}
+
+__global__ void export_series_kernel(const int* __restrict__ pos, const float* __restrict__ q, float* __restrict__ dst,
+                                     int n, int count, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)count * (T + 1)) return;
+    const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
+    dst[i] = q[(size_t)t * n + pos[c]];
+}
+
+__global__ void import_series_kernel(const int* __restrict__ pos, const float* __restrict__ src, float* __restrict__ q,
+                                     int n, int count, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)count * (T + 1)) return;
+    const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
+    if (t == 0) return;
+    q[(size_t)t * n + pos[c]] = src[i];
+}
+
+#define TRT_GRID1D(total, block) (unsigned)(((total) + (block)-1) / (block))
+
+cudaError_t launch_gather_qlat(const float* in, const int* row_of_pos, float* out, int n, int nq, cudaStream_t st)
+{
+    if (n == 0 || nq == 0) return cudaSuccess;
+    gather_qlat_kernel<<<TRT_GRID1D(n, 256), 256, 0, st>>>(in, row_of_pos, out, n, nq);
+    return cudaGetLastError();
+}
+cudaError_t launch_init_state(const float* q0, const int* row_of_pos, float* q, float* v, float* d, int n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    init_state_kernel<<<TRT_GRID1D(n, 256), 256, 0, st>>>(q0, row_of_pos, q, v, d, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_init_levelpool(const int* lp_pos, const float* qd0, const float* h0, float* q, float* v, float* d,
+                                  int n_lp, cudaStream_t st)
+{
+    if (n_lp == 0) return cudaSuccess;
+    init_levelpool_kernel<<<TRT_GRID1D(n_lp, 128), 128, 0, st>>>(lp_pos, qd0, h0, q, v, d, n_lp);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par8, float* par, int n, int n_lp, cudaStream_t st)
+{
+    if (n_lp == 0) return cudaSuccess;
+    scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 8, 128), 128, 0, st>>>(lp_pos, par8, par, n, n_lp);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,
+                                 int n_bnd, int T, cudaStream_t st)
+{
+    const long long total = (long long)n_bnd * T;
+    if (total == 0) return cudaSuccess;
+    fill_boundary_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(bnd_pos, bnd_fvd, q, v, d, n, n_bnd, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st)
+{
+    if (net.n == 0 || run.T == 0) return cudaSuccess;
+    dim3 grid((net.n + 31) / 32, (run.T + 31) / 32);
+    finalize_kernel<<<grid, 256, 0, st>>>(net, run, fvd);
+    return cudaGetLastError();
+}
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* v, float* up, int n, int n_lp,
+                                int T, cudaStream_t st)
+{
+    const long long total = (long long)n_lp * T;
+    if (total == 0) return cudaSuccess;
+    upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, v, up, n, n_lp, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_export_series(const int* pos, const float* q, float* dst, int n, int count, int T, cudaStream_t st)
+{
+    const long long total = (long long)count * (T + 1);
+    if (total == 0) return cudaSuccess;
+    export_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, q, dst, n, count, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_import_series(const int* pos, const float* src, float* q, int n, int count, int T, cudaStream_t st)
+{
+    const long long total = (long long)count * (T + 1);
+    if (total == 0) return cudaSuccess;
+    import_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, src, q, n, count, T);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// known-answer / numerics-contract kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) mc_batch_kernel(const float* __restrict__ in15, float* __restrict__ out6,
+                                                          int* __restrict__ iters, long long count)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= count) return;
+    const float* a = in15 + 15 * i;
+    // (dt,qup,quc,qdp,ql,dx,bw,tw,twcc,n,ncc,cs,s0,velp,depthp) -- reach.pyx:66-81
+    const McResult r = trt_mc_segment<true>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11],
+                                            a[12], a[14], tabs);
+    float* o = out6 + 6 * i;
+    o[0] = r.qdc; o[1] = r.velc; o[2] = r.depthc; o[3] = r.ck; o[4] = r.cn; o[5] = r.X;
+    if (iters) iters[i] = r.iters;
+}
+
+__global__ void levelpool_series_kernel(const float* __restrict__ lp9, float h0, const float* __restrict__ inflow,
+                                        float ql, float dt, float* __restrict__ outflow, float* __restrict__ elev,
+                                        long long nsteps)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    LpParams lp;
+    lp.area = lp9[0]; lp.max_depth = lp9[1]; lp.orifice_area = lp9[2]; lp.orifice_coefficient = lp9[3];
+    lp.orifice_elevation = lp9[4]; lp.weir_coefficient = lp9[5]; lp.weir_elevation = lp9[6]; lp.weir_length = lp9[7];
+    lp.dam_length = lp9[8];
+    float H = h0;
+    for (long long t = 0; t < nsteps; ++t) {
+        float q;
+        trt_levelpool_step(lp, inflow[t], ql, dt, H, q, tabs);
+        outflow[t] = q; elev[t] = H;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) powf_batch_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            float* __restrict__ out, long long count)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i < count) out[i] = dpow(x[i], y[i], tabs);
+}
+
+cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long long count, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    mc_batch_kernel<<<TRT_GRID1D(count, kBlock), kBlock, 0, st>>>(in15, out6, iters, count);
+    return cudaGetLastError();
+}
+cudaError_t launch_levelpool_series(const float* lp9, float h0, const float* inflow, float ql, float dt, float* outflow,
+                                    float* elev, long long nsteps, cudaStream_t st)
+{
+    levelpool_series_kernel<<<1, 32, 0, st>>>(lp9, h0, inflow, ql, dt, outflow, elev, nsteps);
+    return cudaGetLastError();
+}
+cudaError_t launch_powf_batch(const float* x, const float* y, float* out, long long count, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    powf_batch_kernel<<<TRT_GRID1D(count, kBlock), kBlock, 0, st>>>(x, y, out, count);
+    return cudaGetLastError();
+}
+
+}  // namespace trt

@@ -1,0 +1,243 @@
+"""RoutingNetwork -- flat-array host interface of the B200 routing engine.
+
+A `RoutingNetwork` is the device-resident twin of what compute_network_structured builds per call out
+of Python objects (/root/reference/src/troute-routing/troute/routing/fast_reach/mc_reach.pyx:287-378,
+:472-481): the reach / segment structs, their upstream id arrays and parameter rows.  It is built
+once from CSR arrays in the caller's row order (rows = positions in the sorted segment index
+`data_idx`) and then routes any number of forcing chunks.
+
+Only numpy and ctypes are used here; all arithmetic happens in libtroute_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import TRT_KIND_BOUNDARY, TRT_KIND_LEVELPOOL, TRT_KIND_MC, as_c, check, ptr
+
+# order of the nine per-segment parameters the kernel consumes (column_mapper, mc_reach.pyx:150-162)
+PARAM_COLUMNS = ["dt", "dx", "bw", "tw", "twcc", "n", "ncc", "cs", "s0"]
+
+
+def column_mapper(src_cols):
+    """Map source column labels to the order the kernel expects (mc_reach.pyx:150-162)."""
+    index = {label: i for i, label in enumerate(src_cols)}
+    return [index[label] for label in PARAM_COLUMNS]
+
+
+class RoutingNetwork:
+    """Handle on a levelled, device-resident river network.
+
+    Parameters
+    ----------
+    up_ptr, up_rows : CSR of upstream rows (reference summation order, mc_reach.pyx:499-502)
+    kind            : [n_rows] uint8, TRT_KIND_MC / TRT_KIND_LEVELPOOL / TRT_KIND_BOUNDARY
+    data_values     : [n_rows, ncols] float32 parameter table
+    data_cols       : column labels of data_values (must contain PARAM_COLUMNS)
+    device          : CUDA device ordinal
+    """
+
+    def __init__(self, up_ptr, up_rows, kind, data_values, data_cols, device=0):
+        L = _lib.lib()
+        self._L = L
+        self._h = C.c_void_p()
+        up_ptr = as_c(up_ptr, np.int64)
+        up_rows = as_c(up_rows, np.int64)
+        kind = as_c(kind, np.uint8)
+        data_values = as_c(data_values, np.float32)
+        n_rows = int(kind.shape[0])
+        if up_ptr.shape[0] != n_rows + 1:
+            raise ValueError(f"up_ptr must have n_rows+1 = {n_rows + 1} entries, got {up_ptr.shape[0]}")
+        if data_values.ndim != 2 or data_values.shape[0] != n_rows or data_values.shape[1] != len(data_cols):
+            raise ValueError("data_values shape mismatch")            # mc_reach.pyx:249-250
+        if n_rows and int(up_ptr[-1]) != up_rows.shape[0]:
+            raise ValueError("up_ptr[-1] must equal len(up_rows)")
+        scols = np.asarray(column_mapper(list(data_cols)), dtype=np.int32)
+        self.n_rows = n_rows
+        self.device = int(device)
+        self.kind = kind
+        self._keep = (up_ptr, up_rows, kind, data_values, scols)
+        check(L.trt_network_create(self.device, n_rows, ptr(up_ptr, C.c_int64), ptr(up_rows, C.c_int64),
+                                   ptr(kind, C.c_uint8), ptr(data_values, C.c_float), int(data_values.shape[1]),
+                                   ptr(scols, C.c_int32), C.byref(self._h)))
+        self._keep = None
+        self.nsteps = 0
+        self._lp_rows = np.zeros(0, dtype=np.int64)
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.trt_network_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- topology -----------------------------------------------------------------------------
+    @property
+    def num_levels(self):
+        out = C.c_int32()
+        check(self._L.trt_network_num_levels(self._h, C.byref(out)))
+        return out.value
+
+    def levels(self):
+        out = np.empty(self.n_rows, dtype=np.int32)
+        check(self._L.trt_network_get_levels(self._h, ptr(out, C.c_int32)))
+        return out
+
+    def positions(self):
+        out = np.empty(self.n_rows, dtype=np.int32)
+        check(self._L.trt_network_get_positions(self._h, ptr(out, C.c_int32)))
+        return out
+
+    # -- configuration ------------------------------------------------------------------------
+    def set_levelpools(self, lp_rows, wbody_cols):
+        """wbody_cols: [n_lp, 11] float64 rows (LkArea, LkMxE, OrificeA, OrificeC, OrificeE, WeirC, WeirE,
+        WeirL, ifd, qd0, h0) -- compute.py:1416-1430."""
+        lp_rows = as_c(lp_rows, np.int64)
+        wbody_cols = as_c(wbody_cols, np.float64).reshape(-1, 11) if len(lp_rows) else np.zeros((0, 11))
+        if wbody_cols.shape[0] != lp_rows.shape[0]:
+            raise ValueError("one wbody_cols row per level-pool row is required")
+        check(self._L.trt_network_set_levelpools(self._h, int(lp_rows.shape[0]), ptr(lp_rows, C.c_int64),
+                                                 ptr(wbody_cols, C.c_double)))
+        self._lp_rows = lp_rows
+
+    def set_option(self, key, value):
+        check(self._L.trt_set_option(self._h, key.encode(), int(value)))
+
+    # -- routing ------------------------------------------------------------------------------
+    def _check_forcing(self, nsteps, qts_subdivisions, qlat, q0):
+        if qlat.ndim != 2 or qlat.shape[0] != self.n_rows:
+            raise ValueError(
+                f"Number of rows in Qlat is incorrect: expected ({self.n_rows}), got ({qlat.shape[0]})")  # :243-244
+        if q0.shape != (self.n_rows, 3):
+            raise ValueError(f"initial_conditions must be ({self.n_rows}, 3), got {q0.shape}")
+
+    def upload(self, nsteps, qts_subdivisions, qlat, q0, bnd_rows=None, bnd_fvd=None):
+        """Host -> device: qlat [n_rows, nqcols], q0 [n_rows, 3], optional prescribed rows."""
+        qlat = as_c(qlat, np.float32)
+        q0 = as_c(q0, np.float32)
+        self._check_forcing(nsteps, qts_subdivisions, qlat, q0)
+        n_bnd = 0
+        rows_p = None
+        fvd_p = None
+        if bnd_rows is not None and len(bnd_rows):
+            bnd_rows = as_c(bnd_rows, np.int64)
+            bnd_fvd = as_c(bnd_fvd, np.float32)
+            if bnd_fvd.shape != (bnd_rows.shape[0], 3 * nsteps):
+                raise ValueError("bnd_fvd must be [n_bnd, 3*nsteps]")
+            n_bnd = int(bnd_rows.shape[0])
+            rows_p = ptr(bnd_rows, C.c_int64)
+            fvd_p = bnd_fvd.ctypes.data
+        check(self._L.trt_upload_forcing(self._h, int(nsteps), int(qts_subdivisions), qlat.ctypes.data,
+                                         int(qlat.shape[1]), q0.ctypes.data, n_bnd, rows_p, fvd_p))
+        self.nsteps = int(nsteps)
+
+    def upload_ptr(self, nsteps, qts_subdivisions, qlat_ptr, nqcols, q0_ptr):
+        """Same as upload() for raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        check(self._L.trt_upload_forcing(self._h, int(nsteps), int(qts_subdivisions), qlat_ptr, int(nqcols), q0_ptr,
+                                         0, None, None))
+        self.nsteps = int(nsteps)
+
+    def run(self, assume_short_ts=False):
+        check(self._L.trt_run(self._h, 1 if assume_short_ts else 0))
+
+    def run_async(self, assume_short_ts=False):
+        check(self._L.trt_run_async(self._h, 1 if assume_short_ts else 0))
+
+    def sync(self):
+        check(self._L.trt_sync(self._h))
+
+    def download(self, want_upstream=False, out=None):
+        """Device -> host: ([n_rows, 3*nsteps] float32, [n_rows, nsteps] float32 | None)."""
+        fvd = out if out is not None else np.empty((self.n_rows, 3 * self.nsteps), dtype=np.float32)
+        up = np.empty((self.n_rows, self.nsteps), dtype=np.float32) if want_upstream else None
+        check(self._L.trt_download_results(self._h, fvd.ctypes.data, up.ctypes.data if up is not None else None))
+        return fvd, up
+
+    def download_ptr(self, fvd_ptr):
+        check(self._L.trt_download_results(self._h, fvd_ptr, None))
+
+    def route(self, nsteps, qts_subdivisions, qlat, q0, assume_short_ts=False, bnd_rows=None, bnd_fvd=None,
+              want_upstream=False):
+        """upload + run + download.  Returns (fvd [n_rows, 3*nsteps], upstream [n_rows, nsteps] | None)."""
+        self.upload(nsteps, qts_subdivisions, qlat, q0, bnd_rows, bnd_fvd)
+        self.run(assume_short_ts)
+        return self.download(want_upstream)
+
+    def route_ptr(self, nsteps, qts_subdivisions, assume_short_ts, qlat_ptr, nqcols, q0_ptr, fvd_ptr):
+        """The single-call C entry point trt_route on raw host addresses (end-to-end timing path)."""
+        check(self._L.trt_route(self._h, int(nsteps), int(qts_subdivisions), 1 if assume_short_ts else 0, qlat_ptr,
+                                int(nqcols), q0_ptr, 0, None, None, fvd_ptr, None))
+        self.nsteps = int(nsteps)
+
+    # -- device-side access -------------------------------------------------------------------
+    def export_flow_series(self, rows, dst_device_ptr):
+        rows = as_c(rows, np.int64)
+        check(self._L.trt_export_flow_series(self._h, int(rows.shape[0]), ptr(rows, C.c_int64), dst_device_ptr))
+
+    def import_boundary_flow(self, rows, src_device_ptr):
+        rows = as_c(rows, np.int64)
+        check(self._L.trt_import_boundary_flow(self._h, int(rows.shape[0]), ptr(rows, C.c_int64), src_device_ptr))
+
+    def device_results_ptr(self):
+        out = C.c_void_p()
+        check(self._L.trt_device_results(self._h, C.byref(out)))
+        return out.value
+
+    def last_run_stats(self):
+        ms = C.c_double()
+        launches = C.c_int64()
+        stages = C.c_int64()
+        lane_steps = C.c_int64()
+        check(self._L.trt_last_run_stats(self._h, C.byref(ms), C.byref(launches), C.byref(stages), C.byref(lane_steps)))
+        return {"kernel_ms": ms.value, "launches": launches.value, "stages": stages.value,
+                "lane_steps": lane_steps.value}
+
+
+# -------------------------------------------------------------------------------------------------
+# known-answer entry points (GPU twins of the reference's python-callable kernels)
+# -------------------------------------------------------------------------------------------------
+def mc_segment_batch(in15, device=0, want_iters=False):
+    """in15 [count, 15] rows (dt,qup,quc,qdp,ql,dx,bw,tw,twcc,n,ncc,cs,s0,velp,depthp) -> [count, 6]
+    rows (qdc, velc, depthc, ck, cn, X)."""
+    L = _lib.lib()
+    in15 = as_c(in15, np.float32).reshape(-1, 15)
+    out = np.empty((in15.shape[0], 6), dtype=np.float32)
+    iters = np.empty(in15.shape[0], dtype=np.int32)
+    check(L.trt_mc_segment_batch(int(device), int(in15.shape[0]), ptr(in15, C.c_float), ptr(out, C.c_float),
+                                 ptr(iters, C.c_int32)))
+    return (out, iters) if want_iters else out
+
+
+def levelpool_series(wbody_row, inflow, lateral_inflow=0.0, routing_period=300.0, device=0):
+    L = _lib.lib()
+    wbody_row = as_c(wbody_row, np.float64).reshape(11)
+    inflow = as_c(inflow, np.float32)
+    q = np.empty_like(inflow)
+    h = np.empty_like(inflow)
+    check(L.trt_levelpool_series(int(device), ptr(wbody_row, C.c_double), int(inflow.shape[0]), ptr(inflow, C.c_float),
+                                 float(lateral_inflow), float(routing_period), ptr(q, C.c_float), ptr(h, C.c_float)))
+    return q, h
+
+
+def powf_batch(x, y, device=0):
+    L = _lib.lib()
+    x = as_c(x, np.float32)
+    y = as_c(y, np.float32)
+    out = np.empty_like(x)
+    check(L.trt_powf_batch(int(device), int(x.shape[0]), ptr(x, C.c_float), ptr(y, C.c_float), ptr(out, C.c_float)))
+    return out
+
+
+__all__ = ["RoutingNetwork", "PARAM_COLUMNS", "column_mapper", "mc_segment_batch", "levelpool_series", "powf_batch",
+           "TRT_KIND_MC", "TRT_KIND_LEVELPOOL", "TRT_KIND_BOUNDARY"]
