@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- routed segment-timesteps/sec of the B200 routing path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[2] -- the synthetic CONUS-scale forest the metric is quoted on:
+2,729,077 segments in 14,713 basins (largest ~50 %), MC-only, 288 x 300 s steps, dependent upstream flows
+(assume_short_ts = False, the reference default).  One bench "step" = ONE routing call = all 288 timesteps of
+all segments (786 M segment-timesteps).  Synthetic parameters/forcing, cold start; see troute_b200/synth.py.
+
+  value     segment-timesteps/s with forcing and state already resident in HBM: K x (wavefront kernel + result
+            transpose) timed with CUDA events on the launching stream.  Working set (q, v, d, fvd: 4 x 9.4 GB)
+            is far larger than the 126 MB L2, so no explicit flush between iterations.
+  e2e       the same metric through the C-ABI call a T-Route maintainer would bind (trt_route): pinned HOST
+            qlat / q0 in, pinned HOST [n, 3*nsteps] result out, copies inside the timed region.
+  roofline  wavefront kernel only: algorithmic bytes (68 B per segment-timestep, SURVEY.md 8d / DESIGN.md) x
+            lane-steps per launch / the kernel's CUDA-event duration (events recorded by the engine on its
+            stream around that launch), against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle's platform-libm build (C restatement of the Fortran; the reference cannot be
+            compiled here: no Fortran compiler) on a bounded sample of the same workload, rank 0, N = 1 only.
+
+--impl reference times that CPU restatement with every host thread, decomposed the way the reference's
+parallel modes do (orders of sub-networks, jobs of an order in parallel), on a bounded sample.
+
+N > 1: torchrun, one rank per GPU; the network is sharded by sub-basin (troute_b200/partition.py), total work
+fixed -> "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "t-route_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+BYTES_PER_SEGSTEP = 68.0       # 12 write + 8 own state + 32 params + 4 qlat + 8 gather + 4 index
+DT = 300.0
+QTS = 12
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="conus", choices=["conus", "tree"])
+    ap.add_argument("--segments", type=int, default=0, help="override the segment count (testing only)")
+    ap.add_argument("--nsteps", type=int, default=288, help="routing timesteps per call")
+    ap.add_argument("--short-ts", type=int, default=0)
+    ap.add_argument("--mode", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def build_workload(args):
+    from troute_b200 import synth
+    if args.workload == "conus":
+        n = args.segments or 2_729_077
+        basins = max(1, int(round(14_713 * n / 2_729_077)))
+        down = synth.conus_like(n_total=n, n_basins=basins, seed=16)
+        name = f"synthetic CONUS-scale forest, {n} segments / {basins} basins, MC-only, {args.nsteps} x 300 s"
+    else:
+        n = args.segments or 1_048_576
+        down = synth.binary_tree(n)
+        name = f"synthetic balanced binary tree, {n} segments, MC-only, {args.nsteps} x 300 s"
+    params = synth.channel_params(down, dt=DT, seed=16)
+    qlat = synth.lateral_inflow(n, args.nsteps, QTS, seed=16)
+    q0 = np.zeros((n, 3), dtype=np.float32)
+    up_ptr, up_rows = synth.upstream_csr(down)
+    return dict(name=name, n=n, down=down, params=params, cols=synth.PARAM_COLS, qlat=qlat, q0=q0, up_ptr=up_ptr,
+                up_rows=up_rows, kind=np.zeros(n, dtype=np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference's Fortran + Cython loop), platform-libm arithmetic
+# ---------------------------------------------------------------------------------------------------
+def cpu_arm(wl, args, threads, budget_s):
+    """Time the CPU path on a bounded sample: the FULL network for `ts` timesteps (ts chosen from a probe so that
+    the run takes about budget_s).  Returns (seg-steps/s, description, cores)."""
+    from oracle import oracle as o
+    from troute_b200 import hostgraph
+    o.build()
+    n = wl["n"]
+    scols = np.asarray(o.column_mapper(wl["cols"]), dtype=np.int32)
+    reaches = hostgraph.segment_reaches_level_order(wl["down"], wl["up_ptr"], wl["up_rows"])
+    jobs = None
+    if threads > 1:
+        jobs = hostgraph.subnetwork_jobs(wl["down"], wl["up_ptr"], wl["up_rows"], reaches["order"], target_size=10000)
+
+    def run(ts):
+        nq = max(1, int(np.ceil(ts / QTS)))
+        t0 = time.perf_counter()
+        o.route_network_flat(ts, DT, QTS, n, reaches["reach_ptr"], reaches["reach_rows"], reaches["reach_type"],
+                             reaches["reach_up_ptr"], reaches["reach_up_rows"], wl["params"], scols, wl["q0"],
+                             wl["qlat"][:, :nq], assume_short_ts=bool(args.short_ts), pow_mode=o.POW_LIBM,
+                             jobs=jobs, nthreads=threads)
+        return time.perf_counter() - t0
+
+    probe_ts = 2
+    tp = run(probe_ts)
+    rate = n * probe_ts / tp
+    ts = int(max(2, min(args.nsteps, budget_s * rate / n)))
+    tt = run(ts)
+    value = n * ts / tt
+    kind = "by-subnetwork-jit orders/jobs over OpenMP threads" if jobs is not None else "serial reference loop order"
+    sample = f"all {n} segments x first {ts} of {args.nsteps} timesteps ({tt:.1f} s), {kind}"
+    return value, sample, threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl = build_workload(args)
+    threads = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    budget = max(5.0, 90.0 / max(1, args.steps + args.warmup))
+    for i in range(args.warmup + args.steps):
+        v, sample, cores = cpu_arm(wl, args, threads, budget)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "routed segment-timesteps/sec", "value": value, "unit": "segment-timesteps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wl["n"] * args.nsteps / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "assume_short_ts": bool(args.short_ts), "qts_subdivisions": QTS,
+                   "note": "ms_per_step extrapolates the sampled rate to one full routing call"},
+        "cpu_baseline": {"value": value, "unit": "segment-timesteps/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "segment-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from troute_b200 import _lib
+    _lib.lib()   # fail loudly if the CUDA extension is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the routing path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = build_workload(args)
+    T = args.nsteps
+    if world > 1:
+        from troute_b200 import multigpu
+        runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
+    else:
+        from troute_b200 import multigpu
+        runner = multigpu.SingleRouter(wl, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    clocks = Clocks(local_rank)
+
+    # ---- device-resident throughput ("value") ----
+    runner.upload()
+    for _ in range(args.warmup):
+        runner.run_resident()
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, launches = [], 0
+    ev0.record(runner.stream)
+    for _ in range(args.steps):
+        runner.run_resident()
+        # stats of this call are read after the final synchronize (events stay valid per handle until the next run);
+        # the per-step kernel time is collected by the runner itself
+    ev1.record(runner.stream)
+    barrier()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop() if rank == 0 else None
+    stats = runner.collect_stats()
+    kern_ms = stats["kernel_ms_per_call"]            # mean duration of the wavefront kernel on this rank
+    lane_steps_rank = stats["lane_steps"]
+    launches = stats["launches_per_call"] * args.steps
+    total_units = sum_over_ranks(float(lane_steps_rank))     # whole job, per routing call
+    value = total_units * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        runner.alloc_host()
+        for _ in range(min(args.warmup, 2)):
+            runner.run_e2e()
+        barrier()
+        t_e2e = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(runner.stream)
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            runner.run_e2e()
+        e1.record(runner.stream)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        # trt_route is synchronous (it returns when the result is in host memory), so wall clock and the event pair
+        # bracket the same region; report the larger, max over ranks
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+        e2e = {"value": total_units * args.steps / (e2e_ms * 1e-3), "unit": "segment-timesteps/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(float(runner.h2d_bytes))),
+               "d2h_bytes_per_step": int(sum_over_ranks(float(runner.d2h_bytes))),
+               "ms_per_step": e2e_ms / args.steps}
+        launches += stats["launches_per_call_e2e"] * args.steps
+
+    # ---- roofline of the dominant (wavefront) kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    achieved = BYTES_PER_SEGSTEP * lane_steps_rank / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("wavefront_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": stats["kernel_name"], "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": BYTES_PER_SEGSTEP * lane_steps_rank, "peak_source": peak_src,
+                "note": "per-rank kernel on rank 0; the solve is FP-issue/latency bound (DESIGN.md), HBM fraction is "
+                        "reported as the contract asks"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sample, cores = cpu_arm(wl, args, 1, args.cpu_sample_seconds)
+        cpu = {"value": v, "unit": "segment-timesteps/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "routed segment-timesteps/sec", "value": value, "unit": "segment-timesteps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "assume_short_ts": bool(args.short_ts), "qts_subdivisions": QTS,
+                       "levels": stats["levels"], "stages_per_call": stats["stages"],
+                       "schedule": "persistent cooperative wavefront" if args.mode == 1 else "launch per stage",
+                       "l2": "inputs larger than L2 (38 GB working set), no flush", "sharding": stats["sharding"]},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    runner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29513", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,251 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): streamflow within 1e-5 relative of the reference arithmetic.  What is asserted
+here is stronger: BIT equality of q, v, d with the oracle's deterministic-powf build (the numerics contract of
+include/trt_detmath.h), and <= 1e-5 relative agreement with the oracle's platform-libm build on all but the
+secant-termination flips a 1-ulp powf difference causes (measured and bounded below)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-5   # north_star tolerance on streamflow
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from troute_b200 import network
+    from troute_b200 import _lib
+    assert _lib.lib().trt_device_count() >= 1, "no CUDA device: the routing path has no CPU fallback"
+    return network
+
+
+def test_powf_det_bits(eng, oracle):
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    x = np.exp(rng.uniform(np.log(1e-30), np.log(1e30), n)).astype(np.float32)
+    x[:8] = [0.0, -0.0, np.inf, -1.0, np.nan, 1.0, 1e-45, 3.4e38]
+    y = np.array([2 / 3, 5 / 3, 0.5, 1.5], dtype=np.float32)[rng.integers(0, 4, n)]
+    H.assert_bit_equal(eng.powf_batch(x, y), oracle.powf(x, y, oracle.POW_DET), "powf_det")
+
+
+def test_mc_demo_kat_on_gpu(eng):
+    k = json.load(open(os.path.join(GOLD, "mc_demo_kat.json")))
+    c, s = k["channel"], k["single"]
+    row = np.array([[c["dt"], s["qup"], s["quc"], s["qdp"], c["ql"], c["dx"], c["bw"], c["tw"], c["twcc"], c["n"],
+                     c["ncc"], c["cs"], c["s0"], s["velp"], s["depthp"]]], dtype=np.float32)
+    out = eng.mc_segment_batch(row)[0]
+    e = s["expected"]
+    assert out[2] == np.float32(e["depthc"])
+    assert abs(float(out[0]) - e["qdc"]) / e["qdc"] < 1e-6      # 1 ulp, see tests/test_oracle_kat.py
+    assert abs(float(out[1]) - e["velc"]) / e["velc"] < 1e-6
+
+
+def test_mc_suite_bits(eng, oracle):
+    """The reference's 5000 randomized kernel inputs: all six outputs and the iteration count, bit for bit."""
+    in15 = np.load(os.path.join(GOLD, "mc_suite_seed16.npy"))
+    got, it_g = eng.mc_segment_batch(in15, want_iters=True)
+    ref, it_r = oracle.mc_segment_batch(in15, pow_mode=oracle.POW_DET)
+    H.assert_bit_equal(got, ref, "mc suite")
+    assert np.array_equal(it_g, it_r)
+    # vs the platform-libm build: within 1e-5 relative except on termination flips
+    lib, _ = oracle.mc_segment_batch(in15, pow_mode=oracle.POW_LIBM)
+    rel = np.abs(got[:, 0] - lib[:, 0]) / np.maximum(np.abs(lib[:, 0]), 1e-6)
+    assert (rel <= REL_TOL).mean() >= 0.999
+
+
+def test_mc_edge_inputs_bits(eng, oracle):
+    """Edge rows: zero flows, cs == 0, bw > tw, bw == tw, twcc == 0 (NWM 3.0 exception), huge flows (retry ladder),
+    tiny depth, negative lateral inflow."""
+    base = np.array([300, 1, 1, 1, 0.1, 1000, 5, 8, 24, 0.06, 0.12, 0.6, 0.01, 0, 0.5], dtype=np.float32)
+    rows = []
+    def add(**kw):
+        r = base.copy()
+        names = ["dt", "qup", "quc", "qdp", "ql", "dx", "bw", "tw", "twcc", "n", "ncc", "cs", "s0", "velp", "depthp"]
+        for k2, v in kw.items():
+            r[names.index(k2)] = v
+        rows.append(r)
+    add(qup=0, quc=0, qdp=0, ql=0)
+    add(cs=0)
+    add(bw=10, tw=8)
+    add(bw=8, tw=8)
+    add(twcc=0, depthp=30, qup=5000, quc=5000, qdp=5000)
+    add(ncc=0, depthp=30, qup=5000, quc=5000, qdp=5000)
+    add(qup=70000, quc=70000, qdp=70000, ql=70000, depthp=100)
+    add(depthp=1e-6, qup=1e-6, quc=1e-6, qdp=1e-6, ql=1e-7)
+    add(ql=-5.0)
+    add(ql=-0.5, qup=0.1, quc=0.1, qdp=0.1)
+    add(dx=1, s0=4.6)
+    add(dx=95714, s0=1e-5, depthp=0)
+    add(depthp=-1.0)
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        r = base.copy()
+        r[1:5] = np.exp(rng.uniform(np.log(1e-5), np.log(7e4), 4))
+        r[4] *= rng.choice([1, 1, 1, -1e-3, 0])
+        r[5] = np.exp(rng.uniform(0, np.log(95714)))
+        r[6] = np.exp(rng.uniform(np.log(0.135), np.log(230)))
+        r[7] = r[6] * rng.choice([1 / 0.6, 1.0, 0.9, 3.0])
+        r[8] = r[7] * rng.choice([3.0, 0.0, 1.0])
+        r[9] = rng.uniform(0.02, 0.2); r[10] = r[9] * rng.choice([2.0, 1.0, 0.0])
+        r[11] = rng.choice([0.0, 0.0846, 0.5857, 2.254]); r[12] = np.exp(rng.uniform(np.log(1e-5), np.log(4.6)))
+        r[14] = rng.choice([0.0, 1e-3, 0.3, 3.0, 40.0])
+        rows.append(r)
+    in15 = np.asarray(rows, dtype=np.float32)
+    got, it_g = eng.mc_segment_batch(in15, want_iters=True)
+    ref, it_r = oracle.mc_segment_batch(in15, pow_mode=oracle.POW_DET)
+    H.assert_bit_equal(got, ref, "mc edge rows")
+    assert np.array_equal(it_g, it_r)
+
+
+def test_levelpool_kats_on_gpu(eng, oracle):
+    k = json.load(open(os.path.join(GOLD, "levelpool_kats.json")))
+    for c in k["cases"]:
+        q, h = eng.levelpool_series(c["wbody_row"], c["inflow"], 0.0, c["routing_period"])
+        assert q[-1] == np.float32(c["expected_final_outflow"]), c["fixture"]
+        assert h[-1] == np.float32(c["expected_final_water_elevation"]), c["fixture"]
+        qo, ho = oracle.levelpool_series(c["wbody_row"], c["inflow"], 0.0, c["routing_period"], pow_mode=oracle.POW_DET)
+        H.assert_bit_equal(q, qo, "lp outflow series")
+        H.assert_bit_equal(h, ho, "lp elevation series")
+
+
+def _networks():
+    from troute_b200 import synth
+    return {
+        "tree4095": (synth.binary_tree(4095), 0),
+        "chain300": (synth.chain(300), 0),
+        "single": (synth.chain(1), 0),
+        "hack20k_lp": (synth.hack_tree(20000, seed=5), 25),
+        "forest": (synth.conus_like(n_total=30000, n_basins=160, seed=4), 10),
+    }
+
+
+@pytest.mark.parametrize("name", ["tree4095", "chain300", "single", "hack20k_lp", "forest"])
+@pytest.mark.parametrize("short_ts", [False, True])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_network_bits(eng, oracle, name, short_ts, mode):
+    down, n_lp = _networks()[name]
+    case = H.make_case(down, nsteps=36, n_lp=n_lp, warm=(name != "forest"))
+    ref, upref, extras = H.oracle_route(oracle, case, short_ts)
+    out, up, stats = H.engine_route(case, short_ts, mode=mode)
+    assert np.isfinite(out).all()
+    H.assert_bit_equal(out, ref, f"{name} fvd")
+    if n_lp:
+        H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], f"{name} reservoir inflow")
+        assert (np.delete(up, case["lp_rows"], axis=0) == 0).all()
+    assert stats["lane_steps"] == case["n"] * case["nsteps"]
+
+
+def test_network_vs_libm_oracle_tolerance(eng, oracle):
+    """Against the platform-libm arithmetic (what a gfortran build of the reference computes): streamflow within
+    1e-5 relative wherever q is not negligible, except segment-steps downstream of a secant-termination flip;
+    those are bounded in count (< 0.1 %) -- the oracle's own libm-vs-det distance is the same set."""
+    from troute_b200 import synth
+    case = H.make_case(synth.hack_tree(20000, seed=9), nsteps=48, warm=False)
+    ref, _, _ = H.oracle_route(oracle, case, False, pow_mode=oracle.POW_LIBM)
+    out, _, _ = H.engine_route(case, False)
+    q_ref, q_out = ref[:, 0::3], out[:, 0::3]
+    rel = np.abs(q_out - q_ref) / np.maximum(np.abs(q_ref), 1e-3)
+    assert (rel <= REL_TOL).mean() >= 0.999, float((rel <= REL_TOL).mean())
+    assert np.median(rel) <= 1e-6
+
+
+def test_restart_chunks_equal_one_run(eng, oracle):
+    """Checkpoint/resume contract (AbstractNetwork.new_q0, AbstractNetwork.py:177-191): two 24-step calls with the
+    state hand-off q0 = fvd[:, [-3, -3, -1]] reproduce one 48-step call bit for bit."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.hack_tree(8000, seed=2), nsteps=48, warm=True)
+    full, _, _ = H.engine_route(case, False)
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+    a, _ = net.route(24, 12, case["qlat"][:, :2], case["q0"])
+    q0b = a[:, [-3, -3, -1]].copy()
+    b, _ = net.route(24, 12, case["qlat"][:, 2:4], q0b)
+    net.close()
+    H.assert_bit_equal(np.concatenate([a, b], axis=1), full, "chunked run")
+
+
+def test_boundary_rows_prescribed(eng, oracle):
+    """upstream_results injection (mc_reach.pyx:458-469): cutting a network at a segment and prescribing that
+    segment's flow series reproduces the uncut downstream results."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork, TRT_KIND_BOUNDARY
+    down = synth.hack_tree(5000, seed=11)
+    case = H.make_case(down, nsteps=30, warm=True)
+    full, _, _ = H.engine_route(case, False)
+    sizes = synth.subtree_sizes(down)
+    cut = int(np.argmin(np.abs(sizes - 1500)))           # a segment with ~1500 segments upstream
+    # rows upstream of `cut` (excluded from the cut network)
+    up_ptr, up_rows = case["up_ptr"], case["up_rows"]
+    mask = np.zeros(case["n"], dtype=bool)
+    stack = list(up_rows[up_ptr[cut]:up_ptr[cut + 1]])
+    while stack:
+        r = int(stack.pop())
+        mask[r] = True
+        stack.extend(up_rows[up_ptr[r]:up_ptr[r + 1]].tolist())
+    keep = np.nonzero(~mask)[0]
+    remap = -np.ones(case["n"], dtype=np.int64); remap[keep] = np.arange(keep.size)
+    down2 = np.where(down[keep] >= 0, remap[np.maximum(down[keep], 0)], -1)
+    p2, r2 = synth.upstream_csr(down2)
+    kind = np.zeros(keep.size, dtype=np.uint8); kind[remap[cut]] = TRT_KIND_BOUNDARY
+    net = RoutingNetwork(p2, r2, kind, case["params"][keep], case["cols"])
+    out, _ = net.route(30, 12, case["qlat"][keep], case["q0"][keep], bnd_rows=[remap[cut]], bnd_fvd=full[cut][None, :])
+    net.close()
+    H.assert_bit_equal(out, full[keep], "cut network")
+
+
+def test_argument_errors(eng):
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.binary_tree(63), nsteps=24)
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+    with pytest.raises(ValueError):      # mc_reach.pyx:246-247
+        net.route(24, 12, case["qlat"][:, :1], case["q0"])
+    with pytest.raises(ValueError):      # mc_reach.pyx:243-244
+        net.route(24, 12, case["qlat"][:-1], case["q0"])
+    net.close()
+    # a cycle is not a river network
+    with pytest.raises(ValueError):
+        RoutingNetwork(np.array([0, 1, 2]), np.array([1, 0]), np.zeros(2, np.uint8), case["params"][:2], case["cols"])
+    # empty network / zero steps
+    empty = RoutingNetwork(np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint8),
+                           np.zeros((0, 10), np.float32), case["cols"])
+    fvd, _ = empty.route(12, 12, np.zeros((0, 1), np.float32), np.zeros((0, 3), np.float32))
+    assert fvd.shape == (0, 36)
+    empty.close()
+
+
+def test_full_size_config2_properties(eng, oracle):
+    """BASELINE config 2 (binary tree, 1,048,576 segments) at full width, 48 steps: (i) the persistent kernel and
+    the launch-per-stage schedule agree bit for bit; (ii) a complete sub-tree (4,095 segments upstream of one node)
+    is independent of the rest of the network, so the oracle run on it alone must reproduce those rows exactly."""
+    from troute_b200 import synth
+    N, T = 1_048_576, 48
+    down = synth.binary_tree(N)
+    case = H.make_case(down, nsteps=T)
+    a, _, st = H.engine_route(case, False, mode=1, want_upstream=False)
+    b, _, _ = H.engine_route(case, False, mode=0, want_upstream=False)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    assert np.isfinite(a).all() and st["stages"] == 20 + T
+    root = 300                                            # heap index; its subtree has 2^12 - 1 nodes at N = 2^20
+    ids = [root]
+    frontier = [root]
+    while frontier:
+        nxt = [c for f in frontier for c in (2 * f + 1, 2 * f + 2) if c < N]
+        ids.extend(nxt); frontier = nxt
+    ids = np.asarray(sorted(ids), dtype=np.int64)
+    remap = -np.ones(N, dtype=np.int64); remap[ids] = np.arange(ids.size)
+    d2 = np.where(ids == root, -1, remap[np.maximum(down[ids], 0)])
+    sub = dict(case)
+    p2, r2 = synth.upstream_csr(d2)
+    sub.update(n=ids.size, down=d2, params=case["params"][ids], qlat=case["qlat"][ids], q0=case["q0"][ids],
+               up_ptr=p2, up_rows=r2, kind=case["kind"][ids])
+    ref, _, _ = H.oracle_route(oracle, sub, False)
+    H.assert_bit_equal(a[ids], ref, "sub-tree of the full-size run")
