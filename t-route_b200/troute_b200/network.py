@@ -114,6 +114,17 @@ class RoutingNetwork:
     def set_option(self, key, value):
         check(self._L.trt_set_option(self._h, key.encode(), int(value)))
 
+    def set_gages(self, gages, nsteps):
+        """Streamflow nudging set-up (mc_reach.pyx:380-411).  Returns (nudge [n_gages, nsteps+1], lastobs_times,
+        lastobs_values) placeholders for a gage-free call."""
+        if gages is not None:
+            raise NotImplementedError("streamflow nudging (simple_da) is not on the GPU path yet")
+        return (np.zeros((0, nsteps + 1), dtype=np.float32), np.zeros(0, dtype=np.float32),
+                np.zeros(0, dtype=np.float32))
+
+    def download_gages(self):
+        raise NotImplementedError("streamflow nudging (simple_da) is not on the GPU path yet")
+
     # -- routing ------------------------------------------------------------------------------
     def _check_forcing(self, nsteps, qts_subdivisions, qlat, q0):
         if qlat.ndim != 2 or qlat.shape[0] != self.n_rows:

@@ -1,0 +1,172 @@
+"""GPU twin of troute.routing.compute (/root/reference/src/troute-routing/troute/routing/compute.py).
+
+`compute_nhd_routing_v02` keeps the reference's 38-parameter signature (:507-545) and its
+`(results, subnetwork_list)` return (:1738), so `nwm_route` (src/troute-nwm/src/nwm_routing/__main__.py:1215-1253)
+and the BMI driver (src/troute_model.py:228-271) can call it unchanged.
+
+The reference spends this function decomposing the network for CPU parallelism (serial / by-network /
+by-subnetwork-jit / -clustered / bmi, :553-1736): slicing pandas frames per (sub)network, pickling them to joblib-loky
+workers and handing tail-water series from one order of sub-networks to the next.  On the GPU the parallelism is
+inside the kernel (topological wavefront over ALL segments of ALL independent networks at once), so every
+`parallel_compute_method` maps to ONE call of compute_network_structured on the union of the tail-waters.  The
+caller only concatenates result tuples (nwm_routing/output.py:213-216, AbstractNetwork.new_q0 :177-191), so
+returning a single tuple is within the contract ("row order inside a tuple is free").
+"""
+import time
+from collections import defaultdict
+from itertools import chain
+import logging
+
+import numpy as np
+import pandas as pd
+
+from .fast_reach.mc_reach import compute_network_structured
+
+LOG = logging.getLogger("")
+
+# compute.py:21-26 -- a new backend registers under a new key; the default stays the structured kernel
+_compute_func_map = defaultdict(
+    lambda: compute_network_structured,
+    {
+        "V02-structured": compute_network_structured,
+        "V02-structured-b200": compute_network_structured,
+    },
+)
+
+_WB_COLS = ["LkArea", "LkMxE", "OrificeA", "OrificeC", "OrificeE", "WeirC", "WeirE", "WeirL", "ifd", "qd0", "h0"]
+_PARAM_COLS = ["dt", "bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"]
+
+
+def _build_reach_type_list(reach_list, wbodies_segs):
+    """compute.py:41-47."""
+    reach_type_list = [1 if (set(reaches) & wbodies_segs) else 0 for reaches in reach_list]
+    return list(zip(reach_list, reach_type_list))
+
+
+def _nonempty(df):
+    return df is not None and hasattr(df, "empty") and not df.empty
+
+
+def compute_nhd_routing_v02(
+    connections,
+    rconn,
+    wbody_conn,
+    reaches_bytw,
+    compute_func_name,
+    parallel_compute_method,
+    subnetwork_target_size,
+    cpu_pool,
+    t0,
+    dt,
+    nts,
+    qts_subdivisions,
+    independent_networks,
+    param_df,
+    q0,
+    qlats,
+    usgs_df,
+    lastobs_df,
+    reservoir_usgs_df,
+    reservoir_usgs_param_df,
+    reservoir_usace_df,
+    reservoir_usace_param_df,
+    reservoir_rfc_df,
+    reservoir_rfc_param_df,
+    great_lakes_df,
+    great_lakes_param_df,
+    great_lakes_climatology_df,
+    da_parameter_dict,
+    assume_short_ts,
+    return_courant,
+    waterbodies_df,
+    data_assimilation_parameters,
+    waterbody_types_df,
+    waterbody_type_specified,
+    subnetwork_list,
+    flowveldepth_interorder={},
+    from_files=True,
+    device=0,
+):
+    da_decay_coefficient = da_parameter_dict.get("da_decay_coefficient", 0) if da_parameter_dict else 0
+    param_df["dt"] = dt                                                        # :547-549
+    param_df = param_df.astype("float32")
+    start_time = time.time()
+    compute_func = _compute_func_map[compute_func_name]
+
+    for name, df in (("reservoir_usgs_df", reservoir_usgs_df), ("reservoir_usace_df", reservoir_usace_df),
+                     ("reservoir_rfc_df", reservoir_rfc_df), ("great_lakes_df", great_lakes_df)):
+        if _nonempty(df):
+            raise NotImplementedError(f"{name}: hybrid / RFC / Great-Lakes reservoir DA is outside the GPU path")
+
+    # union of all tail-waters: one device call routes every independent network
+    reach_list = list(chain.from_iterable(reaches_bytw.values()))
+    segs = list(chain.from_iterable(reach_list))
+    offnetwork_upstreams = set(flowveldepth_interorder.keys()) if parallel_compute_method == "bmi" else set()
+    segs_all = segs + list(offnetwork_upstreams)
+    common_segs = param_df.index.intersection(segs_all)
+    wbodies_segs = set(segs_all).symmetric_difference(common_segs)             # :1406-1408
+
+    waterbody_types_df_sub = pd.DataFrame()
+    if _nonempty(waterbodies_df):
+        lake_segs = list(waterbodies_df.index.intersection(segs))
+        waterbodies_df_sub = waterbodies_df.loc[lake_segs, _WB_COLS]
+        if _nonempty(waterbody_types_df):
+            waterbody_types_df_sub = waterbody_types_df.loc[lake_segs, ["reservoir_type"]]
+    else:
+        lake_segs = []
+        waterbodies_df_sub = pd.DataFrame()
+
+    param_df_sub = param_df.loc[common_segs, _PARAM_COLS].sort_index()         # :1443-1446
+    reaches_list_with_type = _build_reach_type_list(reach_list, wbodies_segs)
+    param_df_sub = param_df_sub.reindex(param_df_sub.index.tolist() + lake_segs).sort_index()   # :1455-1457
+    # forcing / state rows follow the parameter index; lake and off-network rows carry no lateral inflow
+    qlat_sub = qlats.reindex(param_df_sub.index)
+    q0_sub = q0.reindex(param_df_sub.index)
+
+    upstream_results = {}
+    for us_subn_tw in offnetwork_upstreams:                                    # :1652-1658
+        pos = param_df_sub.index.get_loc(us_subn_tw)
+        flowveldepth_interorder[us_subn_tw]["position_index"] = pos
+        upstream_results[us_subn_tw] = flowveldepth_interorder[us_subn_tw]
+
+    if _nonempty(usgs_df) or _nonempty(lastobs_df):
+        from ._da import prep_da_dataframes, prep_da_positions_byreach
+        usgs_df_sub, lastobs_df_sub, da_positions_list_byseg = prep_da_dataframes(
+            usgs_df, lastobs_df, param_df_sub.index, offnetwork_upstreams)
+        da_positions_list_byreach, da_positions_list_bygage = prep_da_positions_byreach(reach_list, lastobs_df_sub.index)
+        usgs_values = usgs_df_sub.values.astype("float32")
+        lastobs_discharge = lastobs_df_sub.get(
+            "lastobs_discharge", pd.Series(index=lastobs_df_sub.index, name="Null", dtype="float32")).values.astype("float32")
+        time_since_lastobs = lastobs_df_sub.get(
+            "time_since_lastobs", pd.Series(index=lastobs_df_sub.index, name="Null", dtype="float32")).values.astype("float32")
+    else:
+        usgs_values = np.zeros((0, 0), dtype=np.float32)
+        da_positions_list_byseg, da_positions_list_byreach, da_positions_list_bygage = [], [], []
+        lastobs_discharge = np.zeros(0, dtype=np.float32)
+        time_since_lastobs = np.zeros(0, dtype=np.float32)
+
+    # the connections of every tail-water, merged (independent_networks[tw] is rconn restricted to that basin)
+    upstream_connections = rconn if rconn is not None else {
+        k: v for net in independent_networks.values() for k, v in net.items()}
+
+    e_f = np.zeros(0, dtype=np.float32)
+    e_i = np.zeros(0, dtype=np.int32)
+    e_f2 = np.zeros((0, 0), dtype=np.float32)
+    result = compute_func(
+        nts, dt, qts_subdivisions, reaches_list_with_type, upstream_connections,
+        param_df_sub.index.values.astype("int64"), param_df_sub.columns.values, param_df_sub.values,
+        np.nan_to_num(q0_sub.values.astype("float32")), np.nan_to_num(qlat_sub.values.astype("float32")),
+        lake_segs, waterbodies_df_sub.values, data_assimilation_parameters,
+        waterbody_types_df_sub.values.astype("int32"), waterbody_type_specified,
+        t0.strftime("%Y-%m-%d_%H:%M:%S") if hasattr(t0, "strftime") else str(t0),
+        usgs_values, np.array(da_positions_list_byseg, dtype="int32"), np.array(da_positions_list_byreach, dtype="int32"),
+        np.array(da_positions_list_bygage, dtype="int32"), lastobs_discharge, time_since_lastobs, da_decay_coefficient,
+        e_f2, e_i, e_f, e_f, e_f, e_f, e_f,          # USGS hybrid reservoir DA
+        e_f2, e_i, e_f, e_f, e_f, e_f, e_f,          # USACE hybrid reservoir DA
+        e_f2, e_i, e_i, [], e_i, e_i, e_f, e_i, e_i,  # RFC reservoir DA
+        e_i, e_i, e_f, e_i, e_f, e_i, e_i, e_f2,     # Great Lakes DA
+        upstream_results, assume_short_ts, return_courant, from_files=from_files, device=device,
+    )
+    LOG.debug("B200 routing of %d segments x %d steps complete in %s seconds.", len(param_df_sub), nts,
+              time.time() - start_time)
+    return [result], subnetwork_list
