@@ -169,7 +169,7 @@ def route_network_flat(nsteps, dt, qts_subdivisions, n_rows, reach_ptr, reach_ro
     if flowveldepth is None:
         flowveldepth = np.zeros((n_rows, nsteps + 1, 3), dtype=np.float32)      # mc_reach.pyx:253
     upstream_array = np.zeros((n_rows, nsteps + 1), dtype=np.float32)
-    hist = np.zeros(8, dtype=np.int64) if want_hist else None
+    hist = np.zeros(16, dtype=np.int64) if want_hist else None
 
     g = gages or {}
     n_gages = int(len(g.get("usgs_positions", [])))

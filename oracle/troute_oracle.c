@@ -243,7 +243,7 @@ typedef struct {
     lp_t* lps;                   /* [n_reaches] (only type 1 entries used) */
     float* fvd;                  /* [n_rows, nsteps+1, 3] */
     float* upstream_array;       /* [n_rows, nsteps+1] */
-    int64_t* iter_hist;          /* optional [8]: secant iteration histogram (0..6, >=7) */
+    int64_t* iter_hist;          /* optional [16]: secant iteration histogram, buckets 0..7, 8-15, 16-31, 32-63, 64-127, 128-255, 256-511, 512+ (slot 15 unused) */
 } net_t;
 
 /* one timestep of one reach: mc_reach.pyx:493-796 */
@@ -298,7 +298,8 @@ static void route_reach_step(const net_t* N, int64_t i, int timestep, float* buf
                                     dv[sc[5]], dv[sc[6]], dv[sc[7]], dv[sc[8]], velp, depthp, &o_q, &o_v, &o_d,
                                     0, 0, 0, &iters);
             if (N->iter_hist) {
-                int b = iters > 7 ? 7 : iters;
+                int b = iters;
+                if (iters > 7) { b = 8; for (int v = iters >> 4; v && b < 14; v >>= 1) ++b; }
 #ifdef _OPENMP
 #pragma omp atomic
 #endif
