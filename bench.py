@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--segments", type=int, default=0, help="override the segment count (testing only)")
     ap.add_argument("--nsteps", type=int, default=288, help="routing timesteps per call")
     ap.add_argument("--short-ts", type=int, default=0)
-    ap.add_argument("--mode", type=int, default=1)
+    ap.add_argument("--mode", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
@@ -324,7 +324,7 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "assume_short_ts": bool(args.short_ts), "qts_subdivisions": QTS,
                        "levels": stats["levels"], "stages_per_call": stats["stages"],
-                       "schedule": "persistent cooperative wavefront" if args.mode == 1 else "launch per stage",
+                       "schedule": {0: "launch per stage", 1: "persistent cooperative wavefront (grid.sync per stage)", 2: "dataflow wavefront (ordered unit queue, lanes poll their inputs)"}[args.mode],
                        "l2": "inputs larger than L2 (38 GB working set), no flush", "sharding": stats["sharding"]},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         }

@@ -66,6 +66,12 @@ int trt_device_count(void);
 int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
                        const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
                        trt_network** out);
+/* Same, with the wavefront level of every row given by the caller (NULL = compute).  A shard of a larger network
+ * passes the levels of the WHOLE network so that every shard walks the same stages; level[row] must exceed the level
+ * of each of its upstream rows. */
+int trt_network_create_ex(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
+                          const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
+                          const int32_t* level_of_row, trt_network** out);
 int trt_network_destroy(trt_network* net);
 
 /* topology queries: number of wavefront levels; level of every row; engine position of every row */
@@ -119,9 +125,38 @@ int trt_export_flow_series(trt_network* net, int64_t n, const int64_t* rows, voi
 int trt_import_boundary_flow(trt_network* net, int64_t n, const int64_t* rows, const void* src_device);
 int trt_device_results(trt_network* net, void** fvd_device);
 
+/*
+ * Sub-basin sharding across GPUs (one handle per GPU / process).  A cut edge u -> s between shards is a row of kind
+ * TRT_KIND_BOUNDARY in the downstream shard ("import") whose flow series is written, value by value as it is computed,
+ * by the kernel of the upstream shard straight into the downstream GPU's flow array over NVLink peer memory ("export").
+ * This replaces the pickled tail-water series the reference hands from one order of sub-networks to the next
+ * (compute.py:882-900 -> mc_reach.pyx:458-469).  No collective is involved: a consumer lane polls the slot it reads.
+ *   trt_network_state_ptr   device pointer of this handle's flow array ([nsteps+1, n_rows] float32), valid after
+ *                           trt_upload_forcing and until a later upload needs a larger array
+ *   trt_ipc_get/open/close  CUDA IPC plumbing to map that array into the peer process
+ *   trt_network_set_peer    flow array of peer shard `peer` (mapped pointer) and its row count
+ *   trt_network_set_exports rows of this shard whose outflow enters peer shard peer[i] at engine position
+ *                           peer_pos[i] (= trt_network_get_positions of the peer, for the import row)
+ *   trt_network_set_imports rows of kind TRT_KIND_BOUNDARY that a peer writes (all other boundary rows that are not
+ *                           prescribed by trt_upload_forcing hold zero)
+ *   trt_prepare             reset the flow state for the next run (must complete on ALL shards before ANY shard calls
+ *                           trt_run*, because peers write into it); single-GPU callers never need it
+ */
+int trt_network_state_ptr(trt_network* net, void** q_device);
+int trt_ipc_get_handle(void* device_ptr, uint8_t handle[64]);
+int trt_ipc_open_handle(int device, const uint8_t handle[64], void** device_ptr);
+int trt_ipc_close_handle(void* device_ptr);
+int trt_network_set_peer(trt_network* net, int32_t peer, void* peer_q_device, int64_t peer_n_rows);
+int trt_network_set_exports(trt_network* net, int64_t count, const int64_t* rows, const int32_t* peer,
+                            const int64_t* peer_pos);
+int trt_network_set_imports(trt_network* net, int64_t count, const int64_t* rows);
+int trt_prepare(trt_network* net);
+
 /* run-time knobs:
- *   "mode"        0 = one launch per wavefront stage, 1 = persistent cooperative kernel (default)
- *   "grid_blocks" CTAs of the persistent kernel (0 = as many as are co-resident)
+ *   "mode"        0 = one launch per wavefront stage, 1 = persistent cooperative kernel with a grid barrier per stage,
+ *                 2 = dataflow kernel: units claimed in stage order, lanes wait on the slots they read (default)
+ *   "gate"        mode 2: a unit of stage k starts once stage k - gate is complete (run-ahead bound, default 3)
+ *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
 int trt_set_option(trt_network* net, const char* key, int64_t value);
 /* statistics of the last trt_run: device milliseconds of the wavefront kernels, number of kernel

@@ -89,8 +89,27 @@ struct trt_network {
     bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+    // dataflow schedule (mode 2)
+    DevBuf<int> d_unit_ptr, d_gate_stage, d_done, d_ctrl;     // d_ctrl: [0] claim, [1] frontier, [2] abort
+    DevBuf<unsigned char> d_unit_shift;
+    int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0;
+    int gate = 3;
+    bool prepared = false;                                    // sentinel reset done for the next run
+    std::vector<int32_t> host_bnd_pos;                        // prescribed rows of the last upload (positions)
+    int64_t n_bnd = 0;
+    DevBuf<int> d_zero_pos;                                   // boundary rows nobody prescribes or imports
+    int64_t n_zero = 0;
+
+    // cut edges to / from other shards
+    std::vector<uint8_t> imported;                            // [n] row is written by a peer
+    DevBuf<int> d_exp_slot, d_exp_peer;
+    DevBuf<long long> d_exp_pos;
+    int64_t n_exp = 0;
+    float* peer_q[TRT_MAX_PEERS] = {nullptr};
+    long long peer_n[TRT_MAX_PEERS] = {0};
+
     // options / stats
-    int mode = 1;                  // 0 stage-per-launch, 1 persistent cooperative
+    int mode = 2;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow
     int grid_blocks = 0;           // 0 = max co-resident
     double kernel_ms = 0.0;
     int64_t launches = 0, stages = 0, lane_steps = 0;
@@ -127,6 +146,13 @@ int trt_device_count(void)
 int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows, const uint8_t* kind,
                        const float* data_values, int32_t ncols, const int32_t* scols, trt_network** out)
 {
+    return trt_network_create_ex(device, n_rows, up_ptr, up_rows, kind, data_values, ncols, scols, nullptr, out);
+}
+
+int trt_network_create_ex(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows, const uint8_t* kind,
+                          const float* data_values, int32_t ncols, const int32_t* scols, const int32_t* levels_in,
+                          trt_network** out)
+{
     if (!out) return fail(TRT_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n_rows < 0 || n_rows > 2000000000LL) return fail(TRT_ERR_INVALID, "n_rows out of range: %lld", (long long)n_rows);
@@ -155,10 +181,23 @@ int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const 
     net->device = device;
     net->n = n;
 
-    // ---- levels: longest path from a headwater (Kahn sweep over the downstream adjacency) ----
+    // ---- levels: longest path from a headwater (Kahn sweep over the downstream adjacency), or the caller's ----
     std::vector<int32_t>& level = net->level_of_row;
     level.assign((size_t)n, 0);
-    {
+    if (levels_in) {
+        // a shard of a larger network keeps the levels of the whole network, so that all shards walk the same stages
+        for (int64_t r = 0; r < n; ++r) {
+            if (levels_in[r] < 0) { delete net; return fail(TRT_ERR_INVALID, "level of row %lld is negative", (long long)r); }
+            level[(size_t)r] = levels_in[r];
+        }
+        for (int64_t r = 0; r < n; ++r)
+            for (int64_t e = up_ptr[r]; e < up_ptr[r + 1]; ++e)
+                if (level[(size_t)up_rows[e]] >= level[(size_t)r]) {
+                    delete net;
+                    return fail(TRT_ERR_CYCLE, "level of row %lld does not exceed the level of its upstream row %lld",
+                                (long long)r, (long long)up_rows[e]);
+                }
+    } else {
         std::vector<int64_t> down_ptr((size_t)n + 1, 0);
         for (int64_t e = 0; e < E; ++e) down_ptr[(size_t)up_rows[e] + 1]++;
         for (int64_t r = 0; r < n; ++r) down_ptr[(size_t)r + 1] += down_ptr[(size_t)r];
@@ -205,6 +244,7 @@ int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const 
         }
     }
     net->kind_of_row.assign(kind, kind + n);
+    net->imported.assign((size_t)n, 0);
 
     // ---- position-space arrays ----
     std::vector<int32_t> h_level((size_t)n), h_up_ptr((size_t)n + 1, 0), h_up_idx((size_t)E);
@@ -378,9 +418,45 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
         CU(launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n,
                                 (int)n_bnd, nsteps, st));
         CU(cudaStreamSynchronize(st));   // `pos` is a stack-owned staging vector
+        net->host_bnd_pos = pos;
+    } else {
+        net->host_bnd_pos.clear();
+    }
+    net->n_bnd = n_bnd;
+    {
+        // boundary rows that are neither prescribed here nor written by a peer shard hold zero for every step
+        std::vector<uint8_t> covered((size_t)n, 0);
+        for (int64_t i = 0; i < n_bnd; ++i) covered[(size_t)bnd_rows[i]] = 1;
+        std::vector<int32_t> zero_pos;
+        for (int64_t r = 0; r < n; ++r)
+            if (net->kind_of_row[(size_t)r] == TRT_KIND_BOUNDARY && !covered[(size_t)r] && !net->imported[(size_t)r])
+                zero_pos.push_back(net->pos_of_row[(size_t)r]);
+        net->n_zero = (int64_t)zero_pos.size();
+        if (net->n_zero > 0) {
+            CU(net->d_zero_pos.reserve(zero_pos.size()));
+            CU(cudaMemcpy(net->d_zero_pos.p, zero_pos.data(), zero_pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            CU(launch_fill_zero_rows(net->d_zero_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, (int)net->n_zero,
+                                     nsteps, st));
+        }
     }
     net->uploaded = true;
     return TRT_OK;
+}
+
+// Dataflow runs start from q / d rows 1..T holding TRT_SENTINEL (0xFFFFFFFF) everywhere except on prescribed rows.
+static cudaError_t prepare_dataflow(trt_network* net)
+{
+    cudaStream_t st = net->stream;
+    const size_t n = (size_t)net->n, T = (size_t)net->T;
+    if (n == 0 || T == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(net->d_q.p + n, 0xFF, n * T * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(net->d_d.p + n, 0xFF, n * T * sizeof(float), st);
+    if (e == cudaSuccess && net->n_bnd > 0)
+        e = launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n,
+                                 (int)net->n_bnd, (int)T, st);
+    if (e == cudaSuccess && net->n_zero > 0)
+        e = launch_fill_zero_rows(net->d_zero_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, (int)net->n_zero, (int)T, st);
+    return e;
 }
 
 static int run_async(trt_network* net, int32_t assume_short_ts)
@@ -402,7 +478,65 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
         int64_t routed = 0;
         for (int64_t r = 0; r < net->n; ++r) routed += net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY;
         net->lane_steps = routed * T;
-        if (net->mode == 1) {
+        if (net->mode == 2) {
+            // (re)build the unit table of this (T, schedule) pair
+            const int nstages = k_end - 1;
+            if (net->sched_T != T || net->sched_short != (assume_short_ts ? 1 : 0) || net->sched_gate != net->gate ||
+                net->sched_nstages != nstages) {
+                std::vector<int32_t> unit_ptr((size_t)nstages + 1, 0), gate_stage((size_t)nstages, 0);
+                std::vector<unsigned char> shift((size_t)nstages, 5);
+                std::vector<int32_t> last_nonempty((size_t)nstages + 1, 0);   // last non-empty stage <= k
+                int64_t units = 0;
+                for (int k = 1; k <= nstages; ++k) {
+                    int64_t lo, hi;
+                    if (assume_short_ts) { lo = 0; hi = net->n; }
+                    else {
+                        lo = net->lvl_ptr[(size_t)std::max(0, k - T)];
+                        hi = net->lvl_ptr[(size_t)std::min(L, k)];
+                    }
+                    const int64_t width = hi - lo;
+                    const int sh = width >= 65536 ? 7 : 5;
+                    shift[(size_t)k - 1] = (unsigned char)sh;
+                    units += (width + (1 << sh) - 1) >> sh;
+                    if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
+                    unit_ptr[(size_t)k] = (int32_t)units;
+                    last_nonempty[(size_t)k] = width > 0 ? k : last_nonempty[(size_t)k - 1];
+                    const int j = k - net->gate;
+                    gate_stage[(size_t)k - 1] = j >= 1 ? last_nonempty[(size_t)j] : 0;
+                }
+                CU(net->d_unit_ptr.reserve((size_t)nstages + 1));
+                CU(net->d_gate_stage.reserve((size_t)nstages));
+                CU(net->d_unit_shift.reserve((size_t)nstages));
+                CU(net->d_done.reserve((size_t)nstages));
+                CU(net->d_ctrl.reserve(4));
+                CU(cudaMemcpyAsync(net->d_unit_ptr.p, unit_ptr.data(), ((size_t)nstages + 1) * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(net->d_gate_stage.p, gate_stage.data(), (size_t)nstages * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(net->d_unit_shift.p, shift.data(), (size_t)nstages, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));   // staging vectors go out of scope
+                net->sched_T = T; net->sched_short = assume_short_ts ? 1 : 0; net->sched_gate = net->gate;
+                net->sched_nstages = nstages;
+            }
+            SchedDev sd;
+            sd.nstages = nstages; sd.T = T; sd.unit_ptr = net->d_unit_ptr.p; sd.unit_shift = net->d_unit_shift.p;
+            sd.claim = (unsigned int*)net->d_ctrl.p; sd.frontier = net->d_ctrl.p + 1; sd.abort_flag = net->d_ctrl.p + 2;
+            sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
+            PeerDev pd;
+            pd.exp_slot = net->d_exp_slot.p; pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
+            for (int i = 0; i < TRT_MAX_PEERS; ++i) { pd.q[i] = net->peer_q[i]; pd.n[i] = net->peer_n[i]; }
+            int grid = net->grid_blocks, max_grid = 0;
+            CU(dataflow_max_grid(&max_grid));
+            if (max_grid <= 0) return fail(TRT_ERR_CUDA, "dataflow kernel cannot be made resident");
+            if (grid <= 0) grid = max_grid;
+            CU(cudaMemsetAsync(net->d_ctrl.p, 0, 4 * sizeof(int), st));
+            CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
+            if (!net->prepared) CU(prepare_dataflow(net));
+            net->prepared = false;
+            CU(cudaEventRecord(net->ev0, st));
+            CU(launch_dataflow(nd, rd, sd, pd, grid, st));
+            net->launches = 1;
+        } else if (net->mode == 1) {
             int grid = net->grid_blocks;
             int max_grid = 0;
             CU(persistent_max_grid(&max_grid));
@@ -442,6 +576,13 @@ int trt_sync(trt_network* net)
     if (net->ran) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, net->ev0, net->ev1) == cudaSuccess) net->kernel_ms = ms;
+        if (net->mode == 2 && net->d_ctrl.p && net->launches > 0) {
+            int ctrl[4] = {0, 0, 0, 0};
+            CU(cudaMemcpy(ctrl, net->d_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
+            if (ctrl[2] != 0)
+                return fail(TRT_ERR_STATE, "dataflow run aborted: a lane waited > 8 s for an input that never arrived "
+                                           "(peer shard missing, or an unprescribed boundary row)");
+        }
     }
     return TRT_OK;
 }
@@ -536,15 +677,125 @@ int trt_device_results(trt_network* net, void** fvd_device)
     return TRT_OK;
 }
 
+int trt_prepare(trt_network* net)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_prepare called before trt_upload_forcing");
+    CU(cudaSetDevice(net->device));
+    if (net->mode == 2) {
+        CU(prepare_dataflow(net));
+        CU(cudaStreamSynchronize(net->stream));
+        net->prepared = true;
+    }
+    return TRT_OK;
+}
+
+int trt_network_set_imports(trt_network* net, int64_t count, const int64_t* rows)
+{
+    if (!net || (count > 0 && !rows)) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::fill(net->imported.begin(), net->imported.end(), 0);
+    for (int64_t i = 0; i < count; ++i) {
+        if (rows[i] < 0 || rows[i] >= net->n) return fail(TRT_ERR_INVALID, "import row %lld out of range", (long long)rows[i]);
+        if (net->kind_of_row[(size_t)rows[i]] != TRT_KIND_BOUNDARY)
+            return fail(TRT_ERR_INVALID, "import row %lld is not of kind TRT_KIND_BOUNDARY", (long long)rows[i]);
+        net->imported[(size_t)rows[i]] = 1;
+    }
+    return TRT_OK;
+}
+
+int trt_network_set_exports(trt_network* net, int64_t count, const int64_t* rows, const int32_t* peer,
+                            const int64_t* peer_pos)
+{
+    if (!net || (count > 0 && (!rows || !peer || !peer_pos))) return fail(TRT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(net->device));
+    const int64_t n = net->n;
+    std::vector<int32_t> slot((size_t)std::max<int64_t>(n, 1), -1), h_peer((size_t)count);
+    std::vector<long long> h_pos((size_t)count);
+    std::vector<unsigned char> h_kind((size_t)std::max<int64_t>(n, 1), 0);
+    for (int64_t p = 0; p < n; ++p) h_kind[(size_t)p] = net->kind_of_row[(size_t)net->row_of_pos[(size_t)p]];
+    for (int64_t i = 0; i < count; ++i) {
+        if (rows[i] < 0 || rows[i] >= n) return fail(TRT_ERR_INVALID, "export row %lld out of range", (long long)rows[i]);
+        if (peer[i] < 0 || peer[i] >= TRT_MAX_PEERS) return fail(TRT_ERR_INVALID, "peer index %d out of range", peer[i]);
+        if (net->kind_of_row[(size_t)rows[i]] == TRT_KIND_BOUNDARY)
+            return fail(TRT_ERR_INVALID, "export row %lld is a boundary row", (long long)rows[i]);
+        const int32_t pos = net->pos_of_row[(size_t)rows[i]];
+        if (slot[(size_t)pos] >= 0) return fail(TRT_ERR_INVALID, "row %lld exported twice", (long long)rows[i]);
+        slot[(size_t)pos] = (int32_t)i;
+        h_peer[(size_t)i] = peer[i];
+        h_pos[(size_t)i] = peer_pos[i];
+        h_kind[(size_t)pos] |= TRT_KIND_EXPORT_FLAG;
+    }
+    CU(net->d_exp_slot.reserve((size_t)n));
+    CU(net->d_exp_peer.reserve((size_t)count));
+    CU(net->d_exp_pos.reserve((size_t)count));
+    if (n > 0) {
+        CU(cudaMemcpy(net->d_exp_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_kind.p, h_kind.data(), (size_t)n, cudaMemcpyHostToDevice));
+    }
+    if (count > 0) {
+        CU(cudaMemcpy(net->d_exp_peer.p, h_peer.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_exp_pos.p, h_pos.data(), (size_t)count * sizeof(long long), cudaMemcpyHostToDevice));
+    }
+    net->n_exp = count;
+    return TRT_OK;
+}
+
+int trt_network_set_peer(trt_network* net, int32_t peer, void* peer_q_device, int64_t peer_n_rows)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (peer < 0 || peer >= TRT_MAX_PEERS) return fail(TRT_ERR_INVALID, "peer index %d out of range", peer);
+    net->peer_q[peer] = (float*)peer_q_device;
+    net->peer_n[peer] = peer_n_rows;
+    return TRT_OK;
+}
+
+int trt_network_state_ptr(trt_network* net, void** q_device)
+{
+    if (!net || !q_device) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "no forcing uploaded: the flow array is allocated by trt_upload_forcing");
+    *q_device = net->d_q.p;
+    return TRT_OK;
+}
+
+int trt_ipc_get_handle(void* device_ptr, uint8_t handle[64])
+{
+    if (!device_ptr || !handle) return fail(TRT_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, 64);
+    return TRT_OK;
+}
+
+int trt_ipc_open_handle(int device, const uint8_t handle[64], void** device_ptr)
+{
+    if (!handle || !device_ptr) return fail(TRT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TRT_OK;
+}
+
+int trt_ipc_close_handle(void* device_ptr)
+{
+    if (device_ptr) CU(cudaIpcCloseMemHandle(device_ptr));
+    return TRT_OK;
+}
+
 int trt_set_option(trt_network* net, const char* key, int64_t value)
 {
     if (!net || !key) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "mode")) {
-        if (value != 0 && value != 1) return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches) or 1 (persistent)");
+        if (value < 0 || value > 2)
+            return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches), 1 (persistent, grid.sync) or 2 (dataflow)");
         net->mode = (int)value;
     } else if (!strcmp(key, "grid_blocks")) {
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
         net->grid_blocks = (int)value;
+    } else if (!strcmp(key, "gate")) {
+        if (value < 1 || value > 1000000) return fail(TRT_ERR_INVALID, "gate must be >= 1");
+        net->gate = (int)value;
     } else if (!strcmp(key, "stream")) {
         // adopt a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so that the
         // caller's CUDA events bracket this handle's kernels; 0 restores the private stream

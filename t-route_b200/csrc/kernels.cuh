@@ -42,6 +42,37 @@ struct RunDev {
     float* d;
 };
 
+// Dataflow schedule (mode 2).  Work = the stages of the wavefront, cut into units of 32 or 128 consecutive positions
+// and claimed IN ORDER from one counter; a unit never waits on a stage barrier, its lanes wait on exactly the values
+// they read (a not-yet-written q / d slot holds TRT_SENTINEL).  Because units are claimed in stage order, everything a
+// claimed unit waits for has been claimed earlier by a warp that is running, so the earliest unfinished unit always
+// progresses: no deadlock, and a lane stuck in the 750-iteration retry ladder delays only its own dependents.
+#define TRT_SENTINEL 0xFFFFFFFFu
+
+struct SchedDev {
+    int nstages;                      // stages k = 1 .. nstages
+    int T;
+    const int* unit_ptr;              // [nstages + 1] first unit of stage k is unit_ptr[k - 1]
+    const unsigned char* unit_shift;  // [nstages] log2 of the unit width of that stage (5 or 7)
+    unsigned int* claim;              // [1] next unit to hand out
+    int* done;                        // [nstages] finished units per stage
+    int* frontier;                    // [1] highest stage known to be complete (run-ahead gate)
+    int* abort_flag;                  // [1] set when a wait timed out
+    const int* gate_stage;            // [nstages] stage that must be complete before a unit of stage k starts:
+                                      // the last non-empty stage <= k - gate (0 = no wait)
+};
+
+// cut edges to other shards: lane s with (kind & TRT_KIND_EXPORT_FLAG) stores q also to peer memory
+#define TRT_KIND_EXPORT_FLAG 0x10
+#define TRT_MAX_PEERS 16
+struct PeerDev {
+    const int* exp_slot;              // [n] index into exp_peer / exp_pos, valid where the flag is set
+    const int* exp_peer;              // [n_exp]
+    const long long* exp_pos;         // [n_exp] position in the peer's arrays
+    float* q[TRT_MAX_PEERS];          // peer q arrays (mapped peer memory), time-major
+    long long n[TRT_MAX_PEERS];       // peer segment counts
+};
+
 // wavefront: stage k routes every (segment s, step t) with level(s) + t == k
 cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st);
 // persistent cooperative kernel over stages [k_begin, k_end)
@@ -49,6 +80,10 @@ cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin,
                               cudaStream_t st);
 // largest co-resident grid (blocks) of the persistent kernel on the current device
 cudaError_t persistent_max_grid(int* blocks);
+cudaError_t dataflow_max_grid(int* blocks);
+cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
+                            int grid_blocks, cudaStream_t st);
+cudaError_t launch_fill_zero_rows(const int* pos, float* q, float* v, float* d, int n, int count, int T, cudaStream_t st);
 
 cudaError_t launch_gather_qlat(const float* qlat_rows, const int* row_of_pos, float* qlat_t, int n, int nq,
                                cudaStream_t st);

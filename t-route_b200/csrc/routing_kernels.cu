@@ -47,35 +47,83 @@ __device__ __forceinline__ PowTabs stage_tables(SmemTabs& s)
     return t;
 }
 
-// route segment `s` (engine position) at step `t`
-__device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs)
+// ---- loads / stores of the flow state --------------------------------------------------------------------
+// Bulk-synchronous schedules read finished rows with ld.cg.  The dataflow schedule reads slots that another warp
+// (or another GPU, over NVLink) may not have written yet: they hold TRT_SENTINEL until the one 4-byte store that
+// publishes the value lands in L2, so a volatile (L1-bypassing) poll is the whole synchronisation.
+__device__ __forceinline__ unsigned ld_volatile_u32(const float* p)
 {
-    const unsigned kind = net.kind[s];
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool WAIT>
+__device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
+{
+    if (!WAIT) return __ldcg(p);
+    unsigned v = ld_volatile_u32(p);
+    if (v == TRT_SENTINEL) {
+        unsigned spins = 0;
+        do {
+            __nanosleep(spins < 16 ? 40 : 400);
+            v = ld_volatile_u32(p);
+            if ((++spins & 0x3FFF) == 0) {
+                // ~6 ms of waiting per check; bail out if somebody flagged an error, or after ~8 s on our own
+                if (*reinterpret_cast<volatile int*>(abort_flag) != 0) return __uint_as_float(0x7FC00000u);
+                if (spins > (1u << 24)) { atomicExch(abort_flag, 1); return __uint_as_float(0x7FC00000u); }
+            }
+        } while (v == TRT_SENTINEL);
+    }
+    return __uint_as_float(v);
+}
+
+template <bool WAIT>
+__device__ __forceinline__ void st_state(float* p, float x)
+{
+    if (WAIT) {
+        unsigned b = __float_as_uint(x);
+        if (b == TRT_SENTINEL) b = 0x7FC00000u;      // a NaN payload that happens to equal the sentinel
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(b) : "memory");
+    } else {
+        *p = x;
+    }
+}
+
+// route segment `s` (engine position) at step `t`
+template <bool WAIT>
+__device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs,
+                                           const PeerDev* peers, int* abort_flag)
+{
+    const unsigned kflags = net.kind[s];
+    const unsigned kind = kflags & 0x0F;
     if (kind == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
 
     const size_t n = (size_t)net.n;
     const float* qc = run.q + (size_t)t * n;          // row t
     const float* qp = qc - n;                         // row t-1
 
-    // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
-    float quc = 0.0f, qup = 0.0f;
-    const int e0 = __ldg(net.up_ptr + s), e1 = __ldg(net.up_ptr + s + 1);
-    if (run.short_ts) {
-        for (int e = e0; e < e1; ++e) qup += __ldcg(qp + __ldg(net.up_idx + e));
-        quc = qup;
-    } else {
-        for (int e = e0; e < e1; ++e) {
-            const int u = __ldg(net.up_idx + e);
-            quc += __ldcg(qc + u);
-            qup += __ldcg(qp + u);
-        }
-    }
-
+    // parameters first: they do not depend on anybody's results, so their latency overlaps the waits below
     const float* par = net.par + s;
     const float p0 = __ldg(par + 0 * n), p1 = __ldg(par + 1 * n), p2 = __ldg(par + 2 * n), p3 = __ldg(par + 3 * n),
                 p4 = __ldg(par + 4 * n), p5 = __ldg(par + 5 * n), p6 = __ldg(par + 6 * n), p7 = __ldg(par + 7 * n),
                 p8 = __ldg(par + 8 * n);
-    const float statep = __ldcg(run.d + (size_t)(t - 1) * n + s);   // depth (MC) / water elevation (level pool) at t-1
+    const int e0 = __ldg(net.up_ptr + s), e1 = __ldg(net.up_ptr + s + 1);
+
+    // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
+    float quc = 0.0f, qup = 0.0f;
+    if (run.short_ts) {
+        for (int e = e0; e < e1; ++e) qup += ld_state<WAIT>(qp + __ldg(net.up_idx + e), abort_flag);
+        quc = qup;
+    } else {
+        for (int e = e0; e < e1; ++e) {
+            const int u = __ldg(net.up_idx + e);
+            quc += ld_state<WAIT>(qc + u, abort_flag);
+            qup += ld_state<WAIT>(qp + u, abort_flag);
+        }
+    }
+    // depth (MC) / water elevation (level pool) at t-1
+    const float statep = ld_state<WAIT>(run.d + (size_t)(t - 1) * n + s, abort_flag);
 
     float o_q, o_v, o_d;
     if (kind == TRT_KIND_LEVELPOOL) {
@@ -90,13 +138,22 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
         o_d = H;
     } else {
         const float ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);   // :723
-        const float qdp = __ldcg(qp + s);                                            // :733
+        const float qdp = ld_state<WAIT>(qp + s, abort_flag);                        // :733
         const McResult r = trt_mc_segment<false>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
     }
-    run.q[(size_t)t * n + s] = o_q;
     run.v[(size_t)t * n + s] = o_v;
-    run.d[(size_t)t * n + s] = o_d;
+    st_state<WAIT>(run.d + (size_t)t * n + s, o_d);
+    st_state<WAIT>(run.q + (size_t)t * n + s, o_q);
+    if (WAIT && (kflags & TRT_KIND_EXPORT_FLAG)) {
+        // this segment drains into another shard: scatter its outflow into that GPU's inflow slot (peer memory)
+        const int x = __ldg(peers->exp_slot + s);
+        const int pr = __ldg(peers->exp_peer + x);
+        float* dst = peers->q[pr] + (size_t)t * (size_t)peers->n[pr] + (size_t)__ldg(peers->exp_pos + x);
+        unsigned b = __float_as_uint(o_q);
+        if (b == TRT_SENTINEL) b = 0x7FC00000u;
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
+    }
 }
 
 __device__ __forceinline__ int lane_step(const NetDev& net, const RunDev& run, int k, int s)
@@ -112,7 +169,7 @@ __global__ void __launch_bounds__(kBlock) stage_kernel(NetDev net, RunDev run, i
     if (s >= hi) return;
     const int t = lane_step(net, run, k, s);
     if (t < 1 || t > run.T) return;
-    route_lane(net, run, s, t, tabs);
+    route_lane<false>(net, run, s, t, tabs, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev run, int k_begin, int k_end)
@@ -132,10 +189,94 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
         }
         for (int s = lo + gtid; s < hi; s += gstride) {
             const int t = lane_step(net, run, k, s);
-            if (t >= 1 && t <= run.T) route_lane(net, run, s, t, tabs);
+            if (t >= 1 && t <= run.T) route_lane<false>(net, run, s, t, tabs, nullptr, nullptr);
         }
         grid.sync();
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dataflow schedule (see kernels.cuh): persistent warps claim units in stage order, lanes wait on their own inputs
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    const int lane = threadIdx.x & 31;
+    const unsigned total = (unsigned)__ldg(sc.unit_ptr + sc.nstages);
+    const int L = run.short_ts ? 1 : net.nlevels;
+    int cursor = 0;                                   // stage index (k - 1) of this warp's previous unit
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(sc.claim, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total) break;
+        // stage of unit u: last index i >= cursor with unit_ptr[i] <= u
+        int lo_i = cursor, hi_i = sc.nstages;         // invariant: unit_ptr[lo_i] <= u < unit_ptr[hi_i]
+        while (hi_i - lo_i > 1) {
+            const int mid = (lo_i + hi_i) >> 1;
+            if ((unsigned)__ldg(sc.unit_ptr + mid) <= u) lo_i = mid; else hi_i = mid;
+        }
+        cursor = lo_i;
+        const int k = lo_i + 1;
+        int lo, hi;
+        if (run.short_ts) { lo = 0; hi = net.n; }
+        else {
+            lo = __ldg(net.lvl_ptr + max(0, k - run.T));
+            hi = __ldg(net.lvl_ptr + min(L, k));
+        }
+        const int shift = __ldg(sc.unit_shift + lo_i);
+        const int p0 = lo + (int)((u - (unsigned)__ldg(sc.unit_ptr + lo_i)) << shift);
+        const int p1 = min(hi, p0 + (1 << shift));
+
+        // run-ahead gate: do not start polling individual slots before stage k - gate is complete
+        const int need = __ldg(sc.gate_stage + lo_i);   // last non-empty stage <= k - gate (0 = none)
+        if (need >= 1) {
+            if (lane == 0) {
+                unsigned spins = 0;
+                while (*reinterpret_cast<volatile int*>(sc.frontier) < need) {
+                    __nanosleep(200);
+                    if ((++spins & 0x3FFF) == 0) {
+                        if (*reinterpret_cast<volatile int*>(sc.abort_flag) != 0) break;
+                        if (spins > (1u << 25)) { atomicExch(sc.abort_flag, 1); break; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        for (int s = p0 + lane; s < p1; s += 32) {
+            const int t = run.short_ts ? k : k - __ldg(net.level + s);
+            route_lane<true>(net, run, s, t, tabs, &peers, sc.abort_flag);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // stage bookkeeping for the gate: the warp that finishes the last unit of stage k advances the frontier
+            const int units_k = __ldg(sc.unit_ptr + lo_i + 1) - __ldg(sc.unit_ptr + lo_i);
+            __threadfence();
+            if (atomicAdd(sc.done + lo_i, 1) + 1 == units_k) atomicMax(sc.frontier, k);
+        }
+    }
+}
+
+cudaError_t dataflow_max_grid(int* blocks)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dataflow_kernel, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    *blocks = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
+                            int grid_blocks, cudaStream_t st)
+{
+    dataflow_kernel<<<grid_blocks, kBlock, 0, st>>>(net, run, sched, peers);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st)
@@ -223,6 +364,16 @@ __global__ void fill_boundary_kernel(const int* __restrict__ bnd_pos, const floa
     q[o] = src[0]; v[o] = src[1]; d[o] = src[2];
 }
 
+// boundary rows nobody prescribes stay zero for every step (flowveldepth is zero-initialised, mc_reach.pyx:253)
+__global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* q, float* v, float* d, int n, int count, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)count * T) return;
+    const int b = (int)(i / T), t = (int)(i % T) + 1;
+    const size_t o = (size_t)t * n + pos[b];
+    q[o] = 0.0f; v[o] = 0.0f; d[o] = 0.0f;
+}
+
 // fvd[row][3*(t-1) + c] = {q, v, d}[t][pos]: 32 positions x 32 steps per block through shared memory so that
 // both the time-major reads and the row-major writes are coalesced.
 __global__ void __launch_bounds__(256) finalize_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
@@ -247,7 +398,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(NetDev net, RunDev run, f
         if (p >= net.n || c >= width) continue;
         const int j = c / 3, comp = c % 3;
         float val = comp == 0 ? sq[j][pl] : (comp == 1 ? sv[j][pl] : sd[j][pl]);
-        if (comp == 1 && net.kind[p] == TRT_KIND_LEVELPOOL) val = 0.0f;   // flowveldepth[r.id, t, 1] = 0.0  (:708)
+        if (comp == 1 && (net.kind[p] & 0x0F) == TRT_KIND_LEVELPOOL) val = 0.0f;   // flowveldepth[r.id, t, 1] = 0.0  (:708)
         fvd[(size_t)net.row_of_pos[p] * (3 * (size_t)run.T) + 3 * (size_t)(t0 - 1) + c] = val;
     }
 }
@@ -315,6 +466,13 @@ cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float
     const long long total = (long long)n_bnd * T;
     if (total == 0) return cudaSuccess;
     fill_boundary_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(bnd_pos, bnd_fvd, q, v, d, n, n_bnd, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_zero_rows(const int* pos, float* q, float* v, float* d, int n, int count, int T, cudaStream_t st)
+{
+    const long long total = (long long)count * T;
+    if (total == 0) return cudaSuccess;
+    fill_zero_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, q, v, d, n, count, T);
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st)

@@ -41,6 +41,7 @@ SYMBOLS = [
     ("trt_version", C.c_int, []),
     ("trt_device_count", C.c_int, []),
     ("trt_network_create", C.c_int, [C.c_int, C.c_int64, _i64p, _i64p, _u8p, _f32p, C.c_int32, _i32p, C.POINTER(_net)]),
+    ("trt_network_create_ex", C.c_int, [C.c_int, C.c_int64, _i64p, _i64p, _u8p, _f32p, C.c_int32, _i32p, _i32p, C.POINTER(_net)]),
     ("trt_network_destroy", C.c_int, [_net]),
     ("trt_network_num_levels", C.c_int, [_net, _i32p]),
     ("trt_network_get_levels", C.c_int, [_net, _i32p]),
@@ -55,6 +56,14 @@ SYMBOLS = [
     ("trt_export_flow_series", C.c_int, [_net, C.c_int64, _i64p, C.c_void_p]),
     ("trt_import_boundary_flow", C.c_int, [_net, C.c_int64, _i64p, C.c_void_p]),
     ("trt_device_results", C.c_int, [_net, C.POINTER(C.c_void_p)]),
+    ("trt_network_state_ptr", C.c_int, [_net, C.POINTER(C.c_void_p)]),
+    ("trt_ipc_get_handle", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("trt_ipc_open_handle", C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("trt_ipc_close_handle", C.c_int, [C.c_void_p]),
+    ("trt_network_set_peer", C.c_int, [_net, C.c_int32, C.c_void_p, C.c_int64]),
+    ("trt_network_set_exports", C.c_int, [_net, C.c_int64, _i64p, _i32p, _i64p]),
+    ("trt_network_set_imports", C.c_int, [_net, C.c_int64, _i64p]),
+    ("trt_prepare", C.c_int, [_net]),
     ("trt_set_option", C.c_int, [_net, C.c_char_p, C.c_int64]),
     ("trt_last_run_stats", C.c_int, [_net, _f64p, _i64p, _i64p, _i64p]),
     ("trt_mc_segment_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _i32p]),

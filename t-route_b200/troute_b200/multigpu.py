@@ -12,9 +12,9 @@ from .network import RoutingNetwork
 
 
 class SingleRouter:
-    kernel_name = "trt::persistent_kernel"
+    kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel"}
 
-    def __init__(self, wl, device, nsteps, qts, short_ts, mode=1):
+    def __init__(self, wl, device, nsteps, qts, short_ts, mode=2):
         import torch
         self.torch = torch
         self.wl = wl
@@ -60,9 +60,108 @@ class SingleRouter:
         st = self.net.last_run_stats()
         launches = st["launches"]
         return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": launches,
-                "launches_per_call_e2e": launches + 2 + (1 if self.n else 0), "stages": st["stages"],
-                "levels": self.net.num_levels, "kernel_name": self.kernel_name if self.mode == 1 else "trt::stage_kernel",
+                "launches_per_call_e2e": launches + 2, "stages": st["stages"],
+                "levels": self.net.num_levels, "kernel_name": self.kernel_names[self.mode],
                 "sharding": "single GPU"}
 
     def close(self):
+        self.net.close()
+
+
+class ShardedRouter:
+    """One sub-basin shard per rank.  Cut-edge flows travel through CUDA-IPC-mapped peer memory inside the routing
+    kernel (no collective on the data path); torch.distributed is used for rendezvous (IPC handles, import positions)
+    and for the barrier between resetting the flow state and launching."""
+    kernel_names = SingleRouter.kernel_names
+
+    def __init__(self, wl, world, rank, device, nsteps, qts, short_ts, mode=2, pieces_per_shard=16):
+        import torch
+        import torch.distributed as dist
+        from . import hostgraph, partition
+        if mode != 2:
+            raise ValueError("sharded routing needs the dataflow schedule (mode 2)")
+        self.torch, self.dist = torch, dist
+        self.wl, self.world, self.rank, self.device = wl, world, rank, device
+        self.T, self.qts, self.short_ts, self.mode = nsteps, qts, short_ts, mode
+        level = hostgraph.levels(wl["down"], wl["up_ptr"])
+        self.shard, plans, self.plan_stats = partition.plan_shards(wl["down"], wl["up_ptr"], wl["up_rows"], wl["kind"],
+                                                                   world, pieces_per_shard=pieces_per_shard, level=level)
+        self.plan = plan = plans[rank]
+        self.n = int(plan.rows.size)
+        self.n_own = int(plan.own.sum())
+        self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
+                                  device=device, levels=plan.levels)
+        self.net.set_option("mode", 2)
+        self.tstream = torch.cuda.Stream(device=device)
+        self.stream = self.tstream
+        self.net.set_option("stream", self.tstream.cuda_stream)
+        self.net.set_imports(plan.imports)
+        self.qlat = np.ascontiguousarray(wl["qlat"][plan.rows])
+        self.q0 = np.ascontiguousarray(wl["q0"][plan.rows])
+        self.nq = self.qlat.shape[1]
+        self.h2d_bytes = self.qlat.nbytes + self.q0.nbytes
+        self.d2h_bytes = self.n * 3 * nsteps * 4
+        self._host = None
+        self._wired = False
+
+    def _wire(self):
+        """After the first upload (the flow array exists): exchange IPC handles and import positions, open peers."""
+        dist, plan = self.dist, self.plan
+        pos = self.net.positions()
+        mine = {"handle": self.net.ipc_handle(), "n": self.n,
+                "import_pos": dict(zip(plan.rows[plan.imports].tolist(), pos[plan.imports].tolist()))}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        exp_rows, exp_shard, exp_global = plan.exports
+        peers = sorted(set(exp_shard.tolist()))
+        if len(peers) > 16:
+            raise ValueError("more than 16 destination shards")
+        for p in peers:
+            self.net.open_peer(p, everyone[p]["handle"], everyone[p]["n"])
+        peer_pos = np.asarray([everyone[int(s)]["import_pos"][int(g)] for s, g in zip(exp_shard, exp_global)],
+                              dtype=np.int64)
+        self.net.set_exports(exp_rows, exp_shard.astype(np.int32), peer_pos)
+        self._wired = True
+        dist.barrier()
+
+    def upload(self):
+        self.net.upload(self.T, self.qts, self.qlat, self.q0)
+        if not self._wired:
+            self._wire()
+
+    def run_resident(self):
+        self.net.prepare()             # flow state back to "not yet written"; complete before any peer may write
+        self.dist.barrier()
+        self.net.run_async(self.short_ts)
+
+    def alloc_host(self):
+        torch = self.torch
+        self._host = (torch.from_numpy(self.qlat).pin_memory(), torch.from_numpy(self.q0).pin_memory(),
+                      torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True))
+
+    def run_e2e(self):
+        qlat, q0, out = self._host
+        self.net.upload_ptr(self.T, self.qts, qlat.data_ptr(), self.nq, q0.data_ptr())
+        self.net.prepare()
+        self.dist.barrier()
+        self.net.run_async(self.short_ts)
+        self.net.download_ptr(out.data_ptr())
+
+    def host_result(self):
+        """(global rows of this shard's own segments, their [n_own, 3T] results)"""
+        return self.plan.rows[self.plan.own], self._host[2].numpy()[self.plan.own]
+
+    def collect_stats(self):
+        self.net.sync()
+        st = self.net.last_run_stats()
+        return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": st["launches"],
+                "launches_per_call_e2e": st["launches"] + 2, "stages": st["stages"], "levels": self.net.num_levels,
+                "kernel_name": self.kernel_names[self.mode],
+                "sharding": f"{self.world} sub-basin shards, {self.plan_stats['n_cut_edges']} cut edges, "
+                            f"imbalance {self.plan_stats['imbalance']:.3f}, peer-memory stores (no collective)"}
+
+    def close(self):
+        self.net.sync()
+        self.dist.barrier()
+        self.net.close_peers()
         self.net.close()

@@ -37,7 +37,7 @@ class RoutingNetwork:
     device          : CUDA device ordinal
     """
 
-    def __init__(self, up_ptr, up_rows, kind, data_values, data_cols, device=0):
+    def __init__(self, up_ptr, up_rows, kind, data_values, data_cols, device=0, levels=None):
         L = _lib.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -57,9 +57,15 @@ class RoutingNetwork:
         self.device = int(device)
         self.kind = kind
         self._keep = (up_ptr, up_rows, kind, data_values, scols)
-        check(L.trt_network_create(self.device, n_rows, ptr(up_ptr, C.c_int64), ptr(up_rows, C.c_int64),
-                                   ptr(kind, C.c_uint8), ptr(data_values, C.c_float), int(data_values.shape[1]),
-                                   ptr(scols, C.c_int32), C.byref(self._h)))
+        lv = None
+        if levels is not None:
+            lv = as_c(levels, np.int32)
+            if lv.shape[0] != n_rows:
+                raise ValueError("levels must have one entry per row")
+        check(L.trt_network_create_ex(self.device, n_rows, ptr(up_ptr, C.c_int64), ptr(up_rows, C.c_int64),
+                                      ptr(kind, C.c_uint8), ptr(data_values, C.c_float), int(data_values.shape[1]),
+                                      ptr(scols, C.c_int32), ptr(lv, C.c_int32) if lv is not None else None,
+                                      C.byref(self._h)))
         self._keep = None
         self.nsteps = 0
         self._lp_rows = np.zeros(0, dtype=np.int64)
@@ -190,6 +196,47 @@ class RoutingNetwork:
         check(self._L.trt_route(self._h, int(nsteps), int(qts_subdivisions), 1 if assume_short_ts else 0, qlat_ptr,
                                 int(nqcols), q0_ptr, 0, None, None, fvd_ptr, None))
         self.nsteps = int(nsteps)
+
+    # -- sharding (peer memory) ---------------------------------------------------------------
+    def prepare(self):
+        check(self._L.trt_prepare(self._h))
+
+    def state_ptr(self):
+        out = C.c_void_p()
+        check(self._L.trt_network_state_ptr(self._h, C.byref(out)))
+        return out.value
+
+    def ipc_handle(self):
+        """64-byte CUDA IPC handle of the flow array (to be opened by the peer process)."""
+        buf = (C.c_uint8 * 64)()
+        check(self._L.trt_ipc_get_handle(C.c_void_p(self.state_ptr()), buf))
+        return bytes(buf)
+
+    def open_peer(self, peer, handle_bytes, peer_n_rows):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        out = C.c_void_p()
+        check(self._L.trt_ipc_open_handle(self.device, buf, C.byref(out)))
+        check(self._L.trt_network_set_peer(self._h, int(peer), out, int(peer_n_rows)))
+        self._peer_ptrs = getattr(self, "_peer_ptrs", []) + [out.value]
+        return out.value
+
+    def set_peer_ptr(self, peer, device_ptr, peer_n_rows):
+        """Same-process peer (tests / single process driving several GPUs): pass the other handle's state_ptr()."""
+        check(self._L.trt_network_set_peer(self._h, int(peer), C.c_void_p(device_ptr), int(peer_n_rows)))
+
+    def close_peers(self):
+        for p in getattr(self, "_peer_ptrs", []):
+            self._L.trt_ipc_close_handle(C.c_void_p(p))
+        self._peer_ptrs = []
+
+    def set_exports(self, rows, peer, peer_pos):
+        rows = as_c(rows, np.int64); peer = as_c(peer, np.int32); peer_pos = as_c(peer_pos, np.int64)
+        check(self._L.trt_network_set_exports(self._h, int(rows.shape[0]), ptr(rows, C.c_int64), ptr(peer, C.c_int32),
+                                              ptr(peer_pos, C.c_int64)))
+
+    def set_imports(self, rows):
+        rows = as_c(rows, np.int64)
+        check(self._L.trt_network_set_imports(self._h, int(rows.shape[0]), ptr(rows, C.c_int64)))
 
     # -- device-side access -------------------------------------------------------------------
     def export_flow_series(self, rows, dst_device_ptr):

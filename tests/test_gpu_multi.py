@@ -1,0 +1,63 @@
+"""Two real ranks on two GPUs (torchrun-style, NCCL rendezvous + CUDA IPC peer memory).  Skipped on a 1-GPU box; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import os, sys
+sys.path[:0] = [{root!r}, os.path.join({root!r}, "t-route_b200"), os.path.join({root!r}, "tests")]
+import numpy as np, torch, torch.distributed as dist
+import helpers as H
+from oracle import oracle as o
+from troute_b200 import synth, multigpu
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+down = synth.conus_like(n_total=60000, n_basins=40, seed=12)
+case = H.make_case(down, nsteps=36, warm=True)
+wl = dict(n=case["n"], down=down, params=case["params"], cols=case["cols"], qlat=case["qlat"], q0=case["q0"],
+          up_ptr=case["up_ptr"], up_rows=case["up_rows"], kind=case["kind"])
+for short in (False, True):
+    r = multigpu.ShardedRouter(wl, world, rank, rank, 36, 12, short, pieces_per_shard=6)
+    r.upload(); r.alloc_host()
+    for rep in range(2):
+        r.run_e2e()
+    rows, out = r.host_result()
+    ref, _, _ = H.oracle_route(o, case, short)
+    ok = bool(np.array_equal(out.view(np.int32), ref[rows].view(np.int32)))
+    res = [None] * world
+    dist.all_gather_object(res, ok)
+    assert all(res), (short, res)
+    if rank == 0:
+        print("OK short_ts=%s cut_edges=%d" % (short, r.plan_stats["n_cut_edges"]), flush=True)
+    r.close()
+dist.destroy_process_group()
+"""
+
+
+def test_two_gpu_sharded_routing_matches_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=900)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "OK short_ts=True" in outs[0]

@@ -129,7 +129,7 @@ def _networks():
 
 @pytest.mark.parametrize("name", ["tree4095", "chain300", "single", "hack20k_lp", "forest"])
 @pytest.mark.parametrize("short_ts", [False, True])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_network_bits(eng, oracle, name, short_ts, mode):
     down, n_lp = _networks()[name]
     case = H.make_case(down, nsteps=36, n_lp=n_lp, warm=(name != "forest"))
@@ -144,17 +144,25 @@ def test_network_bits(eng, oracle, name, short_ts, mode):
 
 
 def test_network_vs_libm_oracle_tolerance(eng, oracle):
-    """Against the platform-libm arithmetic (what a gfortran build of the reference computes): streamflow within
-    1e-5 relative wherever q is not negligible, except segment-steps downstream of a secant-termination flip;
-    those are bounded in count (< 0.1 %) -- the oracle's own libm-vs-det distance is the same set."""
+    """Against the platform-libm arithmetic (what a gfortran build of the reference computes on THIS machine).
+
+    The secant solve stops at a 1 % tolerance far from its fixed point, so the reference amplifies a 1-ulp difference
+    between two powf implementations: its own two arithmetic builds (platform powf vs the bit-specified powf) agree
+    bit for bit on ~97.5 % of the segment-timesteps of this case and within 1e-5 relative on 99.6 %; the remainder
+    are lanes whose iteration count flipped and everything downstream of them (measured in
+    tests/test_oracle_network.py, recorded in DESIGN.md "Numerics contract").  The GPU reproduces the bit-specified
+    build exactly, so its distance to the libm build must be that same set -- not one lane more."""
     from troute_b200 import synth
     case = H.make_case(synth.hack_tree(20000, seed=9), nsteps=48, warm=False)
     ref, _, _ = H.oracle_route(oracle, case, False, pow_mode=oracle.POW_LIBM)
+    det, _, _ = H.oracle_route(oracle, case, False, pow_mode=oracle.POW_DET)
     out, _, _ = H.engine_route(case, False)
+    H.assert_bit_equal(out, det, "GPU vs bit-specified oracle")
     q_ref, q_out = ref[:, 0::3], out[:, 0::3]
     rel = np.abs(q_out - q_ref) / np.maximum(np.abs(q_ref), 1e-3)
-    assert (rel <= REL_TOL).mean() >= 0.999, float((rel <= REL_TOL).mean())
-    assert np.median(rel) <= 1e-6
+    assert (rel <= REL_TOL).mean() >= 0.99, float((rel <= REL_TOL).mean())
+    assert (q_ref == q_out).mean() >= 0.95
+    assert np.median(rel) == 0.0
 
 
 def test_restart_chunks_equal_one_run(eng, oracle):
@@ -223,16 +231,19 @@ def test_argument_errors(eng):
 
 
 def test_full_size_config2_properties(eng, oracle):
-    """BASELINE config 2 (binary tree, 1,048,576 segments) at full width, 48 steps: (i) the persistent kernel and
-    the launch-per-stage schedule agree bit for bit; (ii) a complete sub-tree (4,095 segments upstream of one node)
+    """BASELINE config 2 (binary tree, 1,048,576 segments) at full width, 48 steps: (i) the dataflow kernel, the
+    grid-barrier persistent kernel and the launch-per-stage schedule agree bit for bit; (ii) a complete sub-tree (4,095 segments upstream of one node)
     is independent of the rest of the network, so the oracle run on it alone must reproduce those rows exactly."""
     from troute_b200 import synth
     N, T = 1_048_576, 48
     down = synth.binary_tree(N)
     case = H.make_case(down, nsteps=T)
-    a, _, st = H.engine_route(case, False, mode=1, want_upstream=False)
+    a, _, st = H.engine_route(case, False, mode=2, want_upstream=False)
     b, _, _ = H.engine_route(case, False, mode=0, want_upstream=False)
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    b, _, _ = H.engine_route(case, False, mode=1, want_upstream=False)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))
+    del b
     assert np.isfinite(a).all() and st["stages"] == 20 + T
     root = 300                                            # heap index; its subtree has 2^12 - 1 nodes at N = 2^20
     ids = [root]
@@ -249,3 +260,65 @@ def test_full_size_config2_properties(eng, oracle):
                up_ptr=p2, up_rows=r2, kind=case["kind"][ids])
     ref, _, _ = H.oracle_route(oracle, sub, False)
     H.assert_bit_equal(a[ids], ref, "sub-tree of the full-size run")
+
+
+def test_gate_and_grid_options_do_not_change_results(eng, oracle):
+    """Dataflow schedule knobs: run-ahead gate 1 / 50, tiny grid (2 CTAs) -- same bits."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.hack_tree(12000, seed=21), nsteps=30, n_lp=8, warm=True)
+    ref, _, _ = H.oracle_route(oracle, case, False)
+    for gate, grid in ((1, 0), (50, 0), (3, 2)):
+        net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+        net.set_levelpools(case["lp_rows"], case["wbody"])
+        net.set_option("gate", gate); net.set_option("grid_blocks", grid)
+        out, _ = net.route(30, 12, case["qlat"], case["q0"])
+        net.close()
+        H.assert_bit_equal(out, ref, f"gate={gate} grid={grid}")
+
+
+@pytest.mark.parametrize("P", [2, 3])
+@pytest.mark.parametrize("short_ts", [False, True])
+def test_sharded_on_one_gpu_concurrent_kernels(eng, oracle, P, short_ts):
+    """The sharding path without a second GPU: P shard handles on the SAME device, wired through each other's flow
+    arrays exactly as peers are wired through CUDA IPC, their kernels running concurrently on P streams with a
+    quarter-size grid each.  Results of all shards together == the unsharded oracle, bit for bit."""
+    from troute_b200 import synth, partition, hostgraph
+    from troute_b200.network import RoutingNetwork
+    down = synth.conus_like(n_total=40000, n_basins=30, seed=12)
+    case = H.make_case(down, nsteps=30, n_lp=20, warm=True)
+    ref, upref, _ = H.oracle_route(oracle, case, short_ts)
+    level = hostgraph.levels(down, case["up_ptr"])
+    shard, plans, stats = partition.plan_shards(down, case["up_ptr"], case["up_rows"], case["kind"], P,
+                                                pieces_per_shard=6, level=level)
+    assert stats["n_cut_edges"] > 0
+    nets = []
+    lp_index = {int(r): i for i, r in enumerate(case["lp_rows"])}
+    for p in plans:
+        net = RoutingNetwork(p.up_ptr, p.up_rows, p.kind, case["params"][p.rows], case["cols"], levels=p.levels)
+        loc_lp = np.nonzero(p.kind == 1)[0]
+        net.set_levelpools(loc_lp, case["wbody"][[lp_index[int(g)] for g in p.rows[loc_lp]]] if loc_lp.size else np.zeros((0, 11)))
+        net.set_option("grid_blocks", 74)
+        net.set_imports(p.imports)
+        net.upload(30, 12, case["qlat"][p.rows], case["q0"][p.rows])
+        nets.append(net)
+    pos = [net.positions() for net in nets]
+    for p, net in zip(plans, nets):
+        rows, dst, glob = p.exports
+        for d in sorted(set(dst.tolist())):
+            net.set_peer_ptr(d, nets[d].state_ptr(), plans[d].rows.size)
+        loc = [dict(zip(q.rows.tolist(), range(q.rows.size))) for q in plans]
+        peer_pos = [pos[int(d)][loc[int(d)][int(g)]] for d, g in zip(dst, glob)]
+        net.set_exports(rows, dst.astype(np.int32), np.asarray(peer_pos, dtype=np.int64))
+    for net in nets:
+        net.prepare()
+    for net in nets:
+        net.run_async(short_ts)
+    for net in nets:
+        net.sync()
+    for p, net in zip(plans, nets):
+        out, up = net.download(want_upstream=True)
+        H.assert_bit_equal(out[p.own], ref[p.rows[p.own]], f"shard {p.rank}")
+        loc_lp = np.nonzero(p.kind == 1)[0]
+        H.assert_bit_equal(up[loc_lp], upref[p.rows[loc_lp]], f"shard {p.rank} reservoir inflow")
+        net.close()

@@ -19,7 +19,7 @@ print("powf det GPU==CPU:", np.array_equal(g.view(np.int32), c.view(np.int32)), 
 case = H.make_case(synth.binary_tree(4095), nsteps=48, warm=True)
 for short in (True, False):
     ref, _, ex = H.oracle_route(o, case, short)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         t = time.time(); out, _, st = H.engine_route(case, short, mode=mode); dt = time.time() - t
         same = np.array_equal(out.view(np.int32), ref.view(np.int32))
         print(f"tree4095 short={short} mode={mode}: bit-equal={same} maxrel={np.max(np.abs(out-ref)/(np.abs(ref)+1e-30)):.3g} stats={st} wall={dt:.3f}", flush=True)
@@ -37,7 +37,7 @@ N, T = 1_048_576, 288
 down = synth.binary_tree(N)
 case = H.make_case(down, nsteps=T)
 net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
-for mode in (1, 0):
+for mode in (2, 1, 0):
     net.set_option("mode", mode)
     for short in (False, True):
         net.upload(T, 12, case["qlat"], case["q0"])
