@@ -83,9 +83,12 @@ int trt_network_get_positions(const trt_network* net, int32_t* pos_of_row /* [n_
  * Level-pool reservoirs.  wbody_cols rows are (LkArea, LkMxE, OrificeA, OrificeC, OrificeE, WeirC,
  * WeirE, WeirL, ifd, qd0, h0) as in compute.py:1416-1430 / levelpool.pyx:48-57; dam length is 10 m
  * (levelpool.pyx:66); h0 < -9e8 selects the cold-start elevation (levelpool_structs.c:97-103).
+ * routing_period is the `dt` argument of compute_network_structured (run_lp_c(..., routing_period, ...),
+ * mc_reach.pyx:272,553); lake rows of data_values hold NaN and are never read.
  * May be called before every trt_upload_forcing (the reference passes the table on every call).
  */
-int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols);
+int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols,
+                               float routing_period);
 
 /*
  * One routing call = upload, run, download.  Shapes follow compute_network_structured:
@@ -155,7 +158,8 @@ int trt_prepare(trt_network* net);
 /* run-time knobs:
  *   "mode"        0 = one launch per wavefront stage, 1 = persistent cooperative kernel with a grid barrier per stage,
  *                 2 = dataflow kernel: units claimed in stage order, lanes wait on the slots they read (default)
- *   "gate"        mode 2: a unit of stage k starts once stage k - gate is complete (run-ahead bound, default 3)
+ *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
+ *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
 int trt_set_option(trt_network* net, const char* key, int64_t value);

@@ -86,14 +86,9 @@ TRT_HD double trt_dadd(double a, double b) {
 }
 
 /* tl: TRT_LOG2_TAB_N {invc, logc} pairs; te: TRT_EXP2_TAB_N entries; both as binary64 bit patterns */
-TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te) {
-    if (!(x > 0.0f)) {                       /* x <= 0 or NaN */
-        if (x == 0.0f) return 0.0f;          /* +-0 ** (y>0) = +0 */
-        return x != x ? x : trt_u2d(0x7ff8000000000000ULL) /* NaN */;
-    }
-    if (x > 3.402823466e+38f) return x;      /* +inf */
 
-    /* ---- log2(x) in binary64 ---- */
+/* log2(x) in binary64 for finite x > 0 */
+TRT_HD double trt_log2_pos(float x, const trt_u64* tl) {
     const trt_u64 ix  = trt_d2u((double)x);
     const trt_u64 tmp = ix - 0x3fe6000000000000ULL;                /* OFF = bits(0.6875) */
     const int i       = (int)((tmp >> 45) & (TRT_LOG2_TAB_N - 1));
@@ -116,9 +111,11 @@ TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te
     p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A2_BITS));
     p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A1_BITS));
     const double l     = trt_dadd((double)k, logc);
-    const double log2x = trt_dfma(p, r, l);
+    return trt_dfma(p, r, l);
+}
 
-    /* ---- 2^(y*log2x) ---- */
+/* (float) 2^(y * log2x) with one final rounding */
+TRT_HD float trt_exp2_scaled(double log2x, float y, const trt_u64* te) {
     const double t = trt_dmul((double)y, log2x);
     if (t >= 130.0) return trt_u2d(0x7ff0000000000000ULL);         /* overflows binary32 */
     if (t <= -160.0) return 0.0f;                                  /* below half the least subnormal */
@@ -142,6 +139,36 @@ TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te
     const double m  = trt_dfma(s, w, s);                           /* 2^(j/32 + g) in [1, 2) */
     const double sc = trt_u2d((trt_u64)(long long)(q + 1023) << 52); /* 2^q, q in [-161, 130] */
     return (float)trt_dmul(m, sc);                                 /* single rounding to binary32 */
+}
+
+/* result for the arguments that never reach the logarithm (x <= 0, NaN, +inf); *special = 0 otherwise */
+TRT_HD float trt_pow_special(float x, int* special) {
+    *special = 1;
+    if (!(x > 0.0f)) {                       /* x <= 0 or NaN */
+        if (x == 0.0f) return 0.0f;          /* +-0 ** (y>0) = +0 */
+        return x != x ? x : trt_u2d(0x7ff8000000000000ULL) /* NaN */;
+    }
+    if (x > 3.402823466e+38f) return x;      /* +inf */
+    *special = 0;
+    return 0.0f;
+}
+
+TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te) {
+    int special;
+    const float r = trt_pow_special(x, &special);
+    if (special) return r;
+    return trt_exp2_scaled(trt_log2_pos(x, tl), y, te);
+}
+
+/* x**y1 and x**y2 from ONE logarithm: bit-identical to two trt_powf_det calls (both are pure functions of the same
+ * log2(x)), at 2/3 of the cost.  The Muskingum-Cunge celerity needs R**(2/3) and R**(5/3) of the same R. */
+TRT_HD void trt_powf_det2(float x, float y1, float y2, float* o1, float* o2, const trt_u64* tl, const trt_u64* te) {
+    int special;
+    const float r = trt_pow_special(x, &special);
+    if (special) { *o1 = r; *o2 = r; return; }
+    const double l = trt_log2_pos(x, tl);
+    *o1 = trt_exp2_scaled(l, y1, te);
+    *o2 = trt_exp2_scaled(l, y2, te);
 }
 
 #endif /* TRT_DETMATH_H */

@@ -93,7 +93,9 @@ struct trt_network {
     DevBuf<int> d_unit_ptr, d_gate_stage, d_done, d_ctrl;     // d_ctrl: [0] claim, [1] frontier, [2] abort
     DevBuf<unsigned char> d_unit_shift;
     int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0;
-    int gate = 3;
+    int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
+    int gate_min = 12;
+    int64_t gate_lanes = 16384;
     bool prepared = false;                                    // sentinel reset done for the next run
     std::vector<int32_t> host_bnd_pos;                        // prescribed rows of the last upload (positions)
     int64_t n_bnd = 0;
@@ -322,14 +324,15 @@ int trt_network_get_positions(const trt_network* net, int32_t* pos_of_row)
     return TRT_OK;
 }
 
-int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols)
+int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp_rows, const double* wbody_cols,
+                               float routing_period)
 {
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (n_lp < 0 || (n_lp > 0 && (!lp_rows || !wbody_cols))) return fail(TRT_ERR_INVALID, "bad level-pool arguments");
     CU(cudaSetDevice(net->device));
     const int64_t n = net->n;
     std::vector<int32_t> pos((size_t)n_lp);
-    std::vector<float> qd0((size_t)n_lp), h0((size_t)n_lp), par((size_t)n_lp * 8);
+    std::vector<float> qd0((size_t)n_lp), h0((size_t)n_lp), par((size_t)n_lp * 9);
     for (int64_t i = 0; i < n_lp; ++i) {
         const int64_t r = lp_rows[i];
         if (r < 0 || r >= n) return fail(TRT_ERR_INVALID, "level-pool row %lld out of range", (long long)r);
@@ -345,8 +348,11 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
         if (we0 < -900000000.0f) H = oe + ((max_depth - oe) * ifd);   // levelpool_structs.c:97-103
         qd0[(size_t)i] = (float)a[9];                                  // mc_reach.pyx:298
         h0[(size_t)i] = H;
-        float* p = &par[(size_t)i * 8];
-        p[0] = area; p[1] = max_depth; p[2] = oa; p[3] = oc; p[4] = oe; p[5] = wc; p[6] = we; p[7] = wl;
+        float* p = &par[(size_t)i * 9];
+        // slot 0 is the routing period the reservoir runs with: the `dt` ARGUMENT of the call (routing_period,
+        // mc_reach.pyx:272,553), not a table column -- lake rows carry NaN channel parameters (compute.py:1455-1457)
+        p[0] = routing_period;
+        p[1] = area; p[2] = max_depth; p[3] = oa; p[4] = oc; p[5] = oe; p[6] = wc; p[7] = we; p[8] = wl;
     }
     CU(net->d_lp_pos.reserve((size_t)n_lp));
     CU(net->d_lp_qd0.reserve((size_t)n_lp));
@@ -355,10 +361,10 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
         CU(cudaMemcpy(net->d_lp_pos.p, pos.data(), (size_t)n_lp * sizeof(int32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(net->d_lp_qd0.p, qd0.data(), (size_t)n_lp * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(net->d_lp_h0.p, h0.data(), (size_t)n_lp * sizeof(float), cudaMemcpyHostToDevice));
-        DevBuf<float> d_par8;
-        CU(d_par8.reserve((size_t)n_lp * 8));
-        CU(cudaMemcpy(d_par8.p, par.data(), (size_t)n_lp * 8 * sizeof(float), cudaMemcpyHostToDevice));
-        CU(launch_scatter_lp_params(net->d_lp_pos.p, d_par8.p, net->d_par.p, (int)n, (int)n_lp, net->stream));
+        DevBuf<float> d_par9;
+        CU(d_par9.reserve((size_t)n_lp * 9));
+        CU(cudaMemcpy(d_par9.p, par.data(), (size_t)n_lp * 9 * sizeof(float), cudaMemcpyHostToDevice));
+        CU(launch_scatter_lp_params(net->d_lp_pos.p, d_par9.p, net->d_par.p, (int)n, (int)n_lp, net->stream));
         CU(cudaStreamSynchronize(net->stream));
     }
     net->n_lp = n_lp;
@@ -486,7 +492,9 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 std::vector<int32_t> unit_ptr((size_t)nstages + 1, 0), gate_stage((size_t)nstages, 0);
                 std::vector<unsigned char> shift((size_t)nstages, 5);
                 std::vector<int32_t> last_nonempty((size_t)nstages + 1, 0);   // last non-empty stage <= k
+                std::vector<int64_t> cum((size_t)nstages + 1, 0);             // lanes in stages 1..k
                 int64_t units = 0;
+                int win = 1;                                                  // first stage of the run-ahead window
                 for (int k = 1; k <= nstages; ++k) {
                     int64_t lo, hi;
                     if (assume_short_ts) { lo = 0; hi = net->n; }
@@ -501,7 +509,17 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                     if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
                     unit_ptr[(size_t)k] = (int32_t)units;
                     last_nonempty[(size_t)k] = width > 0 ? k : last_nonempty[(size_t)k - 1];
-                    const int j = k - net->gate;
+                    cum[(size_t)k] = cum[(size_t)k - 1] + width;
+                    // Run-ahead window of stage k: the stages (j, k] a unit of stage k may overtake.  Fixed gate:
+                    // j = k - gate.  Adaptive (gate = 0): at least gate_min stages -- a wide stage must be able to
+                    // overtake a lane stuck in the retry ladder for milliseconds -- and beyond that as many stages as
+                    // hold <= gate_lanes lanes, which bounds the number of lanes polling in the narrow deep levels.
+                    int j;
+                    if (net->gate > 0) j = k - net->gate;
+                    else {
+                        while (win < k && cum[(size_t)k] - cum[(size_t)win] > net->gate_lanes) ++win;
+                        j = std::min(win, k - net->gate_min);
+                    }
                     gate_stage[(size_t)k - 1] = j >= 1 ? last_nonempty[(size_t)j] : 0;
                 }
                 CU(net->d_unit_ptr.reserve((size_t)nstages + 1));
@@ -794,8 +812,17 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
         net->grid_blocks = (int)value;
     } else if (!strcmp(key, "gate")) {
-        if (value < 1 || value > 1000000) return fail(TRT_ERR_INVALID, "gate must be >= 1");
+        if (value < 0 || value > 1000000) return fail(TRT_ERR_INVALID, "gate must be >= 0");
         net->gate = (int)value;
+        net->sched_T = -1;
+    } else if (!strcmp(key, "gate_min")) {
+        if (value < 1 || value > 1000000) return fail(TRT_ERR_INVALID, "gate_min must be >= 1");
+        net->gate_min = (int)value;
+        net->sched_T = -1;
+    } else if (!strcmp(key, "gate_lanes")) {
+        if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
+        net->gate_lanes = value;
+        net->sched_T = -1;
     } else if (!strcmp(key, "stream")) {
         // adopt a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so that the
         // caller's CUDA events bracket this handle's kernels; 0 restores the private stream

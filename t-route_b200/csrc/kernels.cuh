@@ -91,7 +91,7 @@ cudaError_t launch_init_state(const float* q0_rows, const int* row_of_pos, float
                               cudaStream_t st);
 cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const float* lp_h0, float* q, float* v,
                                   float* d, int n_lp, cudaStream_t st);
-cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par8, float* par, int n, int n_lp, cudaStream_t st);
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st);
 cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,
                                  int n_bnd, int T, cudaStream_t st);
 cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st);

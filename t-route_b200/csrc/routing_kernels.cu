@@ -342,14 +342,14 @@ __global__ void init_levelpool_kernel(const int* __restrict__ lp_pos, const floa
     q[pos] = qd0[i]; v[pos] = 0.0f; d[pos] = h0[i];
 }
 
-// overlay the 8 reservoir parameters on the channel-geometry slots 1..8 of the level-pool positions
-__global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const float* __restrict__ par8, float* par, int n,
+// overlay the routing period and the 8 reservoir parameters on the 9 parameter slots of the level-pool positions
+__global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const float* __restrict__ par9, float* par, int n,
                                          int n_lp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_lp * 8) return;
-    const int l = i / 8, c = i % 8;
-    par[(size_t)(c + 1) * n + lp_pos[l]] = par8[i];
+    if (i >= n_lp * 9) return;
+    const int l = i / 9, c = i % 9;
+    par[(size_t)c * n + lp_pos[l]] = par9[i];
 }
 
 // prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463)
@@ -454,10 +454,10 @@ cudaError_t launch_init_levelpool(const int* lp_pos, const float* qd0, const flo
     init_levelpool_kernel<<<TRT_GRID1D(n_lp, 128), 128, 0, st>>>(lp_pos, qd0, h0, q, v, d, n_lp);
     return cudaGetLastError();
 }
-cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par8, float* par, int n, int n_lp, cudaStream_t st)
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st)
 {
     if (n_lp == 0) return cudaSuccess;
-    scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 8, 128), 128, 0, st>>>(lp_pos, par8, par, n, n_lp);
+    scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 9, 128), 128, 0, st>>>(lp_pos, par9, par, n, n_lp);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,

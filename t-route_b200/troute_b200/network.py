@@ -106,7 +106,7 @@ class RoutingNetwork:
         return out
 
     # -- configuration ------------------------------------------------------------------------
-    def set_levelpools(self, lp_rows, wbody_cols):
+    def set_levelpools(self, lp_rows, wbody_cols, routing_period=300.0):
         """wbody_cols: [n_lp, 11] float64 rows (LkArea, LkMxE, OrificeA, OrificeC, OrificeE, WeirC, WeirE,
         WeirL, ifd, qd0, h0) -- compute.py:1416-1430."""
         lp_rows = as_c(lp_rows, np.int64)
@@ -114,7 +114,7 @@ class RoutingNetwork:
         if wbody_cols.shape[0] != lp_rows.shape[0]:
             raise ValueError("one wbody_cols row per level-pool row is required")
         check(self._L.trt_network_set_levelpools(self._h, int(lp_rows.shape[0]), ptr(lp_rows, C.c_int64),
-                                                 ptr(wbody_cols, C.c_double)))
+                                                 ptr(wbody_cols, C.c_double), float(routing_period)))
         self._lp_rows = lp_rows
 
     def set_option(self, key, value):

@@ -209,7 +209,7 @@ def compute_network_structured(
             wb_idx = order[binary_find(lake_arr[order], data_idx[lp_rows])]
         else:
             wb_idx = binary_find(lake_arr, data_idx[lp_rows])                  # wbody_index (:294)
-        net.set_levelpools(lp_rows, wbody[wb_idx])
+        net.set_levelpools(lp_rows, wbody[wb_idx], routing_period=dt)
     else:
         net.set_levelpools(np.zeros(0, np.int64), np.zeros((0, 11)))
 
