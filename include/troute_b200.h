@@ -134,7 +134,7 @@ int trt_device_results(trt_network* net, void** fvd_device);
  * by the kernel of the upstream shard straight into the downstream GPU's flow array over NVLink peer memory ("export").
  * This replaces the pickled tail-water series the reference hands from one order of sub-networks to the next
  * (compute.py:882-900 -> mc_reach.pyx:458-469).  No collective is involved: a consumer lane polls the slot it reads.
- *   trt_network_state_ptr   device pointer of this handle's flow array ([nsteps+1, n_rows] float32), valid after
+ *   trt_network_state_ptr   device pointer of this handle's flow state ([n_rows, nsteps+1, 3] float32), valid after
  *                           trt_upload_forcing and until a later upload needs a larger array
  *   trt_ipc_get/open/close  CUDA IPC plumbing to map that array into the peer process
  *   trt_network_set_peer    flow array of peer shard `peer` (mapped pointer) and its row count
@@ -163,6 +163,9 @@ int trt_prepare(trt_network* net);
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
 int trt_set_option(trt_network* net, const char* key, int64_t value);
+/* "profile_stages" = 1 with "mode" = 0: device time and width (lanes) of every wavefront stage of the last run;
+ * entry k describes stage k (entry 0 unused); *count = entries available */
+int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms, int64_t* stage_width, int64_t* count);
 /* statistics of the last trt_run: device milliseconds of the wavefront kernels, number of kernel
  * launches, wavefront stages, lane-steps executed */
 int trt_last_run_stats(const trt_network* net, double* kernel_ms, int64_t* launches, int64_t* stages,

@@ -242,14 +242,24 @@ def flatten_reaches(reaches_wTypes, upstream_connections, data_idx, lake_numbers
             np.asarray(reach_up_ptr, np.int64), np.asarray(reach_up_rows, np.int64), np.asarray(reach_wbody, np.int32))
 
 
-def compute_network_structured(nsteps, dt, qts_subdivisions, reaches_wTypes, upstream_connections, data_idx, data_cols,
-                               data_values, initial_conditions, qlat_values, lake_numbers_col, wbody_cols,
-                               data_assimilation_parameters, reservoir_types, reservoir_type_specified,
-                               model_start_time, usgs_values, usgs_positions, usgs_positions_reach,
-                               usgs_positions_gage, lastobs_values_init, time_since_lastobs_init,
-                               da_decay_coefficient, *unused_reservoir_da_args, upstream_results={},
-                               assume_short_ts=False, return_courant=False, da_check_gage=-1, from_files=True,
-                               pow_mode=POW_DET):
+def compute_network_structured(
+    nsteps, dt, qts_subdivisions, reaches_wTypes, upstream_connections, data_idx, data_cols, data_values,
+    initial_conditions, qlat_values, lake_numbers_col, wbody_cols, data_assimilation_parameters, reservoir_types,
+    reservoir_type_specified, model_start_time, usgs_values, usgs_positions, usgs_positions_reach,
+    usgs_positions_gage, lastobs_values_init, time_since_lastobs_init, da_decay_coefficient,
+    reservoir_usgs_obs=None, reservoir_usgs_wbody_idx=None, reservoir_usgs_time=None, reservoir_usgs_update_time=None,
+    reservoir_usgs_prev_persisted_flow=None, reservoir_usgs_persistence_update_time=None,
+    reservoir_usgs_persistence_index=None, reservoir_usace_obs=None, reservoir_usace_wbody_idx=None,
+    reservoir_usace_time=None, reservoir_usace_update_time=None, reservoir_usace_prev_persisted_flow=None,
+    reservoir_usace_persistence_update_time=None, reservoir_usace_persistence_index=None, reservoir_rfc_obs=None,
+    reservoir_rfc_wbody_idx=None, reservoir_rfc_totalCounts=None, reservoir_rfc_file=None,
+    reservoir_rfc_use_forecast=None, reservoir_rfc_timeseries_idx=None, reservoir_rfc_update_time=None,
+    reservoir_rfc_da_timestep=None, reservoir_rfc_persist_days=None, great_lakes_idx=None, great_lakes_times=None,
+    great_lakes_discharge=None, great_lakes_param_idx=None, great_lakes_param_prev_assim_flow=None,
+    great_lakes_param_prev_assim_times=None, great_lakes_param_update_times=None, great_lakes_climatology=None,
+    upstream_results={}, assume_short_ts=False, return_courant=False, da_check_gage=-1, from_files=True,
+    pow_mode=POW_DET,
+):
     """Oracle with the reference's signature (mc_reach.pyx:164-224); hybrid / RFC / Great-Lakes DA
     arguments are accepted and ignored (they must be empty: those reservoir types are out of scope)."""
     data_idx = np.asarray(data_idx, dtype=np.int64)

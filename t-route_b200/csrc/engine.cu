@@ -82,7 +82,7 @@ struct trt_network {
     // per-call state
     int T = 0, qts = 1, nq = 0;
     bool uploaded = false, ran = false;
-    DevBuf<float> d_qlat_in, d_q0_in, d_qlat_t, d_q, d_v, d_d, d_fvd, d_up_out, d_bnd_fvd;
+    DevBuf<float> d_qlat_in, d_q0_in, d_qlat_t, d_S, d_fvd, d_up_out, d_bnd_fvd;
     DevBuf<int> d_bnd_pos, d_tmp_pos;
 
     cudaStream_t stream = nullptr;
@@ -96,6 +96,10 @@ struct trt_network {
     int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
     int gate_min = 12;
     int64_t gate_lanes = 16384;
+    bool profile_stages = false;                              // mode 0: time every stage launch
+    std::vector<cudaEvent_t> stage_events;
+    std::vector<float> stage_ms;
+    std::vector<int64_t> stage_width;
     bool prepared = false;                                    // sentinel reset done for the next run
     std::vector<int32_t> host_bnd_pos;                        // prescribed rows of the last upload (positions)
     int64_t n_bnd = 0;
@@ -126,8 +130,7 @@ struct trt_network {
     RunDev rundev(int short_ts) const
     {
         RunDev r;
-        r.T = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.q = d_q.p; r.v = d_v.p;
-        r.d = d_d.p;
+        r.T = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
         return r;
     }
 };
@@ -394,18 +397,15 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
     CU(net->d_qlat_in.reserve((size_t)n * nqcols));
     CU(net->d_q0_in.reserve((size_t)n * 3));
     CU(net->d_qlat_t.reserve((size_t)n * nqcols));
-    CU(net->d_q.reserve(rows_t));
-    CU(net->d_v.reserve(rows_t));
-    CU(net->d_d.reserve(rows_t));
+    CU(net->d_S.reserve(rows_t * 3));
     CU(net->d_fvd.reserve((size_t)n * 3 * (size_t)nsteps));
 
     if (n > 0) {
         CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(launch_gather_qlat(net->d_qlat_in.p, net->d_row_of_pos.p, net->d_qlat_t.p, (int)n, nqcols, st));
-        CU(launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, st));
-        CU(launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_q.p, net->d_v.p, net->d_d.p,
-                                 (int)net->n_lp, st));
+        CU(launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_S.p, (int)n, nsteps, st));
+        CU(launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_S.p, nsteps, (int)net->n_lp, st));
     }
     if (n_bnd > 0) {
         std::vector<int32_t> pos((size_t)n_bnd);
@@ -421,8 +421,7 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
         CU(cudaMemcpyAsync(net->d_bnd_pos.p, pos.data(), (size_t)n_bnd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(net->d_bnd_fvd.p, bnd_fvd, (size_t)n_bnd * 3 * (size_t)nsteps * sizeof(float),
                            cudaMemcpyHostToDevice, st));
-        CU(launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n,
-                                (int)n_bnd, nsteps, st));
+        CU(launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_S.p, (int)n_bnd, nsteps, st));
         CU(cudaStreamSynchronize(st));   // `pos` is a stack-owned staging vector
         net->host_bnd_pos = pos;
     } else {
@@ -441,8 +440,7 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
         if (net->n_zero > 0) {
             CU(net->d_zero_pos.reserve(zero_pos.size()));
             CU(cudaMemcpy(net->d_zero_pos.p, zero_pos.data(), zero_pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            CU(launch_fill_zero_rows(net->d_zero_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, (int)net->n_zero,
-                                     nsteps, st));
+            CU(launch_fill_zero_rows(net->d_zero_pos.p, net->d_S.p, (int)net->n_zero, nsteps, st));
         }
     }
     net->uploaded = true;
@@ -455,13 +453,15 @@ static cudaError_t prepare_dataflow(trt_network* net)
     cudaStream_t st = net->stream;
     const size_t n = (size_t)net->n, T = (size_t)net->T;
     if (n == 0 || T == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(net->d_q.p + n, 0xFF, n * T * sizeof(float), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(net->d_d.p + n, 0xFF, n * T * sizeof(float), st);
+    // everything "not yet written" (0xFFFFFFFF == TRT_SENTINEL), then the initial state and the prescribed series again
+    cudaError_t e = cudaMemsetAsync(net->d_S.p, 0xFF, n * (T + 1) * 3 * sizeof(float), st);
+    if (e == cudaSuccess) e = launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_S.p, (int)n, (int)T, st);
+    if (e == cudaSuccess)
+        e = launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_S.p, (int)T, (int)net->n_lp, st);
     if (e == cudaSuccess && net->n_bnd > 0)
-        e = launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n,
-                                 (int)net->n_bnd, (int)T, st);
+        e = launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_S.p, (int)net->n_bnd, (int)T, st);
     if (e == cudaSuccess && net->n_zero > 0)
-        e = launch_fill_zero_rows(net->d_zero_pos.p, net->d_q.p, net->d_v.p, net->d_d.p, (int)n, (int)net->n_zero, (int)T, st);
+        e = launch_fill_zero_rows(net->d_zero_pos.p, net->d_S.p, (int)net->n_zero, (int)T, st);
     return e;
 }
 
@@ -542,7 +542,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
             PeerDev pd;
             pd.exp_slot = net->d_exp_slot.p; pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
-            for (int i = 0; i < TRT_MAX_PEERS; ++i) { pd.q[i] = net->peer_q[i]; pd.n[i] = net->peer_n[i]; }
+            for (int i = 0; i < TRT_MAX_PEERS; ++i) pd.S[i] = net->peer_q[i];
             int grid = net->grid_blocks, max_grid = 0;
             CU(dataflow_max_grid(&max_grid));
             if (max_grid <= 0) return fail(TRT_ERR_CUDA, "dataflow kernel cannot be made resident");
@@ -553,7 +553,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             net->prepared = false;
             CU(cudaEventRecord(net->ev0, st));
             CU(launch_dataflow(nd, rd, sd, pd, grid, st));
-            net->launches = 1;
+            net->launches = 1 + 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);   // + state reset kernels
         } else if (net->mode == 1) {
             int grid = net->grid_blocks;
             int max_grid = 0;
@@ -563,6 +563,13 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             CU(launch_persistent(nd, rd, k_begin, k_end, grid, st));
             net->launches = 1;
         } else {
+            if (net->profile_stages) {
+                while ((int)net->stage_events.size() < k_end) {
+                    cudaEvent_t ev; CU(cudaEventCreate(&ev)); net->stage_events.push_back(ev);
+                }
+                net->stage_width.assign((size_t)k_end, 0);
+                CU(cudaEventRecord(net->stage_events[0], st));
+            }
             for (int k = k_begin; k < k_end; ++k) {
                 int lo, hi;
                 if (assume_short_ts) { lo = 0; hi = (int)net->n; }
@@ -573,6 +580,10 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 if (hi > lo) {
                     CU(launch_stage(nd, rd, k, lo, hi, st));
                     net->launches++;
+                }
+                if (net->profile_stages) {
+                    net->stage_width[(size_t)k] = hi - lo;
+                    CU(cudaEventRecord(net->stage_events[(size_t)k], st));
                 }
             }
         }
@@ -594,6 +605,11 @@ int trt_sync(trt_network* net)
     if (net->ran) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, net->ev0, net->ev1) == cudaSuccess) net->kernel_ms = ms;
+        if (net->mode == 0 && net->profile_stages && net->stages > 0) {
+            net->stage_ms.assign((size_t)net->stages + 1, 0.f);
+            for (int64_t k = 1; k <= net->stages; ++k)
+                cudaEventElapsedTime(&net->stage_ms[(size_t)k], net->stage_events[(size_t)k - 1], net->stage_events[(size_t)k]);
+        }
         if (net->mode == 2 && net->d_ctrl.p && net->launches > 0) {
             int ctrl[4] = {0, 0, 0, 0};
             CU(cudaMemcpy(ctrl, net->d_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
@@ -624,8 +640,7 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
     if (upstream_out && n * T > 0) {
         CU(net->d_up_out.reserve(n * T));
         CU(cudaMemsetAsync(net->d_up_out.p, 0, n * T * sizeof(float), st));
-        CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_v.p, net->d_up_out.p, (int)n, (int)net->n_lp,
-                               (int)T, st));
+        CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_S.p, net->d_up_out.p, (int)net->n_lp, (int)T, st));
         CU(cudaMemcpyAsync(upstream_out, net->d_up_out.p, n * T * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
@@ -666,7 +681,7 @@ int trt_export_flow_series(trt_network* net, int64_t count, const int64_t* rows,
     CU(cudaSetDevice(net->device));
     int rc = rows_to_device_pos(net, count, rows);
     if (rc != TRT_OK) return rc;
-    CU(launch_export_series(net->d_tmp_pos.p, net->d_q.p, (float*)dst_device, (int)net->n, (int)count, net->T, net->stream));
+    CU(launch_export_series(net->d_tmp_pos.p, net->d_S.p, (float*)dst_device, (int)count, net->T, net->stream));
     CU(cudaStreamSynchronize(net->stream));
     return TRT_OK;
 }
@@ -681,8 +696,7 @@ int trt_import_boundary_flow(trt_network* net, int64_t count, const int64_t* row
     CU(cudaSetDevice(net->device));
     int rc = rows_to_device_pos(net, count, rows);
     if (rc != TRT_OK) return rc;
-    CU(launch_import_series(net->d_tmp_pos.p, (const float*)src_device, net->d_q.p, (int)net->n, (int)count, net->T,
-                            net->stream));
+    CU(launch_import_series(net->d_tmp_pos.p, (const float*)src_device, net->d_S.p, (int)count, net->T, net->stream));
     CU(cudaStreamSynchronize(net->stream));
     return TRT_OK;
 }
@@ -771,7 +785,7 @@ int trt_network_state_ptr(trt_network* net, void** q_device)
 {
     if (!net || !q_device) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!net->uploaded) return fail(TRT_ERR_STATE, "no forcing uploaded: the flow array is allocated by trt_upload_forcing");
-    *q_device = net->d_q.p;
+    *q_device = net->d_S.p;
     return TRT_OK;
 }
 
@@ -811,6 +825,8 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
     } else if (!strcmp(key, "grid_blocks")) {
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
         net->grid_blocks = (int)value;
+    } else if (!strcmp(key, "profile_stages")) {
+        net->profile_stages = value != 0;
     } else if (!strcmp(key, "gate")) {
         if (value < 0 || value > 1000000) return fail(TRT_ERR_INVALID, "gate must be >= 0");
         net->gate = (int)value;
@@ -840,6 +856,18 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         }
     } else {
         return fail(TRT_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return TRT_OK;
+}
+
+int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms, int64_t* stage_width, int64_t* count)
+{
+    if (!net || !count) return fail(TRT_ERR_INVALID, "NULL argument");
+    const int64_t m = (int64_t)net->stage_ms.size();
+    *count = m;
+    for (int64_t k = 0; k < m && k < capacity; ++k) {
+        if (stage_ms) stage_ms[k] = net->stage_ms[(size_t)k];
+        if (stage_width) stage_width[k] = net->stage_width[(size_t)k];
     }
     return TRT_OK;
 }

@@ -9,8 +9,14 @@
  *   level    [n] i32     wavefront level; positions are sorted by it, lvl_ptr[L+1] delimits the levels
  *   up_ptr   [n+1] i32, up_idx [E] i32   CSR of upstream positions, reference summation order
  *   qlat_t   [nq][n]     lateral inflow, time-major
- *   q, v, d  [T+1][n]    flow / velocity / depth, time-major; row 0 = initial state.  Rows are the only
- *                        state of the model: step t reads row t-1 (own) and rows t, t-1 (upstream).
+ *   S        [n][T+1][3] flow / velocity / depth of every position for t = 0..T (t = 0 = initial state), each
+ *                        segment's series contiguous.  This is the only state of the model: (s, t) reads (s, t-1) and
+ *                        (u, t), (u, t-1) of its upstream neighbours.  A time-major [T+1][n] layout coalesces better in
+ *                        the wide headwater levels but makes the ~600 lanes of a deep-mainstem stage (one segment per
+ *                        level, each at a different t) touch ~1200 distinct 2 MB pages per stage: measured 95 us per
+ *                        stage of TLB misses instead of 12 us (profiles/r01_*).  Position-major keeps such a stage inside
+ *                        one or two pages, and it IS the reference's result layout, so the final transpose
+ *                        degenerates into a row permutation.
  *   fvd      [n_rows][3T] the reference's result layout (mc_reach.pyx:807-813), caller row order
  */
 #pragma once
@@ -37,9 +43,7 @@ struct RunDev {
     int nq;         // qlat columns
     int short_ts;   // assume_short_ts
     const float* qlat_t;
-    float* q;
-    float* v;
-    float* d;
+    float* S;       // flow state [n][T + 1][3] = (q, v, d) of every position for t = 0 .. T (t = 0: initial state)
 };
 
 // Dataflow schedule (mode 2).  Work = the stages of the wavefront, cut into units of 32 or 128 consecutive positions
@@ -69,8 +73,7 @@ struct PeerDev {
     const int* exp_slot;              // [n] index into exp_peer / exp_pos, valid where the flag is set
     const int* exp_peer;              // [n_exp]
     const long long* exp_pos;         // [n_exp] position in the peer's arrays
-    float* q[TRT_MAX_PEERS];          // peer q arrays (mapped peer memory), time-major
-    long long n[TRT_MAX_PEERS];       // peer segment counts
+    float* S[TRT_MAX_PEERS];          // peer flow-state arrays (mapped peer memory)
 };
 
 // wavefront: stage k routes every (segment s, step t) with level(s) + t == k
@@ -83,24 +86,20 @@ cudaError_t persistent_max_grid(int* blocks);
 cudaError_t dataflow_max_grid(int* blocks);
 cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
                             int grid_blocks, cudaStream_t st);
-cudaError_t launch_fill_zero_rows(const int* pos, float* q, float* v, float* d, int n, int count, int T, cudaStream_t st);
+cudaError_t launch_fill_zero_rows(const int* pos, float* S, int count, int T, cudaStream_t st);
 
 cudaError_t launch_gather_qlat(const float* qlat_rows, const int* row_of_pos, float* qlat_t, int n, int nq,
                                cudaStream_t st);
-cudaError_t launch_init_state(const float* q0_rows, const int* row_of_pos, float* q, float* v, float* d, int n,
-                              cudaStream_t st);
-cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const float* lp_h0, float* q, float* v,
-                                  float* d, int n_lp, cudaStream_t st);
+cudaError_t launch_init_state(const float* q0_rows, const int* row_of_pos, float* S, int n, int T, cudaStream_t st);
+cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const float* lp_h0, float* S, int T, int n_lp,
+                                  cudaStream_t st);
 cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st);
-cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,
-                                 int n_bnd, int T, cudaStream_t st);
+cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* S, int n_bnd, int T, cudaStream_t st);
 cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st);
-cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* v, float* up_rows, int n,
-                                int n_lp, int T, cudaStream_t st);
-cudaError_t launch_export_series(const int* pos, const float* q, float* dst, int n, int count, int T,
-                                 cudaStream_t st);
-cudaError_t launch_import_series(const int* pos, const float* src, float* q, int n, int count, int T,
-                                 cudaStream_t st);
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up_rows, int n_lp, int T,
+                                cudaStream_t st);
+cudaError_t launch_export_series(const int* pos, const float* S, float* dst, int count, int T, cudaStream_t st);
+cudaError_t launch_import_series(const int* pos, const float* src, float* S, int count, int T, cudaStream_t st);
 
 cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long long count, cudaStream_t st);
 cudaError_t launch_levelpool_series(const float* lp9, float h0, const float* inflow, float ql, float dt,

@@ -19,6 +19,7 @@
  *
  * Compile with -fmad=false (see mc_device.cuh).
  */
+#include <algorithm>
 #include <cooperative_groups.h>
 #include "kernels.cuh"
 #include "mc_device.cuh"
@@ -100,8 +101,8 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
     if (kind == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
 
     const size_t n = (size_t)net.n;
-    const float* qc = run.q + (size_t)t * n;          // row t
-    const float* qp = qc - n;                         // row t-1
+    const size_t T1 = (size_t)run.T + 1;
+    float* own = run.S + ((size_t)s * T1 + (size_t)t) * 3;   // (q, v, d) of (s, t); own - 3 is (s, t-1)
 
     // parameters first: they do not depend on anybody's results, so their latency overlaps the waits below
     const float* par = net.par + s;
@@ -113,17 +114,20 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
     // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
     float quc = 0.0f, qup = 0.0f;
     if (run.short_ts) {
-        for (int e = e0; e < e1; ++e) qup += ld_state<WAIT>(qp + __ldg(net.up_idx + e), abort_flag);
+        for (int e = e0; e < e1; ++e) {
+            const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)t) * 3;
+            qup += ld_state<WAIT>(up - 3, abort_flag);
+        }
         quc = qup;
     } else {
         for (int e = e0; e < e1; ++e) {
-            const int u = __ldg(net.up_idx + e);
-            quc += ld_state<WAIT>(qc + u, abort_flag);
-            qup += ld_state<WAIT>(qp + u, abort_flag);
+            const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)t) * 3;
+            quc += ld_state<WAIT>(up, abort_flag);
+            qup += ld_state<WAIT>(up - 3, abort_flag);
         }
     }
     // depth (MC) / water elevation (level pool) at t-1
-    const float statep = ld_state<WAIT>(run.d + (size_t)(t - 1) * n + s, abort_flag);
+    const float statep = ld_state<WAIT>(own - 1, abort_flag);
 
     float o_q, o_v, o_d;
     if (kind == TRT_KIND_LEVELPOOL) {
@@ -138,18 +142,18 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
         o_d = H;
     } else {
         const float ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);   // :723
-        const float qdp = ld_state<WAIT>(qp + s, abort_flag);                        // :733
+        const float qdp = ld_state<WAIT>(own - 3, abort_flag);                       // :733
         const McResult r = trt_mc_segment<false>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
     }
-    run.v[(size_t)t * n + s] = o_v;
-    st_state<WAIT>(run.d + (size_t)t * n + s, o_d);
-    st_state<WAIT>(run.q + (size_t)t * n + s, o_q);
+    own[1] = o_v;
+    st_state<WAIT>(own + 2, o_d);
+    st_state<WAIT>(own, o_q);
     if (WAIT && (kflags & TRT_KIND_EXPORT_FLAG)) {
         // this segment drains into another shard: scatter its outflow into that GPU's inflow slot (peer memory)
         const int x = __ldg(peers->exp_slot + s);
         const int pr = __ldg(peers->exp_peer + x);
-        float* dst = peers->q[pr] + (size_t)t * (size_t)peers->n[pr] + (size_t)__ldg(peers->exp_pos + x);
+        float* dst = peers->S[pr] + ((size_t)__ldg(peers->exp_pos + x) * T1 + (size_t)t) * 3;
         unsigned b = __float_as_uint(o_q);
         if (b == TRT_SENTINEL) b = 0x7FC00000u;
         asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
@@ -322,24 +326,25 @@ __global__ void gather_qlat_kernel(const float* __restrict__ in, const int* __re
     for (int c = 0; c < nq; ++c) out[(size_t)c * n + pos] = __ldg(src + c);
 }
 
-// row 0 of q, v, d = initial_conditions columns (flowveldepth_nd[ids, 0] = init_array[ids], mc_reach.pyx:361)
-__global__ void init_state_kernel(const float* __restrict__ q0, const int* __restrict__ row_of_pos,
-                                  float* __restrict__ q, float* __restrict__ v, float* __restrict__ d, int n)
+// state[pos][0][:] = initial_conditions[row][:]  (flowveldepth_nd[ids, 0] = init_array[ids], mc_reach.pyx:361)
+__global__ void init_state_kernel(const float* __restrict__ q0, const int* __restrict__ row_of_pos, float* __restrict__ S,
+                                  int n, int T1)
 {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n) return;
     const float* src = q0 + (size_t)row_of_pos[pos] * 3;
-    q[pos] = src[0]; v[pos] = src[1]; d[pos] = src[2];
+    float* dst = S + (size_t)pos * T1 * 3;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
 }
 
-// reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth row
+// reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth slot
 __global__ void init_levelpool_kernel(const int* __restrict__ lp_pos, const float* __restrict__ qd0,
-                                      const float* __restrict__ h0, float* q, float* v, float* d, int n_lp)
+                                      const float* __restrict__ h0, float* S, int T1, int n_lp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lp) return;
-    const int pos = lp_pos[i];
-    q[pos] = qd0[i]; v[pos] = 0.0f; d[pos] = h0[i];
+    float* dst = S + (size_t)lp_pos[i] * T1 * 3;
+    dst[0] = qd0[i]; dst[1] = 0.0f; dst[2] = h0[i];
 }
 
 // overlay the routing period and the 8 reservoir parameters on the 9 parameter slots of the level-pool positions
@@ -352,85 +357,76 @@ __global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const f
     par[(size_t)c * n + lp_pos[l]] = par9[i];
 }
 
-// prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463)
-__global__ void fill_boundary_kernel(const int* __restrict__ bnd_pos, const float* __restrict__ bnd_fvd, float* q,
-                                     float* v, float* d, int n, int n_bnd, int T)
+// prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463) -- one contiguous series
+__global__ void fill_boundary_kernel(const int* __restrict__ bnd_pos, const float* __restrict__ bnd_fvd, float* S,
+                                     int n_bnd, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n_bnd * T) return;
-    const int b = (int)(i / T), t = (int)(i % T) + 1;
-    const float* src = bnd_fvd + ((size_t)b * T + (t - 1)) * 3;
-    const size_t o = (size_t)t * n + bnd_pos[b];
-    q[o] = src[0]; v[o] = src[1]; d[o] = src[2];
+    const long long w = 3LL * T;
+    if (i >= (long long)n_bnd * w) return;
+    const int b = (int)(i / w);
+    const long long c = i % w;
+    S[((size_t)bnd_pos[b] * (T + 1) + 1) * 3 + c] = bnd_fvd[(size_t)b * w + c];
 }
 
 // boundary rows nobody prescribes stay zero for every step (flowveldepth is zero-initialised, mc_reach.pyx:253)
-__global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* q, float* v, float* d, int n, int count, int T)
+__global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* S, int count, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)count * T) return;
-    const int b = (int)(i / T), t = (int)(i % T) + 1;
-    const size_t o = (size_t)t * n + pos[b];
-    q[o] = 0.0f; v[o] = 0.0f; d[o] = 0.0f;
+    const long long w = 3LL * T;
+    if (i >= (long long)count * w) return;
+    S[((size_t)pos[i / w] * (T + 1) + 1) * 3 + (i % w)] = 0.0f;
 }
 
-// fvd[row][3*(t-1) + c] = {q, v, d}[t][pos]: 32 positions x 32 steps per block through shared memory so that
-// both the time-major reads and the row-major writes are coalesced.
-__global__ void __launch_bounds__(256) finalize_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
+// Result in the reference's layout (mc_reach.pyx:807-813): fvd[row][3*(t-1) + c] = state[pos][t][c], t = 1..T.
+// The engine already keeps every segment's series contiguous, so this is one 12*T-byte copy per segment -- a
+// permutation from level-sorted positions to the caller's rows, one warp per segment.
+__global__ void __launch_bounds__(256) permute_rows_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
 {
-    __shared__ float sq[32][33], sv[32][33], sd[32][33];
-    const int p0 = blockIdx.x * 32, t0 = blockIdx.y * 32 + 1;     // steps t0 .. t0+31
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
-    const size_t n = (size_t)net.n;
-    for (int j = ty; j < 32; j += 8) {
-        const int t = t0 + j, p = p0 + tx;
-        if (t <= run.T && p < net.n) {
-            const size_t o = (size_t)t * n + p;
-            sq[j][tx] = run.q[o]; sv[j][tx] = run.v[o]; sd[j][tx] = run.d[o];
+    const int warps_per_block = 256 / 32;
+    const int lane = threadIdx.x & 31;
+    const int w = 3 * run.T;
+    for (long long p = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < net.n;
+         p += (long long)gridDim.x * warps_per_block) {
+        const float* src = run.S + ((size_t)p * (run.T + 1) + 1) * 3;
+        float* dst = fvd + (size_t)net.row_of_pos[p] * w;
+        const bool lp = (net.kind[p] & 0x0F) == TRT_KIND_LEVELPOOL;
+        for (int c = lane; c < w; c += 32) {
+            float v = __ldcs(src + c);
+            if (lp && (c % 3) == 1) v = 0.0f;          // flowveldepth[r.id, t, 1] = 0.0  (:708)
+            __stcs(dst + c, v);
         }
-    }
-    __syncthreads();
-    const int nt = min(32, run.T - t0 + 1);                       // valid steps in this tile
-    const int width = 3 * nt;
-    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
-        const int pl = idx / 96, c = idx % 96;
-        const int p = p0 + pl;
-        if (p >= net.n || c >= width) continue;
-        const int j = c / 3, comp = c % 3;
-        float val = comp == 0 ? sq[j][pl] : (comp == 1 ? sv[j][pl] : sd[j][pl]);
-        if (comp == 1 && (net.kind[p] & 0x0F) == TRT_KIND_LEVELPOOL) val = 0.0f;   // flowveldepth[r.id, t, 1] = 0.0  (:708)
-        fvd[(size_t)net.row_of_pos[p] * (3 * (size_t)run.T) + 3 * (size_t)(t0 - 1) + c] = val;
     }
 }
 
 // upstream_array[row, t] = reservoir inflow (mc_reach.pyx:710), carried in the velocity slot of level-pool rows
 __global__ void upstream_out_kernel(const int* __restrict__ lp_pos, const int* __restrict__ row_of_pos,
-                                    const float* __restrict__ v, float* __restrict__ up, int n, int n_lp, int T)
+                                    const float* __restrict__ S, float* __restrict__ up, int n_lp, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_lp * T) return;
     const int l = (int)(i / T), t = (int)(i % T) + 1;
     const int pos = lp_pos[l];
-    up[(size_t)row_of_pos[pos] * T + (t - 1)] = v[(size_t)t * n + pos];
+    up[(size_t)row_of_pos[pos] * T + (t - 1)] = S[((size_t)pos * (T + 1) + t) * 3 + 1];
 }
 
-__global__ void export_series_kernel(const int* __restrict__ pos, const float* __restrict__ q, float* __restrict__ dst,
-                                     int n, int count, int T)
+__global__ void export_series_kernel(const int* __restrict__ pos, const float* __restrict__ S, float* __restrict__ dst,
+                                     int count, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)count * (T + 1)) return;
     const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
-    dst[i] = q[(size_t)t * n + pos[c]];
+    dst[i] = S[((size_t)pos[c] * (T + 1) + t) * 3];
 }
 
-__global__ void import_series_kernel(const int* __restrict__ pos, const float* __restrict__ src, float* __restrict__ q,
-                                     int n, int count, int T)
+__global__ void import_series_kernel(const int* __restrict__ pos, const float* __restrict__ src, float* __restrict__ S,
+                                     int count, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)count * (T + 1)) return;
     const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
     if (t == 0) return;
-    q[(size_t)t * n + pos[c]] = src[i];
+    S[((size_t)pos[c] * (T + 1) + t) * 3] = src[i];
 }
 
 #define TRT_GRID1D(total, block) (unsigned)(((total) + (block)-1) / (block))
@@ -441,17 +437,17 @@ cudaError_t launch_gather_qlat(const float* in, const int* row_of_pos, float* ou
     gather_qlat_kernel<<<TRT_GRID1D(n, 256), 256, 0, st>>>(in, row_of_pos, out, n, nq);
     return cudaGetLastError();
 }
-cudaError_t launch_init_state(const float* q0, const int* row_of_pos, float* q, float* v, float* d, int n, cudaStream_t st)
+cudaError_t launch_init_state(const float* q0, const int* row_of_pos, float* S, int n, int T, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    init_state_kernel<<<TRT_GRID1D(n, 256), 256, 0, st>>>(q0, row_of_pos, q, v, d, n);
+    init_state_kernel<<<TRT_GRID1D(n, 256), 256, 0, st>>>(q0, row_of_pos, S, n, T + 1);
     return cudaGetLastError();
 }
-cudaError_t launch_init_levelpool(const int* lp_pos, const float* qd0, const float* h0, float* q, float* v, float* d,
-                                  int n_lp, cudaStream_t st)
+cudaError_t launch_init_levelpool(const int* lp_pos, const float* qd0, const float* h0, float* S, int T, int n_lp,
+                                  cudaStream_t st)
 {
     if (n_lp == 0) return cudaSuccess;
-    init_levelpool_kernel<<<TRT_GRID1D(n_lp, 128), 128, 0, st>>>(lp_pos, qd0, h0, q, v, d, n_lp);
+    init_levelpool_kernel<<<TRT_GRID1D(n_lp, 128), 128, 0, st>>>(lp_pos, qd0, h0, S, T + 1, n_lp);
     return cudaGetLastError();
 }
 cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st)
@@ -460,48 +456,48 @@ cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float
     scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 9, 128), 128, 0, st>>>(lp_pos, par9, par, n, n_lp);
     return cudaGetLastError();
 }
-cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* q, float* v, float* d, int n,
-                                 int n_bnd, int T, cudaStream_t st)
+cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* S, int n_bnd, int T, cudaStream_t st)
 {
-    const long long total = (long long)n_bnd * T;
+    const long long total = 3LL * n_bnd * T;
     if (total == 0) return cudaSuccess;
-    fill_boundary_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(bnd_pos, bnd_fvd, q, v, d, n, n_bnd, T);
+    fill_boundary_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(bnd_pos, bnd_fvd, S, n_bnd, T);
     return cudaGetLastError();
 }
-cudaError_t launch_fill_zero_rows(const int* pos, float* q, float* v, float* d, int n, int count, int T, cudaStream_t st)
+cudaError_t launch_fill_zero_rows(const int* pos, float* S, int count, int T, cudaStream_t st)
 {
-    const long long total = (long long)count * T;
+    const long long total = 3LL * count * T;
     if (total == 0) return cudaSuccess;
-    fill_zero_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, q, v, d, n, count, T);
+    fill_zero_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, S, count, T);
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st)
 {
     if (net.n == 0 || run.T == 0) return cudaSuccess;
-    dim3 grid((net.n + 31) / 32, (run.T + 31) / 32);
-    finalize_kernel<<<grid, 256, 0, st>>>(net, run, fvd);
+    const long long rows_per_block = 8;
+    const unsigned blocks = (unsigned)std::min<long long>((net.n + rows_per_block - 1) / rows_per_block, 148LL * 32);
+    permute_rows_kernel<<<blocks, 256, 0, st>>>(net, run, fvd);
     return cudaGetLastError();
 }
-cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* v, float* up, int n, int n_lp,
-                                int T, cudaStream_t st)
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up, int n_lp, int T,
+                                cudaStream_t st)
 {
     const long long total = (long long)n_lp * T;
     if (total == 0) return cudaSuccess;
-    upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, v, up, n, n_lp, T);
+    upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, S, up, n_lp, T);
     return cudaGetLastError();
 }
-cudaError_t launch_export_series(const int* pos, const float* q, float* dst, int n, int count, int T, cudaStream_t st)
+cudaError_t launch_export_series(const int* pos, const float* S, float* dst, int count, int T, cudaStream_t st)
 {
     const long long total = (long long)count * (T + 1);
     if (total == 0) return cudaSuccess;
-    export_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, q, dst, n, count, T);
+    export_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, S, dst, count, T);
     return cudaGetLastError();
 }
-cudaError_t launch_import_series(const int* pos, const float* src, float* q, int n, int count, int T, cudaStream_t st)
+cudaError_t launch_import_series(const int* pos, const float* src, float* S, int count, int T, cudaStream_t st)
 {
     const long long total = (long long)count * (T + 1);
     if (total == 0) return cudaSuccess;
-    import_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, src, q, n, count, T);
+    import_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, src, S, count, T);
     return cudaGetLastError();
 }
 

@@ -252,6 +252,15 @@ class RoutingNetwork:
         check(self._L.trt_device_results(self._h, C.byref(out)))
         return out.value
 
+    def stage_profile(self):
+        """(stage_ms, stage_width) of the last mode-0 run with option profile_stages=1; index = stage k."""
+        cnt = C.c_int64()
+        check(self._L.trt_stage_profile(self._h, 0, None, None, C.byref(cnt)))
+        ms = np.zeros(cnt.value, dtype=np.float32)
+        w = np.zeros(cnt.value, dtype=np.int64)
+        check(self._L.trt_stage_profile(self._h, cnt.value, ptr(ms, C.c_float), ptr(w, C.c_int64), C.byref(cnt)))
+        return ms, w
+
     def last_run_stats(self):
         ms = C.c_double()
         launches = C.c_int64()

@@ -1,0 +1,26 @@
+"""Where does the time go, stage by stage (mode 0 + events)?  CONUS workload."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "t-route_b200"), os.path.join(ROOT, "tests")]
+import numpy as np
+from troute_b200 import synth
+from troute_b200.network import RoutingNetwork
+T = 288
+down = synth.conus_like(); n = down.size
+params = synth.channel_params(down, seed=16)
+qlat = synth.lateral_inflow(n, T, 12, seed=16)
+q0 = np.zeros((n, 3), np.float32)
+up_ptr, up_rows = synth.upstream_csr(down)
+net = RoutingNetwork(up_ptr, up_rows, np.zeros(n, np.uint8), params, synth.PARAM_COLS)
+net.upload(T, 12, qlat, q0)
+net.set_option("mode", 0); net.set_option("profile_stages", 1)
+net.run(False); net.run(False)
+ms, w = net.stage_profile()
+print("total kernel_ms", net.last_run_stats()["kernel_ms"], "sum stage ms", ms.sum())
+for lo, hi in ((1, 50), (50, 150), (150, 289), (289, 400), (400, 600), (600, 1000), (1000, 2000), (2000, 3000), (3000, 4571)):
+    sl = slice(lo, min(hi, ms.size))
+    print(f"stages {lo:5d}-{hi:5d}: ms={ms[sl].sum():8.2f} lanes={w[sl].sum():12d} mean us/stage={1e3*ms[sl].mean():8.1f} mean width={w[sl].mean():10.0f} ns/lane={1e6*ms[sl].sum()/max(1,w[sl].sum()):.3f}")
+top = np.argsort(-ms)[:25]
+print("slowest stages:", [(int(k), round(float(ms[k]), 3), int(w[k])) for k in top])
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+np.save(os.path.join(ROOT, "gpurun_out", "stage_profile_ms.npy"), ms)
