@@ -92,6 +92,7 @@ struct trt_network {
     // dataflow schedule (mode 2)
     DevBuf<int> d_unit_ptr, d_gate_stage, d_done, d_ctrl;     // d_ctrl: [0] claim, [1] frontier, [2] abort
     DevBuf<unsigned char> d_unit_shift;
+    DevBuf<unsigned long long> d_stage_time;                  // mode 2 + profile_stages: completion time of every stage
     int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0;
     int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
     int gate_min = 12;
@@ -540,6 +541,16 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             sd.nstages = nstages; sd.T = T; sd.unit_ptr = net->d_unit_ptr.p; sd.unit_shift = net->d_unit_shift.p;
             sd.claim = (unsigned int*)net->d_ctrl.p; sd.frontier = net->d_ctrl.p + 1; sd.abort_flag = net->d_ctrl.p + 2;
             sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
+            sd.stage_time = nullptr;
+            if (net->profile_stages) {
+                CU(net->d_stage_time.reserve((size_t)nstages + 1));
+                CU(cudaMemsetAsync(net->d_stage_time.p, 0, ((size_t)nstages + 1) * sizeof(unsigned long long), st));
+                sd.stage_time = net->d_stage_time.p;
+                net->stage_width.assign((size_t)nstages + 1, 0);
+                for (int k = 1; k <= nstages; ++k)
+                    net->stage_width[(size_t)k] = assume_short_ts ? net->n
+                        : net->lvl_ptr[(size_t)std::min(L, k)] - net->lvl_ptr[(size_t)std::max(0, k - T)];
+            }
             PeerDev pd;
             pd.exp_slot = net->d_exp_slot.p; pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
             for (int i = 0; i < TRT_MAX_PEERS; ++i) pd.S[i] = net->peer_q[i];
@@ -609,6 +620,18 @@ int trt_sync(trt_network* net)
             net->stage_ms.assign((size_t)net->stages + 1, 0.f);
             for (int64_t k = 1; k <= net->stages; ++k)
                 cudaEventElapsedTime(&net->stage_ms[(size_t)k], net->stage_events[(size_t)k - 1], net->stage_events[(size_t)k]);
+        }
+        if (net->mode == 2 && net->profile_stages && net->d_stage_time.p && net->stages > 0) {
+            // dataflow stages overlap: report the time between consecutive stage completions
+            std::vector<unsigned long long> ts((size_t)net->stages + 1);
+            CU(cudaMemcpy(ts.data(), net->d_stage_time.p, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            net->stage_ms.assign((size_t)net->stages + 1, 0.f);
+            unsigned long long prev = ts[0];
+            for (int64_t k = 1; k <= net->stages; ++k) {
+                const unsigned long long tk = ts[(size_t)k] ? std::max(ts[(size_t)k], prev) : prev;   // empty stage
+                net->stage_ms[(size_t)k] = (float)((double)(tk - prev) * 1e-6);
+                prev = tk;
+            }
         }
         if (net->mode == 2 && net->d_ctrl.p && net->launches > 0) {
             int ctrl[4] = {0, 0, 0, 0};

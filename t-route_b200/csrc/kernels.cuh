@@ -64,6 +64,8 @@ struct SchedDev {
     int* abort_flag;                  // [1] set when a wait timed out
     const int* gate_stage;            // [nstages] stage that must be complete before a unit of stage k starts:
                                       // the last non-empty stage <= k - gate (0 = no wait)
+    unsigned long long* stage_time;   // [nstages + 1] or NULL: %globaltimer (ns) when stage k completed, in slot k;
+                                      // slot 0 = kernel start ("profile_stages" option)
 };
 
 // cut edges to other shards: lane s with (kind & TRT_KIND_EXPORT_FLAG) stores q also to peer memory

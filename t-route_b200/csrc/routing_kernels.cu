@@ -59,6 +59,13 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const float* p)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool WAIT>
 __device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
 {
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run
     const unsigned total = (unsigned)__ldg(sc.unit_ptr + sc.nstages);
     const int L = run.short_ts ? 1 : net.nlevels;
     int cursor = 0;                                   // stage index (k - 1) of this warp's previous unit
+    if (sc.stage_time && blockIdx.x == 0 && threadIdx.x == 0) sc.stage_time[0] = globaltimer_ns();
     for (;;) {
         unsigned u = 0;
         if (lane == 0) u = atomicAdd(sc.claim, 1u);
@@ -258,7 +266,10 @@ __global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run
             // stage bookkeeping for the gate: the warp that finishes the last unit of stage k advances the frontier
             const int units_k = __ldg(sc.unit_ptr + lo_i + 1) - __ldg(sc.unit_ptr + lo_i);
             __threadfence();
-            if (atomicAdd(sc.done + lo_i, 1) + 1 == units_k) atomicMax(sc.frontier, k);
+            if (atomicAdd(sc.done + lo_i, 1) + 1 == units_k) {
+                atomicMax(sc.frontier, k);
+                if (sc.stage_time) sc.stage_time[k] = globaltimer_ns();
+            }
         }
     }
 }

@@ -13,9 +13,11 @@ q0 = np.zeros((n, 3), np.float32)
 up_ptr, up_rows = synth.upstream_csr(down)
 net = RoutingNetwork(up_ptr, up_rows, np.zeros(n, np.uint8), params, synth.PARAM_COLS)
 net.upload(T, 12, qlat, q0)
-net.set_option("mode", 0); net.set_option("profile_stages", 1)
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+net.set_option("mode", MODE); net.set_option("profile_stages", 1)
 net.run(False); net.run(False)
 ms, w = net.stage_profile()
+print("mode", MODE, "(mode 2: time between consecutive stage completions)")
 print("total kernel_ms", net.last_run_stats()["kernel_ms"], "sum stage ms", ms.sum())
 for lo, hi in ((1, 50), (50, 150), (150, 289), (289, 400), (400, 600), (600, 1000), (1000, 2000), (2000, 3000), (3000, 4571)):
     sl = slice(lo, min(hi, ms.size))
@@ -23,4 +25,4 @@ for lo, hi in ((1, 50), (50, 150), (150, 289), (289, 400), (400, 600), (600, 100
 top = np.argsort(-ms)[:25]
 print("slowest stages:", [(int(k), round(float(ms[k]), 3), int(w[k])) for k in top])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-np.save(os.path.join(ROOT, "gpurun_out", "stage_profile_ms.npy"), ms)
+np.save(os.path.join(ROOT, "gpurun_out", f"stage_profile_ms_mode{MODE}.npy"), ms)
