@@ -52,14 +52,38 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="conus", choices=["conus", "tree"])
+    ap.add_argument("--style", default="nhd", choices=["nhd", "hack"],
+                    help="basin generator of the conus workload: nhd = NHD-like confluences (SURVEY.md 8d in-degree mix), "
+                         "hack = main stems with dozens of tributaries per node (gather stress case)")
     ap.add_argument("--segments", type=int, default=0, help="override the segment count (testing only)")
     ap.add_argument("--nsteps", type=int, default=288, help="routing timesteps per call")
     ap.add_argument("--short-ts", type=int, default=0)
-    ap.add_argument("--mode", type=int, default=2)
+    ap.add_argument("--mode", type=int, default=4)
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
     return ap.parse_args()
+
+
+def _cached(key, make):
+    """Synthetic topologies take ~10-30 s of host time to generate; keep them in /tmp between bench invocations."""
+    d = os.path.join("/tmp", "trt_synth_cache")
+    f = os.path.join(d, key + ".npy")
+    try:
+        if os.path.exists(f):
+            return np.load(f)
+    except Exception:
+        pass
+    a = make()
+    try:
+        os.makedirs(d, exist_ok=True)
+        tmp = f + f".{os.getpid()}.tmp.npy"
+        np.save(tmp, a)
+        os.replace(tmp, f)
+    except Exception:
+        pass
+    return a
 
 
 def build_workload(args):
@@ -67,8 +91,10 @@ def build_workload(args):
     if args.workload == "conus":
         n = args.segments or 2_729_077
         basins = max(1, int(round(14_713 * n / 2_729_077)))
-        down = synth.conus_like(n_total=n, n_basins=basins, seed=16)
-        name = f"synthetic CONUS-scale forest, {n} segments / {basins} basins, MC-only, {args.nsteps} x 300 s"
+        down = _cached(f"conus_{args.style}_{n}_{basins}_16",
+                       lambda: synth.conus_like(n_total=n, n_basins=basins, seed=16, style=args.style))
+        name = (f"synthetic CONUS-scale forest ({args.style}-style basins), {n} segments / {basins} basins, MC-only, "
+                f"{args.nsteps} x 300 s")
     else:
         n = args.segments or 1_048_576
         down = synth.binary_tree(n)
@@ -220,6 +246,10 @@ def run_ours(args, rank, world, local_rank):
         from troute_b200 import multigpu
         runner = multigpu.SingleRouter(wl, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
 
+    for kv in args.opt:
+        k, v = kv.split("=")
+        runner.net.set_option(k, int(v))
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -324,7 +354,11 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "assume_short_ts": bool(args.short_ts), "qts_subdivisions": QTS,
                        "levels": stats["levels"], "stages_per_call": stats["stages"],
-                       "schedule": {0: "launch per stage", 1: "persistent cooperative wavefront (grid.sync per stage)", 2: "dataflow wavefront (ordered unit queue, lanes poll their inputs)"}[args.mode],
+                       "schedule": {0: "launch per stage", 1: "persistent cooperative wavefront (grid.sync per stage)",
+                                    2: "dataflow wavefront (ordered unit queue, lanes poll their inputs)",
+                                    3: "marching lanes (one lane per segment, all timesteps)",
+                                    4: "dataflow wavefront over the wide shallow levels, marching lanes over the deep "
+                                       "levels"}[args.mode],
                        "l2": "inputs larger than L2 (38 GB working set), no flush", "sharding": stats["sharding"]},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         }

@@ -157,7 +157,14 @@ int trt_prepare(trt_network* net);
 
 /* run-time knobs:
  *   "mode"        0 = one launch per wavefront stage, 1 = persistent cooperative kernel with a grid barrier per stage,
- *                 2 = dataflow kernel: units claimed in stage order, lanes wait on the slots they read (default)
+ *                 2 = dataflow kernel: units claimed in stage order, lanes wait on the slots they read,
+ *                 3 = marching kernel: a lane owns one segment and walks it through every timestep, waiting on the
+ *                     flow slots of its upstream neighbours,
+ *                 4 = (default) mode 2 for the wide shallow levels, then mode 3 for the deep levels
+ *   "deep_level"  mode 4: first level that marches; -1 (default) = as many of the deepest levels as hold at most
+ *                 "deep_lanes" segments (default 32768)
+ *   "march_group" segments per marching warp, 1..32 (default 8): fewer = shorter dependency-chain latency, more =
+ *                 more segments resident at once
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
@@ -170,6 +177,14 @@ int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms,
  * launches, wavefront stages, lane-steps executed */
 int trt_last_run_stats(const trt_network* net, double* kernel_ms, int64_t* launches, int64_t* stages,
                        int64_t* lane_steps);
+
+/* the two phases of a mode-4 run: device milliseconds of the dataflow kernel (levels below first_marching_level) and of
+ * the marching kernel (the levels from there on) */
+int trt_last_run_phases(const trt_network* net, double* wide_ms, double* march_ms, int32_t* first_marching_level);
+/* "march_profile" = 1: per row of the last run, {ns from kernel start until its first step was done, ns until its last
+ * step was done, ns spent solving (inputs arrived -> flow published, summed over the steps), failed polls}; rows that did not march hold zeros.
+ * *rows = rows available (0 when profiling was off); out4 may be NULL to query. */
+int trt_march_profile(trt_network* net, int64_t capacity_rows, uint64_t* out4, int64_t* rows);
 
 /*
  * Batch of independent single-segment solves on the device: the GPU twin of

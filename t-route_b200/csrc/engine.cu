@@ -93,7 +93,7 @@ struct trt_network {
     DevBuf<int> d_unit_ptr, d_gate_stage, d_done, d_ctrl;     // d_ctrl: [0] claim, [1] frontier, [2] abort
     DevBuf<unsigned char> d_unit_shift;
     DevBuf<unsigned long long> d_stage_time;                  // mode 2 + profile_stages: completion time of every stage
-    int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0;
+    int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0, sched_lw = -1;
     int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
     int gate_min = 12;
     int64_t gate_lanes = 16384;
@@ -101,6 +101,19 @@ struct trt_network {
     std::vector<cudaEvent_t> stage_events;
     std::vector<float> stage_ms;
     std::vector<int64_t> stage_width;
+    // marching schedule (mode 3: every level; mode 4: levels >= deep_level_used after the dataflow kernel)
+    DevBuf<int> d_march_start;
+    DevBuf<unsigned char> d_march_cnt;
+    int march_group = 8;                                      // positions per marching warp (1..32)
+    int deep_level = -1;                                      // mode 4: first marching level (-1 = from deep_lanes)
+    int64_t deep_lanes = 32768;                               // mode 4 auto: march as many of the deepest levels as fit
+    int march_sched_first = -1, march_sched_group = -1, march_units = 0;
+    bool march_profile = false;
+    int poll_mode = 0, poll_sleep = -1;
+    DevBuf<unsigned long long> d_march_prof;                  // [n][4] + 1
+    cudaEvent_t ev_mid = nullptr;                             // between the dataflow and the marching kernel
+    double wide_ms = 0.0, march_ms = 0.0;
+    int deep_level_used = 0;
     bool prepared = false;                                    // sentinel reset done for the next run
     std::vector<int32_t> host_bnd_pos;                        // prescribed rows of the last upload (positions)
     int64_t n_bnd = 0;
@@ -116,7 +129,8 @@ struct trt_network {
     long long peer_n[TRT_MAX_PEERS] = {0};
 
     // options / stats
-    int mode = 2;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow
+    int mode = 4;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow,
+                                   // 3 marching lanes, 4 dataflow for the wide shallow levels + marching for the deep ones
     int grid_blocks = 0;           // 0 = max co-resident
     double kernel_ms = 0.0;
     int64_t launches = 0, stages = 0, lane_steps = 0;
@@ -304,6 +318,7 @@ int trt_network_destroy(trt_network* net)
     cudaSetDevice(net->device);
     if (net->ev0) cudaEventDestroy(net->ev0);
     if (net->ev1) cudaEventDestroy(net->ev1);
+    if (net->ev_mid) cudaEventDestroy(net->ev_mid);
     if (net->stream && net->own_stream) cudaStreamDestroy(net->stream);
     delete net;
     return TRT_OK;
@@ -485,11 +500,26 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
         int64_t routed = 0;
         for (int64_t r = 0; r < net->n; ++r) routed += net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY;
         net->lane_steps = routed * T;
-        if (net->mode == 2) {
+        if (net->mode >= 2) {
+            // levels [0, Lw) go through the dataflow wavefront, levels [Lw, nlevels) march
+            int Lw = net->nlevels;
+            if (net->mode == 3) Lw = 0;
+            else if (net->mode == 4) {
+                if (net->deep_level >= 0) Lw = std::min(net->deep_level, net->nlevels);
+                else {
+                    Lw = net->nlevels;
+                    while (Lw > 0 && net->n - net->lvl_ptr[(size_t)Lw - 1] <= net->deep_lanes) --Lw;
+                }
+            }
+            net->deep_level_used = Lw;
+            const int pos_deep = net->lvl_ptr[(size_t)Lw];
+            const int Lk = assume_short_ts ? (Lw > 0 ? 1 : 0) : Lw;   // levels the stage index runs over
             // (re)build the unit table of this (T, schedule) pair
-            const int nstages = k_end - 1;
-            if (net->sched_T != T || net->sched_short != (assume_short_ts ? 1 : 0) || net->sched_gate != net->gate ||
-                net->sched_nstages != nstages) {
+            const int nstages = Lk > 0 ? Lk + T - 1 : 0;
+            net->stages = nstages + (pos_deep < net->n ? T : 0);
+            if (nstages > 0 && (net->sched_T != T || net->sched_short != (assume_short_ts ? 1 : 0) ||
+                                net->sched_gate != net->gate || net->sched_nstages != nstages ||
+                                net->sched_lw != Lw)) {
                 std::vector<int32_t> unit_ptr((size_t)nstages + 1, 0), gate_stage((size_t)nstages, 0);
                 std::vector<unsigned char> shift((size_t)nstages, 5);
                 std::vector<int32_t> last_nonempty((size_t)nstages + 1, 0);   // last non-empty stage <= k
@@ -498,10 +528,10 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 int win = 1;                                                  // first stage of the run-ahead window
                 for (int k = 1; k <= nstages; ++k) {
                     int64_t lo, hi;
-                    if (assume_short_ts) { lo = 0; hi = net->n; }
+                    if (assume_short_ts) { lo = 0; hi = pos_deep; }
                     else {
                         lo = net->lvl_ptr[(size_t)std::max(0, k - T)];
-                        hi = net->lvl_ptr[(size_t)std::min(L, k)];
+                        hi = net->lvl_ptr[(size_t)std::min(Lw, k)];
                     }
                     const int64_t width = hi - lo;
                     const int sh = width >= 65536 ? 7 : 5;
@@ -527,7 +557,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 CU(net->d_gate_stage.reserve((size_t)nstages));
                 CU(net->d_unit_shift.reserve((size_t)nstages));
                 CU(net->d_done.reserve((size_t)nstages));
-                CU(net->d_ctrl.reserve(4));
+                CU(net->d_ctrl.reserve(8));
                 CU(cudaMemcpyAsync(net->d_unit_ptr.p, unit_ptr.data(), ((size_t)nstages + 1) * sizeof(int32_t),
                                    cudaMemcpyHostToDevice, st));
                 CU(cudaMemcpyAsync(net->d_gate_stage.p, gate_stage.data(), (size_t)nstages * sizeof(int32_t),
@@ -535,21 +565,39 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 CU(cudaMemcpyAsync(net->d_unit_shift.p, shift.data(), (size_t)nstages, cudaMemcpyHostToDevice, st));
                 CU(cudaStreamSynchronize(st));   // staging vectors go out of scope
                 net->sched_T = T; net->sched_short = assume_short_ts ? 1 : 0; net->sched_gate = net->gate;
-                net->sched_nstages = nstages;
+                net->sched_nstages = nstages; net->sched_lw = Lw;
             }
+            // marching units over positions [pos_deep, n)
+            if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != net->march_group)) {
+                const int G = net->march_group;
+                std::vector<int32_t> start;
+                std::vector<unsigned char> cnt;
+                for (int64_t q = pos_deep; q < net->n; q += G) {
+                    start.push_back((int32_t)q);
+                    cnt.push_back((unsigned char)std::min<int64_t>(G, net->n - q));
+                }
+                CU(net->d_march_start.reserve(start.size()));
+                CU(net->d_march_cnt.reserve(cnt.size()));
+                CU(cudaMemcpy(net->d_march_start.p, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(net->d_march_cnt.p, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
+                net->march_units = (int)start.size();
+                net->march_sched_first = pos_deep; net->march_sched_group = G;
+            }
+            CU(net->d_ctrl.reserve(8));
             SchedDev sd;
+            sd.wide_levels = Lk; sd.pos_end = pos_deep;
             sd.nstages = nstages; sd.T = T; sd.unit_ptr = net->d_unit_ptr.p; sd.unit_shift = net->d_unit_shift.p;
             sd.claim = (unsigned int*)net->d_ctrl.p; sd.frontier = net->d_ctrl.p + 1; sd.abort_flag = net->d_ctrl.p + 2;
             sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
             sd.stage_time = nullptr;
-            if (net->profile_stages) {
+            if (net->profile_stages && nstages > 0) {
                 CU(net->d_stage_time.reserve((size_t)nstages + 1));
                 CU(cudaMemsetAsync(net->d_stage_time.p, 0, ((size_t)nstages + 1) * sizeof(unsigned long long), st));
                 sd.stage_time = net->d_stage_time.p;
                 net->stage_width.assign((size_t)nstages + 1, 0);
                 for (int k = 1; k <= nstages; ++k)
-                    net->stage_width[(size_t)k] = assume_short_ts ? net->n
-                        : net->lvl_ptr[(size_t)std::min(L, k)] - net->lvl_ptr[(size_t)std::max(0, k - T)];
+                    net->stage_width[(size_t)k] = assume_short_ts ? pos_deep
+                        : net->lvl_ptr[(size_t)std::min(Lw, k)] - net->lvl_ptr[(size_t)std::max(0, k - T)];
             }
             PeerDev pd;
             pd.exp_slot = net->d_exp_slot.p; pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
@@ -558,13 +606,37 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             CU(dataflow_max_grid(&max_grid));
             if (max_grid <= 0) return fail(TRT_ERR_CUDA, "dataflow kernel cannot be made resident");
             if (grid <= 0) grid = max_grid;
-            CU(cudaMemsetAsync(net->d_ctrl.p, 0, 4 * sizeof(int), st));
-            CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
+            CU(cudaMemsetAsync(net->d_ctrl.p, 0, 8 * sizeof(int), st));
+            if (nstages > 0) CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
             if (!net->prepared) CU(prepare_dataflow(net));
             net->prepared = false;
             CU(cudaEventRecord(net->ev0, st));
-            CU(launch_dataflow(nd, rd, sd, pd, grid, st));
-            net->launches = 1 + 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);   // + state reset kernels
+            net->launches = 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);       // state reset kernels
+            if (nstages > 0) {
+                CU(launch_dataflow(nd, rd, sd, pd, grid, st));
+                net->launches++;
+            }
+            if (pos_deep < net->n) {
+                MarchDev md;
+                md.n_units = net->march_units; md.unit_start = net->d_march_start.p; md.unit_cnt = net->d_march_cnt.p;
+                md.claim = (unsigned int*)net->d_ctrl.p + 4; md.abort_flag = net->d_ctrl.p + 2;
+                md.prof = nullptr; md.t_start = nullptr; md.poll_mode = net->poll_mode; md.poll_sleep = net->poll_sleep;
+                if (net->march_profile) {
+                    CU(net->d_march_prof.reserve((size_t)net->n * 4 + 1));
+                    CU(cudaMemsetAsync(net->d_march_prof.p, 0, (size_t)net->n * 4 * sizeof(unsigned long long), st));
+                    CU(cudaMemsetAsync(net->d_march_prof.p + (size_t)net->n * 4, 0xFF, sizeof(unsigned long long), st));
+                    md.prof = net->d_march_prof.p; md.t_start = net->d_march_prof.p + (size_t)net->n * 4;
+                }
+                if (!net->ev_mid) CU(cudaEventCreate(&net->ev_mid));
+                CU(cudaEventRecord(net->ev_mid, st));
+                int mgrid = 0;
+                CU(march_max_grid(&mgrid));
+                if (mgrid <= 0) return fail(TRT_ERR_CUDA, "marching kernel cannot be made resident");
+                if (net->grid_blocks > 0) mgrid = std::min(mgrid, net->grid_blocks);
+                mgrid = std::min<int64_t>(mgrid, (net->march_units + 7) / 8);
+                CU(launch_march(nd, rd, md, pd, mgrid, st));
+                net->launches++;
+            }
         } else if (net->mode == 1) {
             int grid = net->grid_blocks;
             int max_grid = 0;
@@ -616,24 +688,32 @@ int trt_sync(trt_network* net)
     if (net->ran) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, net->ev0, net->ev1) == cudaSuccess) net->kernel_ms = ms;
+        net->wide_ms = net->kernel_ms; net->march_ms = 0.0;
+        if (net->mode >= 3 && net->ev_mid && net->march_units > 0 && net->deep_level_used < net->nlevels) {
+            float a = 0.f, b = 0.f;
+            if (cudaEventElapsedTime(&a, net->ev0, net->ev_mid) == cudaSuccess &&
+                cudaEventElapsedTime(&b, net->ev_mid, net->ev1) == cudaSuccess) { net->wide_ms = a; net->march_ms = b; }
+        }
         if (net->mode == 0 && net->profile_stages && net->stages > 0) {
             net->stage_ms.assign((size_t)net->stages + 1, 0.f);
             for (int64_t k = 1; k <= net->stages; ++k)
                 cudaEventElapsedTime(&net->stage_ms[(size_t)k], net->stage_events[(size_t)k - 1], net->stage_events[(size_t)k]);
         }
-        if (net->mode == 2 && net->profile_stages && net->d_stage_time.p && net->stages > 0) {
+        if (net->mode >= 2 && net->profile_stages && net->d_stage_time.p && net->sched_nstages > 0 &&
+            net->deep_level_used > 0) {
             // dataflow stages overlap: report the time between consecutive stage completions
-            std::vector<unsigned long long> ts((size_t)net->stages + 1);
+            const int64_t ns = net->sched_nstages;
+            std::vector<unsigned long long> ts((size_t)ns + 1);
             CU(cudaMemcpy(ts.data(), net->d_stage_time.p, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-            net->stage_ms.assign((size_t)net->stages + 1, 0.f);
+            net->stage_ms.assign((size_t)ns + 1, 0.f);
             unsigned long long prev = ts[0];
-            for (int64_t k = 1; k <= net->stages; ++k) {
+            for (int64_t k = 1; k <= ns; ++k) {
                 const unsigned long long tk = ts[(size_t)k] ? std::max(ts[(size_t)k], prev) : prev;   // empty stage
                 net->stage_ms[(size_t)k] = (float)((double)(tk - prev) * 1e-6);
                 prev = tk;
             }
         }
-        if (net->mode == 2 && net->d_ctrl.p && net->launches > 0) {
+        if (net->mode >= 2 && net->d_ctrl.p && net->launches > 0) {
             int ctrl[4] = {0, 0, 0, 0};
             CU(cudaMemcpy(ctrl, net->d_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
             if (ctrl[2] != 0)
@@ -737,7 +817,7 @@ int trt_prepare(trt_network* net)
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_prepare called before trt_upload_forcing");
     CU(cudaSetDevice(net->device));
-    if (net->mode == 2) {
+    if (net->mode >= 2) {
         CU(prepare_dataflow(net));
         CU(cudaStreamSynchronize(net->stream));
         net->prepared = true;
@@ -842,8 +922,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
 {
     if (!net || !key) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "mode")) {
-        if (value < 0 || value > 2)
-            return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches), 1 (persistent, grid.sync) or 2 (dataflow)");
+        if (value < 0 || value > 4)
+            return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches), 1 (persistent, grid.sync), 2 (dataflow), "
+                                         "3 (marching) or 4 (dataflow + marching)");
         net->mode = (int)value;
     } else if (!strcmp(key, "grid_blocks")) {
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
@@ -862,6 +943,21 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
+    } else if (!strcmp(key, "march_group")) {
+        if (value < 1 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 1..32");
+        net->march_group = (int)value;
+    } else if (!strcmp(key, "poll_mode")) {
+        net->poll_mode = (int)value;
+    } else if (!strcmp(key, "poll_sleep")) {
+        net->poll_sleep = (int)value;
+    } else if (!strcmp(key, "march_profile")) {
+        net->march_profile = value != 0;
+    } else if (!strcmp(key, "deep_level")) {
+        if (value < -1) return fail(TRT_ERR_INVALID, "deep_level must be >= -1");
+        net->deep_level = (int)value;
+    } else if (!strcmp(key, "deep_lanes")) {
+        if (value < 0) return fail(TRT_ERR_INVALID, "deep_lanes must be >= 0");
+        net->deep_lanes = value;
     } else if (!strcmp(key, "stream")) {
         // adopt a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so that the
         // caller's CUDA events bracket this handle's kernels; 0 restores the private stream
@@ -892,6 +988,29 @@ int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms,
         if (stage_ms) stage_ms[k] = net->stage_ms[(size_t)k];
         if (stage_width) stage_width[k] = net->stage_width[(size_t)k];
     }
+    return TRT_OK;
+}
+
+int trt_last_run_phases(const trt_network* net, double* wide_ms, double* march_ms, int32_t* first_marching_level)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (wide_ms) *wide_ms = net->wide_ms;
+    if (march_ms) *march_ms = net->march_ms;
+    if (first_marching_level) *first_marching_level = net->deep_level_used;
+    return TRT_OK;
+}
+
+int trt_march_profile(trt_network* net, int64_t capacity_rows, uint64_t* out4, int64_t* rows)
+{
+    if (!net || !rows) return fail(TRT_ERR_INVALID, "NULL argument");
+    *rows = net->d_march_prof.p ? net->n : 0;
+    if (!out4 || !net->d_march_prof.p) return TRT_OK;
+    CU(cudaSetDevice(net->device));
+    // device order is engine position; hand it back in the caller's row order
+    std::vector<unsigned long long> h((size_t)net->n * 4);
+    CU(cudaMemcpy(h.data(), net->d_march_prof.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < net->n && r < capacity_rows; ++r)
+        for (int c = 0; c < 4; ++c) out4[(size_t)r * 4 + c] = h[(size_t)net->pos_of_row[(size_t)r] * 4 + c];
     return TRT_OK;
 }
 

@@ -56,6 +56,9 @@ struct RunDev {
 struct SchedDev {
     int nstages;                      // stages k = 1 .. nstages
     int T;
+    int wide_levels;                  // levels [0, wide_levels) are routed by this schedule (the rest march, mode 4);
+                                      // 1 with assume_short_ts: every segment of a step is independent
+    int pos_end;                      // positions [0, pos_end) belong to this schedule
     const int* unit_ptr;              // [nstages + 1] first unit of stage k is unit_ptr[k - 1]
     const unsigned char* unit_shift;  // [nstages] log2 of the unit width of that stage (5 or 7)
     unsigned int* claim;              // [1] next unit to hand out
@@ -77,6 +80,24 @@ struct PeerDev {
     const long long* exp_pos;         // [n_exp] position in the peer's arrays
     float* S[TRT_MAX_PEERS];          // peer flow-state arrays (mapped peer memory)
 };
+
+// Marching schedule (mode 3, and the deep levels of mode 4): units of <= 32 consecutive positions, claimed in position
+// order; every lane walks its segment through all T timesteps, waiting on the q slots of its upstream neighbours.
+struct MarchDev {
+    int n_units;
+    const int* unit_start;            // [n_units] first position of the unit
+    const unsigned char* unit_cnt;    // [n_units] lanes in use (1..32)
+    unsigned int* claim;              // [1] next unit to hand out
+    int* abort_flag;                  // [1]
+    unsigned long long* prof;         // NULL, or [n][4] per position: ns from kernel start to its first / last step
+                                      // done, ns between the inputs of a step arriving and its flow being published (summed over steps), failed polls ("march_profile" option)
+    unsigned long long* t_start;      // [1] %globaltimer at kernel start (prof only)
+    int poll_mode;                    // experiment: 0 ld.volatile, 1 ld.relaxed.gpu, 2 atomicOr(p, 0)
+    int poll_sleep;                   // experiment: ns of back-off between polls of an idle warp (-1 = adaptive)
+};
+cudaError_t march_max_grid(int* blocks);
+cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
+                         int grid_blocks, cudaStream_t st);
 
 // wavefront: stage k routes every (segment s, step t) with level(s) + t == k
 cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st);

@@ -98,6 +98,27 @@ __device__ __forceinline__ void st_state(float* p, float x)
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const float* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// q[s, t] becomes visible to every consumer (same GPU: the poll of a downstream lane; other GPU: the import row of the
+// downstream shard, written over NVLink peer memory) with ONE 4-byte store each.
+__device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflags, int s, int t, size_t T1,
+                                             const PeerDev& peers)
+{
+    unsigned b = __float_as_uint(q);
+    if (b == TRT_SENTINEL) b = 0x7FC00000u;      // a NaN payload that happens to equal the sentinel
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(own), "r"(b) : "memory");
+    if (kflags & TRT_KIND_EXPORT_FLAG) {
+        const int x = __ldg(peers.exp_slot + s);
+        const int pr = __ldg(peers.exp_peer + x);
+        float* dst = peers.S[pr] + ((size_t)__ldg(peers.exp_pos + x) * T1 + (size_t)t) * 3;
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
+    }
+}
+
 // route segment `s` (engine position) at step `t`
 template <bool WAIT>
 __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs,
@@ -137,6 +158,7 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
     const float statep = ld_state<WAIT>(own - 1, abort_flag);
 
     float o_q, o_v, o_d;
+    bool write_v = true;
     if (kind == TRT_KIND_LEVELPOOL) {
         // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
         LpParams lp;
@@ -150,10 +172,12 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
     } else {
         const float ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);   // :723
         const float qdp = ld_state<WAIT>(own - 3, abort_flag);                       // :733
-        const McResult r = trt_mc_segment<false>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
+        // polling schedules (WAIT): the velocity slot keeps TRT_SENTINEL and the result pass fills it in from the depth
+        const McResult r = trt_mc_segment<false, !WAIT>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
+        write_v = !WAIT || !(ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);   // no-flow branch: v = 0 (:171-178)
     }
-    own[1] = o_v;
+    if (write_v) own[1] = o_v;
     st_state<WAIT>(own + 2, o_d);
     st_state<WAIT>(own, o_q);
     if (WAIT && (kflags & TRT_KIND_EXPORT_FLAG)) {
@@ -215,7 +239,8 @@ __global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run
     const PowTabs tabs = stage_tables(smem);
     const int lane = threadIdx.x & 31;
     const unsigned total = (unsigned)__ldg(sc.unit_ptr + sc.nstages);
-    const int L = run.short_ts ? 1 : net.nlevels;
+    const int L = sc.wide_levels;
+    const int pos_end = sc.pos_end;
     int cursor = 0;                                   // stage index (k - 1) of this warp's previous unit
     if (sc.stage_time && blockIdx.x == 0 && threadIdx.x == 0) sc.stage_time[0] = globaltimer_ns();
     for (;;) {
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run
         cursor = lo_i;
         const int k = lo_i + 1;
         int lo, hi;
-        if (run.short_ts) { lo = 0; hi = net.n; }
+        if (run.short_ts) { lo = 0; hi = pos_end; }
         else {
             lo = __ldg(net.lvl_ptr + max(0, k - run.T));
             hi = __ldg(net.lvl_ptr + min(L, k));
@@ -272,6 +297,203 @@ __global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// marching schedule (see kernels.cuh): a lane owns ONE segment and walks it through all T timesteps
+// ---------------------------------------------------------------------------------------------------------
+// Where the wavefront is narrow (the deep main stems: a few hundred segments per stage for thousands of stages) the
+// run time is the length of the dependency chain times the latency of one link.  A link here costs: one L2 round trip
+// (the upstream lane's st.volatile of q[u][t], this lane's ld.volatile poll) plus one secant solve whose channel
+// geometry, previous flow and previous depth are already in registers.  Lanes of a warp are independent state
+// machines (WAIT for inputs of step t / ITERATE one secant trip / DONE), so a lane stalled on its upstream neighbour
+// or in the retry ladder never holds up the other lanes, and lanes that are iterating execute the same instructions
+// whatever timestep each of them is at.  Units (<= 32 consecutive positions) are claimed in position order: every
+// upstream position is lower, hence claimed earlier and resident or finished -- no deadlock.
+enum { MARCH_WAIT = 0, MARCH_ITER = 1, MARCH_DONE = 2 };
+
+__global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, MarchDev mk, PeerDev peers)
+{
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
+    const int lane = threadIdx.x & 31;
+    const size_t n = (size_t)net.n;
+    const int T = run.T;
+    const size_t T1 = (size_t)T + 1;
+    if (mk.prof && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(mk.t_start, globaltimer_ns());
+    for (;;) {
+        unsigned u = 0;
+        if (lane == 0) u = atomicAdd(mk.claim, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= (unsigned)mk.n_units) break;
+        const int p = __ldg(mk.unit_start + u) + lane;
+        unsigned long long prof_first = 0, prof_wait = 0, prof_fail = 0;
+        long long wait_since = 0;
+        const bool mine = lane < (int)__ldg(mk.unit_cnt + u);
+
+        int state = MARCH_DONE;
+        unsigned kflags = 0, kind = TRT_KIND_BOUNDARY;
+        if (mine) { kflags = net.kind[p]; kind = kflags & 0x0F; }
+        float* row = run.S;                       // (q, v, d) series of this lane's segment
+        float p0 = 0.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, p4 = 0.f, p5 = 1.f, p6 = 0.f, p7 = 1.f, p8 = 1.f;
+        int e0 = 0, e1 = 0;
+        if (kind != TRT_KIND_BOUNDARY) {          // prescribed rows are never computed
+            state = MARCH_WAIT;
+            row = run.S + (size_t)p * T1 * 3;
+            const float* par = net.par + p;
+            p0 = __ldg(par + 0 * n); p1 = __ldg(par + 1 * n); p2 = __ldg(par + 2 * n); p3 = __ldg(par + 3 * n);
+            p4 = __ldg(par + 4 * n); p5 = __ldg(par + 5 * n); p6 = __ldg(par + 6 * n); p7 = __ldg(par + 7 * n);
+            p8 = __ldg(par + 8 * n);
+            e0 = __ldg(net.up_ptr + p); e1 = __ldg(net.up_ptr + p + 1);
+        }
+        const bool is_lp = kind == TRT_KIND_LEVELPOOL;
+        const McChannel c = mc_channel(p0, p1, p2, p3, p4, p5, p6, p7, p8);
+        McSolve s;
+        int t = 1;
+        float qdp = 0.f, statep = 0.f, upsum_prev = 0.f, ql = 0.f;
+        int ql_left = 0;
+        unsigned waited = 0;
+        int e_cur = e0;                           // next upstream slot to read for the current step
+        float psum = 0.0f;                        // flows of the slots before e_cur, summed in order
+        if (state == MARCH_WAIT) {
+            qdp = __ldcg(row);                    // t = 0: initial state (init_state_kernel / init_levelpool_kernel)
+            statep = __ldcg(row + 2);
+            for (int e = e0; e < e1; ++e)         // previous_upstream_flows of step 1  (mc_reach.pyx:499-502)
+                upsum_prev += __ldcg(run.S + (size_t)__ldg(net.up_idx + e) * T1 * 3);
+            if (T < 1) state = MARCH_DONE;
+        }
+
+        for (;;) {
+            if (state == MARCH_WAIT) {
+                // inputs of step t: every upstream flow at step t (t - 1 with assume_short_ts), summed in reference order.
+                // Main-stem segments can have dozens of tributaries: the slots are read eight at a time (independent
+                // loads, one L2 round trip) and the walk resumes where it stopped, so a poll re-reads only the slot it
+                // is waiting for and the flows behind it are fetched after the awaited one has arrived.
+                const int ti = run.short_ts ? t - 1 : t;
+                bool ok = true;
+                while (e_cur < e1) {
+                    unsigned v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = min(e_cur + j, e1 - 1);
+                        const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)ti) * 3;
+                        if (mk.poll_mode == 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[j]) : "l"(up) : "memory");
+                        else v[j] = ld_volatile_u32(up);
+                    }
+                    const int m = min(8, e1 - e_cur);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (ok && j < m) {
+                            if (v[j] == TRT_SENTINEL) ok = false;
+                            else { psum += __uint_as_float(v[j]); ++e_cur; }
+                        }
+                    }
+                    if (!ok) break;
+                }
+                const float sum = psum;
+                if (mk.prof) {
+                    if (!ok) ++prof_fail;
+                    else wait_since = (long long)globaltimer_ns();      // start of the busy part of this step
+                }
+                if (ok) {
+                    waited = 0;
+                    e_cur = e0; psum = 0.0f;
+                    if (ql_left == 0) {                                              // :723
+                        ql = is_lp ? 0.0f : __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + p);
+                        ql_left = run.qts - ((t - 1) % run.qts);
+                    }
+                    --ql_left;
+                    const float quc = sum;
+                    const float qup = run.short_ts ? sum : upsum_prev;
+                    upsum_prev = sum;
+                    mc_begin(s, qup, quc, qdp, ql, statep);
+                    state = MARCH_ITER;
+                    if (!is_lp && !s.flow) {                                         // :171-178
+                        float* own = row + (size_t)t * 3;
+                        own[1] = 0.0f; own[2] = 0.0f;
+                        publish_flow(own, 0.0f, kflags, p, t, T1, peers);
+                        qdp = 0.0f; statep = 0.0f;
+                        ++t;
+                        state = t > T ? MARCH_DONE : MARCH_WAIT;
+                    }
+                } else if ((++waited & 0xFFF) == 0) {
+                    // every 4096 failed polls: somebody flagged an error, or this lane has been starving for seconds
+                    if (*reinterpret_cast<volatile int*>(mk.abort_flag) != 0) state = MARCH_DONE;
+                    else if (waited >= (1u << 26)) { atomicExch(mk.abort_flag, 1); state = MARCH_DONE; }
+                }
+            }
+            if (state == MARCH_ITER) {
+                float* own = row + (size_t)t * 3;
+                if (is_lp) {
+                    // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
+                    LpParams lp;
+                    lp.area = p1; lp.max_depth = p2; lp.orifice_area = p3; lp.orifice_coefficient = p4;
+                    lp.orifice_elevation = p5; lp.weir_coefficient = p6; lp.weir_elevation = p7; lp.weir_length = p8;
+                    lp.dam_length = 10.0f;
+                    float H = statep, outflow;
+                    trt_levelpool_step(lp, s.quc, 0.0f, p0, H, outflow, tabs);
+                    publish_flow(own, outflow, kflags, p, t, T1, peers);
+                    own[1] = s.quc;             // reservoir inflow rides in the velocity slot (upstream_array, :710)
+                    own[2] = H;
+                    qdp = outflow; statep = H;
+                    ++t;
+                    state = t > T ? MARCH_DONE : MARCH_WAIT;
+                } else if (mc_iterate(c, s, tabs)) {
+                    const float q = mc_outflow(s);
+                    publish_flow(own, q, kflags, p, t, T1, peers);   // downstream lanes are waiting for this
+                    if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
+                    own[2] = s.h;                                    // own[1] (velocity): result pass, from this depth
+                    if ((t & 1) == 0) {
+                        // cold tributary rows (finished long ago, evicted from L2): pull the sectors of the coming steps
+                        // in, off the critical path.  One 32-byte sector holds 2.67 steps of (q, v, d).
+                        const int tp = min(t + 8, T);
+                        for (int e = e0; e < e1; ++e)
+                            prefetch_l2(run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)tp) * 3);
+                    }
+                    qdp = q; statep = s.h;
+                    if (mk.prof && t == 1) prof_first = globaltimer_ns();
+                    ++t;
+                    state = t > T ? MARCH_DONE : MARCH_WAIT;
+                }
+            }
+            const unsigned iterating = __ballot_sync(0xffffffffu, state == MARCH_ITER);
+            if (iterating == 0) {
+                if (__all_sync(0xffffffffu, state == MARCH_DONE)) {
+                    if (mk.prof && mine) {
+                        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(mk.t_start);
+                        unsigned long long* o = mk.prof + (size_t)p * 4;
+                        o[0] = prof_first ? prof_first - t0 : 0; o[1] = globaltimer_ns() - t0; o[2] = prof_wait; o[3] = prof_fail;
+                    }
+                    break;
+                }
+                // nobody has work: every live lane polls.  Back off a little so that thousands of waiting warps do not
+                // crowd the L2 slices the producers are writing to.
+                if (mk.poll_sleep < 0) {
+                    if (__all_sync(0xffffffffu, state != MARCH_WAIT || waited > 8)) __nanosleep(waited > 64 ? 256 : 32);
+                } else if (mk.poll_sleep > 0) __nanosleep(mk.poll_sleep);
+            }
+        }
+    }
+}
+
+cudaError_t march_max_grid(int* blocks)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_kernel, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    *blocks = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
+                         int grid_blocks, cudaStream_t st)
+{
+    march_kernel<<<grid_blocks, kBlock, 0, st>>>(net, run, march, peers);
+    return cudaGetLastError();
 }
 
 cudaError_t dataflow_max_grid(int* blocks)
@@ -391,21 +613,32 @@ __global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* S, int
 
 // Result in the reference's layout (mc_reach.pyx:807-813): fvd[row][3*(t-1) + c] = state[pos][t][c], t = 1..T.
 // The engine already keeps every segment's series contiguous, so this is one 12*T-byte copy per segment -- a
-// permutation from level-sorted positions to the caller's rows, one warp per segment.
+// permutation from level-sorted positions to the caller's rows, one warp per segment.  The polling schedules leave the
+// velocity slot of a Muskingum-Cunge step at TRT_SENTINEL: velocity is a function of the final depth and the channel
+// alone (:163-169), nobody downstream reads it, and here one warp = one segment evaluates it with uniform parameters and
+// no divergence instead of inside the branchy solve.
 __global__ void __launch_bounds__(256) permute_rows_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
 {
+    __shared__ SmemTabs smem;
+    const PowTabs tabs = stage_tables(smem);
     const int warps_per_block = 256 / 32;
     const int lane = threadIdx.x & 31;
-    const int w = 3 * run.T;
+    const size_t n = (size_t)net.n;
     for (long long p = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < net.n;
          p += (long long)gridDim.x * warps_per_block) {
         const float* src = run.S + ((size_t)p * (run.T + 1) + 1) * 3;
-        float* dst = fvd + (size_t)net.row_of_pos[p] * w;
-        const bool lp = (net.kind[p] & 0x0F) == TRT_KIND_LEVELPOOL;
-        for (int c = lane; c < w; c += 32) {
-            float v = __ldcs(src + c);
-            if (lp && (c % 3) == 1) v = 0.0f;          // flowveldepth[r.id, t, 1] = 0.0  (:708)
-            __stcs(dst + c, v);
+        float* dst = fvd + (size_t)net.row_of_pos[p] * 3 * run.T;
+        const unsigned kind = net.kind[p] & 0x0F;
+        const float* par = net.par + p;
+        const McChannel c = mc_channel(__ldg(par + 0 * n), __ldg(par + 1 * n), __ldg(par + 2 * n), __ldg(par + 3 * n),
+                                       __ldg(par + 4 * n), __ldg(par + 5 * n), __ldg(par + 6 * n), __ldg(par + 7 * n),
+                                       __ldg(par + 8 * n));
+        for (int t = lane; t < run.T; t += 32) {
+            const float q = __ldcs(src + 3 * t), d = __ldcs(src + 3 * t + 2);
+            float v = __ldcs(src + 3 * t + 1);
+            if (kind == TRT_KIND_LEVELPOOL) v = 0.0f;      // flowveldepth[r.id, t, 1] = 0.0  (:708)
+            else if (kind == TRT_KIND_MC && __float_as_uint(v) == TRT_SENTINEL) v = mc_velocity(c, d, tabs);
+            __stcs(dst + 3 * t, q); __stcs(dst + 3 * t + 1, v); __stcs(dst + 3 * t + 2, d);
         }
     }
 }

@@ -66,6 +66,8 @@ SYMBOLS = [
     ("trt_prepare", C.c_int, [_net]),
     ("trt_set_option", C.c_int, [_net, C.c_char_p, C.c_int64]),
     ("trt_stage_profile", C.c_int, [_net, C.c_int64, _f32p, _i64p, _i64p]),
+    ("trt_last_run_phases", C.c_int, [_net, _f64p, _f64p, _i32p]),
+    ("trt_march_profile", C.c_int, [_net, C.c_int64, C.POINTER(C.c_uint64), _i64p]),
     ("trt_last_run_stats", C.c_int, [_net, _f64p, _i64p, _i64p, _i64p]),
     ("trt_mc_segment_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _i32p]),
     ("trt_levelpool_series", C.c_int, [C.c_int, _f64p, C.c_int64, _f32p, C.c_float, C.c_float, _f32p, _f32p]),

@@ -12,7 +12,8 @@ from .network import RoutingNetwork
 
 
 class SingleRouter:
-    kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel"}
+    kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel",
+                    3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel"}
 
     def __init__(self, wl, device, nsteps, qts, short_ts, mode=2):
         import torch
@@ -78,8 +79,8 @@ class ShardedRouter:
         import torch
         import torch.distributed as dist
         from . import hostgraph, partition
-        if mode != 2:
-            raise ValueError("sharded routing needs the dataflow schedule (mode 2)")
+        if mode not in (2, 3, 4):
+            raise ValueError("sharded routing needs a polling schedule (mode 2, 3 or 4)")
         self.torch, self.dist = torch, dist
         self.wl, self.world, self.rank, self.device = wl, world, rank, device
         self.T, self.qts, self.short_ts, self.mode = nsteps, qts, short_ts, mode
@@ -91,7 +92,7 @@ class ShardedRouter:
         self.n_own = int(plan.own.sum())
         self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
                                   device=device, levels=plan.levels)
-        self.net.set_option("mode", 2)
+        self.net.set_option("mode", mode)
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
         self.net.set_option("stream", self.tstream.cuda_stream)

@@ -267,8 +267,20 @@ class RoutingNetwork:
         stages = C.c_int64()
         lane_steps = C.c_int64()
         check(self._L.trt_last_run_stats(self._h, C.byref(ms), C.byref(launches), C.byref(stages), C.byref(lane_steps)))
+        wide, march, lvl = C.c_double(), C.c_double(), C.c_int32()
+        check(self._L.trt_last_run_phases(self._h, C.byref(wide), C.byref(march), C.byref(lvl)))
         return {"kernel_ms": ms.value, "launches": launches.value, "stages": stages.value,
-                "lane_steps": lane_steps.value}
+                "lane_steps": lane_steps.value, "wide_ms": wide.value, "march_ms": march.value,
+                "first_marching_level": lvl.value}
+
+    def march_profile(self):
+        """[n_rows, 4] uint64 of the last run with option march_profile=1 (see trt_march_profile)."""
+        rows = C.c_int64()
+        check(self._L.trt_march_profile(self._h, 0, None, C.byref(rows)))
+        out = np.zeros((rows.value, 4), dtype=np.uint64)
+        if rows.value:
+            check(self._L.trt_march_profile(self._h, rows.value, out.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(rows)))
+        return out
 
 
 # -------------------------------------------------------------------------------------------------

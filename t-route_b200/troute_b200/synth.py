@@ -65,9 +65,70 @@ def hack_tree(n, seed=16, hack_c=1.6, hack_h=0.55, trib_shape=1.15):
     return down
 
 
-def conus_like(n_total=2_729_077, n_basins=14_713, largest_frac=0.5, seed=16, hack_c=1.6, hack_h=0.55):
+# tributaries per interior main-stem node -> in-degree 1 + k.  Tuned so that a whole forest reproduces the in-degree
+# mix of the LowerColorado v4 hydrofabric quoted in SURVEY.md 8(d): 0: 48 %, 1: 19 %, 2: 23 %, 3: 6 %, >= 4: 4 %.
+_NHD_TRIB_P = np.array([0.365, 0.44, 0.115, 0.055, 0.025])
+
+
+def nhd_tree(n, seed=16, hack_c=1.15, hack_h=0.55, trib_shape=1.15, trib_p=_NHD_TRIB_P):
+    """One river basin of n segments with Hack's-law depth AND NHD-like confluences: every interior main-stem node
+    receives 0..4 tributaries (mostly 0 or 1: binary confluences), never dozens as hack_tree() allows.  The remaining
+    m - l segments of a (sub)basin are split over its tributaries with heavy-tailed (Pareto) sizes, each tributary
+    being a basin of the same kind.  Returns down[n]."""
+    rng = np.random.default_rng(seed)
+    down = np.full(n, -1, dtype=np.int64)
+    next_id = 0
+    stack = [(n, -1)]
+    kmax = trib_p.shape[0] - 1
+    trib_cdf = np.cumsum(trib_p)[:-1]
+    while stack:
+        m, parent = stack.pop()
+        length = int(min(m, max(1, round(hack_c * m ** hack_h))))
+        if m >= 2:
+            length = max(length, 2)                       # a basin with tributaries needs an interior node
+        ids = np.arange(next_id, next_id + length, dtype=np.int64)
+        next_id += length
+        down[ids[0]] = parent
+        if length > 1:
+            down[ids[1:]] = ids[:-1]
+        rest = m - length
+        if rest <= 0:
+            continue
+        # ids[0] is the outlet, ids[-1] the headwater of this main stem; interior nodes = all but the headwater
+        k = np.searchsorted(trib_cdf, rng.random(length - 1), side="right")
+        K = int(k.sum())
+        if K > rest:                                      # thin basin: drop tributaries at random
+            slots = np.repeat(np.arange(length - 1), k)
+            keep = rng.choice(slots.shape[0], size=rest, replace=False)
+            k = np.bincount(slots[keep], minlength=length - 1)
+            K = rest
+        elif K == 0:
+            k[rng.integers(0, length - 1)] = 1
+            K = 1
+        w = rng.pareto(trib_shape, size=K) + 1.0
+        sizes = 1 + np.floor(w / w.sum() * (rest - K)).astype(np.int64)
+        sizes[np.argmax(w)] += rest - int(sizes.sum())
+        attach = np.repeat(ids[:-1], k)
+        rng.shuffle(sizes)
+        one = sizes == 1                                  # single-segment tributaries: no recursion needed
+        c1 = int(one.sum())
+        if c1:
+            down[next_id:next_id + c1] = attach[one]
+            next_id += c1
+        for s_, a_ in zip(sizes[~one].tolist(), attach[~one].tolist()):
+            stack.append((s_, a_))
+    assert next_id == n
+    return down
+
+
+def conus_like(n_total=2_729_077, n_basins=14_713, largest_frac=0.5, seed=16, hack_c=None, hack_h=0.55, style="hack"):
     """CONUS-scale forest (config 3): n_basins independent basins, the largest holding ~largest_frac of
-    all segments (doc/AGU_Poster.md:35-41, :208-214).  Returns down[n_total]."""
+    all segments (doc/AGU_Poster.md:35-41, :208-214).  style "hack": hack_tree() basins (main stems collect dozens
+    of tributaries per node -- a stress case for the upstream gather); style "nhd": nhd_tree() basins (NHD-like
+    confluences and in-degree mix, the bench workload).  Returns down[n_total]."""
+    tree = hack_tree if style == "hack" else nhd_tree
+    if hack_c is None:
+        hack_c = 1.6 if style == "hack" else 1.15
     rng = np.random.default_rng(seed)
     big = int(n_total * largest_frac)
     rest = n_total - big
@@ -77,11 +138,11 @@ def conus_like(n_total=2_729_077, n_basins=14_713, largest_frac=0.5, seed=16, ha
     diff = rest - int(sizes.sum())
     sizes[np.argmax(sizes)] += diff
     assert sizes.min() >= 1 and int(sizes.sum()) == rest
-    parts = [hack_tree(big, seed=seed + 1, hack_c=hack_c, hack_h=hack_h)]
+    parts = [tree(big, seed=seed + 1, hack_c=hack_c, hack_h=hack_h)]
     offs = [0]
     off = big
     for i, s in enumerate(sizes.tolist()):
-        t = hack_tree(s, seed=seed + 2 + i, hack_c=hack_c, hack_h=hack_h)
+        t = tree(s, seed=seed + 2 + i, hack_c=hack_c, hack_h=hack_h)
         t = np.where(t >= 0, t + off, -1)
         parts.append(t)
         offs.append(off)

@@ -85,13 +85,16 @@ def _gather(case, order, counts, starts):
     return out
 
 
-def engine_route(case, assume_short_ts, mode=1, device=0, want_upstream=True):
+def engine_route(case, assume_short_ts, mode=None, device=0, want_upstream=True, options=None):
     from troute_b200.network import RoutingNetwork
     net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"], device=device)
     try:
         if case["lp_rows"].size:
             net.set_levelpools(case["lp_rows"], case["wbody"])
-        net.set_option("mode", mode)
+        if mode is not None:
+            net.set_option("mode", mode)
+        for k, v in (options or {}).items():
+            net.set_option(k, v)
         fvd, up = net.route(case["nsteps"], case["qts"], case["qlat"], case["q0"], assume_short_ts=assume_short_ts,
                             want_upstream=want_upstream)
         stats = net.last_run_stats()

@@ -129,7 +129,7 @@ def _networks():
 
 @pytest.mark.parametrize("name", ["tree4095", "chain300", "single", "hack20k_lp", "forest"])
 @pytest.mark.parametrize("short_ts", [False, True])
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_network_bits(eng, oracle, name, short_ts, mode):
     down, n_lp = _networks()[name]
     case = H.make_case(down, nsteps=36, n_lp=n_lp, warm=(name != "forest"))
@@ -245,6 +245,9 @@ def test_full_size_config2_properties(eng, oracle):
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
     del b
     assert np.isfinite(a).all() and st["stages"] == 20 + T
+    for m in (3, 4):
+        b, _, _ = H.engine_route(case, False, mode=m, want_upstream=False)
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"mode {m}"
     root = 300                                            # heap index; its subtree has 2^12 - 1 nodes at N = 2^20
     ids = [root]
     frontier = [root]
@@ -262,6 +265,24 @@ def test_full_size_config2_properties(eng, oracle):
     H.assert_bit_equal(a[ids], ref, "sub-tree of the full-size run")
 
 
+@pytest.mark.parametrize("short_ts", [False, True])
+def test_marching_schedule_options_do_not_change_results(eng, oracle, short_ts):
+    """Marching lanes (mode 3) and the dataflow + marching hybrid (mode 4): any lanes-per-warp packing, any split level,
+    a 2-CTA grid (units far outnumber the resident warps, so later units start long after their upstream units
+    finished) -- same bits as the oracle."""
+    from troute_b200 import synth
+    case = H.make_case(synth.conus_like(n_total=25000, n_basins=40, seed=8), nsteps=30, n_lp=12, warm=True)
+    ref, upref, _ = H.oracle_route(oracle, case, short_ts)
+    trials = [dict(mode=3, march_group=1), dict(mode=3, march_group=5), dict(mode=3, march_group=32),
+              dict(mode=3, march_group=32, grid_blocks=2), dict(mode=4, deep_level=0), dict(mode=4, deep_level=3),
+              dict(mode=4, deep_level=40, march_group=4), dict(mode=4, deep_level=100000),
+              dict(mode=4, deep_lanes=500, march_group=2), dict(mode=4, deep_lanes=0)]
+    for opts in trials:
+        out, up, _ = H.engine_route(case, short_ts, options=opts)
+        H.assert_bit_equal(out, ref, f"{opts}")
+        H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], f"{opts} reservoir inflow")
+
+
 def test_gate_and_grid_options_do_not_change_results(eng, oracle):
     """Dataflow schedule knobs: run-ahead gate 1 / 50, tiny grid (2 CTAs) -- same bits."""
     from troute_b200 import synth
@@ -271,7 +292,7 @@ def test_gate_and_grid_options_do_not_change_results(eng, oracle):
     for gate, grid in ((1, 0), (50, 0), (3, 2)):
         net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
         net.set_levelpools(case["lp_rows"], case["wbody"])
-        net.set_option("gate", gate); net.set_option("grid_blocks", grid)
+        net.set_option("mode", 2); net.set_option("gate", gate); net.set_option("grid_blocks", grid)
         out, _ = net.route(30, 12, case["qlat"], case["q0"])
         net.close()
         H.assert_bit_equal(out, ref, f"gate={gate} grid={grid}")
