@@ -358,7 +358,9 @@ def run_ours(args, rank, world, local_rank):
                                     2: "dataflow wavefront (ordered unit queue, lanes poll their inputs)",
                                     3: "marching lanes (one lane per segment, all timesteps)",
                                     4: "dataflow wavefront over the wide shallow levels, marching lanes over the deep "
-                                       "levels"}[args.mode],
+                                       "levels",
+                                    5: "time-blocked marching lanes over the wide shallow levels (stage = level + "
+                                       "block), marching lanes over the deep levels, one persistent kernel"}[args.mode],
                        "l2": "inputs larger than L2 (38 GB working set), no flush", "sharding": stats["sharding"]},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         }

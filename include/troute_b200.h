@@ -162,8 +162,10 @@ int trt_prepare(trt_network* net);
  *                     flow slots of its upstream neighbours,
  *                 4 = (default) mode 2 for the wide shallow levels, then mode 3 for the deep levels
  *   "deep_level"  mode 4: first level that marches; -1 (default) = as many of the deepest levels as hold at most
- *                 "deep_lanes" segments (default 32768)
- *   "march_group" segments per marching warp, 1..32 (default 8): fewer = shorter dependency-chain latency, more =
+ *                 "deep_lanes" segments (default 8192).  Shards of one network must use the SAME
+ *                 deep_level (set it explicitly): a dataflow kernel must never wait for a value that another shard
+ *                 produces only in its marching kernel
+ *   "march_group" segments per marching warp, 1..32 (default 4): fewer = shorter dependency-chain latency, more =
  *                 more segments resident at once
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)

@@ -87,6 +87,17 @@ TRT_HD double trt_dadd(double a, double b) {
 
 /* tl: TRT_LOG2_TAB_N {invc, logc} pairs; te: TRT_EXP2_TAB_N entries; both as binary64 bit patterns */
 
+/* Polynomial coefficients.  Device code may define TRT_DEVICE_COEF as the name of a `__constant__ double[13]` holding
+ * {A1..A7, B1..B6}: a DFMA then takes the coefficient straight from the constant bank instead of building the 64-bit
+ * immediate with two moves per use (174 of the ~2050 instructions per segment-timestep were such moves). */
+#if defined(__CUDA_ARCH__) && defined(TRT_DEVICE_COEF)
+#define TRT_LOG2_A(i) (TRT_DEVICE_COEF[(i) - 1])
+#define TRT_EXP2_B(i) (TRT_DEVICE_COEF[6 + (i)])
+#else
+#define TRT_LOG2_A(i) trt_u2d(TRT_LOG2_A##i##_BITS)
+#define TRT_EXP2_B(i) trt_u2d(TRT_EXP2_B##i##_BITS)
+#endif
+
 /* log2(x) in binary64 for finite x > 0 */
 TRT_HD double trt_log2_pos(float x, const trt_u64* tl) {
     const trt_u64 ix  = trt_d2u((double)x);
@@ -103,22 +114,30 @@ TRT_HD double trt_log2_pos(float x, const trt_u64* tl) {
     const double logc = trt_u2d(tl[2 * i + 1]);
 #endif
     const double r    = trt_dfma(z, invc, -1.0);                   /* exact */
-    double p = trt_u2d(TRT_LOG2_A7_BITS);
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A6_BITS));
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A5_BITS));
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A4_BITS));
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A3_BITS));
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A2_BITS));
-    p = trt_dfma(p, r, trt_u2d(TRT_LOG2_A1_BITS));
+    double p = TRT_LOG2_A(7);
+    p = trt_dfma(p, r, TRT_LOG2_A(6));
+    p = trt_dfma(p, r, TRT_LOG2_A(5));
+    p = trt_dfma(p, r, TRT_LOG2_A(4));
+    p = trt_dfma(p, r, TRT_LOG2_A(3));
+    p = trt_dfma(p, r, TRT_LOG2_A(2));
+    p = trt_dfma(p, r, TRT_LOG2_A(1));
     const double l     = trt_dadd((double)k, logc);
     return trt_dfma(p, r, l);
 }
 
 /* (float) 2^(y * log2x) with one final rounding */
 TRT_HD float trt_exp2_scaled(double log2x, float y, const trt_u64* te) {
-    const double t = trt_dmul((double)y, log2x);
-    if (t >= 130.0) return trt_u2d(0x7ff0000000000000ULL);         /* overflows binary32 */
-    if (t <= -160.0) return 0.0f;                                  /* below half the least subnormal */
+    double t = trt_dmul((double)y, log2x);
+    /* 2^t overflows binary32 for t >= 128 and rounds to +0 for t <= -150.  Clamping t to [-200, 200] keeps the exponent
+     * arithmetic below in range and lets the final binary64 -> binary32 conversion produce +inf / +0 by itself: no
+     * branches (a branch here is two per power in the device code), same results as returning those values early. */
+#ifdef TRT_POW_BRANCHY
+    if (t >= 130.0) return trt_u2d(0x7ff0000000000000ULL);
+    if (t <= -160.0) return 0.0f;
+#else
+    t = t > 200.0 ? 200.0 : t;
+    t = t < -200.0 ? -200.0 : t;
+#endif
     const double SH = 6755399441055744.0;                          /* 1.5 * 2^52 */
     const double u  = trt_dmul(t, 32.0);                           /* exact */
     double kd       = trt_dadd(u, SH);                             /* round to nearest integer */
@@ -128,20 +147,21 @@ TRT_HD float trt_exp2_scaled(double log2x, float y, const trt_u64* te) {
     const int n     = (int)(unsigned int)ki;                       /* low 32 bits: two's complement n */
     const int j     = n & (TRT_EXP2_TAB_N - 1);
     const int q     = n >> 5;                                      /* arithmetic shift */
-    double e = trt_u2d(TRT_EXP2_B6_BITS);
-    e = trt_dfma(e, g, trt_u2d(TRT_EXP2_B5_BITS));
-    e = trt_dfma(e, g, trt_u2d(TRT_EXP2_B4_BITS));
-    e = trt_dfma(e, g, trt_u2d(TRT_EXP2_B3_BITS));
-    e = trt_dfma(e, g, trt_u2d(TRT_EXP2_B2_BITS));
-    e = trt_dfma(e, g, trt_u2d(TRT_EXP2_B1_BITS));
+    double e = TRT_EXP2_B(6);
+    e = trt_dfma(e, g, TRT_EXP2_B(5));
+    e = trt_dfma(e, g, TRT_EXP2_B(4));
+    e = trt_dfma(e, g, TRT_EXP2_B(3));
+    e = trt_dfma(e, g, TRT_EXP2_B(2));
+    e = trt_dfma(e, g, TRT_EXP2_B(1));
     const double w  = trt_dmul(e, g);                              /* 2^g - 1 */
     const double s  = trt_u2d(te[j]);
     const double m  = trt_dfma(s, w, s);                           /* 2^(j/32 + g) in [1, 2) */
-    const double sc = trt_u2d((trt_u64)(long long)(q + 1023) << 52); /* 2^q, q in [-161, 130] */
+    const double sc = trt_u2d((trt_u64)(long long)(q + 1023) << 52); /* 2^q, q in [-201, 200] */
     return (float)trt_dmul(m, sc);                                 /* single rounding to binary32 */
 }
 
-/* result for the arguments that never reach the logarithm (x <= 0, NaN, +inf); *special = 0 otherwise */
+/* Arguments that never reach the logarithm (x <= 0, NaN, +inf) are replaced by 1.0 for the evaluation and their result
+ * is selected afterwards: straight-line code, no divergence between the lanes of a warp. */
 TRT_HD float trt_pow_special(float x, int* special) {
     *special = 1;
     if (!(x > 0.0f)) {                       /* x <= 0 or NaN */
@@ -156,8 +176,11 @@ TRT_HD float trt_pow_special(float x, int* special) {
 TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te) {
     int special;
     const float r = trt_pow_special(x, &special);
+#ifdef TRT_POW_BRANCHY
     if (special) return r;
-    return trt_exp2_scaled(trt_log2_pos(x, tl), y, te);
+#endif
+    const float v = trt_exp2_scaled(trt_log2_pos(special ? 1.0f : x, tl), y, te);
+    return special ? r : v;
 }
 
 /* x**y1 and x**y2 from ONE logarithm: bit-identical to two trt_powf_det calls (both are pure functions of the same
@@ -165,10 +188,14 @@ TRT_HD float trt_powf_det(float x, float y, const trt_u64* tl, const trt_u64* te
 TRT_HD void trt_powf_det2(float x, float y1, float y2, float* o1, float* o2, const trt_u64* tl, const trt_u64* te) {
     int special;
     const float r = trt_pow_special(x, &special);
+#ifdef TRT_POW_BRANCHY
     if (special) { *o1 = r; *o2 = r; return; }
-    const double l = trt_log2_pos(x, tl);
-    *o1 = trt_exp2_scaled(l, y1, te);
-    *o2 = trt_exp2_scaled(l, y2, te);
+#endif
+    const double l = trt_log2_pos(special ? 1.0f : x, tl);
+    const float v1 = trt_exp2_scaled(l, y1, te);
+    const float v2 = trt_exp2_scaled(l, y2, te);
+    *o1 = special ? r : v1;
+    *o2 = special ? r : v2;
 }
 
 #endif /* TRT_DETMATH_H */

@@ -104,10 +104,13 @@ struct trt_network {
     // marching schedule (mode 3: every level; mode 4: levels >= deep_level_used after the dataflow kernel)
     DevBuf<int> d_march_start;
     DevBuf<unsigned char> d_march_cnt;
-    int march_group = 8;                                      // positions per marching warp (1..32)
+    int march_group = 4;                                      // positions per marching warp (1..32)
     int deep_level = -1;                                      // mode 4: first marching level (-1 = from deep_lanes)
-    int64_t deep_lanes = 32768;                               // mode 4 auto: march as many of the deepest levels as fit
+    int64_t deep_lanes = 8192;                                // mode 4 auto: march as many of the deepest levels as fit
     int march_sched_first = -1, march_sched_group = -1, march_units = 0;
+    int time_block = 8;                                       // mode 5: timesteps per wide unit
+    DevBuf<int> d_wide_unit_ptr;
+    int wide_sched_T = -1, wide_sched_lw = -1, wide_sched_tb = -1, wide_units = 0, wide_stages = 0, wide_blocks = 0;
     bool march_profile = false;
     int poll_mode = 0, poll_sleep = -1;
     DevBuf<unsigned long long> d_march_prof;                  // [n][4] + 1
@@ -504,7 +507,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             // levels [0, Lw) go through the dataflow wavefront, levels [Lw, nlevels) march
             int Lw = net->nlevels;
             if (net->mode == 3) Lw = 0;
-            else if (net->mode == 4) {
+            else if (net->mode >= 4) {
                 if (net->deep_level >= 0) Lw = std::min(net->deep_level, net->nlevels);
                 else {
                     Lw = net->nlevels;
@@ -513,10 +516,30 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             }
             net->deep_level_used = Lw;
             const int pos_deep = net->lvl_ptr[(size_t)Lw];
-            const int Lk = assume_short_ts ? (Lw > 0 ? 1 : 0) : Lw;   // levels the stage index runs over
+            const bool unified = net->mode == 5;                      // wide units go through the marching kernel too
+            const int Lk = unified ? 0 : (assume_short_ts ? (Lw > 0 ? 1 : 0) : Lw);   // levels the stage index runs over
             // (re)build the unit table of this (T, schedule) pair
             const int nstages = Lk > 0 ? Lk + T - 1 : 0;
-            net->stages = nstages + (pos_deep < net->n ? T : 0);
+            if (unified && Lw > 0 &&
+                (net->wide_sched_T != T || net->wide_sched_lw != Lw || net->wide_sched_tb != net->time_block)) {
+                // wide units: stage K = level + block, 32 positions x time_block steps each
+                const int Tb = net->time_block, B = (T + Tb - 1) / Tb, ns = Lw + B - 1;
+                std::vector<int32_t> ptr((size_t)ns + 1, 0);
+                int64_t units = 0;
+                for (int K = 0; K < ns; ++K) {
+                    const int64_t lo = net->lvl_ptr[(size_t)std::max(0, K - B + 1)];
+                    const int64_t hi = net->lvl_ptr[(size_t)std::min(Lw, K + 1)];
+                    units += (hi - lo + 31) >> 5;
+                    if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
+                    ptr[(size_t)K + 1] = (int32_t)units;
+                }
+                CU(net->d_wide_unit_ptr.reserve((size_t)ns + 1));
+                CU(cudaMemcpy(net->d_wide_unit_ptr.p, ptr.data(), ((size_t)ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+                net->wide_units = (int)units; net->wide_stages = ns; net->wide_blocks = B;
+                net->wide_sched_T = T; net->wide_sched_lw = Lw; net->wide_sched_tb = Tb;
+            }
+            net->stages = (unified && Lw > 0 ? Lw + (T + net->time_block - 1) / net->time_block - 1 : nstages) +
+                          (pos_deep < net->n ? T : 0);
             if (nstages > 0 && (net->sched_T != T || net->sched_short != (assume_short_ts ? 1 : 0) ||
                                 net->sched_gate != net->gate || net->sched_nstages != nstages ||
                                 net->sched_lw != Lw)) {
@@ -616,9 +639,15 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 CU(launch_dataflow(nd, rd, sd, pd, grid, st));
                 net->launches++;
             }
-            if (pos_deep < net->n) {
+            if (pos_deep < net->n || (unified && Lw > 0)) {
                 MarchDev md;
-                md.n_units = net->march_units; md.unit_start = net->d_march_start.p; md.unit_cnt = net->d_march_cnt.p;
+                md.n_wide_units = 0; md.wide_levels = 0; md.nblocks = 1; md.Tb = T; md.nstages = 0; md.wide_unit_ptr = nullptr;
+                if (unified && Lw > 0) {
+                    md.n_wide_units = net->wide_units; md.wide_levels = Lw; md.nblocks = net->wide_blocks;
+                    md.Tb = net->time_block; md.nstages = net->wide_stages; md.wide_unit_ptr = net->d_wide_unit_ptr.p;
+                }
+                md.n_units = pos_deep < net->n ? net->march_units : 0;
+                md.unit_start = net->d_march_start.p; md.unit_cnt = net->d_march_cnt.p;
                 md.claim = (unsigned int*)net->d_ctrl.p + 4; md.abort_flag = net->d_ctrl.p + 2;
                 md.prof = nullptr; md.t_start = nullptr; md.poll_mode = net->poll_mode; md.poll_sleep = net->poll_sleep;
                 if (net->march_profile) {
@@ -633,7 +662,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 CU(march_max_grid(&mgrid));
                 if (mgrid <= 0) return fail(TRT_ERR_CUDA, "marching kernel cannot be made resident");
                 if (net->grid_blocks > 0) mgrid = std::min(mgrid, net->grid_blocks);
-                mgrid = std::min<int64_t>(mgrid, (net->march_units + 7) / 8);
+                mgrid = (int)std::min<int64_t>(mgrid, ((int64_t)md.n_units + md.n_wide_units + 7) / 8);
                 CU(launch_march(nd, rd, md, pd, mgrid, st));
                 net->launches++;
             }
@@ -922,9 +951,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
 {
     if (!net || !key) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "mode")) {
-        if (value < 0 || value > 4)
+        if (value < 0 || value > 5)
             return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches), 1 (persistent, grid.sync), 2 (dataflow), "
-                                         "3 (marching) or 4 (dataflow + marching)");
+                                         "3 (marching), 4 (dataflow + marching) or 5 (time-blocked + marching)");
         net->mode = (int)value;
     } else if (!strcmp(key, "grid_blocks")) {
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
@@ -943,6 +972,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
+    } else if (!strcmp(key, "time_block")) {
+        if (value < 1 || value > 100000) return fail(TRT_ERR_INVALID, "time_block must be >= 1");
+        net->time_block = (int)value;
     } else if (!strcmp(key, "march_group")) {
         if (value < 1 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 1..32");
         net->march_group = (int)value;

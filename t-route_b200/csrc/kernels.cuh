@@ -83,8 +83,23 @@ struct PeerDev {
 
 // Marching schedule (mode 3, and the deep levels of mode 4): units of <= 32 consecutive positions, claimed in position
 // order; every lane walks its segment through all T timesteps, waiting on the q slots of its upstream neighbours.
+//
+// Mode 5 puts the wide shallow levels through the same lanes, in pieces: a wide unit is 32 consecutive positions x one
+// BLOCK of Tb consecutive timesteps, and units are handed out in order of stage K = level + block index, the wavefront of
+// mode 2 with blocks in place of steps.  Everything a unit reads was produced by a unit of a lower stage (upstream
+// segments: lower level, same block; its own previous block), i.e. by a unit claimed earlier.  Compared with one step
+// per unit the channel geometry is loaded and pre-processed once per Tb steps, flow and depth of the previous step stay
+// in registers, the previous upstream sum is reused as qup, and the lanes of a warp drift apart in time so that a lane
+// needing 5 secant trips does not hold up 31 lanes that needed 2.  The wide units come first in the queue, the deep
+// marching units (all T steps) after them: the deep lanes start while the last wide stages drain.
 struct MarchDev {
-    int n_units;
+    int n_wide_units;                 // units [0, n_wide_units) are wide units
+    int wide_levels;                  // levels [0, wide_levels) are routed by wide units
+    int nblocks;                      // time blocks per segment = ceil(T / Tb)
+    int Tb;                           // timesteps per block
+    int nstages;                      // wide stages K = 0 .. nstages - 1 = wide_levels + nblocks - 1
+    const int* wide_unit_ptr;         // [nstages + 1] first unit of stage K
+    int n_units;                      // deep units follow: unit n_wide_units + i is deep unit i
     const int* unit_start;            // [n_units] first position of the unit
     const unsigned char* unit_cnt;    // [n_units] lanes in use (1..32)
     unsigned int* claim;              // [1] next unit to hand out

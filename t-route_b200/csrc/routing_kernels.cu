@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
 // ---------------------------------------------------------------------------------------------------------
 // dataflow schedule (see kernels.cuh): persistent warps claim units in stage order, lanes wait on their own inputs
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
+__global__ void __launch_bounds__(kBlock, 4) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
 {
     __shared__ SmemTabs smem;
     const PowTabs tabs = stage_tables(smem);
@@ -321,15 +321,39 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
     const int T = run.T;
     const size_t T1 = (size_t)T + 1;
     if (mk.prof && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(mk.t_start, globaltimer_ns());
+    int cursor = 0;                               // stage of this warp's previous wide unit
     for (;;) {
         unsigned u = 0;
         if (lane == 0) u = atomicAdd(mk.claim, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= (unsigned)mk.n_units) break;
-        const int p = __ldg(mk.unit_start + u) + lane;
+        if (u >= (unsigned)(mk.n_wide_units + mk.n_units)) break;
+        int p, t_first = 1, t_last = T;
+        bool mine;
+        if (u < (unsigned)mk.n_wide_units) {
+            // stage of wide unit u: last K >= cursor with wide_unit_ptr[K] <= u
+            int lo_i = cursor, hi_i = mk.nstages;
+            while (hi_i - lo_i > 1) {
+                const int mid = (lo_i + hi_i) >> 1;
+                if ((unsigned)__ldg(mk.wide_unit_ptr + mid) <= u) lo_i = mid; else hi_i = mid;
+            }
+            cursor = lo_i;
+            const int K = lo_i;
+            const int lo = __ldg(net.lvl_ptr + max(0, K - mk.nblocks + 1));
+            const int hi = __ldg(net.lvl_ptr + min(mk.wide_levels, K + 1));
+            p = lo + (int)((u - (unsigned)__ldg(mk.wide_unit_ptr + K)) << 5) + lane;
+            mine = p < hi;
+            if (mine) {
+                const int b = K - __ldg(net.level + p);           // 0 <= b < nblocks by construction of [lo, hi)
+                t_first = b * mk.Tb + 1;
+                t_last = min(T, t_first + mk.Tb - 1);
+            }
+        } else {
+            const unsigned v = u - (unsigned)mk.n_wide_units;
+            p = __ldg(mk.unit_start + v) + lane;
+            mine = lane < (int)__ldg(mk.unit_cnt + v);
+        }
         unsigned long long prof_first = 0, prof_wait = 0, prof_fail = 0;
         long long wait_since = 0;
-        const bool mine = lane < (int)__ldg(mk.unit_cnt + u);
 
         int state = MARCH_DONE;
         unsigned kflags = 0, kind = TRT_KIND_BOUNDARY;
@@ -349,18 +373,23 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
         const bool is_lp = kind == TRT_KIND_LEVELPOOL;
         const McChannel c = mc_channel(p0, p1, p2, p3, p4, p5, p6, p7, p8);
         McSolve s;
-        int t = 1;
+        int t = t_first;
         float qdp = 0.f, statep = 0.f, upsum_prev = 0.f, ql = 0.f;
         int ql_left = 0;
         unsigned waited = 0;
         int e_cur = e0;                           // next upstream slot to read for the current step
         float psum = 0.0f;                        // flows of the slots before e_cur, summed in order
         if (state == MARCH_WAIT) {
-            qdp = __ldcg(row);                    // t = 0: initial state (init_state_kernel / init_levelpool_kernel)
-            statep = __ldcg(row + 2);
-            for (int e = e0; e < e1; ++e)         // previous_upstream_flows of step 1  (mc_reach.pyx:499-502)
-                upsum_prev += __ldcg(run.S + (size_t)__ldg(net.up_idx + e) * T1 * 3);
-            if (T < 1) state = MARCH_DONE;
+            // State at t_first - 1: the initial condition (t_first == 1; init_state_kernel / init_levelpool_kernel) or
+            // the last step of this segment's previous block, written by a unit of the previous stage.  That unit and
+            // the units of the upstream segments were claimed before this one, so waiting here cannot deadlock.
+            const float* prev = row + (size_t)(t_first - 1) * 3;
+            qdp = ld_state<true>(prev, mk.abort_flag);
+            statep = ld_state<true>(prev + 2, mk.abort_flag);
+            for (int e = e0; e < e1; ++e)         // previous_upstream_flows of step t_first  (mc_reach.pyx:499-502)
+                upsum_prev += ld_state<true>(run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)(t_first - 1)) * 3,
+                                             mk.abort_flag);
+            if (t_last < t_first) state = MARCH_DONE;
         }
 
         for (;;) {
@@ -410,11 +439,12 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     state = MARCH_ITER;
                     if (!is_lp && !s.flow) {                                         // :171-178
                         float* own = row + (size_t)t * 3;
-                        own[1] = 0.0f; own[2] = 0.0f;
+                        own[1] = 0.0f;
+                        st_state<true>(own + 2, 0.0f);
                         publish_flow(own, 0.0f, kflags, p, t, T1, peers);
                         qdp = 0.0f; statep = 0.0f;
                         ++t;
-                        state = t > T ? MARCH_DONE : MARCH_WAIT;
+                        state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                     }
                 } else if ((++waited & 0xFFF) == 0) {
                     // every 4096 failed polls: somebody flagged an error, or this lane has been starving for seconds
@@ -434,15 +464,15 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     trt_levelpool_step(lp, s.quc, 0.0f, p0, H, outflow, tabs);
                     publish_flow(own, outflow, kflags, p, t, T1, peers);
                     own[1] = s.quc;             // reservoir inflow rides in the velocity slot (upstream_array, :710)
-                    own[2] = H;
+                    st_state<true>(own + 2, H);
                     qdp = outflow; statep = H;
                     ++t;
-                    state = t > T ? MARCH_DONE : MARCH_WAIT;
+                    state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                 } else if (mc_iterate(c, s, tabs)) {
                     const float q = mc_outflow(s);
                     publish_flow(own, q, kflags, p, t, T1, peers);   // downstream lanes are waiting for this
                     if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
-                    own[2] = s.h;                                    // own[1] (velocity): result pass, from this depth
+                    st_state<true>(own + 2, s.h);                    // own[1] (velocity): result pass, from this depth
                     if ((t & 1) == 0) {
                         // cold tributary rows (finished long ago, evicted from L2): pull the sectors of the coming steps
                         // in, off the critical path.  One 32-byte sector holds 2.67 steps of (q, v, d).
@@ -453,13 +483,13 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     qdp = q; statep = s.h;
                     if (mk.prof && t == 1) prof_first = globaltimer_ns();
                     ++t;
-                    state = t > T ? MARCH_DONE : MARCH_WAIT;
+                    state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                 }
             }
             const unsigned iterating = __ballot_sync(0xffffffffu, state == MARCH_ITER);
             if (iterating == 0) {
                 if (__all_sync(0xffffffffu, state == MARCH_DONE)) {
-                    if (mk.prof && mine) {
+                    if (mk.prof && mine && u >= (unsigned)mk.n_wide_units) {
                         const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(mk.t_start);
                         unsigned long long* o = mk.prof + (size_t)p * 4;
                         o[0] = prof_first ? prof_first - t0 : 0; o[1] = globaltimer_ns() - t0; o[2] = prof_wait; o[3] = prof_fail;
@@ -567,7 +597,12 @@ __global__ void init_state_kernel(const float* __restrict__ q0, const int* __res
     if (pos >= n) return;
     const float* src = q0 + (size_t)row_of_pos[pos] * 3;
     float* dst = S + (size_t)pos * T1 * 3;
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    // a NaN whose bits happen to equal TRT_SENTINEL would read as "not yet written": canonicalise it
+    for (int c = 0; c < 3; ++c) {
+        unsigned b = __float_as_uint(src[c]);
+        if (b == TRT_SENTINEL) b = 0x7FC00000u;
+        dst[c] = __uint_as_float(b);
+    }
 }
 
 // reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth slot

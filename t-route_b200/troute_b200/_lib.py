@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtroute_b200.so")
+LIB_PATH = os.environ.get("TROUTE_B200_LIB") or os.path.join(_HERE, "lib", "libtroute_b200.so")
 
 TRT_KIND_MC = 0
 TRT_KIND_LEVELPOOL = 1

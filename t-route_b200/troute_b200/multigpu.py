@@ -11,11 +11,22 @@ import numpy as np
 from .network import RoutingNetwork
 
 
+def global_deep_level(level, shard, n_shards, deep_lanes):
+    """Smallest level L such that no shard holds more than `deep_lanes` segments of level >= L."""
+    L = 0
+    for r in range(n_shards):
+        lv = np.sort(level[shard == r])[::-1]
+        if lv.size > deep_lanes:
+            L = max(L, int(lv[deep_lanes]) + 1)
+    return L
+
+
 class SingleRouter:
     kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel",
-                    3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel"}
+                    3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel",
+                    5: "trt::march_kernel"}
 
-    def __init__(self, wl, device, nsteps, qts, short_ts, mode=2):
+    def __init__(self, wl, device, nsteps, qts, short_ts, mode=4):
         import torch
         self.torch = torch
         self.wl = wl
@@ -75,11 +86,11 @@ class ShardedRouter:
     and for the barrier between resetting the flow state and launching."""
     kernel_names = SingleRouter.kernel_names
 
-    def __init__(self, wl, world, rank, device, nsteps, qts, short_ts, mode=2, pieces_per_shard=16):
+    def __init__(self, wl, world, rank, device, nsteps, qts, short_ts, mode=4, pieces_per_shard=16, deep_lanes=8192):
         import torch
         import torch.distributed as dist
         from . import hostgraph, partition
-        if mode not in (2, 3, 4):
+        if mode not in (2, 3, 4, 5):
             raise ValueError("sharded routing needs a polling schedule (mode 2, 3 or 4)")
         self.torch, self.dist = torch, dist
         self.wl, self.world, self.rank, self.device = wl, world, rank, device
@@ -93,6 +104,11 @@ class ShardedRouter:
         self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
                                   device=device, levels=plan.levels)
         self.net.set_option("mode", mode)
+        if mode >= 4:
+            # one split level for ALL shards: a dataflow (wide) kernel may wait only for values that other shards produce
+            # in THEIR dataflow kernels; the deepest levels (at most deep_lanes segments on any shard) march
+            self.deep_level = global_deep_level(level, self.shard, world, deep_lanes)
+            self.net.set_option("deep_level", self.deep_level)
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
         self.net.set_option("stream", self.tstream.cuda_stream)

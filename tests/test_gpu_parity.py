@@ -129,7 +129,7 @@ def _networks():
 
 @pytest.mark.parametrize("name", ["tree4095", "chain300", "single", "hack20k_lp", "forest"])
 @pytest.mark.parametrize("short_ts", [False, True])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_network_bits(eng, oracle, name, short_ts, mode):
     down, n_lp = _networks()[name]
     case = H.make_case(down, nsteps=36, n_lp=n_lp, warm=(name != "forest"))
@@ -245,7 +245,7 @@ def test_full_size_config2_properties(eng, oracle):
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
     del b
     assert np.isfinite(a).all() and st["stages"] == 20 + T
-    for m in (3, 4):
+    for m in (3, 4, 5):
         b, _, _ = H.engine_route(case, False, mode=m, want_upstream=False)
         assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"mode {m}"
     root = 300                                            # heap index; its subtree has 2^12 - 1 nodes at N = 2^20
@@ -276,7 +276,10 @@ def test_marching_schedule_options_do_not_change_results(eng, oracle, short_ts):
     trials = [dict(mode=3, march_group=1), dict(mode=3, march_group=5), dict(mode=3, march_group=32),
               dict(mode=3, march_group=32, grid_blocks=2), dict(mode=4, deep_level=0), dict(mode=4, deep_level=3),
               dict(mode=4, deep_level=40, march_group=4), dict(mode=4, deep_level=100000),
-              dict(mode=4, deep_lanes=500, march_group=2), dict(mode=4, deep_lanes=0)]
+              dict(mode=4, deep_lanes=500, march_group=2), dict(mode=4, deep_lanes=0),
+              dict(mode=5, deep_lanes=0, time_block=1), dict(mode=5, deep_lanes=0, time_block=7),
+              dict(mode=5, deep_lanes=2000, time_block=8, march_group=4), dict(mode=5, deep_level=5, time_block=30),
+              dict(mode=5, deep_level=3, time_block=1000, march_group=32), dict(mode=5, deep_lanes=0, time_block=4, grid_blocks=2)]
     for opts in trials:
         out, up, _ = H.engine_route(case, short_ts, options=opts)
         H.assert_bit_equal(out, ref, f"{opts}")
@@ -300,7 +303,8 @@ def test_gate_and_grid_options_do_not_change_results(eng, oracle):
 
 @pytest.mark.parametrize("P", [2, 3])
 @pytest.mark.parametrize("short_ts", [False, True])
-def test_sharded_on_one_gpu_concurrent_kernels(eng, oracle, P, short_ts):
+@pytest.mark.parametrize("split", ["all-march", "dataflow+march", "dataflow"])
+def test_sharded_on_one_gpu_concurrent_kernels(eng, oracle, P, short_ts, split):
     """The sharding path without a second GPU: P shard handles on the SAME device, wired through each other's flow
     arrays exactly as peers are wired through CUDA IPC, their kernels running concurrently on P streams with a
     quarter-size grid each.  Results of all shards together == the unsharded oracle, bit for bit."""
@@ -320,6 +324,12 @@ def test_sharded_on_one_gpu_concurrent_kernels(eng, oracle, P, short_ts):
         loc_lp = np.nonzero(p.kind == 1)[0]
         net.set_levelpools(loc_lp, case["wbody"][[lp_index[int(g)] for g in p.rows[loc_lp]]] if loc_lp.size else np.zeros((0, 11)))
         net.set_option("grid_blocks", 74)
+        if split == "dataflow+march":
+            # every shard splits at the same level (multigpu.global_deep_level): the deepest <= 1500 segments of any shard march
+            from troute_b200 import multigpu
+            net.set_option("deep_level", multigpu.global_deep_level(level, shard, P, 1500))
+        elif split == "dataflow":
+            net.set_option("mode", 2)
         net.set_imports(p.imports)
         net.upload(30, 12, case["qlat"][p.rows], case["q0"][p.rows])
         nets.append(net)

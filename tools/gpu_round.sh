@@ -19,7 +19,7 @@ fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> gpurun_out/box.txt
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:dataflow_kernel -s 1 -c 1 -f -o gpurun_out/prof_wavefront \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dataflow_kernel|march_kernel" -s 2 -c 2 -f -o gpurun_out/prof_wavefront \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?" >> gpurun_out/box.txt
 fi
 tail -5 gpurun_out/box.txt
