@@ -91,6 +91,24 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
                                float routing_period);
 
 /*
+ * Streamflow nudging at gages (simple_da.pyx:21-128; set-up mc_reach.pyx:380-411, call site :761-796).
+ *   gage_rows    [n_gages] row of every gage segment (usgs_positions)
+ *   active       [n_gages] 1 = this gage is the one its reach assimilates (reach_has_gage, :398: the last gage listed
+ *                for a reach wins); inactive gages only seed the initial flow with their first observation (:403-411)
+ *   usgs_values  [n_gages, gage_maxtimestep] observations per routing step, NaN = missing
+ *   lastobs_values_init / time_since_lastobs_init  [n_gages] last observation before the call (NaN = none)
+ *   routing_period  the `dt` argument of compute_network_structured
+ * An active gage must be the LAST segment of its reach -- T-Route's network builder breaks reaches at gages
+ * (nhd_network.py:295-359); the caller checks.  n_gages = 0 switches nudging off.  State is reset at every trt_run.
+ * trt_download_gages: nudge [n_gages, nsteps + 1] (column 0 unused, as in the reference), final last-observation
+ * (time, value) per gage.
+ */
+int trt_network_set_gages(trt_network* net, int64_t n_gages, const int64_t* gage_rows, const uint8_t* active,
+                          const float* usgs_values, int32_t gage_maxtimestep, const float* lastobs_values_init,
+                          const float* time_since_lastobs_init, float da_decay_coefficient, float routing_period);
+int trt_download_gages(trt_network* net, float* nudge, float* lastobs_times, float* lastobs_values);
+
+/*
  * One routing call = upload, run, download.  Shapes follow compute_network_structured:
  *   qlat       [n_rows, nqcols] float32, nqcols >= nsteps/qts_subdivisions   (mc_reach.pyx:243-247)
  *   q0         [n_rows, 3] float32 (qu0, qd0, h0): column 0 seeds flow, column 2 seeds depth (:361)

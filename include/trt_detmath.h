@@ -198,4 +198,12 @@ TRT_HD void trt_powf_det2(float x, float y1, float y2, float* o1, float* o2, con
     *o2 = special ? r : v2;
 }
 
+/* (float) e^x for a binary64 x, as (float) 2^(x * log2 e) through the same exp2 core: the decay weight of streamflow
+ * nudging, exp(|minutes| / -a) (simple_da.pyx:120, a libm double `exp` in the reference).  Within 1 float ulp of a
+ * correctly rounded result, identical on CPU and GPU. */
+TRT_HD float trt_expf_det(double x, const trt_u64* te) {
+    const double log2e = trt_u2d(0x3ff71547652b82feULL);           /* 1.4426950408889634 */
+    return trt_exp2_scaled(trt_dmul(x, log2e), 1.0f, te);
+}
+
 #endif /* TRT_DETMATH_H */

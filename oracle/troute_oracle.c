@@ -165,13 +165,21 @@ void oracle_levelpool_series(int pow_mode, const double* wbody_row, long nsteps,
 }
 
 /* simple_da.pyx:109-128.  `exp` is libc double exp on float operands promoted to double. */
-static float obs_persist_shift(float last_valid_obs, float model_val, float minutes_since_last_valid, float decay_coeff)
+static float obs_persist_shift_mode(int pow_mode, float last_valid_obs, float model_val, float minutes_since_last_valid,
+                                    float decay_coeff)
 {
     float da_weight, da_shift, da_weighted_shift;
-    da_weight = (float)exp(fabs((double)minutes_since_last_valid) / -(double)decay_coeff);
+    const double arg = fabs((double)minutes_since_last_valid) / -(double)decay_coeff;
+    /* pow_mode 1: the bit-specified exponential the CUDA path uses (include/trt_detmath.h trt_expf_det) */
+    da_weight = pow_mode == 0 ? (float)exp(arg) : trt_expf_det(arg, g_te);
     da_shift = last_valid_obs - model_val;
     da_weighted_shift = da_shift * da_weight;
     return da_weighted_shift;
+}
+
+static float obs_persist_shift(float last_valid_obs, float model_val, float minutes_since_last_valid, float decay_coeff)
+{
+    return obs_persist_shift_mode(0, last_valid_obs, model_val, minutes_since_last_valid, decay_coeff);
 }
 
 /* simple_da.pyx:92-107 (python-visible wrapper simple_da_with_decay_py :4-19; KAT routing/test_compute.py:33-42) */
@@ -181,7 +189,7 @@ float oracle_simple_da_with_decay(float last_valid_obs, float model_val, float m
 }
 
 /* simple_da.pyx:21-89.  out4 = {replacement_val, nudge_val, lastobs_time, lastobs_val} */
-static void simple_da(float timestep, float routing_period, float decay_coeff, float gage_maxtimestep,
+static void simple_da(int pow_mode, float timestep, float routing_period, float decay_coeff, float gage_maxtimestep,
                       float target_val, float model_val, float lastobs_time, float lastobs_val, float* out4)
 {
     float replacement_val, nudge_val, da_weighted_shift, da_decay_minutes;
@@ -197,7 +205,7 @@ static void simple_da(float timestep, float routing_period, float decay_coeff, f
         lastobs_time = NAN;
     } else {
         da_decay_minutes = ((timestep)*routing_period - lastobs_time) / 60;
-        da_weighted_shift = obs_persist_shift(lastobs_val, model_val, da_decay_minutes, decay_coeff);
+        da_weighted_shift = obs_persist_shift_mode(pow_mode, lastobs_val, model_val, da_decay_minutes, decay_coeff);
         nudge_val = da_weighted_shift;
         replacement_val = model_val + da_weighted_shift;
     }
@@ -322,7 +330,7 @@ static void route_reach_step(const net_t* N, int64_t i, int timestep, float* buf
                            ? NAN
                            : N->usgs_values[(int64_t)gage_i * N->gage_maxtimestep + timestep];
         float da_buf[4];
-        simple_da((float)timestep, N->routing_period, N->da_decay_coefficient, (float)N->gage_maxtimestep, target,
+        simple_da(N->pow_mode, (float)timestep, N->routing_period, N->da_decay_coefficient, (float)N->gage_maxtimestep, target,
                   FVD(pos, timestep, 0), N->lastobs_times[gage_i], N->lastobs_values[gage_i], da_buf);
         FVD(pos, timestep, 0) = da_buf[0];
         N->nudge[(int64_t)gage_i * T1 + timestep] = da_buf[1];

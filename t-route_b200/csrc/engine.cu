@@ -131,6 +131,16 @@ struct trt_network {
     float* peer_q[TRT_MAX_PEERS] = {nullptr};
     long long peer_n[TRT_MAX_PEERS] = {0};
 
+    // streamflow nudging
+    int64_t n_gages = 0;
+    int gage_max = 0;
+    float gage_dt = 0.f, gage_decay = 0.f;
+    std::vector<uint8_t> gage_flag;                           // [n] position carries an active gage
+    std::vector<uint8_t> export_flag;                         // [n] position exports to a peer
+    DevBuf<int> d_gage_slot, d_gage_pos;
+    DevBuf<unsigned char> d_gage_active;
+    DevBuf<float> d_usgs, d_lastobs, d_lastobs_init, d_nudge;
+
     // options / stats
     int mode = 4;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow,
                                    // 3 marching lanes, 4 dataflow for the wide shallow levels + marching for the deep ones
@@ -149,6 +159,8 @@ struct trt_network {
     {
         RunDev r;
         r.T = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
+        r.gage.n_gages = (int)n_gages; r.gage.gmax = gage_max; r.gage.dt = gage_dt; r.gage.decay = gage_decay;
+        r.gage.slot = d_gage_slot.p; r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
         return r;
     }
 };
@@ -393,6 +405,91 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
     return TRT_OK;
 }
 
+// device kind = reach kind | export flag | gage flag
+static int upload_kind(trt_network* net)
+{
+    const int64_t n = net->n;
+    if (n == 0) return TRT_OK;
+    std::vector<unsigned char> h((size_t)n);
+    for (int64_t p = 0; p < n; ++p) {
+        unsigned char k = net->kind_of_row[(size_t)net->row_of_pos[(size_t)p]];
+        if (!net->export_flag.empty() && net->export_flag[(size_t)p]) k |= TRT_KIND_EXPORT_FLAG;
+        if (!net->gage_flag.empty() && net->gage_flag[(size_t)p]) k |= TRT_KIND_GAGE_FLAG;
+        h[(size_t)p] = k;
+    }
+    CU(cudaMemcpy(net->d_kind.p, h.data(), (size_t)n, cudaMemcpyHostToDevice));
+    return TRT_OK;
+}
+
+int trt_network_set_gages(trt_network* net, int64_t n_gages, const int64_t* gage_rows, const uint8_t* active,
+                          const float* usgs_values, int32_t gage_maxtimestep, const float* lastobs_values_init,
+                          const float* time_since_lastobs_init, float da_decay_coefficient, float routing_period)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (n_gages < 0 || gage_maxtimestep < 0) return fail(TRT_ERR_INVALID, "bad gage arguments");
+    if (n_gages > 0 && (!gage_rows || !active || !lastobs_values_init || !time_since_lastobs_init ||
+                        (gage_maxtimestep > 0 && !usgs_values)))
+        return fail(TRT_ERR_INVALID, "NULL gage array");
+    CU(cudaSetDevice(net->device));
+    const int64_t n = net->n;
+    net->gage_flag.assign((size_t)n, 0);
+    std::vector<int32_t> slot((size_t)std::max<int64_t>(n, 1), -1), pos((size_t)n_gages);
+    std::vector<float> init((size_t)n_gages * 2);
+    for (int64_t g = 0; g < n_gages; ++g) {
+        const int64_t r = gage_rows[g];
+        if (r < 0 || r >= n) return fail(TRT_ERR_INVALID, "gage row %lld out of range", (long long)r);
+        const int32_t p = net->pos_of_row[(size_t)r];
+        pos[(size_t)g] = p;
+        if (active[g]) {
+            if (net->kind_of_row[(size_t)r] == TRT_KIND_BOUNDARY)
+                return fail(TRT_ERR_INVALID, "gage row %lld is a prescribed (boundary) row", (long long)r);
+            if (slot[(size_t)p] >= 0) return fail(TRT_ERR_INVALID, "two active gages on row %lld", (long long)r);
+            slot[(size_t)p] = (int32_t)g;
+            net->gage_flag[(size_t)p] = 1;
+        }
+        init[(size_t)2 * g] = time_since_lastobs_init[g];         // lastobs_times[gage_i]  (mc_reach.pyx:397)
+        init[(size_t)2 * g + 1] = lastobs_values_init[g];         // lastobs_values[gage_i] (:396)
+    }
+    net->n_gages = n_gages; net->gage_max = gage_maxtimestep;
+    net->gage_decay = da_decay_coefficient; net->gage_dt = routing_period;
+    if (n_gages > 0) {
+        CU(net->d_gage_slot.reserve((size_t)n));
+        CU(net->d_gage_pos.reserve((size_t)n_gages));
+        CU(net->d_gage_active.reserve((size_t)n_gages));
+        CU(net->d_usgs.reserve((size_t)n_gages * (size_t)std::max(1, gage_maxtimestep)));
+        CU(net->d_lastobs.reserve((size_t)n_gages * 2));
+        CU(net->d_lastobs_init.reserve((size_t)n_gages * 2));
+        CU(cudaMemcpy(net->d_gage_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_gage_pos.p, pos.data(), (size_t)n_gages * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_gage_active.p, active, (size_t)n_gages, cudaMemcpyHostToDevice));
+        if (gage_maxtimestep > 0)
+            CU(cudaMemcpy(net->d_usgs.p, usgs_values, (size_t)n_gages * gage_maxtimestep * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_lastobs_init.p, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return upload_kind(net);
+}
+
+int trt_download_gages(trt_network* net, float* nudge, float* lastobs_times, float* lastobs_values)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_download_gages called before trt_run");
+    const int64_t G = net->n_gages;
+    if (G == 0) return TRT_OK;
+    CU(cudaSetDevice(net->device));
+    CU(cudaStreamSynchronize(net->stream));
+    if (nudge)
+        CU(cudaMemcpy(nudge, net->d_nudge.p, (size_t)G * (size_t)(net->T + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    if (lastobs_times || lastobs_values) {
+        std::vector<float> lo((size_t)G * 2);
+        CU(cudaMemcpy(lo.data(), net->d_lastobs.p, lo.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int64_t g = 0; g < G; ++g) {
+            if (lastobs_times) lastobs_times[g] = lo[(size_t)2 * g];
+            if (lastobs_values) lastobs_values[g] = lo[(size_t)2 * g + 1];
+        }
+    }
+    return TRT_OK;
+}
+
 int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, const float* q0,
                        int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd)
 {
@@ -490,6 +587,13 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run called before trt_upload_forcing");
     CU(cudaSetDevice(net->device));
     cudaStream_t st = net->stream;
+    if (net->n_gages > 0) {
+        // nudging state back to its initial values; the flow-state reset must come first (it rewrites t = 0)
+        CU(net->d_nudge.reserve((size_t)net->n_gages * (size_t)(net->T + 1)));
+        if (net->mode >= 2 && !net->prepared) { CU(prepare_dataflow(net)); net->prepared = true; }
+        RunDev rg = net->rundev(0);
+        CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
+    }
     const NetDev nd = net->netdev();
     const RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
     const int T = net->T;
@@ -875,8 +979,7 @@ int trt_network_set_exports(trt_network* net, int64_t count, const int64_t* rows
     const int64_t n = net->n;
     std::vector<int32_t> slot((size_t)std::max<int64_t>(n, 1), -1), h_peer((size_t)count);
     std::vector<long long> h_pos((size_t)count);
-    std::vector<unsigned char> h_kind((size_t)std::max<int64_t>(n, 1), 0);
-    for (int64_t p = 0; p < n; ++p) h_kind[(size_t)p] = net->kind_of_row[(size_t)net->row_of_pos[(size_t)p]];
+    net->export_flag.assign((size_t)n, 0);
     for (int64_t i = 0; i < count; ++i) {
         if (rows[i] < 0 || rows[i] >= n) return fail(TRT_ERR_INVALID, "export row %lld out of range", (long long)rows[i]);
         if (peer[i] < 0 || peer[i] >= TRT_MAX_PEERS) return fail(TRT_ERR_INVALID, "peer index %d out of range", peer[i]);
@@ -887,14 +990,15 @@ int trt_network_set_exports(trt_network* net, int64_t count, const int64_t* rows
         slot[(size_t)pos] = (int32_t)i;
         h_peer[(size_t)i] = peer[i];
         h_pos[(size_t)i] = peer_pos[i];
-        h_kind[(size_t)pos] |= TRT_KIND_EXPORT_FLAG;
+        net->export_flag[(size_t)pos] = 1;
     }
     CU(net->d_exp_slot.reserve((size_t)n));
     CU(net->d_exp_peer.reserve((size_t)count));
     CU(net->d_exp_pos.reserve((size_t)count));
     if (n > 0) {
         CU(cudaMemcpy(net->d_exp_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(net->d_kind.p, h_kind.data(), (size_t)n, cudaMemcpyHostToDevice));
+        const int rc = upload_kind(net);
+        if (rc != TRT_OK) return rc;
     }
     if (count > 0) {
         CU(cudaMemcpy(net->d_exp_peer.p, h_peer.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice));

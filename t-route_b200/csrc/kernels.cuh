@@ -37,7 +37,25 @@ struct NetDev {
     const int* row_of_pos;     // [n]
 };
 
+// Streamflow nudging (simple_da.pyx:21-128, call site mc_reach.pyx:761-796): the flow of a gage segment is replaced, right
+// after it is computed and before anybody downstream reads it, by the observation of that step or -- outside the
+// observation window -- by the model value pulled towards the last observation with an exponentially decaying weight.
+// State per gage: (time, value) of the last observation; written and read only by the lanes that route the gage segment,
+// in timestep order.
+#define TRT_KIND_GAGE_FLAG 0x20
+struct GageDev {
+    int n_gages;                 // 0: no nudging
+    int gmax;                    // observation columns per gage (gage_maxtimestep)
+    float dt;                    // routing period of the call
+    float decay;                 // da_decay_coefficient
+    const int* slot;             // [n] gage index of a position whose kind carries TRT_KIND_GAGE_FLAG
+    const float* usgs;           // [n_gages][gmax] observations (NaN = missing)
+    float* lastobs;              // [n_gages][2] (time, value)
+    float* nudge;                // [n_gages][T + 1]
+};
+
 struct RunDev {
+    GageDev gage;
     int T;          // timesteps
     int qts;        // qts_subdivisions
     int nq;         // qlat columns
@@ -136,6 +154,8 @@ cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float
 cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st);
 cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up_rows, int n_lp, int T,
                                 cudaStream_t st);
+cudaError_t launch_reset_gages(const GageDev& g, const int* gage_pos, const unsigned char* gage_active,
+                               const float* lastobs_init, float* S, int T, cudaStream_t st);
 cudaError_t launch_export_series(const int* pos, const float* S, float* dst, int count, int T, cudaStream_t st);
 cudaError_t launch_import_series(const int* pos, const float* src, float* S, int count, int T, cudaStream_t st);
 

@@ -119,6 +119,46 @@ __device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflag
     }
 }
 
+// simple_da (simple_da.pyx:21-89) for gage `g` at step `t`: returns the value that replaces the modelled flow, records the
+// nudge and updates the last-observation state.  Float expressions keep the operand order of the Cython source; the decay
+// weight is trt_expf_det (include/trt_detmath.h).  Ordering: the lane of step t reads the state the lane of step t - 1
+// wrote; that lane fences before it publishes its flow / depth and this one fences after it has seen them.
+__device__ __forceinline__ float apply_nudging(const RunDev& run, int s, int t, float model_val, const PowTabs& tabs)
+{
+    const GageDev& G = run.gage;
+    const int g = __ldg(G.slot + s);
+    __threadfence();
+    float lastobs_time = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g));
+    float lastobs_val = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g + 1));
+    const float timestep = (float)t, gage_maxtimestep = (float)G.gmax;
+    const float target_val = (t >= G.gmax) ? __uint_as_float(0x7FC00000u) : __ldg(G.usgs + (size_t)g * G.gmax + t);
+    float replacement_val, nudge_val;
+    if ((timestep <= gage_maxtimestep) && !(target_val != target_val)) {           // :47-55
+        replacement_val = target_val;
+        nudge_val = target_val - model_val;
+        lastobs_time = (timestep) * G.dt;
+        lastobs_val = target_val;
+    } else if ((target_val != target_val) && (lastobs_val != lastobs_val)) {       // :58-62
+        replacement_val = model_val;
+        nudge_val = 0.0f;
+        lastobs_val = __uint_as_float(0x7FC00000u);
+        lastobs_time = __uint_as_float(0x7FC00000u);
+    } else {                                                                       // :66-75, obs_persist_shift :109-128
+        const float da_decay_minutes = ((timestep) * G.dt - lastobs_time) / 60;
+        const double arg = fabs((double)da_decay_minutes) / -(double)G.decay;
+        const float da_weight = trt_expf_det(arg, tabs.te);
+        const float da_shift = lastobs_val - model_val;
+        const float da_weighted_shift = da_shift * da_weight;
+        nudge_val = da_weighted_shift;
+        replacement_val = model_val + da_weighted_shift;
+    }
+    G.nudge[(size_t)g * (run.T + 1) + t] = nudge_val;
+    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(G.lastobs + 2 * g), "f"(lastobs_time) : "memory");
+    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(G.lastobs + 2 * g + 1), "f"(lastobs_val) : "memory");
+    __threadfence();
+    return replacement_val;
+}
+
 // route segment `s` (engine position) at step `t`
 template <bool WAIT>
 __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs,
@@ -177,6 +217,7 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
         write_v = !WAIT || !(ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);   // no-flow branch: v = 0 (:171-178)
     }
+    if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, s, t, o_q, tabs);    // mc_reach.pyx:761-796
     if (write_v) own[1] = o_v;
     st_state<WAIT>(own + 2, o_d);
     st_state<WAIT>(own, o_q);
@@ -440,9 +481,11 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     if (!is_lp && !s.flow) {                                         // :171-178
                         float* own = row + (size_t)t * 3;
                         own[1] = 0.0f;
+                        float q = 0.0f;
+                        if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, p, t, q, tabs);
                         st_state<true>(own + 2, 0.0f);
-                        publish_flow(own, 0.0f, kflags, p, t, T1, peers);
-                        qdp = 0.0f; statep = 0.0f;
+                        publish_flow(own, q, kflags, p, t, T1, peers);
+                        qdp = q; statep = 0.0f;
                         ++t;
                         state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                     }
@@ -462,6 +505,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     lp.dam_length = 10.0f;
                     float H = statep, outflow;
                     trt_levelpool_step(lp, s.quc, 0.0f, p0, H, outflow, tabs);
+                    if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, p, t, outflow, tabs);
                     publish_flow(own, outflow, kflags, p, t, T1, peers);
                     own[1] = s.quc;             // reservoir inflow rides in the velocity slot (upstream_array, :710)
                     st_state<true>(own + 2, H);
@@ -469,7 +513,8 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                 } else if (mc_iterate(c, s, tabs)) {
-                    const float q = mc_outflow(s);
+                    float q = mc_outflow(s);
+                    if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, p, t, q, tabs);
                     publish_flow(own, q, kflags, p, t, T1, peers);   // downstream lanes are waiting for this
                     if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
                     st_state<true>(own + 2, s.h);                    // own[1] (velocity): result pass, from this depth
@@ -689,6 +734,24 @@ __global__ void upstream_out_kernel(const int* __restrict__ lp_pos, const int* _
     up[(size_t)row_of_pos[pos] * T + (t - 1)] = S[((size_t)pos * (T + 1) + t) * 3 + 1];
 }
 
+// start of a run: last-observation state back to its initial values, nudge cleared, and the initial flow of every gage
+// segment with an observation at step 0 replaced by it (mc_reach.pyx:403-411; inactive gages included)
+__global__ void reset_gages_kernel(GageDev g, const int* __restrict__ gage_pos, const unsigned char* __restrict__ active,
+                                   const float* __restrict__ lastobs_init, float* S, int T)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = T + 1;
+    if (i < (long long)g.n_gages * w) g.nudge[i] = 0.0f;
+    if (i < g.n_gages) {
+        g.lastobs[2 * i] = lastobs_init[2 * i];
+        g.lastobs[2 * i + 1] = lastobs_init[2 * i + 1];
+        if (g.gmax > 0) {
+            const float v = g.usgs[(size_t)i * g.gmax];
+            if (!(v != v)) S[(size_t)gage_pos[i] * w * 3] = v;
+        }
+    }
+}
+
 __global__ void export_series_kernel(const int* __restrict__ pos, const float* __restrict__ S, float* __restrict__ dst,
                                      int count, int T)
 {
@@ -763,6 +826,14 @@ cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const 
     const long long total = (long long)n_lp * T;
     if (total == 0) return cudaSuccess;
     upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, S, up, n_lp, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_reset_gages(const GageDev& g, const int* gage_pos, const unsigned char* gage_active,
+                               const float* lastobs_init, float* S, int T, cudaStream_t st)
+{
+    if (g.n_gages == 0) return cudaSuccess;
+    const long long total = (long long)g.n_gages * (T + 1);
+    reset_gages_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(g, gage_pos, gage_active, lastobs_init, S, T);
     return cudaGetLastError();
 }
 cudaError_t launch_export_series(const int* pos, const float* S, float* dst, int count, int T, cudaStream_t st)

@@ -71,7 +71,11 @@ class SingleRouter:
         self.net.sync()
         st = self.net.last_run_stats()
         launches = st["launches"]
+        lev = self.net.levels()
+        wide_rows = int((lev < st["first_marching_level"]).sum()) if self.mode == 4 else (self.n if self.mode < 3 else 0)
         return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": launches,
+                "wide_ms": st["wide_ms"], "march_ms": st["march_ms"], "wide_lane_steps": wide_rows * self.T,
+                "first_marching_level": st["first_marching_level"],
                 "launches_per_call_e2e": launches + 2, "stages": st["stages"],
                 "levels": self.net.num_levels, "kernel_name": self.kernel_names[self.mode],
                 "sharding": "single GPU"}
@@ -171,7 +175,13 @@ class ShardedRouter:
     def collect_stats(self):
         self.net.sync()
         st = self.net.last_run_stats()
+        lev = self.net.levels()
+        kinds = self.plan.kind
+        wide_rows = int(((lev < st["first_marching_level"]) & (kinds != 2)).sum()) if self.mode == 4 else (
+            self.n_own if self.mode < 3 else 0)
         return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": st["launches"],
+                "wide_ms": st["wide_ms"], "march_ms": st["march_ms"], "wide_lane_steps": wide_rows * self.T,
+                "first_marching_level": st["first_marching_level"],
                 "launches_per_call_e2e": st["launches"] + 2, "stages": st["stages"], "levels": self.net.num_levels,
                 "kernel_name": self.kernel_names[self.mode],
                 "sharding": f"{self.world} sub-basin shards, {self.plan_stats['n_cut_edges']} cut edges, "

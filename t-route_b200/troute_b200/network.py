@@ -120,16 +120,57 @@ class RoutingNetwork:
     def set_option(self, key, value):
         check(self._L.trt_set_option(self._h, key.encode(), int(value)))
 
-    def set_gages(self, gages, nsteps):
-        """Streamflow nudging set-up (mc_reach.pyx:380-411).  Returns (nudge [n_gages, nsteps+1], lastobs_times,
-        lastobs_values) placeholders for a gage-free call."""
-        if gages is not None:
-            raise NotImplementedError("streamflow nudging (simple_da) is not on the GPU path yet")
-        return (np.zeros((0, nsteps + 1), dtype=np.float32), np.zeros(0, dtype=np.float32),
-                np.zeros(0, dtype=np.float32))
+    def set_gages(self, gages, nsteps, routing_period=300.0):
+        """Streamflow nudging set-up (mc_reach.pyx:380-411).  `gages` holds the reference's arguments (usgs_values,
+        usgs_positions, usgs_positions_reach, usgs_positions_gage, lastobs_values_init, time_since_lastobs_init,
+        da_decay_coefficient) plus the reach structure (seg_rows, reach_len); None switches nudging off.
+        Returns (nudge, lastobs_times, lastobs_values) placeholders for a gage-free call."""
+        self._n_gages = 0
+        if gages is None or len(gages["usgs_positions"]) == 0:
+            check(self._L.trt_network_set_gages(self._h, 0, None, None, None, 0, None, None, 0.0, float(routing_period)))
+            return (np.zeros((0, nsteps + 1), dtype=np.float32), np.zeros(0, dtype=np.float32),
+                    np.zeros(0, dtype=np.float32))
+        pos = as_c(gages["usgs_positions"], np.int64)
+        G = int(pos.shape[0])
+        usgs = as_c(gages["usgs_values"], np.float32)
+        usgs = usgs.reshape(G, -1) if usgs.size else np.zeros((G, 0), dtype=np.float32)
+        # reach_has_gage[usgs_positions_reach[i]] = usgs_positions_gage[i]: the last gage listed for a reach wins (:398)
+        reach_gage = {}
+        for r, g in zip(np.asarray(gages["usgs_positions_reach"]).tolist(), np.asarray(gages["usgs_positions_gage"]).tolist()):
+            reach_gage[int(r)] = int(g)
+        active = np.zeros(G, dtype=np.uint8)
+        starts = np.concatenate([[0], np.cumsum(gages["reach_len"])])
+        for r, g in reach_gage.items():
+            if g < 0:
+                continue
+            if not (0 <= g < G and 0 <= r < len(starts) - 1):
+                raise ValueError(f"gage {g} / reach {r} out of range")
+            last = int(gages["seg_rows"][starts[r + 1] - 1])
+            if int(pos[g]) != last:
+                raise NotImplementedError(
+                    f"gage at row {int(pos[g])} is not the last segment of reach {r}: reaches must be broken at gages "
+                    f"(nhd_network.split_at_gages_waterbodies_and_junctions)")
+            active[g] = 1
+        lv = as_c(gages["lastobs_values_init"], np.float32)
+        lt = as_c(gages["time_since_lastobs_init"], np.float32)
+        if lv.shape[0] != G or lt.shape[0] != G:
+            raise ValueError("one last-observation value and time per gage is required")
+        check(self._L.trt_network_set_gages(self._h, G, ptr(pos, C.c_int64), ptr(active, C.c_uint8),
+                                            ptr(usgs, C.c_float) if usgs.size else None, int(usgs.shape[1]),
+                                            ptr(lv, C.c_float), ptr(lt, C.c_float),
+                                            float(gages["da_decay_coefficient"]), float(routing_period)))
+        self._n_gages = G
+        return None
 
     def download_gages(self):
-        raise NotImplementedError("streamflow nudging (simple_da) is not on the GPU path yet")
+        """(nudge [n_gages, nsteps + 1], lastobs_times, lastobs_values) of the last run."""
+        G = self._n_gages
+        nudge = np.zeros((G, self.nsteps + 1), dtype=np.float32)
+        t = np.zeros(G, dtype=np.float32)
+        v = np.zeros(G, dtype=np.float32)
+        if G:
+            check(self._L.trt_download_gages(self._h, ptr(nudge, C.c_float), ptr(t, C.c_float), ptr(v, C.c_float)))
+        return nudge, t, v
 
     # -- routing ------------------------------------------------------------------------------
     def _check_forcing(self, nsteps, qts_subdivisions, qlat, q0):

@@ -105,6 +105,7 @@ def flatten_network(reaches_wTypes, upstream_connections, data_idx):
 # -------------------------------------------------------------------------------------------------
 _NET_CACHE = OrderedDict()
 _NET_CACHE_MAX = 4
+DEFAULT_OPTIONS = {}          # engine options (trt_set_option) applied to every network built here, e.g. {"mode": 2}
 
 
 def _fingerprint(reaches_wTypes, data_idx, data_cols, data_values, device):
@@ -139,6 +140,8 @@ def _get_network(reaches_wTypes, upstream_connections, data_idx, data_cols, data
     # level-pool rows carry NaN channel parameters in param_df_sub (compute.py:1458-1460); the engine ignores them
     vals = np.nan_to_num(np.asarray(data_values, dtype=np.float32), nan=0.0)
     net = RoutingNetwork(up_ptr, up_rows, kind, vals, [str(c) for c in data_cols], device=device)
+    for k, v in DEFAULT_OPTIONS.items():
+        net.set_option(k, v)
     entry = dict(net=net, kind=kind, seg_rows=seg_rows, reach_len=reach_len, reach_type=reach_type)
     _NET_CACHE[key] = entry
     while len(_NET_CACHE) > _NET_CACHE_MAX:
@@ -250,7 +253,9 @@ def compute_network_structured(
                      time_since_lastobs_init=np.asarray(time_since_lastobs_init, dtype=np.float32),
                      da_decay_coefficient=float(da_decay_coefficient),
                      reach_len=entry["reach_len"], seg_rows=entry["seg_rows"])
-    nudge, lastobs_times, lastobs_values = net.set_gages(gages, nsteps)
+    placeholders = net.set_gages(gages, nsteps, routing_period=dt)
+    if gages is None:
+        nudge, lastobs_times, lastobs_values = placeholders
 
     fvd, upstream = net.route(nsteps, qts_subdivisions, qlat_values, q0, assume_short_ts=bool(assume_short_ts),
                               bnd_rows=bnd_rows if bnd_rows.size else None, bnd_fvd=bnd_fvd, want_upstream=True)

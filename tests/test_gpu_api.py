@@ -58,12 +58,15 @@ def _reference_style_case(n=4000, seed=7, n_lp=12, nsteps=36, qts=12, single=Fal
                 lake_numbers=lake_numbers, wbody=wbody, nsteps=nsteps, qts=qts, lp_rows=lp_rows)
 
 
-def _call(fn, c, upstream_results=None, assume_short_ts=False, **kw):
+def _call(fn, c, upstream_results=None, assume_short_ts=False, gages=None, **kw):
     e_f = np.zeros(0, np.float32); e_i = np.zeros(0, np.int32); e_f2 = np.zeros((0, 0), np.float32)
+    g = gages or dict(usgs_values=e_f2, usgs_positions=e_i, usgs_positions_reach=e_i, usgs_positions_gage=e_i,
+                      lastobs_values_init=e_f, time_since_lastobs_init=e_f, da_decay_coefficient=0.0)
     return fn(
         c["nsteps"], 300.0, c["qts"], c["reaches_wTypes"], c["upstream_connections"], c["ids"], c["cols"], c["params"],
         c["q0"], c["qlat"], c["lake_numbers"], c["wbody"], {}, np.ones((len(c["lake_numbers"]), 1), np.int32), False,
-        "2021-08-23_13:00:00", e_f2, e_i, e_i, e_i, e_f, e_f, 0.0,
+        "2021-08-23_13:00:00", g["usgs_values"], g["usgs_positions"], g["usgs_positions_reach"], g["usgs_positions_gage"],
+        g["lastobs_values_init"], g["time_since_lastobs_init"], g["da_decay_coefficient"],
         e_f2, e_i, e_f, e_f, e_f, e_f, e_f,
         e_f2, e_i, e_f, e_f, e_f, e_f, e_f,
         e_f2, e_i, e_i, [], e_i, e_i, e_f, e_i, e_i,
@@ -86,6 +89,68 @@ def test_compute_network_structured_matches_oracle(oracle, short_ts):
     again = _call(compute_network_structured, c, assume_short_ts=short_ts)
     H.assert_bit_equal(again[1], got[1], "cached network")
     clear_network_cache()
+
+
+def _gage_inputs(c, n_gages, seed, obs_steps):
+    """Gages at the last segment of randomly chosen reaches (T-Route breaks reaches at gages), the four observation
+    regimes of simple_da: observations (with gaps), window ended -> decay from the last one, no observation at all,
+    last observation carried in from before the call."""
+    rng = np.random.default_rng(seed)
+    reach_idx = np.sort(rng.choice(len(c["reaches_wTypes"]), size=n_gages, replace=False))
+    last_ids = np.asarray([c["reaches_wTypes"][r][0][-1] for r in reach_idx], dtype=np.int64)
+    order = np.argsort(last_ids)                               # gage arrays follow the sorted usgs index
+    reach_idx, last_ids = reach_idx[order], last_ids[order]
+    pos = np.searchsorted(c["ids"], last_ids).astype(np.int32)
+    usgs = rng.uniform(0.5, 30.0, size=(n_gages, obs_steps)).astype(np.float32)
+    usgs[rng.random(usgs.shape) < 0.25] = np.nan               # gaps
+    usgs[: n_gages // 5] = np.nan                              # gages that never report
+    lastobs = rng.uniform(0.5, 30.0, n_gages).astype(np.float32)
+    since = -rng.uniform(0.0, 7200.0, n_gages).astype(np.float32)   # seconds before the start of the call
+    none = rng.random(n_gages) < 0.3
+    lastobs[none] = np.nan; since[none] = np.nan
+    # the reference lists one (reach, gage) pair per gage, in reach order (compute.py:124-140)
+    by_reach = np.argsort(reach_idx, kind="stable")
+    return dict(usgs_values=usgs, usgs_positions=pos, usgs_positions_reach=reach_idx[by_reach].astype(np.int32),
+                usgs_positions_gage=by_reach.astype(np.int32), lastobs_values_init=lastobs,
+                time_since_lastobs_init=since, da_decay_coefficient=120.0)
+
+
+@pytest.mark.parametrize("short_ts", [False, True])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_streamflow_nudging_matches_oracle(oracle, short_ts, mode):
+    """simple_da on the device (mc_reach.pyx:380-411, :761-796; simple_da.pyx:21-128): replaced flows, nudge series and
+    final last-observation state equal the oracle's, bit for bit, in every schedule; observation window shorter than
+    the run so that the persistence/decay branch is exercised."""
+    from troute_b200.routing.fast_reach import mc_reach
+    c = _reference_style_case(n=6000, seed=11, n_lp=10, nsteps=48)
+    gages = _gage_inputs(c, n_gages=150, seed=3, obs_steps=30)
+    ref = _call(oracle.compute_network_structured, c, assume_short_ts=short_ts, gages=gages)
+    nogage = _call(oracle.compute_network_structured, c, assume_short_ts=short_ts)
+    assert not np.array_equal(ref[1], nogage[1])               # nudging changes the answer
+    mc_reach.DEFAULT_OPTIONS = {"mode": mode}
+    try:
+        got = _call(mc_reach.compute_network_structured, c, assume_short_ts=short_ts, gages=gages)
+    finally:
+        mc_reach.DEFAULT_OPTIONS = {}
+        mc_reach.clear_network_cache()
+    H.assert_bit_equal(got[1], ref[1], "flowveldepth with nudging")
+    H.assert_bit_equal(got[8], ref[8], "nudge")
+    assert np.array_equal(got[3][0], ref[3][0])
+    H.assert_bit_equal(got[3][1], ref[3][1], "lastobs_times")
+    H.assert_bit_equal(got[3][2], ref[3][2], "lastobs_values")
+
+
+def test_nudging_requires_gage_at_reach_end(oracle):
+    from troute_b200.routing.fast_reach import mc_reach
+    c = _reference_style_case(n=2000, seed=5, n_lp=0, nsteps=12)
+    gages = _gage_inputs(c, n_gages=20, seed=3, obs_steps=12)
+    r = next(i for i in gages["usgs_positions_reach"] if len(c["reaches_wTypes"][i][0]) > 1)
+    k = list(gages["usgs_positions_reach"]).index(r)
+    g = gages["usgs_positions_gage"][k]
+    gages["usgs_positions"][g] = np.searchsorted(c["ids"], c["reaches_wTypes"][r][0][0])   # first, not last, segment
+    with pytest.raises(NotImplementedError):
+        _call(mc_reach.compute_network_structured, c, gages=gages)
+    mc_reach.clear_network_cache()
 
 
 def test_upstream_results_injection(oracle):
