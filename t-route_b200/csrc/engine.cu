@@ -112,7 +112,7 @@ struct trt_network {
     DevBuf<int> d_wide_unit_ptr;
     int wide_sched_T = -1, wide_sched_lw = -1, wide_sched_tb = -1, wide_units = 0, wide_stages = 0, wide_blocks = 0;
     bool march_profile = false;
-    int poll_mode = 0, poll_sleep = -1;
+    int poll_mode = 0, poll_sleep = -1, march_prepare = 1;
     DevBuf<unsigned long long> d_march_prof;                  // [n][4] + 1
     cudaEvent_t ev_mid = nullptr;                             // between the dataflow and the marching kernel
     double wide_ms = 0.0, march_ms = 0.0;
@@ -753,7 +753,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 md.n_units = pos_deep < net->n ? net->march_units : 0;
                 md.unit_start = net->d_march_start.p; md.unit_cnt = net->d_march_cnt.p;
                 md.claim = (unsigned int*)net->d_ctrl.p + 4; md.abort_flag = net->d_ctrl.p + 2;
-                md.prof = nullptr; md.t_start = nullptr; md.poll_mode = net->poll_mode; md.poll_sleep = net->poll_sleep;
+                md.prof = nullptr; md.t_start = nullptr; md.poll_mode = net->poll_mode; md.poll_sleep = net->poll_sleep; md.prepare = net->march_prepare;
                 if (net->march_profile) {
                     CU(net->d_march_prof.reserve((size_t)net->n * 4 + 1));
                     CU(cudaMemsetAsync(net->d_march_prof.p, 0, (size_t)net->n * 4 * sizeof(unsigned long long), st));
@@ -1082,6 +1082,8 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
     } else if (!strcmp(key, "march_group")) {
         if (value < 1 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 1..32");
         net->march_group = (int)value;
+    } else if (!strcmp(key, "march_prepare")) {
+        net->march_prepare = value != 0;
     } else if (!strcmp(key, "poll_mode")) {
         net->poll_mode = (int)value;
     } else if (!strcmp(key, "poll_sleep")) {

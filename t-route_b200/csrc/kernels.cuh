@@ -125,6 +125,7 @@ struct MarchDev {
     unsigned long long* prof;         // NULL, or [n][4] per position: ns from kernel start to its first / last step
                                       // done, ns between the inputs of a step arriving and its flow being published (summed over steps), failed polls ("march_profile" option)
     unsigned long long* t_start;      // [1] %globaltimer at kernel start (prof only)
+    int prepare;                      // 1: evaluate the first-trip phase A of the next step right after a step is done
     int poll_mode;                    // experiment: 0 ld.volatile, 1 ld.relaxed.gpu, 2 atomicOr(p, 0)
     int poll_sleep;                   // experiment: ns of back-off between polls of an idle warp (-1 = adaptive)
 };

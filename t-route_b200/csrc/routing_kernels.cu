@@ -353,7 +353,10 @@ __global__ void __launch_bounds__(kBlock, 4) dataflow_kernel(NetDev net, RunDev 
 // upstream position is lower, hence claimed earlier and resident or finished -- no deadlock.
 enum { MARCH_WAIT = 0, MARCH_ITER = 1, MARCH_DONE = 2 };
 
-__global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, MarchDev mk, PeerDev peers)
+#ifndef TRT_MARCH_MIN_BLOCKS
+#define TRT_MARCH_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(NetDev net, RunDev run, MarchDev mk, PeerDev peers)
 {
     __shared__ SmemTabs smem;
     const PowTabs tabs = stage_tables(smem);
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
         const bool is_lp = kind == TRT_KIND_LEVELPOOL;
         const McChannel c = mc_channel(p0, p1, p2, p3, p4, p5, p6, p7, p8);
         McSolve s;
+        s.have0 = false; s.have1 = false;
         int t = t_first;
         float qdp = 0.f, statep = 0.f, upsum_prev = 0.f, ql = 0.f;
         int ql_left = 0;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     const float quc = sum;
                     const float qup = run.short_ts ? sum : upsum_prev;
                     upsum_prev = sum;
-                    mc_begin(s, qup, quc, qdp, ql, statep);
+                    mc_begin<true>(s, qup, quc, qdp, ql, statep);
                     state = MARCH_ITER;
                     if (!is_lp && !s.flow) {                                         // :171-178
                         float* own = row + (size_t)t * 3;
@@ -486,6 +490,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                         st_state<true>(own + 2, 0.0f);
                         publish_flow(own, q, kflags, p, t, T1, peers);
                         qdp = q; statep = 0.0f;
+                        s.have0 = false; s.have1 = false;
                         ++t;
                         state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                     }
@@ -529,6 +534,7 @@ __global__ void __launch_bounds__(kBlock) march_kernel(NetDev net, RunDev run, M
                     if (mk.prof && t == 1) prof_first = globaltimer_ns();
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
+                    if (state == MARCH_WAIT && mk.prepare) mc_prepare(c, s, statep, tabs);   // while the lane would only poll
                 }
             }
             const unsigned iterating = __ballot_sync(0xffffffffu, state == MARCH_ITER);

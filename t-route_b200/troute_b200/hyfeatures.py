@@ -1,0 +1,82 @@
+"""Minimal HYFeatures (NextGen hydrofabric v2.x GeoPackage) and channel-forcing readers on the standard library.
+
+The reference reads the GeoPackage with geopandas/fiona (troute/HYFeaturesNetwork.py:33-107 read_geopkg) and renames /
+re-indexes it in preprocess_network (:369-444).  A GeoPackage is an SQLite file, so the two attribute tables the
+routing path needs can be read with `sqlite3` -- no geometry, no GDAL.  This covers the MC-only plumbing configuration
+(BASELINE config 0: test/LowerColorado_TX_v4, waterbodies not broken out); lakes / gages / coastal boundaries are not
+read here.
+"""
+import glob
+import os
+import sqlite3
+
+import numpy as np
+import pandas as pd
+
+# network_topology_parameters.supernetwork_parameters.columns of the shipped v4 configs
+# (test/LowerColorado_TX_v4/test_AnA_V4_HYFeature.yaml:13-29): standard name -> hydrofabric column
+DEFAULT_COLUMNS = {"key": "id", "downstream": "toid", "dx": "length_m", "n": "n", "ncc": "nCC", "s0": "So",
+                   "bw": "BtmWdth", "waterbody": "rl_NHDWaterbodyComID", "gages": "rl_gages", "tw": "TopWdth",
+                   "twcc": "TopWdthCC", "musk": "MusK", "musx": "MusX", "cs": "ChSlp", "alt": "alt",
+                   "mainstem": "mainstem"}
+
+
+def _numeric_id(s):
+    """'wb-2420800' / 'nex-2420801' / 'tnx-1000000123' -> 2420800 (HYFeaturesNetwork.numeric_id)."""
+    return int(str(s).split("-")[-1])
+
+
+def read_flowpaths(gpkg_path, columns=None):
+    """flowpaths JOIN flowpath_attributes ON id, renamed to the standard parameter names, indexed by the numeric
+    flowpath id and sorted (read_geopkg :92-98 + preprocess_network :373-408).  The `downstream` column holds the
+    numeric id of the nexus the flowpath drains to, which is the id of the flowpath below that nexus; ids that are not
+    in the index (terminal nexuses, 'tnx-*') are terminal codes."""
+    columns = dict(DEFAULT_COLUMNS if columns is None else columns)
+    con = sqlite3.connect(f"file:{gpkg_path}?mode=ro", uri=True)
+    try:
+        fp = pd.read_sql_query('SELECT id, toid, mainstem FROM flowpaths', con)
+        at = pd.read_sql_query('SELECT * FROM flowpath_attributes', con)
+    finally:
+        con.close()
+    if "link" in at.columns:
+        at = at.rename(columns={"link": "id"})
+    df = pd.merge(fp, at.drop(columns=[c for c in ("fid",) if c in at.columns]), on="id", how="inner")
+    keep = [v for v in columns.values() if v in df.columns]
+    df = df[keep].rename(columns={v: k for k, v in columns.items()})
+    terminal = df["downstream"].astype(str).str.startswith("tnx")
+    df["key"] = df["key"].map(_numeric_id)
+    df["downstream"] = df["downstream"].map(_numeric_id)
+    df = df.set_index("key").sort_index()
+    if "alt" not in df.columns:
+        df["alt"] = 1.0                                                     # :404-405
+    if "gages" in df.columns:
+        df = df.drop(columns="gages")
+    df.attrs["terminal_rows"] = int(terminal.sum())
+    return df
+
+
+def connections(df):
+    """nhd_network.extract_connections (nhd_network.py:26-53): id -> [downstream id] ([] at a terminal)."""
+    index = set(df.index.tolist())
+    return {int(k): ([int(d)] if int(d) in index else []) for k, d in df["downstream"].items()}
+
+
+def read_channel_forcing(folder, pattern="*.CHRTOUT_DOMAIN1.csv", index=None):
+    """One CSV per forcing hour, columns (feature_id, <timestamp>): -> DataFrame indexed by segment id, one column per
+    file in name order (the qlat frame the reference assembles, nhd_io.get_ql_from_csv)."""
+    files = sorted(glob.glob(os.path.join(folder, pattern)))
+    if not files:
+        raise FileNotFoundError(f"no forcing files matching {pattern} in {folder}")
+    frames = [pd.read_csv(f, index_col=0) for f in files]
+    q = pd.concat(frames, axis=1)
+    q.index = q.index.astype("int64")
+    if index is not None:
+        q = q.reindex(index).fillna(0.0)
+    return q.astype("float32")
+
+
+def param_frame(df, dt):
+    """The parameter table compute_nhd_routing_v02 slices (compute.py:1443-1446 column set), float32."""
+    p = df[["bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"]].copy()
+    p.insert(0, "dt", float(dt))
+    return p.astype("float32")

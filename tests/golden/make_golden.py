@@ -20,6 +20,9 @@ Writes
                           (src/troute-network/troute/network/reservoirs/test/test_compute_kernel.py:28-110,
                            :376-505, :508-637, :640-949)
   simple_da_kat.json      nudging known answer (src/troute-routing/troute/routing/test_compute.py:33-42)
+  lowercolorado_v4.npz    LowerColorado_TX NextGen hydrofabric (test/LowerColorado_TX_v4/domain/*.gpkg): ids, downstream
+                          ids, channel parameters, 49 h of lateral inflow (channel_forcing/*.csv) and the reach lists
+                          the reference's own nhd_network.dfs_decomposition yields for it (BASELINE config 0)
   nhd_graph.json          graph fixture of troute/test_nhd_network.py:1-142 with the outputs of the reference's
                           nhd_network.{reverse_network, dfs_decomposition, build_subnetworks,
                           reachable_network} on it and on a seeded random forest
@@ -210,7 +213,49 @@ def nhd_graph():
     return out
 
 
+def lowercolorado_v4():
+    """BASELINE config 0 plumbing case: the LowerColorado_TX NextGen hydrofabric (6,971 flowpaths) with its own channel
+    forcing (49 hourly CSV files), read with troute_b200.hyfeatures (sqlite3; the reference needs geopandas), and the reach
+    decomposition the REFERENCE's own code produces for an MC-only run: nhd_network.extract_connections ->
+    reverse_network -> reachable_network -> dfs_decomposition(split_at_junction)  (AbstractNetwork.py:212-257)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(OUT)), "t-route_b200"))
+    from functools import partial
+    from troute_b200 import hyfeatures as hy
+    if "toolz" not in sys.modules:
+        tz = types.ModuleType("toolz")
+        tz.pluck = lambda ind, seqs: (s_[ind] for s_ in seqs)
+        sys.modules["toolz"] = tz
+    nn = _load(f"{REF}/src/troute-network/troute/nhd_network.py", "ref_nhd_network")
+    base = f"{REF}/test/LowerColorado_TX_v4"
+    df = hy.read_flowpaths(f"{base}/domain/LowerColorado_NGEN_v201.gpkg")
+    terminal_codes = {0} | set(df[~df["downstream"].isin(df.index)]["downstream"].values.tolist())
+    conn = nn.extract_connections(df, "downstream", terminal_codes=terminal_codes)
+    assert {int(k): [int(x) for x in v] for k, v in conn.items()} == hy.connections(df)
+    rconn = nn.reverse_network(conn)
+    indep = nn.reachable_network(rconn)
+    reaches = []
+    tw_of_reach = []
+    for tw, net in indep.items():
+        for r in nn.dfs_decomposition(net, partial(nn.split_at_junction, net)):
+            reaches.append([int(x) for x in r]); tw_of_reach.append(int(tw))
+    qlat = hy.read_channel_forcing(f"{base}/channel_forcing", index=df.index)
+    params = hy.param_frame(df, 300.0)
+    np.savez_compressed(
+        f"{OUT}/lowercolorado_v4.npz",
+        ids=df.index.values.astype(np.int64), downstream=df["downstream"].values.astype(np.int64),
+        param_cols=np.array(params.columns.tolist()), params=params.values.astype(np.float32),
+        qlat=qlat.values.astype(np.float32),
+        reach_len=np.asarray([len(r) for r in reaches], dtype=np.int64),
+        reach_ids=np.asarray([x for r in reaches for x in r], dtype=np.int64),
+        reach_tw=np.asarray(tw_of_reach, dtype=np.int64))
+    return dict(n=len(df), reaches=len(reaches), tailwaters=len(indep), qlat_cols=qlat.shape[1],
+                longest_reach=max(len(r) for r in reaches))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "lowercolorado":
+        print("LowerColorado v4:", lowercolorado_v4())
+        sys.exit(0)
     k = mc_demo_kat()
     print("mc demo KAT:", k["single"]["expected"])
     a = mc_suite()
@@ -221,3 +266,4 @@ if __name__ == "__main__":
     g = nhd_graph()
     print("graph: reaches", {k: len(v) for k, v in g["fixture"]["reaches_bytw"].items()},
           "forest tw", len(g["forest300"]["reaches_bytw"]))
+    print("LowerColorado v4:", lowercolorado_v4())

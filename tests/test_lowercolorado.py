@@ -1,0 +1,107 @@
+"""BASELINE config 0 -- the LowerColorado_TX NextGen hydrofabric (test/LowerColorado_TX_v4 of the reference), MC-only:
+6,971 real flowpaths with their channel parameters, the reference's own reach decomposition and 24 h of its channel
+forcing (fixture tests/golden/lowercolorado_v4.npz, made by tests/golden/make_golden.py from the reference tree).
+CPU: the fixture is self-consistent and the oracle routes it.  GPU: compute_nhd_routing_v02 on DataFrames, called the way
+nwm_route calls it (__main__.py:1215-1253), equals the oracle called with the reference's arguments, bit for bit."""
+import os
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NTS, QTS, DT = 288, 12, 300.0          # forcing_parameters of test_AnA_V4_HYFeature_noDA.yaml: nts 288, dt 300, qts 12
+
+
+def _load():
+    z = np.load(os.path.join(GOLD, "lowercolorado_v4.npz"))
+    ids = z["ids"]
+    starts = np.concatenate([[0], np.cumsum(z["reach_len"])])
+    reaches = [z["reach_ids"][a:b].tolist() for a, b in zip(starts[:-1], starts[1:])]
+    index = set(ids.tolist())
+    connections = {int(k): ([int(d)] if int(d) in index else []) for k, d in zip(ids, z["downstream"])}
+    rconn = {int(k): [] for k in ids}
+    for k, v in connections.items():
+        for d in v:
+            rconn[d].append(k)
+    return dict(ids=ids, cols=[str(c) for c in z["param_cols"]], params=z["params"], qlat=z["qlat"], reaches=reaches,
+                reach_tw=z["reach_tw"], connections=connections, rconn=rconn)
+
+
+def _oracle_call(oracle, c, short_ts):
+    e_f = np.zeros(0, np.float32); e_i = np.zeros(0, np.int32); e_f2 = np.zeros((0, 0), np.float32)
+    n = c["ids"].shape[0]
+    return oracle.compute_network_structured(
+        NTS, DT, QTS, [(r, 0) for r in c["reaches"]], c["rconn"], c["ids"], np.array(c["cols"], dtype=object), c["params"],
+        np.zeros((n, 3), np.float32), c["qlat"], [], np.zeros((0, 11)), {}, np.zeros((0, 1), np.int32), False,
+        "2023-04-02_00:00:00", e_f2, e_i, e_i, e_i, e_f, e_f, 0.0,
+        e_f2, e_i, e_f, e_f, e_f, e_f, e_f, e_f2, e_i, e_f, e_f, e_f, e_f, e_f,
+        e_f2, e_i, e_i, [], e_i, e_i, e_f, e_i, e_i, e_i, e_i, e_f, e_i, e_f, e_i, e_i, e_f2,
+        {}, short_ts, False)
+
+
+def test_fixture_is_the_reference_network():
+    c = _load()
+    n = c["ids"].shape[0]
+    assert n == 6971 and len(c["reaches"]) == 5630 and c["qlat"].shape == (n, 49)
+    assert sorted(s for r in c["reaches"] for s in r) == c["ids"].tolist()          # every flowpath in exactly one reach
+    # inside a reach each segment drains into the next one; a reach head has != 1 upstream or follows a junction
+    for r in c["reaches"]:
+        for a, b in zip(r[:-1], r[1:]):
+            assert c["connections"][a] == [b] and c["rconn"][b] == [a]
+    assert sum(1 for v in c["connections"].values() if not v) == 1                   # one tail-water
+    p = c["params"]
+    assert np.isfinite(p).all() and (p[:, c["cols"].index("dx")] > 0).all() and (p[:, c["cols"].index("n")] > 0).all()
+
+
+def test_flatten_reproduces_the_graph():
+    from troute_b200.routing.fast_reach.mc_reach import flatten_network
+    c = _load()
+    up_ptr, up_rows, kind, seg_rows, reach_len, reach_type = flatten_network([(r, 0) for r in c["reaches"]], c["rconn"], c["ids"])
+    assert (kind == 0).all() and up_ptr[-1] == c["ids"].shape[0] - 1
+    for row in np.random.default_rng(0).choice(c["ids"].shape[0], 300, replace=False):
+        ups = sorted(c["ids"][up_rows[up_ptr[row]:up_ptr[row + 1]]].tolist())
+        assert ups == sorted(c["rconn"][int(c["ids"][row])])
+
+
+@pytest.mark.parametrize("short_ts", [True, False])
+def test_oracle_routes_lowercolorado(oracle, short_ts):
+    c = _load()
+    out = _oracle_call(oracle, c, short_ts)
+    fvd = out[1].reshape(c["ids"].shape[0], NTS, 3)
+    assert np.isfinite(fvd).all() and (fvd[:, :, 0] >= 0).all()
+    tw = int(c["reach_tw"][0])
+    row = int(np.searchsorted(c["ids"], tw))
+    assert fvd[row, -1, 0] > 1.0                                # the forcing reaches the outlet within the day
+    # volume balance: what left through the outlet cannot exceed what was put in
+    vol_in = float(c["qlat"][:, :NTS // QTS].astype(np.float64).sum() * QTS * DT)
+    vol_out = float(fvd[row, :, 0].astype(np.float64).sum() * DT)
+    assert 0 < vol_out < vol_in
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("short_ts", [True, False])
+def test_gpu_routes_lowercolorado_like_the_reference(oracle, short_ts):
+    import pandas as pd
+    from troute_b200.routing.compute import compute_nhd_routing_v02
+    from troute_b200.routing.fast_reach.mc_reach import clear_network_cache
+    c = _load()
+    ids = c["ids"]
+    tw = int(c["reach_tw"][0])
+    param_df = pd.DataFrame(c["params"][:, 1:], index=ids, columns=c["cols"][1:])       # dt is added by the callee
+    qlats = pd.DataFrame(c["qlat"], index=ids)
+    q0 = pd.DataFrame(np.zeros((ids.shape[0], 3), np.float32), index=ids, columns=["qu0", "qd0", "h0"])
+    empty = pd.DataFrame()
+    results, _ = compute_nhd_routing_v02(
+        c["connections"], c["rconn"], {}, {tw: c["reaches"]}, "V02-structured", "by-subnetwork-jit-clustered", 10000, 36,
+        datetime(2023, 4, 2), DT, NTS, QTS, {tw: c["rconn"]}, param_df, q0, qlats, empty, empty,
+        empty, empty, empty, empty, empty, empty, empty, empty, empty, {}, short_ts, False, empty, {}, empty, False,
+        [None, None])
+    ref = _oracle_call(oracle, c, short_ts)
+    got_ids, got_fvd = results[0][0], results[0][1]
+    order = np.argsort(got_ids)
+    assert np.array_equal(got_ids[order], ref[0])
+    H.assert_bit_equal(got_fvd[order], ref[1], "LowerColorado flowveldepth")
+    clear_network_cache()
