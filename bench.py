@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--short-ts", type=int, default=0)
     ap.add_argument("--mode", type=int, default=4)
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--deep-lanes", type=int, default=8192, help="segments per GPU that march (deepest levels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
@@ -235,16 +236,20 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device; the routing path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: some boxes export NCCL_DEBUG=VERSION, which prints a banner on stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("TRT_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = build_workload(args)
     T = args.nsteps
     if world > 1:
         from troute_b200 import multigpu
-        runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
+        runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode,
+                                        deep_lanes=args.deep_lanes)
     else:
         from troute_b200 import multigpu
         runner = multigpu.SingleRouter(wl, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
+        runner.net.set_option("deep_lanes", args.deep_lanes)
 
     for kv in args.opt:
         k, v = kv.split("=")

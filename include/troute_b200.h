@@ -183,7 +183,8 @@ int trt_prepare(trt_network* net);
  *                 "deep_lanes" segments (default 8192).  Shards of one network must use the SAME
  *                 deep_level (set it explicitly): a dataflow kernel must never wait for a value that another shard
  *                 produces only in its marching kernel
- *   "march_group" segments per marching warp, 1..32 (default 4): fewer = shorter dependency-chain latency, more =
+ *   "march_group" segments per marching warp, 1..32; 0 (default) = the smallest power of two for which all marching
+ *                 units are resident at once: fewer = shorter dependency-chain latency, more =
  *                 more segments resident at once
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)

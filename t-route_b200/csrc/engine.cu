@@ -104,7 +104,8 @@ struct trt_network {
     // marching schedule (mode 3: every level; mode 4: levels >= deep_level_used after the dataflow kernel)
     DevBuf<int> d_march_start;
     DevBuf<unsigned char> d_march_cnt;
-    int march_group = 4;                                      // positions per marching warp (1..32)
+    int march_group = 0;                                      // positions per marching warp (1..32), 0 = auto
+    int march_group_used = 0;
     int deep_level = -1;                                      // mode 4: first marching level (-1 = from deep_lanes)
     int64_t deep_lanes = 8192;                                // mode 4 auto: march as many of the deepest levels as fit
     int march_sched_first = -1, march_sched_group = -1, march_units = 0;
@@ -661,7 +662,10 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                         hi = net->lvl_ptr[(size_t)std::min(Lw, k)];
                     }
                     const int64_t width = hi - lo;
-                    const int sh = width >= 65536 ? 7 : 5;
+                    // 128-position units amortise the claim when a stage is many waves wide; narrower stages (a shard
+                    // of a multi-GPU run, the medium-depth levels) use 32-position units so that a stage is not four
+                    // sequential chunks long
+                    const int sh = width >= (int64_t)1 << 20 ? 7 : (width >= 400000 ? 6 : 5);
                     shift[(size_t)k - 1] = (unsigned char)sh;
                     units += (width + (1 << sh) - 1) >> sh;
                     if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
@@ -695,8 +699,17 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 net->sched_nstages = nstages; net->sched_lw = Lw;
             }
             // marching units over positions [pos_deep, n)
-            if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != net->march_group)) {
-                const int G = net->march_group;
+            int G = net->march_group;
+            if (G == 0) {
+                // auto: the fewest segments per warp that still lets every marching unit be resident at once
+                int mg = 0;
+                CU(march_max_grid(&mg));
+                if (net->grid_blocks > 0) mg = std::min(mg, net->grid_blocks);
+                const int64_t warps = std::max<int64_t>(1, (int64_t)mg * 8);
+                G = 1;
+                while (G < 32 && (net->n - pos_deep + G - 1) / G > warps) G *= 2;
+            }
+            if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != G)) {
                 std::vector<int32_t> start;
                 std::vector<unsigned char> cnt;
                 for (int64_t q = pos_deep; q < net->n; q += G) {
@@ -708,7 +721,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
                 CU(cudaMemcpy(net->d_march_start.p, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
                 CU(cudaMemcpy(net->d_march_cnt.p, cnt.data(), cnt.size(), cudaMemcpyHostToDevice));
                 net->march_units = (int)start.size();
-                net->march_sched_first = pos_deep; net->march_sched_group = G;
+                net->march_sched_first = pos_deep; net->march_sched_group = G; net->march_group_used = G;
             }
             CU(net->d_ctrl.reserve(8));
             SchedDev sd;
@@ -1080,7 +1093,7 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1 || value > 100000) return fail(TRT_ERR_INVALID, "time_block must be >= 1");
         net->time_block = (int)value;
     } else if (!strcmp(key, "march_group")) {
-        if (value < 1 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 1..32");
+        if (value < 0 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 0..32");
         net->march_group = (int)value;
     } else if (!strcmp(key, "march_prepare")) {
         net->march_prepare = value != 0;
