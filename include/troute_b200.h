@@ -129,7 +129,11 @@ int trt_run(trt_network* net, int32_t assume_short_ts);
 int trt_run_async(trt_network* net, int32_t assume_short_ts);
 int trt_sync(trt_network* net);
 int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out);
-/* the three calls above in sequence */
+/* trt_run + trt_download_results with the two overlapped: the call is cut into "route_chunks" time chunks and the
+ * finished columns of chunk c are copied to the host while chunk c + 1 is computed (see trt_route).  Shards of one
+ * network must use the same "route_chunks". */
+int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, float* upstream_out);
+/* trt_upload_forcing + trt_run_download */
 int trt_route(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, int32_t assume_short_ts,
               const float* qlat, int32_t nqcols, const float* q0, int64_t n_bnd, const int64_t* bnd_rows,
               const float* bnd_fvd, float* fvd_out, float* upstream_out);
@@ -189,6 +193,7 @@ int trt_prepare(trt_network* net);
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
+ *   "route_chunks" time chunks of trt_route / trt_run_download (default 4; 1 = compute everything, then copy)
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
 int trt_set_option(trt_network* net, const char* key, int64_t value);
 /* "profile_stages" = 1 with "mode" = 0: device time and width (lanes) of every wavefront stage of the last run;

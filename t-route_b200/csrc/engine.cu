@@ -87,6 +87,11 @@ struct trt_network {
 
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;                       // trt_route: results of chunk c go home while c + 1 runs
+    std::vector<cudaEvent_t> chunk_events;
+    int route_chunks = 4;
+    DevBuf<float> d_deep_fvd;                                 // [n_deep][3T] results of the marching rows (chunked trt_route)
+    std::vector<float> h_deep_fvd;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // dataflow schedule (mode 2)
@@ -159,7 +164,7 @@ struct trt_network {
     RunDev rundev(int short_ts) const
     {
         RunDev r;
-        r.T = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
+        r.T = T; r.t_off = 0; r.Tc = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
         r.gage.n_gages = (int)n_gages; r.gage.gmax = gage_max; r.gage.dt = gage_dt; r.gage.decay = gage_decay;
         r.gage.slot = d_gage_slot.p; r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
         return r;
@@ -335,6 +340,8 @@ int trt_network_destroy(trt_network* net)
     if (net->ev0) cudaEventDestroy(net->ev0);
     if (net->ev1) cudaEventDestroy(net->ev1);
     if (net->ev_mid) cudaEventDestroy(net->ev_mid);
+    for (cudaEvent_t ev : net->chunk_events) cudaEventDestroy(ev);
+    if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
     if (net->stream && net->own_stream) cudaStreamDestroy(net->stream);
     delete net;
     return TRT_OK;
@@ -582,13 +589,17 @@ static cudaError_t prepare_dataflow(trt_network* net)
     return e;
 }
 
-static int run_async(trt_network* net, int32_t assume_short_ts)
+// Route the steps t_off + 1 .. t_off + Tc of the uploaded call (the whole call: 0, net->T).  Chunks must be issued in
+// time order on the handle's stream; `first` resets the flow state, the nudging state and the statistics.
+// phase: 0 = everything, 1 = only the dataflow (wide) levels, 2 = only the marching (deep) levels.
+enum { PHASE_ALL = 0, PHASE_WIDE = 1, PHASE_DEEP = 2 };
+static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int Tc, bool first, int phase = PHASE_ALL)
 {
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run called before trt_upload_forcing");
     CU(cudaSetDevice(net->device));
     cudaStream_t st = net->stream;
-    if (net->n_gages > 0) {
+    if (net->n_gages > 0 && first) {
         // nudging state back to its initial values; the flow-state reset must come first (it rewrites t = 0)
         CU(net->d_nudge.reserve((size_t)net->n_gages * (size_t)(net->T + 1)));
         if (net->mode >= 2 && !net->prepared) { CU(prepare_dataflow(net)); net->prepared = true; }
@@ -596,18 +607,20 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
         CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
     }
     const NetDev nd = net->netdev();
-    const RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
-    const int T = net->T;
+    RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
+    rd.t_off = t_off; rd.Tc = Tc;
+    const int T = Tc;                          // steps this launch schedules
     const int L = assume_short_ts ? 1 : net->nlevels;
-    net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0;
+    if (first) { net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0; }
+    const int64_t launches_before = net->launches;
 
-    CU(cudaEventRecord(net->ev0, st));
+    if (first) CU(cudaEventRecord(net->ev0, st));
     if (net->n > 0 && T > 0 && L > 0) {
         const int k_begin = 1, k_end = L + T;   // stages k = level + t, level in [0, L), t in [1, T]
         net->stages = k_end - k_begin;
         int64_t routed = 0;
         for (int64_t r = 0; r < net->n; ++r) routed += net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY;
-        net->lane_steps = routed * T;
+        net->lane_steps += routed * T;
         if (net->mode >= 2) {
             // levels [0, Lw) go through the dataflow wavefront, levels [Lw, nlevels) march
             int Lw = net->nlevels;
@@ -748,15 +761,17 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             if (grid <= 0) grid = max_grid;
             CU(cudaMemsetAsync(net->d_ctrl.p, 0, 8 * sizeof(int), st));
             if (nstages > 0) CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
-            if (!net->prepared) CU(prepare_dataflow(net));
-            net->prepared = false;
-            CU(cudaEventRecord(net->ev0, st));
-            net->launches = 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);       // state reset kernels
-            if (nstages > 0) {
+            if (first) {
+                if (!net->prepared) CU(prepare_dataflow(net));
+                net->prepared = false;
+                CU(cudaEventRecord(net->ev0, st));
+                net->launches += 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);  // state reset kernels
+            }
+            if (nstages > 0 && phase != PHASE_DEEP) {
                 CU(launch_dataflow(nd, rd, sd, pd, grid, st));
                 net->launches++;
             }
-            if (pos_deep < net->n || (unified && Lw > 0)) {
+            if ((pos_deep < net->n || (unified && Lw > 0)) && phase != PHASE_WIDE) {
                 MarchDev md;
                 md.n_wide_units = 0; md.wide_levels = 0; md.nblocks = 1; md.Tb = T; md.nstages = 0; md.wide_unit_ptr = nullptr;
                 if (unified && Lw > 0) {
@@ -790,7 +805,7 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
             if (max_grid <= 0) return fail(TRT_ERR_CUDA, "persistent kernel cannot be made resident");
             if (grid <= 0 || grid > max_grid) grid = max_grid;
             CU(launch_persistent(nd, rd, k_begin, k_end, grid, st));
-            net->launches = 1;
+            net->launches += 1;
         } else {
             if (net->profile_stages) {
                 while ((int)net->stage_events.size() < k_end) {
@@ -818,10 +833,26 @@ static int run_async(trt_network* net, int32_t assume_short_ts)
         }
     }
     CU(cudaEventRecord(net->ev1, st));
-    CU(launch_finalize(nd, rd, net->d_fvd.p, st));
+    if (phase == PHASE_ALL) CU(launch_finalize(nd, rd, net->d_fvd.p, st));
+    else {
+        // split result pass: the dataflow rows in place; the marching rows into a compact buffer that goes home on its own
+        const int pos_deep = net->mode >= 2 ? net->lvl_ptr[(size_t)net->deep_level_used] : (int)net->n;
+        if (phase == PHASE_WIDE) CU(launch_finalize(nd, rd, net->d_fvd.p, st, 0, pos_deep, -1));
+        else {
+            CU(net->d_deep_fvd.reserve((size_t)(net->n - pos_deep) * 3 * (size_t)net->T));
+            CU(launch_finalize(nd, rd, net->d_deep_fvd.p, st, pos_deep, (int)net->n, pos_deep));
+        }
+    }
     net->launches += (net->n > 0 && T > 0) ? 1 : 0;
+    (void)launches_before;
     net->ran = true;
     return TRT_OK;
+}
+
+static int run_async(trt_network* net, int32_t assume_short_ts)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    return run_chunk(net, assume_short_ts, 0, net->T, true);
 }
 
 int trt_run_async(trt_network* net, int32_t assume_short_ts) { return run_async(net, assume_short_ts); }
@@ -896,16 +927,80 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
     return TRT_OK;
 }
 
+// One routing call, host buffers in and out.  With a polling schedule (mode >= 2) and "route_chunks" > 1 the call is cut
+// into time chunks: while the kernels of chunk c + 1 run, the finished columns of chunk c travel to the host on a second
+// stream (a strided 2-D copy out of the [n_rows, 3T] result) -- the 9.4 GB result of a CONUS day takes longer to cross
+// PCIe than to compute, so hiding one behind the other is worth more than any kernel tuning.  Every chunk pays the
+// latency-bound main-stem tail once, which bounds the useful number of chunks (default 2).
 int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_short_ts, const float* qlat, int32_t nqcols,
               const float* q0, int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd, float* fvd_out,
               float* upstream_out)
 {
     int rc = trt_upload_forcing(net, nsteps, qts, qlat, nqcols, q0, n_bnd, bnd_rows, bnd_fvd);
     if (rc != TRT_OK) return rc;
-    rc = run_async(net, assume_short_ts);
-    if (rc != TRT_OK) return rc;
-    rc = trt_download_results(net, fvd_out, upstream_out);
-    if (rc != TRT_OK) return rc;
+    return trt_run_download(net, assume_short_ts, fvd_out, upstream_out);
+}
+
+int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, float* upstream_out)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run_download called before trt_upload_forcing");
+    int rc;
+    const int nsteps = net->T;
+    const int C = (net->mode >= 2 && fvd_out && net->n > 0) ? std::max(1, std::min(net->route_chunks, nsteps)) : 1;
+    if (C <= 1) {
+        rc = run_async(net, assume_short_ts);
+        if (rc != TRT_OK) return rc;
+        rc = trt_download_results(net, fvd_out, upstream_out);
+        if (rc != TRT_OK) return rc;
+        return trt_sync(net);
+    }
+    CU(cudaSetDevice(net->device));
+    if (!net->copy_stream) CU(cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking));
+    while ((int)net->chunk_events.size() < C + 1) {
+        cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); net->chunk_events.push_back(ev);
+    }
+    const size_t n = (size_t)net->n, T = (size_t)nsteps;
+    // Mode 4: only the dataflow (wide) levels are chunked -- their rows are 99 % of the result; the marching levels run
+    // ONCE over all steps after the last wide chunk (a marching lane needs nothing from a later wide chunk), so the
+    // latency-bound main stem is paid once, and its ~1 % of rows go home through a compact buffer + a host scatter.
+    int Lw = 0;
+    if (net->mode == 4) {
+        if (net->deep_level >= 0) Lw = std::min(net->deep_level, net->nlevels);
+        else { Lw = net->nlevels; while (Lw > 0 && net->n - net->lvl_ptr[(size_t)Lw - 1] <= net->deep_lanes) --Lw; }
+    }
+    const bool split = net->mode == 4 && Lw > 0 && Lw < net->nlevels;
+    int t_off = 0;
+    for (int c = 0; c < C; ++c) {
+        const int Tc = (nsteps - t_off + (C - c) - 1) / (C - c);          // equal chunks, the longer ones first
+        rc = run_chunk(net, assume_short_ts, t_off, Tc, c == 0, split ? PHASE_WIDE : PHASE_ALL);
+        if (rc != TRT_OK) return rc;
+        CU(cudaEventRecord(net->chunk_events[(size_t)c], net->stream));
+        CU(cudaStreamWaitEvent(net->copy_stream, net->chunk_events[(size_t)c], 0));
+        CU(cudaMemcpy2DAsync(fvd_out + (size_t)t_off * 3, 3 * T * sizeof(float), net->d_fvd.p + (size_t)t_off * 3,
+                             3 * T * sizeof(float), (size_t)Tc * 3 * sizeof(float), n, cudaMemcpyDeviceToHost,
+                             net->copy_stream));
+        t_off += Tc;
+    }
+    if (split) {
+        rc = run_chunk(net, assume_short_ts, 0, nsteps, false, PHASE_DEEP);
+        if (rc != TRT_OK) return rc;
+        const int pos_deep = net->lvl_ptr[(size_t)Lw];
+        const size_t n_deep = n - (size_t)pos_deep;
+        net->h_deep_fvd.resize(n_deep * 3 * T);
+        CU(cudaMemcpyAsync(net->h_deep_fvd.data(), net->d_deep_fvd.p, n_deep * 3 * T * sizeof(float), cudaMemcpyDeviceToHost,
+                           net->stream));
+        CU(cudaStreamSynchronize(net->stream));
+        CU(cudaStreamSynchronize(net->copy_stream));          // the chunk copies wrote stale values into these rows
+        for (size_t i = 0; i < n_deep; ++i)
+            memcpy(fvd_out + (size_t)net->row_of_pos[(size_t)pos_deep + i] * 3 * T, net->h_deep_fvd.data() + i * 3 * T,
+                   3 * T * sizeof(float));
+    }
+    if (upstream_out) {
+        rc = trt_download_results(net, nullptr, upstream_out);
+        if (rc != TRT_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(net->copy_stream));
     return trt_sync(net);
 }
 
@@ -1089,6 +1184,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
+    } else if (!strcmp(key, "route_chunks")) {
+        if (value < 1 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 1..1024");
+        net->route_chunks = (int)value;
     } else if (!strcmp(key, "time_block")) {
         if (value < 1 || value > 100000) return fail(TRT_ERR_INVALID, "time_block must be >= 1");
         net->time_block = (int)value;

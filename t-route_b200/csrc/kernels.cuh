@@ -56,7 +56,9 @@ struct GageDev {
 
 struct RunDev {
     GageDev gage;
-    int T;          // timesteps
+    int T;          // timesteps of the call (the flow state holds T + 1 columns)
+    int t_off;      // this launch routes steps t_off + 1 .. t_off + Tc (a time chunk of the call; whole call: 0, T)
+    int Tc;
     int qts;        // qts_subdivisions
     int nq;         // qlat columns
     int short_ts;   // assume_short_ts
@@ -152,7 +154,10 @@ cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const 
                                   cudaStream_t st);
 cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st);
 cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* S, int n_bnd, int T, cudaStream_t st);
-cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st);
+// result pass over the steps of run's time chunk
+// positions [p_begin, p_end) (p_end < 0: all); compact_from >= 0: destination row = position - compact_from
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st, int p_begin = 0,
+                            int p_end = -1, int compact_from = -1);
 cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up_rows, int n_lp, int T,
                                 cudaStream_t st);
 cudaError_t launch_reset_gages(const GageDev& g, const int* gage_pos, const unsigned char* gage_active,

@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(kBlock) stage_kernel(NetDev net, RunDev run, i
     const int s = lo + blockIdx.x * kBlock + threadIdx.x;
     if (s >= hi) return;
     const int t = lane_step(net, run, k, s);
-    if (t < 1 || t > run.T) return;
-    route_lane<false>(net, run, s, t, tabs, nullptr, nullptr);
+    if (t < 1 || t > run.Tc) return;
+    route_lane<false>(net, run, s, t + run.t_off, tabs, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev run, int k_begin, int k_end)
@@ -260,12 +260,12 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
         int lo, hi;
         if (run.short_ts) { lo = 0; hi = net.n; }
         else {
-            lo = __ldg(net.lvl_ptr + max(0, k - run.T));
+            lo = __ldg(net.lvl_ptr + max(0, k - run.Tc));
             hi = __ldg(net.lvl_ptr + min(L, k));
         }
         for (int s = lo + gtid; s < hi; s += gstride) {
             const int t = lane_step(net, run, k, s);
-            if (t >= 1 && t <= run.T) route_lane<false>(net, run, s, t, tabs, nullptr, nullptr);
+            if (t >= 1 && t <= run.Tc) route_lane<false>(net, run, s, t + run.t_off, tabs, nullptr, nullptr);
         }
         grid.sync();
     }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kBlock, 4) dataflow_kernel(NetDev net, RunDev 
         int lo, hi;
         if (run.short_ts) { lo = 0; hi = pos_end; }
         else {
-            lo = __ldg(net.lvl_ptr + max(0, k - run.T));
+            lo = __ldg(net.lvl_ptr + max(0, k - run.Tc));
             hi = __ldg(net.lvl_ptr + min(L, k));
         }
         const int shift = __ldg(sc.unit_shift + lo_i);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlock, 4) dataflow_kernel(NetDev net, RunDev 
         }
 
         for (int s = p0 + lane; s < p1; s += 32) {
-            const int t = run.short_ts ? k : k - __ldg(net.level + s);
+            const int t = (run.short_ts ? k : k - __ldg(net.level + s)) + run.t_off;
             route_lane<true>(net, run, s, t, tabs, &peers, sc.abort_flag);
         }
         __syncwarp();
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
         if (lane == 0) u = atomicAdd(mk.claim, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= (unsigned)(mk.n_wide_units + mk.n_units)) break;
-        int p, t_first = 1, t_last = T;
+        int p, t_first = run.t_off + 1, t_last = run.t_off + run.Tc;
         bool mine;
         if (u < (unsigned)mk.n_wide_units) {
             // stage of wide unit u: last K >= cursor with wide_unit_ptr[K] <= u
@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
             mine = p < hi;
             if (mine) {
                 const int b = K - __ldg(net.level + p);           // 0 <= b < nblocks by construction of [lo, hi)
-                t_first = b * mk.Tb + 1;
-                t_last = min(T, t_first + mk.Tb - 1);
+                t_first = run.t_off + b * mk.Tb + 1;
+                t_last = min(run.t_off + run.Tc, t_first + mk.Tb - 1);
             }
         } else {
             const unsigned v = u - (unsigned)mk.n_wide_units;
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     if ((t & 1) == 0) {
                         // cold tributary rows (finished long ago, evicted from L2): pull the sectors of the coming steps
                         // in, off the critical path.  One 32-byte sector holds 2.67 steps of (q, v, d).
-                        const int tp = min(t + 8, T);
+                        const int tp = min(t + 8, T);      // T: last column of the flow state
                         for (int e = e0; e < e1; ++e)
                             prefetch_l2(run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)tp) * 3);
                     }
@@ -703,23 +703,26 @@ __global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* S, int
 // velocity slot of a Muskingum-Cunge step at TRT_SENTINEL: velocity is a function of the final depth and the channel
 // alone (:163-169), nobody downstream reads it, and here one warp = one segment evaluates it with uniform parameters and
 // no divergence instead of inside the branchy solve.
-__global__ void __launch_bounds__(256) permute_rows_kernel(NetDev net, RunDev run, float* __restrict__ fvd)
+// Positions [p_begin, p_end); compact_from >= 0: row (p - compact_from) of a compact buffer instead of the caller's row
+// (the marching rows of a time-chunked trt_route go home separately, see engine.cu).
+__global__ void __launch_bounds__(256) permute_rows_kernel(NetDev net, RunDev run, float* __restrict__ fvd, int p_begin,
+                                                           int p_end, int compact_from)
 {
     __shared__ SmemTabs smem;
     const PowTabs tabs = stage_tables(smem);
     const int warps_per_block = 256 / 32;
     const int lane = threadIdx.x & 31;
     const size_t n = (size_t)net.n;
-    for (long long p = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < net.n;
+    for (long long p = p_begin + (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < p_end;
          p += (long long)gridDim.x * warps_per_block) {
         const float* src = run.S + ((size_t)p * (run.T + 1) + 1) * 3;
-        float* dst = fvd + (size_t)net.row_of_pos[p] * 3 * run.T;
+        float* dst = fvd + (size_t)(compact_from >= 0 ? (int)p - compact_from : net.row_of_pos[p]) * 3 * run.T;
         const unsigned kind = net.kind[p] & 0x0F;
         const float* par = net.par + p;
         const McChannel c = mc_channel(__ldg(par + 0 * n), __ldg(par + 1 * n), __ldg(par + 2 * n), __ldg(par + 3 * n),
                                        __ldg(par + 4 * n), __ldg(par + 5 * n), __ldg(par + 6 * n), __ldg(par + 7 * n),
                                        __ldg(par + 8 * n));
-        for (int t = lane; t < run.T; t += 32) {
+        for (int t = run.t_off + lane; t < run.t_off + run.Tc; t += 32) {
             const float q = __ldcs(src + 3 * t), d = __ldcs(src + 3 * t + 2);
             float v = __ldcs(src + 3 * t + 1);
             if (kind == TRT_KIND_LEVELPOOL) v = 0.0f;      // flowveldepth[r.id, t, 1] = 0.0  (:708)
@@ -818,12 +821,14 @@ cudaError_t launch_fill_zero_rows(const int* pos, float* S, int count, int T, cu
     fill_zero_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, S, count, T);
     return cudaGetLastError();
 }
-cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st)
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st, int p_begin, int p_end,
+                            int compact_from)
 {
-    if (net.n == 0 || run.T == 0) return cudaSuccess;
+    if (p_end < 0) p_end = net.n;
+    if (p_end <= p_begin || run.Tc == 0) return cudaSuccess;
     const long long rows_per_block = 8;
-    const unsigned blocks = (unsigned)std::min<long long>((net.n + rows_per_block - 1) / rows_per_block, 148LL * 32);
-    permute_rows_kernel<<<blocks, 256, 0, st>>>(net, run, fvd);
+    const unsigned blocks = (unsigned)std::min<long long>((p_end - p_begin + rows_per_block - 1) / rows_per_block, 148LL * 32);
+    permute_rows_kernel<<<blocks, 256, 0, st>>>(net, run, fvd, p_begin, p_end, compact_from);
     return cudaGetLastError();
 }
 cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up, int n_lp, int T,

@@ -165,8 +165,7 @@ class ShardedRouter:
         self.net.upload_ptr(self.T, self.qts, qlat.data_ptr(), self.nq, q0.data_ptr())
         self.net.prepare()
         self.dist.barrier()
-        self.net.run_async(self.short_ts)
-        self.net.download_ptr(out.data_ptr())
+        self.net.run_download_ptr(self.short_ts, out.data_ptr())
 
     def host_result(self):
         """(global rows of this shard's own segments, their [n_own, 3T] results)"""

@@ -222,6 +222,10 @@ class RoutingNetwork:
         check(self._L.trt_download_results(self._h, fvd.ctypes.data, up.ctypes.data if up is not None else None))
         return fvd, up
 
+    def run_download_ptr(self, assume_short_ts, fvd_ptr):
+        """Time-chunked run with the result copies overlapped (trt_run_download) into a raw host address."""
+        check(self._L.trt_run_download(self._h, 1 if assume_short_ts else 0, fvd_ptr, None))
+
     def download_ptr(self, fvd_ptr):
         check(self._L.trt_download_results(self._h, fvd_ptr, None))
 
@@ -231,6 +235,19 @@ class RoutingNetwork:
         self.upload(nsteps, qts_subdivisions, qlat, q0, bnd_rows, bnd_fvd)
         self.run(assume_short_ts)
         return self.download(want_upstream)
+
+    def route_call(self, nsteps, qts_subdivisions, qlat, q0, assume_short_ts=False, want_upstream=False):
+        """The single-call C entry point trt_route on numpy arrays (time-chunked, copies overlapped with compute)."""
+        qlat = as_c(qlat, np.float32)
+        q0 = as_c(q0, np.float32)
+        self._check_forcing(nsteps, qts_subdivisions, qlat, q0)
+        fvd = np.empty((self.n_rows, 3 * int(nsteps)), dtype=np.float32)
+        up = np.empty((self.n_rows, int(nsteps)), dtype=np.float32) if want_upstream else None
+        check(self._L.trt_route(self._h, int(nsteps), int(qts_subdivisions), 1 if assume_short_ts else 0,
+                                qlat.ctypes.data, int(qlat.shape[1]), q0.ctypes.data, 0, None, None, fvd.ctypes.data,
+                                up.ctypes.data if up is not None else None))
+        self.nsteps = int(nsteps)
+        return fvd, up
 
     def route_ptr(self, nsteps, qts_subdivisions, assume_short_ts, qlat_ptr, nqcols, q0_ptr, fvd_ptr):
         """The single-call C entry point trt_route on raw host addresses (end-to-end timing path)."""

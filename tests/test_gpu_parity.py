@@ -286,6 +286,24 @@ def test_marching_schedule_options_do_not_change_results(eng, oracle, short_ts):
         H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], f"{opts} reservoir inflow")
 
 
+@pytest.mark.parametrize("short_ts", [False, True])
+def test_time_chunked_route_call(eng, oracle, short_ts):
+    """trt_route cuts the call into time chunks and copies the finished columns home while the next chunk runs: any
+    number of chunks (also one that does not divide the step count) gives the bits of the unchunked run."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.conus_like(n_total=20000, n_basins=30, seed=3, style="nhd"), nsteps=50, n_lp=10, warm=True)
+    ref, upref, _ = H.oracle_route(oracle, case, short_ts)
+    for mode, chunks in ((4, 1), (4, 2), (4, 3), (4, 7), (2, 4), (3, 2), (5, 3), (4, 50), (1, 2)):
+        net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+        net.set_levelpools(case["lp_rows"], case["wbody"])
+        net.set_option("mode", mode); net.set_option("route_chunks", chunks); net.set_option("deep_lanes", 3000)
+        out, up = net.route_call(50, 12, case["qlat"], case["q0"], assume_short_ts=short_ts, want_upstream=True)
+        net.close()
+        H.assert_bit_equal(out, ref, f"mode {mode}, {chunks} chunks")
+        H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], f"mode {mode}, {chunks} chunks: reservoir inflow")
+
+
 def test_gate_and_grid_options_do_not_change_results(eng, oracle):
     """Dataflow schedule knobs: run-ahead gate 1 / 50, tiny grid (2 CTAs) -- same bits."""
     from troute_b200 import synth
