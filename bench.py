@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--short-ts", type=int, default=0)
     ap.add_argument("--mode", type=int, default=4)
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--levelpools", type=int, default=0,
+                    help="replace this many in-line segments by level-pool reservoirs (BASELINE config 5; 1 GPU only)")
     ap.add_argument("--deep-lanes", type=int, default=8192, help="segments per GPU that march (deepest levels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -104,8 +106,17 @@ def build_workload(args):
     qlat = synth.lateral_inflow(n, args.nsteps, QTS, seed=16)
     q0 = np.zeros((n, 3), dtype=np.float32)
     up_ptr, up_rows = synth.upstream_csr(down)
+    kind = np.zeros(n, dtype=np.uint8)
+    lp_rows, wbody = np.zeros(0, np.int64), np.zeros((0, 11))
+    if args.levelpools:
+        rng = np.random.default_rng(23)
+        cand = np.nonzero(np.diff(up_ptr) > 0)[0]
+        lp_rows = np.sort(rng.choice(cand, size=min(args.levelpools, cand.size), replace=False)).astype(np.int64)
+        kind[lp_rows] = 1
+        wbody = synth.levelpool_params(lp_rows.size, seed=16)
+        name += f", {lp_rows.size} level-pool reservoirs"
     return dict(name=name, n=n, down=down, params=params, cols=synth.PARAM_COLS, qlat=qlat, q0=q0, up_ptr=up_ptr,
-                up_rows=up_rows, kind=np.zeros(n, dtype=np.uint8))
+                up_rows=up_rows, kind=kind, lp_rows=lp_rows, wbody=wbody)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -242,6 +253,8 @@ def run_ours(args, rank, world, local_rank):
 
     wl = build_workload(args)
     T = args.nsteps
+    if world > 1 and args.levelpools:
+        raise SystemExit("--levelpools is a single-GPU option")
     if world > 1:
         from troute_b200 import multigpu
         runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode,
@@ -250,6 +263,8 @@ def run_ours(args, rank, world, local_rank):
         from troute_b200 import multigpu
         runner = multigpu.SingleRouter(wl, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
         runner.net.set_option("deep_lanes", args.deep_lanes)
+        if args.levelpools:
+            runner.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=DT)
 
     for kv in args.opt:
         k, v = kv.split("=")
