@@ -62,7 +62,9 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--levelpools", type=int, default=0,
                     help="replace this many in-line segments by level-pool reservoirs (BASELINE config 5; 1 GPU only)")
-    ap.add_argument("--deep-lanes", type=int, default=8192, help="segments per GPU that march (deepest levels)")
+    ap.add_argument("--deep-lanes", type=int, default=0,
+                    help="segments per GPU that march (deepest levels); 0 = 8192 on 1-2 GPUs, 2048 on 4+ (one lane per "
+                         "warp: the main stem is the critical path once the wide levels are spread over many GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
@@ -87,6 +89,10 @@ def _cached(key, make):
     except Exception:
         pass
     return a
+
+
+def deep_lanes_for(args, world):
+    return args.deep_lanes or (8192 if world <= 2 else 2048)
 
 
 def build_workload(args):
@@ -258,11 +264,11 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         from troute_b200 import multigpu
         runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode,
-                                        deep_lanes=args.deep_lanes)
+                                        deep_lanes=deep_lanes_for(args, world))
     else:
         from troute_b200 import multigpu
         runner = multigpu.SingleRouter(wl, local_rank, T, QTS, bool(args.short_ts), mode=args.mode)
-        runner.net.set_option("deep_lanes", args.deep_lanes)
+        runner.net.set_option("deep_lanes", deep_lanes_for(args, world))
         if args.levelpools:
             runner.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=DT)
 
