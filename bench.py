@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--mode", type=int, default=4)
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--levelpools", type=int, default=0,
-                    help="replace this many in-line segments by level-pool reservoirs (BASELINE config 5; 1 GPU only)")
+                    help="replace this many in-line segments by level-pool reservoirs (BASELINE config 5)")
     ap.add_argument("--deep-lanes", type=int, default=0,
                     help="segments per GPU that march (deepest levels); 0 = 8192 on 1-2 GPUs, 2048 on 4+ (one lane per "
                          "warp: the main stem is the critical path once the wide levels are spread over many GPUs)")
@@ -259,8 +259,6 @@ def run_ours(args, rank, world, local_rank):
 
     wl = build_workload(args)
     T = args.nsteps
-    if world > 1 and args.levelpools:
-        raise SystemExit("--levelpools is a single-GPU option")
     if world > 1:
         from troute_b200 import multigpu
         runner = multigpu.ShardedRouter(wl, world, rank, local_rank, T, QTS, bool(args.short_ts), mode=args.mode,

@@ -108,6 +108,12 @@ class ShardedRouter:
         self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
                                   device=device, levels=plan.levels)
         self.net.set_option("mode", mode)
+        lp_local = np.nonzero(plan.kind == 1)[0]
+        if lp_local.size:
+            # level pools of this shard: the rows of wl["wbody"] that belong to its reservoirs
+            lp_index = {int(r): i for i, r in enumerate(np.asarray(wl["lp_rows"]).tolist())}
+            rows = np.asarray([lp_index[int(g)] for g in plan.rows[lp_local]], dtype=np.int64)
+            self.net.set_levelpools(lp_local, np.asarray(wl["wbody"])[rows], routing_period=wl.get("dt", 300.0))
         if mode >= 4:
             # one split level for ALL shards: a dataflow (wide) kernel may wait only for values that other shards produce
             # in THEIR dataflow kernels; the deepest levels (at most deep_lanes segments on any shard) march

@@ -21,9 +21,9 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 down = synth.conus_like(n_total=60000, n_basins=40, seed=12)
-case = H.make_case(down, nsteps=36, warm=True)
+case = H.make_case(down, nsteps=36, warm=True, n_lp=40)
 wl = dict(n=case["n"], down=down, params=case["params"], cols=case["cols"], qlat=case["qlat"], q0=case["q0"],
-          up_ptr=case["up_ptr"], up_rows=case["up_rows"], kind=case["kind"])
+          up_ptr=case["up_ptr"], up_rows=case["up_rows"], kind=case["kind"], lp_rows=case["lp_rows"], wbody=case["wbody"])
 for short in (False, True):
     r = multigpu.ShardedRouter(wl, world, rank, rank, 36, 12, short, pieces_per_shard=6)
     r.upload(); r.alloc_host()

@@ -1,0 +1,53 @@
+"""troute_b200.hyfeatures on a hand-made GeoPackage (an SQLite file with the two attribute tables of a NextGen
+hydrofabric) and hand-made forcing CSVs: the reader reproduces what HYFeaturesNetwork.read_geopkg + preprocess_network
+(HYFeaturesNetwork.py:33-107, :369-444) hand to the routing path.  CPU only, no reference tree needed."""
+import os
+import sqlite3
+
+import numpy as np
+import pytest
+
+from troute_b200 import hyfeatures as hy
+
+
+def _make_gpkg(path):
+    con = sqlite3.connect(path)
+    con.execute("CREATE TABLE flowpaths (fid INTEGER, geom BLOB, id TEXT, toid TEXT, mainstem REAL)")
+    con.execute("CREATE TABLE flowpath_attributes (fid INTEGER, id TEXT, rl_gages TEXT, rl_NHDWaterbodyComID REAL, Qi REAL,"
+                " MusK REAL, MusX REAL, n REAL, So REAL, ChSlp REAL, BtmWdth REAL, time REAL, Kchan REAL, nCC REAL,"
+                " TopWdthCC REAL, TopWdth REAL, length_m REAL)")
+    # 5 -> 3 -> 1 -> terminal nexus;  4 -> 3;  2 -> 1   (wb-X drains to nex-Y, nexus nex-Y feeds wb-Y)
+    topo = {5: "nex-3", 4: "nex-3", 3: "nex-1", 2: "nex-1", 1: "tnx-1000000001"}
+    for i, (k, to) in enumerate(sorted(topo.items(), reverse=True)):
+        con.execute("INSERT INTO flowpaths VALUES (?, NULL, ?, ?, ?)", (i, f"wb-{k}", to, 77.0))
+        con.execute("INSERT INTO flowpath_attributes VALUES (?, ?, NULL, NULL, 0, 3600, 0.2, ?, ?, ?, ?, 0, 0, ?, ?, ?, ?)",
+                    (i, f"wb-{k}", 0.05 + 0.001 * k, 0.001 * k, 0.5, 2.0 * k, 0.1 + 0.001 * k, 30.0 * k, 10.0 * k, 1000.0 * k))
+    con.commit(); con.close()
+
+
+def test_read_flowpaths_and_connections(tmp_path):
+    g = str(tmp_path / "toy.gpkg")
+    _make_gpkg(g)
+    df = hy.read_flowpaths(g)
+    assert df.index.tolist() == [1, 2, 3, 4, 5]                     # numeric ids, sorted
+    assert df.loc[5, "downstream"] == 3 and df.loc[1, "downstream"] == 1000000001
+    assert df.attrs["terminal_rows"] == 1
+    assert df.loc[3, "dx"] == 3000.0 and df.loc[3, "bw"] == 6.0 and df.loc[3, "tw"] == 30.0 and df.loc[3, "twcc"] == 90.0
+    assert (df["alt"] == 1.0).all() and "gages" not in df.columns
+    conn = hy.connections(df)
+    assert conn == {1: [], 2: [1], 3: [1], 4: [3], 5: [3]}
+    p = hy.param_frame(df, 300.0)
+    assert p.columns.tolist() == ["dt", "bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"] and (p["dt"] == 300.0).all()
+    assert p.values.dtype == np.float32
+
+
+def test_read_channel_forcing(tmp_path):
+    d = tmp_path / "forcing"; d.mkdir()
+    for h, vals in (("202304010000", {1: 0.5, 3: 1.5}), ("202304010100", {1: 0.25, 2: 2.0, 3: 1.0})):
+        with open(d / f"{h}.CHRTOUT_DOMAIN1.csv", "w") as f:
+            f.write(f"feature_id,{h}\n" + "".join(f"{k},{v}\n" for k, v in vals.items()))
+    q = hy.read_channel_forcing(str(d), index=[1, 2, 3, 4])
+    assert q.shape == (4, 2) and q.values.dtype == np.float32
+    assert q.loc[2].tolist() == [0.0, 2.0] and q.loc[4].tolist() == [0.0, 0.0] and q.loc[3].tolist() == [1.5, 1.0]
+    with pytest.raises(FileNotFoundError):
+        hy.read_channel_forcing(str(tmp_path / "nothing"))
