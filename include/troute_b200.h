@@ -72,6 +72,15 @@ int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const 
 int trt_network_create_ex(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
                           const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
                           const int32_t* level_of_row, trt_network** out);
+/* Same, with a sort key for the order of the segments INSIDE a wavefront level (NULL = caller's row order).  Any order is
+ * valid and gives the same results; lanes of a warp run in lockstep, so rows with equal keys should behave alike -- e.g.
+ * order_key = trt_trip_counts of a previous call on the same network (secant trip counts repeat from step to step). */
+int trt_network_create_ordered(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
+                               const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
+                               const int32_t* level_of_row, const int32_t* order_key, trt_network** out);
+/* option "collect_trips" = 1 before a run: secant trips of every row summed over the steps of that run (rows routed by the
+ * marching kernel report 0) */
+int trt_trip_counts(trt_network* net, int32_t* trips_of_row /* [n_rows] */);
 int trt_network_destroy(trt_network* net);
 
 /* topology queries: number of wavefront levels; level of every row; engine position of every row */

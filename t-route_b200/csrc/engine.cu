@@ -147,6 +147,9 @@ struct trt_network {
     DevBuf<unsigned char> d_gage_active;
     DevBuf<float> d_usgs, d_lastobs, d_lastobs_init, d_nudge;
 
+    bool collect_trips = false;                               // sum the secant trips of every segment over a run
+    DevBuf<int> d_trip_sum;                                   // [n] by position
+
     // options / stats
     int mode = 4;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow,
                                    // 3 marching lanes, 4 dataflow for the wide shallow levels + marching for the deep ones
@@ -165,6 +168,7 @@ struct trt_network {
     {
         RunDev r;
         r.T = T; r.t_off = 0; r.Tc = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
+        r.trip_sum = collect_trips ? d_trip_sum.p : nullptr;
         r.gage.n_gages = (int)n_gages; r.gage.gmax = gage_max; r.gage.dt = gage_dt; r.gage.decay = gage_decay;
         r.gage.slot = d_gage_slot.p; r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
         return r;
@@ -193,6 +197,14 @@ int trt_network_create(int device, int64_t n_rows, const int64_t* up_ptr, const 
 int trt_network_create_ex(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows, const uint8_t* kind,
                           const float* data_values, int32_t ncols, const int32_t* scols, const int32_t* levels_in,
                           trt_network** out)
+{
+    return trt_network_create_ordered(device, n_rows, up_ptr, up_rows, kind, data_values, ncols, scols, levels_in, nullptr,
+                                      out);
+}
+
+int trt_network_create_ordered(int device, int64_t n_rows, const int64_t* up_ptr, const int64_t* up_rows,
+                               const uint8_t* kind, const float* data_values, int32_t ncols, const int32_t* scols,
+                               const int32_t* levels_in, const int32_t* order_key, trt_network** out)
 {
     if (!out) return fail(TRT_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -282,6 +294,15 @@ int trt_network_create_ex(int device, int64_t n_rows, const int64_t* up_ptr, con
             const int32_t p = cursor[(size_t)level[(size_t)r]]++;
             net->pos_of_row[(size_t)r] = p;
             net->row_of_pos[(size_t)p] = (int32_t)r;
+        }
+        if (order_key) {
+            // inside a level any order is valid: sort by the caller's key (stable), e.g. the secant trip counts a previous
+            // call collected, so that the lanes of a warp need the same number of trips
+            for (int l = 0; l < nlev; ++l)
+                std::stable_sort(net->row_of_pos.begin() + net->lvl_ptr[(size_t)l],
+                                 net->row_of_pos.begin() + net->lvl_ptr[(size_t)l + 1],
+                                 [&](int32_t a, int32_t b) { return order_key[a] < order_key[b]; });
+            for (int64_t p = 0; p < n; ++p) net->pos_of_row[(size_t)net->row_of_pos[(size_t)p]] = (int32_t)p;
         }
     }
     net->kind_of_row.assign(kind, kind + n);
@@ -606,12 +627,14 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         RunDev rg = net->rundev(0);
         CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
     }
+    if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1)));
     const NetDev nd = net->netdev();
     RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
     rd.t_off = t_off; rd.Tc = Tc;
     const int T = Tc;                          // steps this launch schedules
     const int L = assume_short_ts ? 1 : net->nlevels;
     if (first) { net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0; }
+    if (first && net->collect_trips && net->n > 0) CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * sizeof(int), st));
     const int64_t launches_before = net->launches;
 
     if (first) CU(cudaEventRecord(net->ev0, st));
@@ -1184,6 +1207,8 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
+    } else if (!strcmp(key, "collect_trips")) {
+        net->collect_trips = value != 0;
     } else if (!strcmp(key, "route_chunks")) {
         if (value < 1 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 1..1024");
         net->route_chunks = (int)value;
@@ -1237,6 +1262,19 @@ int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms,
         if (stage_ms) stage_ms[k] = net->stage_ms[(size_t)k];
         if (stage_width) stage_width[k] = net->stage_width[(size_t)k];
     }
+    return TRT_OK;
+}
+
+int trt_trip_counts(trt_network* net, int32_t* trips_of_row)
+{
+    if (!net || !trips_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->collect_trips || !net->d_trip_sum.p || !net->ran)
+        return fail(TRT_ERR_STATE, "no trip counts: set option collect_trips = 1 before trt_run");
+    CU(cudaSetDevice(net->device));
+    CU(cudaStreamSynchronize(net->stream));
+    std::vector<int32_t> h((size_t)net->n);
+    CU(cudaMemcpy(h.data(), net->d_trip_sum.p, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < net->n; ++r) trips_of_row[r] = h[(size_t)net->pos_of_row[(size_t)r]];
     return TRT_OK;
 }
 

@@ -41,6 +41,7 @@ class SingleRouter:
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
         self.net.set_option("stream", self.tstream.cuda_stream)
+        self.reordered = False
         self.nq = wl["qlat"].shape[1]
         self.h2d_bytes = wl["qlat"].nbytes + wl["q0"].nbytes
         self.d2h_bytes = self.n * 3 * nsteps * 4
@@ -49,6 +50,28 @@ class SingleRouter:
 
     def upload(self):
         self.net.upload(self.T, self.qts, self.wl["qlat"], self.wl["q0"])
+
+    def reorder_by_trip_history(self, options=None):
+        """One calibration call that records how many secant trips every segment needed, then the network is rebuilt
+        with the segments of every wavefront level ordered by that count: a segment's trip count repeats from step to
+        step (p = 0.82), so the 32 lanes of a warp -- which run in lockstep -- now mostly need the same number of trips.
+        What an operational deployment would do once per network (the handle is cached across calls); the results do
+        not depend on the order."""
+        self.net.set_option("collect_trips", 1)
+        self.net.run(self.short_ts)
+        key = self.net.trip_counts()
+        wl = self.wl
+        self.net.close()
+        self.net = RoutingNetwork(wl["up_ptr"], wl["up_rows"], wl["kind"], wl["params"], wl["cols"], device=self.device,
+                                  order_key=key)
+        self.net.set_option("mode", self.mode)
+        self.net.set_option("stream", self.tstream.cuda_stream)
+        for k, v in (options or {}).items():
+            self.net.set_option(k, v)
+        if len(wl.get("lp_rows", ())):
+            self.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=wl.get("dt", 300.0))
+        self.upload()
+        self.reordered = True
 
     def run_resident(self):
         self.net.run_async(self.short_ts)

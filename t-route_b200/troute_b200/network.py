@@ -37,7 +37,7 @@ class RoutingNetwork:
     device          : CUDA device ordinal
     """
 
-    def __init__(self, up_ptr, up_rows, kind, data_values, data_cols, device=0, levels=None):
+    def __init__(self, up_ptr, up_rows, kind, data_values, data_cols, device=0, levels=None, order_key=None):
         L = _lib.lib()
         self._L = L
         self._h = C.c_void_p()
@@ -62,10 +62,16 @@ class RoutingNetwork:
             lv = as_c(levels, np.int32)
             if lv.shape[0] != n_rows:
                 raise ValueError("levels must have one entry per row")
-        check(L.trt_network_create_ex(self.device, n_rows, ptr(up_ptr, C.c_int64), ptr(up_rows, C.c_int64),
-                                      ptr(kind, C.c_uint8), ptr(data_values, C.c_float), int(data_values.shape[1]),
-                                      ptr(scols, C.c_int32), ptr(lv, C.c_int32) if lv is not None else None,
-                                      C.byref(self._h)))
+        ok = None
+        if order_key is not None:
+            # within-level order of the segments in the engine (any order gives the same results), e.g. trip_counts()
+            ok = as_c(order_key, np.int32)
+            if ok.shape[0] != n_rows:
+                raise ValueError("order_key must have one entry per row")
+        check(L.trt_network_create_ordered(self.device, n_rows, ptr(up_ptr, C.c_int64), ptr(up_rows, C.c_int64),
+                                           ptr(kind, C.c_uint8), ptr(data_values, C.c_float), int(data_values.shape[1]),
+                                           ptr(scols, C.c_int32), ptr(lv, C.c_int32) if lv is not None else None,
+                                           ptr(ok, C.c_int32) if ok is not None else None, C.byref(self._h)))
         self._keep = None
         self.nsteps = 0
         self._lp_rows = np.zeros(0, dtype=np.int64)
@@ -330,6 +336,12 @@ class RoutingNetwork:
         return {"kernel_ms": ms.value, "launches": launches.value, "stages": stages.value,
                 "lane_steps": lane_steps.value, "wide_ms": wide.value, "march_ms": march.value,
                 "first_marching_level": lvl.value}
+
+    def trip_counts(self):
+        """Secant trips of every row summed over the last run (option collect_trips = 1 must have been set before it)."""
+        out = np.zeros(self.n_rows, dtype=np.int32)
+        check(self._L.trt_trip_counts(self._h, ptr(out, C.c_int32)))
+        return out
 
     def march_profile(self):
         """[n_rows, 4] uint64 of the last run with option march_profile=1 (see trt_march_profile)."""

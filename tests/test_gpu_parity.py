@@ -304,6 +304,38 @@ def test_time_chunked_route_call(eng, oracle, short_ts):
         H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], f"mode {mode}, {chunks} chunks: reservoir inflow")
 
 
+def test_within_level_order_and_trip_counts(eng, oracle):
+    """Any order of the segments inside a wavefront level gives the same bits; the trip counts the engine collects add
+    up to the oracle's iteration histogram; ordering by them (what bench.py does after a calibration call) is one such
+    order."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.conus_like(n_total=20000, n_basins=30, seed=9, style="nhd"), nsteps=30, n_lp=10, warm=True)
+    ref, upref, extras = H.oracle_route(oracle, case, False)
+    hist = extras["iter_hist"]
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+    net.set_levelpools(case["lp_rows"], case["wbody"])
+    net.set_option("mode", 2); net.set_option("collect_trips", 1)
+    out, _ = net.route(30, 12, case["qlat"], case["q0"])
+    trips = net.trip_counts()
+    net.close()
+    H.assert_bit_equal(out, ref, "collecting run")
+    # oracle histogram buckets: 0..7 exact, then 8-15, 16-31, 32-63, 64-127, 128-255, 256-511, 512+ (troute_oracle.c)
+    lo = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 16, 32, 64, 128, 256, 512, 0])
+    hi = np.array([0, 1, 2, 3, 4, 5, 6, 7, 15, 31, 63, 127, 255, 511, 760, 0])
+    assert int((hist * lo).sum()) <= int(trips.sum()) <= int((hist * hi).sum())
+    assert int((trips > 0).sum()) == case["n"] - case["lp_rows"].size
+    assert (trips[case["lp_rows"]] == 0).all()
+    rng = np.random.default_rng(0)
+    for key in (trips, rng.integers(0, 5, case["n"]).astype(np.int32)):
+        net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"], order_key=key)
+        net.set_levelpools(case["lp_rows"], case["wbody"])
+        out, up = net.route(30, 12, case["qlat"], case["q0"], want_upstream=True)
+        net.close()
+        H.assert_bit_equal(out, ref, "ordered network")
+        H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], "ordered network: reservoir inflow")
+
+
 def test_gate_and_grid_options_do_not_change_results(eng, oracle):
     """Dataflow schedule knobs: run-ahead gate 1 / 50, tiny grid (2 CTAs) -- same bits."""
     from troute_b200 import synth
