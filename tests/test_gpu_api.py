@@ -153,6 +153,29 @@ def test_nudging_requires_gage_at_reach_end(oracle):
     mc_reach.clear_network_cache()
 
 
+def test_cached_network_is_reordered_after_first_call(oracle):
+    """Large networks are rebuilt after their first call with each wavefront level ordered by the trip counts that call
+    collected (mc_reach.REORDER_MIN_ROWS); results of the first and of later calls are the oracle's, bit for bit."""
+    from troute_b200.routing.fast_reach import mc_reach
+    c = _reference_style_case(n=5000, seed=21, n_lp=8, nsteps=24)
+    gages = _gage_inputs(c, n_gages=40, seed=5, obs_steps=24)
+    ref = _call(oracle.compute_network_structured, c, gages=gages)
+    old = mc_reach.REORDER_MIN_ROWS
+    mc_reach.REORDER_MIN_ROWS = 1000
+    try:
+        first = _call(mc_reach.compute_network_structured, c, gages=gages)
+        entry = next(iter(mc_reach._NET_CACHE.values()))
+        assert entry["ordered"] and "flat" not in entry
+        second = _call(mc_reach.compute_network_structured, c, gages=gages)
+    finally:
+        mc_reach.REORDER_MIN_ROWS = old
+        mc_reach.clear_network_cache()
+    for got in (first, second):
+        H.assert_bit_equal(got[1], ref[1], "flowveldepth")
+        H.assert_bit_equal(got[8], ref[8], "nudge")
+        H.assert_bit_equal(got[6][c["lp_rows"]], ref[6][c["lp_rows"]], "reservoir inflow")
+
+
 def test_upstream_results_injection(oracle):
     """by-subnetwork hand-off (compute.py:882-900 -> mc_reach.pyx:458-469): route the part of the basin below a cut
     with the cut segment's series prescribed; rows of prescribed segments are masked out of the result."""

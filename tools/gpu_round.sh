@@ -9,6 +9,9 @@ has() { [[ $STAGE == all || " $STAGE " == *" $1 "* ]]; }
 if has light; then
   timeout 900 python tools/gpu_first_light.py > gpurun_out/first_light.log 2>&1; echo "first_light rc=$?" >> gpurun_out/box.txt
 fi
+if has smoke; then
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/box.txt
+fi
 if has test; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/box.txt
 fi
