@@ -4,26 +4,33 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (config.workload): BASELINE.json configs[2] -- the synthetic CONUS-scale forest the metric is quoted on:
-2,729,077 segments in 14,713 basins (largest ~50 %), MC-only, 288 x 300 s steps, dependent upstream flows
-(assume_short_ts = False, the reference default).  One bench "step" = ONE routing call = all 288 timesteps of
-all segments (786 M segment-timesteps).  Synthetic parameters/forcing, cold start; see troute_b200/synth.py.
+2,729,077 segments in 14,713 basins (largest ~50 %), NHD-like confluences (SURVEY.md 8d in-degree mix), MC-only,
+288 x 300 s steps, dependent upstream flows (assume_short_ts = False, the reference default).  One bench "step" = ONE
+routing call = all 288 timesteps of all segments (786 M segment-timesteps).  Synthetic parameters/forcing, cold start; see
+troute_b200/synth.py.  --workload tree is BASELINE configs[1] (binary tree, 1,048,576 segments); --levelpools N adds
+reservoirs (configs[4]).
 
-  value     segment-timesteps/s with forcing and state already resident in HBM: K x (wavefront kernel + result
-            transpose) timed with CUDA events on the launching stream.  Working set (q, v, d, fvd: 4 x 9.4 GB)
+  set-up    (not timed, once per network as in production where the handle is cached across calls): flatten + upload of the
+            network, one calibration call that records the secant trip count of every segment, rebuild with the segments of
+            every wavefront level ordered by it (config.within_level_order; --no-trip-order skips it).
+  value     segment-timesteps/s with forcing and state already resident in HBM: K x (flow-state reset + routing kernels +
+            result pass) timed with CUDA events on the launching stream.  Working set (flow state 9.4 GB + result 9.4 GB)
             is far larger than the 126 MB L2, so no explicit flush between iterations.
-  e2e       the same metric through the C-ABI call a T-Route maintainer would bind (trt_route): pinned HOST
-            qlat / q0 in, pinned HOST [n, 3*nsteps] result out, copies inside the timed region.
-  roofline  wavefront kernel only: algorithmic bytes (68 B per segment-timestep, SURVEY.md 8d / DESIGN.md) x
-            lane-steps per launch / the kernel's CUDA-event duration (events recorded by the engine on its
-            stream around that launch), against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the oracle's platform-libm build (C restatement of the Fortran; the reference cannot be
-            compiled here: no Fortran compiler) on a bounded sample of the same workload, rank 0, N = 1 only.
+  e2e       the same metric through the C-ABI call a T-Route maintainer would bind (trt_route): pinned HOST qlat / q0 in,
+            pinned HOST [n, 3*nsteps] result out, copies inside the timed region (trt_route overlaps the result copies
+            with the kernels by time chunks).
+  roofline  dominant kernel (the dataflow kernel over the wide levels): algorithmic bytes (68 B per segment-timestep,
+            SURVEY.md 8d / DESIGN.md) x segment-timesteps of that launch / its CUDA-event duration (events recorded by the
+            engine on its stream around that launch), against MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes of
+            that kernel (profiles/traffic.json).
+  cpu_baseline  the oracle's platform-libm build (C restatement of the Fortran; the reference cannot be compiled here: no
+            Fortran compiler) on a bounded sample of the same workload, one core, rank 0, N = 1 only.
 
---impl reference times that CPU restatement with every host thread, decomposed the way the reference's
-parallel modes do (orders of sub-networks, jobs of an order in parallel), on a bounded sample.
+--impl reference times that CPU restatement with every host thread, decomposed the way the reference's parallel modes do
+(orders of sub-networks, jobs of an order in parallel), on a bounded sample.
 
-N > 1: torchrun, one rank per GPU; the network is sharded by sub-basin (troute_b200/partition.py), total work
-fixed -> "scaling": "strong".
+N > 1: torchrun, one rank per GPU; the network is sharded by sub-basin (troute_b200/partition.py), total work fixed ->
+"scaling": "strong"; cut-edge flows cross GPUs as peer-memory stores inside the kernels (no collective).
 """
 import argparse
 import json

@@ -635,7 +635,6 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
     const int L = assume_short_ts ? 1 : net->nlevels;
     if (first) { net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0; }
     if (first && net->collect_trips && net->n > 0) CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * sizeof(int), st));
-    const int64_t launches_before = net->launches;
 
     if (first) CU(cudaEventRecord(net->ev0, st));
     if (net->n > 0 && T > 0 && L > 0) {
@@ -867,7 +866,6 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         }
     }
     net->launches += (net->n > 0 && T > 0) ? 1 : 0;
-    (void)launches_before;
     net->ran = true;
     return TRT_OK;
 }
