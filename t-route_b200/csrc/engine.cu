@@ -543,7 +543,14 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
     CU(net->d_q0_in.reserve((size_t)n * 3));
     CU(net->d_qlat_t.reserve((size_t)n * nqcols));
     CU(net->d_S.reserve(rows_t * 3));
-    CU(net->d_fvd.reserve((size_t)n * 3 * (size_t)nsteps));
+    {
+        // rows of marching segments are copied home from a compact buffer in the chunked route; the strided chunk copies
+        // still sweep over their (then unwritten) rows of d_fvd, so give a fresh allocation defined contents once
+        const float* before = net->d_fvd.p;
+        CU(net->d_fvd.reserve((size_t)n * 3 * (size_t)nsteps));
+        if (net->d_fvd.p != before && n > 0 && nsteps > 0)
+            CU(cudaMemsetAsync(net->d_fvd.p, 0, net->d_fvd.cap * sizeof(float), st));
+    }
 
     if (n > 0) {
         CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyHostToDevice, st));
