@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--levelpools", type=int, default=0,
                     help="replace this many in-line segments by level-pool reservoirs (BASELINE config 5)")
     ap.add_argument("--deep-lanes", type=int, default=0,
-                    help="segments per GPU that march (deepest levels); 0 = 8192 on 1-2 GPUs, 2048 on 4+ (one lane per "
+                    help="segments per GPU that march (deepest levels); 0 = 8192 on 1 GPU, 4096 on 2, 2048 on 4+ (one lane per "
                          "warp: the main stem is the critical path once the wide levels are spread over many GPUs)")
     ap.add_argument("--no-trip-order", action="store_true",
                     help="skip the calibration call that orders the segments of a level by their secant trip counts")
@@ -101,7 +101,7 @@ def _cached(key, make):
 
 
 def deep_lanes_for(args, world):
-    return args.deep_lanes or (8192 if world <= 2 else 2048)
+    return args.deep_lanes or {1: 8192, 2: 4096}.get(world, 2048)
 
 
 def build_workload(args):
