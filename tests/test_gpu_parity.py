@@ -336,6 +336,28 @@ def test_within_level_order_and_trip_counts(eng, oracle):
         H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], "ordered network: reservoir inflow")
 
 
+@pytest.mark.parametrize("nsteps,qts", [(1, 1), (7, 3), (13, 12), (25, 5), (2, 12)])
+def test_ragged_step_counts(eng, oracle, nsteps, qts):
+    """Step counts that are not multiples of qts_subdivisions, a single step, fewer steps than time chunks or marching
+    lanes: qlat column (t - 1) // qts (mc_reach.pyx:723), every schedule, direct and time-chunked."""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.conus_like(n_total=6000, n_basins=10, seed=31, style="nhd"), nsteps=nsteps, qts=qts, n_lp=6,
+                       warm=True)
+    for short_ts in (False, True):
+        ref, upref, _ = H.oracle_route(oracle, case, short_ts)
+        for mode in (1, 2, 3, 4, 5):
+            net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+            net.set_levelpools(case["lp_rows"], case["wbody"])
+            net.set_option("mode", mode); net.set_option("deep_lanes", 1500); net.set_option("time_block", 4)
+            out, up = net.route(nsteps, qts, case["qlat"], case["q0"], assume_short_ts=short_ts, want_upstream=True)
+            H.assert_bit_equal(out, ref, f"mode {mode} direct")
+            out2, up2 = net.route_call(nsteps, qts, case["qlat"], case["q0"], assume_short_ts=short_ts, want_upstream=True)
+            net.close()
+            H.assert_bit_equal(out2, ref, f"mode {mode} chunked")
+            H.assert_bit_equal(up2[case["lp_rows"]], upref[case["lp_rows"]], f"mode {mode} reservoir inflow")
+
+
 def test_gate_and_grid_options_do_not_change_results(eng, oracle):
     """Dataflow schedule knobs: run-ahead gate 1 / 50, tiny grid (2 CTAs) -- same bits."""
     from troute_b200 import synth
