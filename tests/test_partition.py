@@ -167,3 +167,22 @@ def test_two_process_gloo_sharded_exchange(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o
+
+
+def test_global_deep_level_bounds_every_shard():
+    """multigpu.global_deep_level: the smallest split level such that no shard marches more than `deep_lanes` segments;
+    every shard of a run uses it (a dataflow kernel must not wait for a value another shard produces while marching)."""
+    from troute_b200 import multigpu, synth, hostgraph, partition
+    down = synth.conus_like(n_total=30000, n_basins=20, seed=2, style="nhd")
+    up_ptr, up_rows = synth.upstream_csr(down)
+    level = hostgraph.levels(down, up_ptr)
+    for P in (1, 2, 4):
+        shard, plans, _ = partition.plan_shards(down, up_ptr, up_rows, np.zeros(down.size, np.uint8), P, pieces_per_shard=8,
+                                                level=level)
+        for cap in (100, 1000, 10 ** 6):
+            L = multigpu.global_deep_level(level, shard, P, cap)
+            per_shard = [int(((level >= L) & (shard == r)).sum()) for r in range(P)]
+            assert max(per_shard) <= cap
+            if L > 0:                                   # minimal: one level lower overflows some shard
+                assert max(int(((level >= L - 1) & (shard == r)).sum()) for r in range(P)) > cap
+        assert multigpu.global_deep_level(level, shard, P, 10 ** 6) == 0
