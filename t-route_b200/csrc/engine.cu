@@ -543,6 +543,9 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
     CU(net->d_q0_in.reserve((size_t)n * 3));
     CU(net->d_qlat_t.reserve((size_t)n * nqcols));
     CU(net->d_S.reserve(rows_t * 3));
+    // allocate here, not in trt_run: an allocation may synchronise the device, and a peer handle on the same device may
+    // already be running a kernel that waits for this handle's kernels
+    if (net->n_gages > 0) CU(net->d_nudge.reserve((size_t)net->n_gages * (size_t)(nsteps + 1)));
     {
         // rows of marching segments are copied home from a compact buffer in the chunked route; the strided chunk copies
         // still sweep over their (then unwritten) rows of d_fvd, so give a fresh allocation defined contents once

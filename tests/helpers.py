@@ -45,7 +45,7 @@ def make_case(down, nsteps=48, qts=12, seed=16, n_lp=0, warm=False):
                 up_rows=up_rows, kind=kind, lp_rows=lp_rows, wbody=wbody, nsteps=nsteps, qts=qts)
 
 
-def oracle_route(o, case, assume_short_ts, pow_mode=None, reaches=None, jobs=None, nthreads=0):
+def oracle_route(o, case, assume_short_ts, pow_mode=None, reaches=None, jobs=None, nthreads=0, gages=None):
     """Run the oracle in the reference's loop order.  By default each segment is a single-segment reach
     listed in level order (a valid upstream-first order); `reaches` overrides that."""
     n = case["n"]
@@ -70,7 +70,7 @@ def oracle_route(o, case, assume_short_ts, pow_mode=None, reaches=None, jobs=Non
     fvd, up, extras = o.route_network_flat(
         case["nsteps"], 300.0, case["qts"], n, reach_ptr, reach_rows, reach_type, reach_up_ptr, reach_up_rows,
         case["params"], scols, case["q0"], case["qlat"], assume_short_ts=assume_short_ts, reach_wbody=reach_wbody,
-        wbody_cols=case["wbody"], pow_mode=pow_mode, jobs=jobs, nthreads=nthreads, want_hist=True)
+        wbody_cols=case["wbody"], pow_mode=pow_mode, jobs=jobs, nthreads=nthreads, want_hist=True, gages=gages)
     return fvd[:, 1:, :].reshape(n, -1), up[:, 1:], extras
 
 

@@ -425,3 +425,78 @@ def test_sharded_on_one_gpu_concurrent_kernels(eng, oracle, P, short_ts, split):
         loc_lp = np.nonzero(p.kind == 1)[0]
         H.assert_bit_equal(up[loc_lp], upref[p.rows[loc_lp]], f"shard {p.rank} reservoir inflow")
         net.close()
+
+
+@pytest.mark.skipif(not os.environ.get("TRT_TEST_OPEN_ISSUES"),
+                    reason="open issue (DESIGN.md section 9): failed with a TrouteB200Error on its only GPU run, after the "
+                           "round's GPU minutes were spent; nudging is supported on a single GPU only until this is green")
+@pytest.mark.parametrize("P", [2, 3])
+def test_sharded_nudging_on_one_gpu(eng, oracle, P):
+    """Streamflow nudging in a sharded run: every shard assimilates the gages on its own segments, and a nudged flow
+    that crosses a cut edge reaches the downstream shard as the nudged value (it is exported after the replacement).
+    P shard handles on one device with concurrent kernels, as in test_sharded_on_one_gpu_concurrent_kernels."""
+    from troute_b200 import synth, partition, hostgraph, multigpu
+    from troute_b200.network import RoutingNetwork
+    T = 30
+    down = synth.conus_like(n_total=30000, n_basins=20, seed=14, style="nhd")
+    case = H.make_case(down, nsteps=T, warm=True)
+    n = case["n"]
+    rng = np.random.default_rng(4)
+    G = 150
+    grow = np.sort(rng.choice(n, size=G, replace=False)).astype(np.int32)
+    usgs = rng.uniform(0.2, 20.0, size=(G, 18)).astype(np.float32)
+    usgs[rng.random(usgs.shape) < 0.3] = np.nan
+    lastobs = rng.uniform(0.2, 20.0, G).astype(np.float32)
+    since = -rng.uniform(0.0, 3600.0, G).astype(np.float32)
+    lastobs[::7] = np.nan; since[::7] = np.nan
+    level = hostgraph.levels(down, case["up_ptr"])
+    inv_order = np.empty(n, dtype=np.int64)
+    inv_order[np.argsort(level, kind="stable")] = np.arange(n)          # oracle_route lists one-segment reaches in this order
+    g_oracle = dict(usgs_values=usgs, usgs_positions=grow, usgs_positions_reach=inv_order[grow].astype(np.int32),
+                    usgs_positions_gage=np.arange(G, dtype=np.int32), lastobs_values_init=lastobs,
+                    time_since_lastobs_init=since, da_decay_coefficient=120.0)
+    ref, _, extras = H.oracle_route(oracle, case, False, gages=g_oracle)
+    plain, _, _ = H.oracle_route(oracle, case, False)
+    assert not np.array_equal(ref, plain)
+    shard, plans, stats = partition.plan_shards(down, case["up_ptr"], case["up_rows"], case["kind"], P,
+                                                pieces_per_shard=6, level=level)
+    assert stats["n_cut_edges"] > 0
+    deep = multigpu.global_deep_level(level, shard, P, 2000)
+    nets, gsel = [], []
+    for p in plans:
+        net = RoutingNetwork(p.up_ptr, p.up_rows, p.kind, case["params"][p.rows], case["cols"], levels=p.levels)
+        net.set_option("grid_blocks", 74); net.set_option("deep_level", deep)
+        net.set_imports(p.imports)
+        own_rows = p.rows[p.own]
+        sel = np.nonzero(np.isin(grow, own_rows))[0]                      # gages of this shard
+        loc = np.searchsorted(p.rows, grow[sel]).astype(np.int32)
+        nloc = p.rows.size
+        net.set_gages(dict(usgs_values=usgs[sel], usgs_positions=loc, usgs_positions_reach=loc,
+                           usgs_positions_gage=np.arange(sel.size, dtype=np.int32), lastobs_values_init=lastobs[sel],
+                           time_since_lastobs_init=since[sel], da_decay_coefficient=120.0,
+                           reach_len=np.ones(nloc, dtype=np.int64), seg_rows=np.arange(nloc)), T, routing_period=300.0)
+        net.upload(T, 12, case["qlat"][p.rows], case["q0"][p.rows])
+        nets.append(net); gsel.append(sel)
+    assert sum(s.size for s in gsel) == G
+    pos = [net.positions() for net in nets]
+    loc_of = [dict(zip(q.rows.tolist(), range(q.rows.size))) for q in plans]
+    for p, net in zip(plans, nets):
+        rows, dst, glob = p.exports
+        for d in sorted(set(dst.tolist())):
+            net.set_peer_ptr(d, nets[d].state_ptr(), plans[d].rows.size)
+        peer_pos = [pos[int(d)][loc_of[int(d)][int(g)]] for d, g in zip(dst, glob)]
+        net.set_exports(rows, dst.astype(np.int32), np.asarray(peer_pos, dtype=np.int64))
+    for net in nets:
+        net.prepare()
+    for net in nets:
+        net.run_async(False)
+    for net in nets:
+        net.sync()
+    for p, net, sel in zip(plans, nets, gsel):
+        out, _ = net.download()
+        H.assert_bit_equal(out[p.own], ref[p.rows[p.own]], f"shard {p.rank} flows")
+        nudge, lt, lv = net.download_gages()
+        H.assert_bit_equal(nudge, extras["nudge"][sel], f"shard {p.rank} nudge")
+        H.assert_bit_equal(lt, extras["lastobs_times"][sel], f"shard {p.rank} lastobs_times")
+        H.assert_bit_equal(lv, extras["lastobs_values"][sel], f"shard {p.rank} lastobs_values")
+        net.close()
