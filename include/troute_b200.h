@@ -239,6 +239,37 @@ int trt_powf_batch(int device, int64_t count, const float* x, const float* y, fl
 int trt_host_alloc(void** ptr, uint64_t bytes);
 int trt_host_free(void* ptr);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Diffusive-wave mainstem solver (BASELINE.json configs[3]).
+ *
+ * trt_c_diffnw replaces, argument for argument, the reference's Fortran entry point
+ *     void c_diffnw(double* timestep_ar_g, int* nts_ql_g, ... , double* q_ev_g, double* elv_ev_g, double* depth_ev_g)
+ *     src/kernel/diffusive/pydiffusive.f90:8-52, declared for Cython in
+ *     src/troute-routing/troute/routing/fast_reach/fortran_wrappers.pxd and called from fast_reach/diffusive.pyx:59-103
+ * (42 arguments, every one by reference, arrays in Fortran column-major order: node arrays (mxncomp_g, nrch_g), time series
+ * with time first, outputs (ntss_ev_g, mxncomp_g, nrch_g)).  The only difference is the int return value (the Fortran
+ * subroutine returns nothing): 0 or a negative trt_status with trt_last_error().
+ * Unsupported inputs fail with TRT_ERR_INVALID instead of computing something else: natural cross sections
+ * (mxnbathy_g > 0) and the refactored-hydrofabric crosswalk (cwnrow_g > 0).
+ *
+ * trt_diffnw_batch runs n_domains independent tailwater domains in ONE launch sequence, one CTA per domain (the reference
+ * loops over them serially, compute.py:1764): argv holds n_domains x 42 pointers, the argument lists of c_diffnw one after
+ * the other.  trt_diffusive_set_device selects the CUDA device (default 0); trt_diffusive_last_run returns the device time
+ * of the table kernels and of the time-loop kernel of the last call (ms) and the number of kernel launches. */
+int trt_c_diffnw(const double* timestep_ar_g, const int* nts_ql_g, const int* nts_ub_g, const int* nts_db_g,
+                 const int* ntss_ev_g, const int* nts_qtrib_g, const int* nts_da_g, const int* mxncomp_g, const int* nrch_g,
+                 const double* z_ar_g, const double* bo_ar_g, const double* traps_ar_g, const double* tw_ar_g,
+                 const double* twcc_ar_g, const double* mann_ar_g, const double* manncc_ar_g, double* so_ar_g,
+                 const double* dx_ar_g, const double* iniq, const int* frnw_col, const int* frnw_ar_g, const double* qlat_g,
+                 const double* ubcd_g, const double* dbcd_g, const double* qtrib_g, const int* paradim,
+                 const double* para_ar_g, const int* mxnbathy_g, const double* x_bathy_g, const double* z_bathy_g,
+                 const double* mann_bathy_g, const int* size_bathy_g, const double* usgs_da_g, const int* usgs_da_reach_g,
+                 const double* rdx_ar_g, const int* cwnrow_g, const int* cwncol_g, const double* crosswalk_g,
+                 const double* z_thalweg_g, double* q_ev_g, double* elv_ev_g, double* depth_ev_g);
+int trt_diffnw_batch(int n_domains, const void* const* argv);
+int trt_diffusive_set_device(int device);
+int trt_diffusive_last_run(double* table_ms, double* loop_ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,10 @@
 static int g_pow_mode = 0;
 void trt_oracle_diffnw_pow_mode(int mode) { g_pow_mode = mode; }
 static double P(double x, double y) { return g_pow_mode ? trt_pow64_det(x, y) : pow(x, y); }
+void trt_oracle_pow64_det_array(long n, const double* x, const double* y, double* out)
+{
+    for (long i = 0; i < n; ++i) out[i] = trt_pow64_det(x[i], y[i]);
+}
 
 #define NEL 501
 

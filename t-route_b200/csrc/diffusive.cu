@@ -1,0 +1,258 @@
+/*
+ * diffusive.cu -- kernels and C ABI of the diffusive-wave mainstem solver (include/troute_b200.h: trt_c_diffnw,
+ * trt_diffnw_batch).  Drop-in for c_diffnw (/root/reference/src/kernel/diffusive/pydiffusive.f90:8-52), the Fortran entry
+ * point the reference binds in fast_reach/fortran_wrappers.pxd and calls once per tailwater domain from
+ * compute_diffusive_routing (compute.py:1740-1884).
+ *
+ * Device work per call:
+ *   table1_kernel   thread per (node, table row): cross-section geometry -> elevation, area, perimeter, conveyance, top
+ *                   width, 1/n columns (readXsection :2272-2426); 501 rows x nodes x domains independent threads
+ *   table2_kernel   thread per (node, row): dK/dA and the uniform-flow column (:2395-2402, :487-506); thread per
+ *                   (node, column) for the column minima
+ *   time_loop_kernel  ONE CTA per domain runs the whole simulation (dw_time_loop, diffusive_device.cuh): no launch, no
+ *                   host round trip per time step; the CFL-adaptive step size is a CTA-local reduction
+ * The solver arithmetic lives in diffusive_device.cuh; see its header for what runs in parallel and what is a chain.
+ */
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/troute_b200.h"
+#include "diffusive_setup.h"
+#include "internal.h"
+
+using namespace trtdw;
+
+namespace {
+
+constexpr int kLoopThreads = 256;
+int g_device = 0;
+double g_table_ms = 0.0, g_loop_ms = 0.0;
+long long g_launches = 0;
+
+__global__ void __launch_bounds__(256) table1_kernel(const Dom* __restrict__ doms)
+{
+    Dom D = doms[blockIdx.y];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D.nm * D.mx * NEL) return;
+    const int row = (int)(idx % NEL) + 1;
+    const int node = (int)(idx / NEL);
+    const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
+    if (i <= DW_FRNW(j, 1)) dw_table_pass1(D, i, j, row);
+}
+
+__global__ void __launch_bounds__(256) table2_kernel(const Dom* __restrict__ doms)
+{
+    Dom D = doms[blockIdx.y];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D.nm * D.mx * NEL) return;
+    const int row = (int)(idx % NEL) + 1;
+    const int node = (int)(idx / NEL);
+    const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
+    if (i <= DW_FRNW(j, 1)) dw_table_pass2(D, i, j, row);
+}
+
+__global__ void __launch_bounds__(256) tablemin_kernel(const Dom* __restrict__ doms)
+{
+    Dom D = doms[blockIdx.y];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D.nm * D.mx * NCOL) return;
+    const int col = (int)(idx % NCOL);
+    const int node = (int)(idx / NCOL);
+    const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
+    if (i <= DW_FRNW(j, 1)) dw_table_min(D, i, j, col);
+}
+
+__global__ void __launch_bounds__(kLoopThreads) time_loop_kernel(const Dom* __restrict__ doms)
+{
+    __shared__ Dom D;
+    if (threadIdx.x == 0) D = doms[blockIdx.x];
+    __syncthreads();
+    dw_time_loop(D);
+}
+
+struct DevDomain {
+    DomHost H;
+    double *d_pool = nullptr, *d_tab = nullptr, *d_tabmin = nullptr, *d_out = nullptr;
+    int* i_pool = nullptr;
+    unsigned char* b_pool = nullptr;
+    ~DevDomain()
+    {
+        cudaFree(d_pool); cudaFree(d_tab); cudaFree(d_tabmin); cudaFree(d_out); cudaFree(i_pool); cudaFree(b_pool);
+    }
+};
+
+#define CUD(call)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t e__ = (call);                                                                                 \
+        if (e__ != cudaSuccess) {                                                                                 \
+            char b__[512];                                                                                        \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return trt_internal_fail(TRT_ERR_CUDA, b__);                                                          \
+        }                                                                                                         \
+    } while (0)
+
+/* move every pointer of `D` from the host pools to their device copies */
+template <class T>
+void rebase(T*& p, const void* hbase, size_t hbytes, void* dbase)
+{
+    if (!p) return;
+    const char* c = (const char*)p;
+    if (c >= (const char*)hbase && c < (const char*)hbase + hbytes) p = (T*)((char*)dbase + (c - (const char*)hbase));
+}
+
+int upload_domain(DevDomain& V, Dom& out)
+{
+    DomHost& H = V.H;
+    const size_t db = H.dpool.size() * sizeof(double), ib = H.ipool.size() * sizeof(int), bb = H.bpool.size();
+    CUD(cudaMalloc((void**)&V.d_pool, db));
+    CUD(cudaMalloc((void**)&V.i_pool, ib));
+    CUD(cudaMalloc((void**)&V.b_pool, bb));
+    CUD(cudaMalloc((void**)&V.d_tab, H.n_nodes * NCOL * LD * sizeof(double)));
+    CUD(cudaMalloc((void**)&V.d_tabmin, H.n_nodes * NCOL * sizeof(double)));
+    CUD(cudaMalloc((void**)&V.d_out, 3 * H.n_out * sizeof(double)));
+    CUD(cudaMemcpy(V.d_pool, H.dpool.data(), db, cudaMemcpyHostToDevice));
+    CUD(cudaMemcpy(V.i_pool, H.ipool.data(), ib, cudaMemcpyHostToDevice));
+    CUD(cudaMemcpy(V.b_pool, H.bpool.data(), bb, cudaMemcpyHostToDevice));
+    CUD(cudaMemset(V.d_tab, 0, H.n_nodes * NCOL * LD * sizeof(double)));
+    CUD(cudaMemset(V.d_tabmin, 0, H.n_nodes * NCOL * sizeof(double)));
+    CUD(cudaMemset(V.d_out, 0, 3 * H.n_out * sizeof(double)));        /* q_ev_g = elv_ev_g = depth_ev_g = 0 (:391-393) */
+    Dom D = H.d;
+    const void* hd = H.dpool.data();
+    const double** cdp[] = {&D.z_in, &D.bo_in, &D.traps_in, &D.tw_in, &D.twcc_in, &D.mann_in, &D.manncc_in, &D.dx_in, &D.qlat,
+                            &D.qtrib, &D.dbcd, &D.iniq, &D.tarr_ql, &D.tarr_qtrib, &D.tarr_db};
+    for (const double** q : cdp) rebase(*q, hd, db, V.d_pool);
+    double** dp[] = {&D.rmax, &D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
+                     &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
+                     &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.varr_db, &D.scal};
+    for (double** q : dp) rebase(*q, hd, db, V.d_pool);
+    rebase(D.frnw, H.ipool.data(), ib, V.i_pool);
+    rebase(D.mstem, H.ipool.data(), ib, V.i_pool);
+    rebase(D.hint_q, H.ipool.data(), ib, V.i_pool);
+    rebase(D.status, H.ipool.data(), ib, V.i_pool);
+    rebase(D.is_main, H.bpool.data(), bb, V.b_pool);
+    D.tab = V.d_tab; D.tabmin = V.d_tabmin;
+    D.q_ev = V.d_out; D.elv_ev = V.d_out + H.n_out; D.depth_ev = V.d_out + 2 * H.n_out;
+    out = D;
+    return TRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trt_diffusive_set_device(int device)
+{
+    if (device < 0) return trt_internal_fail(TRT_ERR_INVALID, "device must be >= 0");
+    g_device = device;
+    return TRT_OK;
+}
+
+int trt_diffusive_last_run(double* table_ms, double* loop_ms, long long* launches)
+{
+    if (table_ms) *table_ms = g_table_ms;
+    if (loop_ms) *loop_ms = g_loop_ms;
+    if (launches) *launches = g_launches;
+    return TRT_OK;
+}
+
+int trt_diffnw_batch(int n_domains, const void* const* argv)
+{
+    if (n_domains < 1 || !argv) return trt_internal_fail(TRT_ERR_INVALID, "n_domains < 1 or NULL argument list");
+    std::vector<DevDomain> doms((size_t)n_domains);
+    std::vector<DiffnwArgs> args((size_t)n_domains);
+    for (int d = 0; d < n_domains; ++d) {
+        const void* const* a = argv + (size_t)d * 42;
+        for (int k = 0; k < 42; ++k)
+            if (!a[k]) {
+                char b[96];
+                snprintf(b, sizeof b, "domain %d: argument %d of c_diffnw is NULL", d, k);
+                return trt_internal_fail(TRT_ERR_INVALID, b);
+            }
+        DiffnwArgs& A = args[(size_t)d];
+        A = DiffnwArgs{(const double*)a[0], (const int*)a[1], (const int*)a[2], (const int*)a[3], (const int*)a[4], (const int*)a[5],
+                       (const int*)a[6], (const int*)a[7], (const int*)a[8], (const double*)a[9], (const double*)a[10],
+                       (const double*)a[11], (const double*)a[12], (const double*)a[13], (const double*)a[14],
+                       (const double*)a[15], (double*)a[16], (const double*)a[17], (const double*)a[18], (const int*)a[19],
+                       (const int*)a[20], (const double*)a[21], (const double*)a[22], (const double*)a[23],
+                       (const double*)a[24], (const int*)a[25], (const double*)a[26], (const int*)a[27], (const double*)a[28],
+                       (const double*)a[29], (const double*)a[30], (const int*)a[31], (const double*)a[32], (const int*)a[33],
+                       (const double*)a[34], (const int*)a[35], (const int*)a[36], (const double*)a[37], (const double*)a[38],
+                       (double*)a[39], (double*)a[40], (double*)a[41]};
+        const std::string err = dw_build_host(A, doms[(size_t)d].H);
+        if (!err.empty()) {
+            const std::string m = "domain " + std::to_string(d) + ": " + err;
+            return trt_internal_fail(TRT_ERR_INVALID, m.c_str());
+        }
+    }
+    CUD(cudaSetDevice(g_device));
+    std::vector<Dom> hdoms((size_t)n_domains);
+    long long max_rows = 0, max_cols = 0;
+    for (int d = 0; d < n_domains; ++d) {
+        const int rc = upload_domain(doms[(size_t)d], hdoms[(size_t)d]);
+        if (rc != TRT_OK) return rc;
+        const long long nodes = (long long)hdoms[(size_t)d].nm * hdoms[(size_t)d].mx;
+        max_rows = std::max(max_rows, nodes * NEL);
+        max_cols = std::max(max_cols, nodes * NCOL);
+    }
+    Dom* d_doms = nullptr;
+    CUD(cudaMalloc((void**)&d_doms, sizeof(Dom) * (size_t)n_domains));
+    struct Guard { Dom* p; ~Guard() { cudaFree(p); } } guard{d_doms};
+    CUD(cudaMemcpy(d_doms, hdoms.data(), sizeof(Dom) * (size_t)n_domains, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1, e2;
+    CUD(cudaEventCreate(&e0)); CUD(cudaEventCreate(&e1)); CUD(cudaEventCreate(&e2));
+    CUD(cudaEventRecord(e0));
+    const dim3 g1((unsigned)((max_rows + 255) / 256), (unsigned)n_domains), gm((unsigned)((max_cols + 255) / 256), (unsigned)n_domains);
+    table1_kernel<<<g1, 256>>>(d_doms);
+    table2_kernel<<<g1, 256>>>(d_doms);
+    tablemin_kernel<<<gm, 256>>>(d_doms);
+    CUD(cudaGetLastError());
+    CUD(cudaEventRecord(e1));
+    time_loop_kernel<<<n_domains, kLoopThreads>>>(d_doms);
+    CUD(cudaGetLastError());
+    CUD(cudaEventRecord(e2));
+    CUD(cudaDeviceSynchronize());
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_table_ms = ms;
+    if (cudaEventElapsedTime(&ms, e1, e2) == cudaSuccess) g_loop_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    g_launches = 4;
+    for (int d = 0; d < n_domains; ++d) {
+        DevDomain& V = doms[(size_t)d];
+        const size_t nb = V.H.n_out * sizeof(double);
+        CUD(cudaMemcpy(args[(size_t)d].q_ev_g, V.d_out, nb, cudaMemcpyDeviceToHost));
+        CUD(cudaMemcpy(args[(size_t)d].elv_ev_g, V.d_out + V.H.n_out, nb, cudaMemcpyDeviceToHost));
+        CUD(cudaMemcpy(args[(size_t)d].depth_ev_g, V.d_out + 2 * V.H.n_out, nb, cudaMemcpyDeviceToHost));
+        int status = 0;
+        CUD(cudaMemcpy(&status, hdoms[(size_t)d].status, sizeof(int), cudaMemcpyDeviceToHost));
+        if (status != 0) {
+            const std::string m = "domain " + std::to_string(d) + ": the adaptive time step collapsed to <= 0 (the reference would "
+                                  "never leave its time loop, diffusive.f90:655)";
+            return trt_internal_fail(TRT_ERR_STATE, m.c_str());
+        }
+    }
+    return TRT_OK;
+}
+
+int trt_c_diffnw(const double* timestep_ar_g, const int* nts_ql_g, const int* nts_ub_g, const int* nts_db_g, const int* ntss_ev_g,
+                 const int* nts_qtrib_g, const int* nts_da_g, const int* mxncomp_g, const int* nrch_g, const double* z_ar_g,
+                 const double* bo_ar_g, const double* traps_ar_g, const double* tw_ar_g, const double* twcc_ar_g,
+                 const double* mann_ar_g, const double* manncc_ar_g, double* so_ar_g, const double* dx_ar_g, const double* iniq,
+                 const int* frnw_col, const int* frnw_ar_g, const double* qlat_g, const double* ubcd_g, const double* dbcd_g,
+                 const double* qtrib_g, const int* paradim, const double* para_ar_g, const int* mxnbathy_g,
+                 const double* x_bathy_g, const double* z_bathy_g, const double* mann_bathy_g, const int* size_bathy_g,
+                 const double* usgs_da_g, const int* usgs_da_reach_g, const double* rdx_ar_g, const int* cwnrow_g,
+                 const int* cwncol_g, const double* crosswalk_g, const double* z_thalweg_g, double* q_ev_g, double* elv_ev_g,
+                 double* depth_ev_g)
+{
+    const void* argv[42] = {timestep_ar_g, nts_ql_g, nts_ub_g, nts_db_g, ntss_ev_g, nts_qtrib_g, nts_da_g, mxncomp_g, nrch_g,
+                            z_ar_g, bo_ar_g, traps_ar_g, tw_ar_g, twcc_ar_g, mann_ar_g, manncc_ar_g, so_ar_g, dx_ar_g, iniq,
+                            frnw_col, frnw_ar_g, qlat_g, ubcd_g, dbcd_g, qtrib_g, paradim, para_ar_g, mxnbathy_g, x_bathy_g,
+                            z_bathy_g, mann_bathy_g, size_bathy_g, usgs_da_g, usgs_da_reach_g, rdx_ar_g, cwnrow_g, cwncol_g,
+                            crosswalk_g, z_thalweg_g, q_ev_g, elv_ev_g, depth_ev_g};
+    return trt_diffnw_batch(1, argv);
+}
+
+}  // extern "C"

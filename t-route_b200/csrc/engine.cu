@@ -19,6 +19,7 @@
 
 #include "../../include/troute_b200.h"
 #include "kernels.cuh"
+#include "internal.h"
 
 using namespace trt;
 
@@ -174,6 +175,8 @@ struct trt_network {
         return r;
     }
 };
+
+int trt_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
 extern "C" {
 

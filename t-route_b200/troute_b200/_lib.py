@@ -79,6 +79,10 @@ SYMBOLS = [
     ("trt_powf_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _f32p]),
     ("trt_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("trt_host_free", C.c_int, [C.c_void_p]),
+    ("trt_c_diffnw", C.c_int, [C.c_void_p] * 42),
+    ("trt_diffnw_batch", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("trt_diffusive_set_device", C.c_int, [C.c_int]),
+    ("trt_diffusive_last_run", C.c_int, [_f64p, _f64p, C.POINTER(C.c_longlong)]),
 ]
 
 

@@ -67,3 +67,6 @@ extern "C" int trt_replica_table(const double* z_ar_g, const double* bo_ar_g, co
     }
     return 0;
 }
+
+/* probe of dw_locate_hint for tests/test_diffusive_replica.py */
+extern "C" int trt_replica_locate(const double* xx, int n, double x, int hint) { return dw_locate_hint(xx, n, x, hint); }

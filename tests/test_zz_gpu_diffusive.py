@@ -1,0 +1,94 @@
+"""GPU parity of the diffusive-wave mainstem solver: trt_c_diffnw / trt_diffnw_batch (CUDA, through the C ABI and the
+Python mirror of fast_reach/diffusive.pyx) against oracle/diffusive_oracle.c in its bit-specified-pow build.
+
+Bar: BIT equality of q_ev_g, elv_ev_g, depth_ev_g (binary64).  The device code keeps the operand order of every Fortran
+expression, is compiled with -fmad=false and evaluates x**y with trt_pow64_det (include/trt_detmath64.h); the host build of
+the same source already equals the oracle bit for bit (tests/test_diffusive_replica.py), so any difference here is a
+device-side scheduling or code-generation problem.  The north_star tolerance (1e-5 relative) is asserted as well, against
+the oracle's platform-libm build (what a gfortran build of the reference computes), on the cases where the reference itself
+is insensitive to its libm (see test_diffusive_oracle.py::test_libm_and_bit_specified_pow_builds_agree).
+
+(File name: runs after the Muskingum-Cunge GPU tests; this path had no GPU run in round 1.)"""
+import numpy as np
+import pytest
+
+import helpers_diffusive as HD
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import __graft_entry__ as g
+    g.build()
+    from troute_b200 import _lib
+    assert _lib.lib().trt_device_count() >= 1, "no CUDA device: the diffusive path has no CPU fallback"
+    from troute_b200.routing.fast_reach import diffusive
+    return diffusive
+
+
+@pytest.fixture(scope="module")
+def od():
+    from oracle import diffusive
+    diffusive.build()
+    return diffusive
+
+
+@pytest.mark.parametrize("case", sorted(HD.CASES))
+def test_gpu_equals_oracle_bit_for_bit(gpu, od, case):
+    from troute_b200 import synth_diffusive as sd
+    d = sd.diffusive_domain(**HD.CASES[case])
+    ref = od.compute_diffusive(d, od.POW_DET)
+    got = gpu.compute_diffusive(d)
+    for name, a, b in zip(("q_ev_g", "elv_ev_g", "depth_ev_g"), ref, got):
+        HD.assert_bits64(b, a, f"{case}: {name}")
+    table_ms, loop_ms, launches = gpu.last_run()
+    assert launches == 4 and loop_ms > 0.0
+
+
+@pytest.mark.parametrize("case", ["small", "tailwater-depth", "flashy"])
+def test_gpu_within_tolerance_of_the_libm_build(gpu, od, case):
+    from troute_b200 import synth_diffusive as sd
+    d = sd.diffusive_domain(**HD.CASES[case])
+    ref = od.compute_diffusive(d, od.POW_LIBM)
+    got = gpu.compute_diffusive(d)
+    m = HD.mainstem_nodes(d)
+    for a, b in zip(ref, got):
+        rel = np.abs(a[:, m] - b[:, m]) / np.maximum(np.abs(a[:, m]), 1e-30)
+        assert rel.max() < REL_TOL, rel.max()
+
+
+def test_uniform_flow_on_gpu(gpu):
+    from troute_b200 import synth_diffusive as sd
+    d = sd.uniform_channel(q=60.0)
+    q, elv, dep = gpu.compute_diffusive(d)
+    m = HD.mainstem_nodes(d)
+    assert np.abs(q[:, m] - 60.0).max() < 1e-9
+    assert dep[:, m].max() - dep[:, m].min() < 1e-6
+
+
+def test_batch_of_domains_equals_single_calls(gpu, od):
+    """One CTA per domain, 12 domains of different shapes in one launch: every domain's result equals its own single call
+    and the oracle."""
+    from troute_b200 import synth_diffusive as sd
+    doms = [sd.diffusive_domain(n_mainstem=3 + k % 5, nodes=(3, 6 + k % 4), n_branch=k % 3, nsteps=36 + 12 * (k % 3), seed=100 + k,
+                                dsbc_option=1 + k % 2) for k in range(12)]
+    batch = gpu.compute_diffusive_batch(doms)
+    assert len(batch) == len(doms)
+    for k, (d, got) in enumerate(zip(doms, batch)):
+        ref = od.compute_diffusive(d, od.POW_DET)
+        for name, a, b in zip(("q", "elv", "depth"), ref, got):
+            HD.assert_bits64(b, a, f"domain {k}: {name}")
+    single = gpu.compute_diffusive(doms[5])
+    for a, b in zip(single, batch[5]):
+        HD.assert_bits64(a, b, "single call vs batch")
+
+
+def test_repeated_calls_are_deterministic(gpu):
+    from troute_b200 import synth_diffusive as sd
+    d = sd.diffusive_domain(**HD.CASES["branched"])
+    a = gpu.compute_diffusive(d)
+    b = gpu.compute_diffusive(d)
+    for x, y in zip(a, b):
+        HD.assert_bits64(x, y, "second call")
