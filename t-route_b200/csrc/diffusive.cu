@@ -126,12 +126,15 @@ int upload_domain(DevDomain& V, Dom& out)
     for (const double** q : cdp) rebase(*q, hd, db, V.d_pool);
     double** dp[] = {&D.rmax, &D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
                      &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
-                     &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.varr_db, &D.scal};
+                     &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.b_ynorm, &D.b_x1, &D.b_x2, &D.b_sf1,
+                     &D.b_sf2, &D.varr_db, &D.scal};
     for (double** q : dp) rebase(*q, hd, db, V.d_pool);
     rebase(D.frnw, H.ipool.data(), ib, V.i_pool);
     rebase(D.mstem, H.ipool.data(), ib, V.i_pool);
     rebase(D.hint_q, H.ipool.data(), ib, V.i_pool);
     rebase(D.status, H.ipool.data(), ib, V.i_pool);
+    rebase(D.lvl_ptr, H.ipool.data(), ib, V.i_pool);
+    rebase(D.lvl_reach, H.ipool.data(), ib, V.i_pool);
     rebase(D.is_main, H.bpool.data(), bb, V.b_pool);
     D.tab = V.d_tab; D.tabmin = V.d_tabmin;
     D.q_ev = V.d_out; D.elv_ev = V.d_out + H.n_out; D.depth_ev = V.d_out + 2 * H.n_out;

@@ -16,9 +16,11 @@
  *     the previous step only, and the new junction inflow is written into node 1 AFTER the back substitution
  *     (diffusive.f90:1309-1318).  All reaches are therefore swept concurrently (thread per reach for the two-term
  *     recurrences, thread per node for the Hermite/CN coefficients that hold the powers and divisions).
- *   * The water-surface sweep IS one dependency chain from the tailwater to the heads (y of node i-1 needs y of node i).
- *     Only the Newton solve stays on that chain; conveyance / area / width / roughness interpolation and the celerity
- *     and diffusivity of every node (the pow-heavy part, :1440-1496) move off it and run thread-per-node afterwards.
+ *   * The water-surface sweep IS a dependency chain from the tailwater to the heads (y of node i-1 needs y of node i);
+ *     the arms above a confluence are independent chains and run in different warps.  Only the Newton iterations stay on
+ *     the chain: the normal-depth search, the bracket and the friction slope at its ends (dw_bracket) run thread-per-node
+ *     before it, conveyance / area / width / roughness interpolation and the celerity and diffusivity of every node (the
+ *     pow-heavy part, :1440-1496) thread-per-node after it.
  *   * Table look-ups: the reference scans 501 rows linearly three times per r_interpol (maxval, minval, search) and
  *     bisects in intp_xsec_tab.  Elevation tables are piecewise uniform by construction (:2258-2266), so the row is
  *     computed arithmetically and verified against the table (`dw_locate_hint`, same result as the bisection for a
@@ -47,10 +49,16 @@
 #define DW_TID ((int)threadIdx.x)
 #define DW_NT ((int)blockDim.x)
 #define DW_SYNC() __syncthreads()
+#define DW_WARP ((int)(threadIdx.x >> 5))
+#define DW_NWARP ((int)(blockDim.x >> 5))
+#define DW_LANE ((int)(threadIdx.x & 31))
 #else
 #define DW_TID 0
 #define DW_NT 1
 #define DW_SYNC() ((void)0)
+#define DW_WARP 0
+#define DW_NWARP 1
+#define DW_LANE 0
 #endif
 
 namespace trtdw {
@@ -88,6 +96,10 @@ struct Dom {
     /* state, all (mx, nl) column-major */
     double *z, *dx, *bo, *pere, *qp, *qpx, *sk, *co, *oldQ, *newQ, *oldArea, *newArea, *oldY, *newY, *lateralFlow,
         *celerity, *diffusivity, *celerity2, *diffusivity2, *eei, *ffi, *exi, *fxi, *c_ppi, *c_qqi, *c_rri, *c_ssi, *c_sxi;
+    double *b_ynorm, *b_x1, *b_x2, *b_sf1, *b_sf2;   /* (mx, nl) Newton bracket of every node, see dw_bracket */
+    int nlev;                   /* water-surface sweep: mainstem reaches grouped by their distance (in reaches) from the tailwater */
+    const int* lvl_ptr;         /* [nlev + 1] */
+    const int* lvl_reach;       /* [nm] 1-based reach indices, level by level */
     double* varr_db;            /* [ndb] tailwater elevation series (dsbc_option 1) */
     int* hint_q;                /* (mx, nl) row of the last uniform-flow look-up */
     double* tab;                /* [(j-1)*mx + (i-1)][NCOL][LD] */
@@ -390,6 +402,18 @@ TRT_HD void dw_table_min(Dom& D, int i, int j, int col)
     D.tabmin[((size_t)(j - 1) * D.mx + (size_t)(i - 1)) * NCOL + (size_t)col] = m;
 }
 
+/* intp_xsec_tab(i, j, nel, 10, 1, q): elevation at which node (i, j) carries q as uniform flow */
+TRT_HD double dw_normal_elev(const Dom& D, int i, int j, double q)
+{
+    const double* qn = dw_col(D, i, j, C_QNRM);
+    int* hint = &D.hint_q[(i - 1) + (size_t)(j - 1) * D.mx];
+    int irow = dw_locate_hint(qn, NEL, q, *hint);
+    if (irow == 0) irow = 1;
+    if (irow == NEL) irow = NEL - 1;
+    *hint = irow;
+    return dw_interp_row(qn, dw_col(D, i, j, C_ELEV), irow, q);
+}
+
 /* ---- water-surface solve ------------------------------------------------------------------------------------------- */
 /* funcd_diffdepth :1664-1711 with the downstream friction slope (constant during a solve) passed in */
 TRT_HD void dw_funcd(const Dom& D, int i, int j, double Q_cur, double sf_ds, double z_cur, double y_cur, double y_ds,
@@ -406,25 +430,38 @@ TRT_HD void dw_funcd(const Dom& D, int i, int j, double Q_cur, double sf_ds, dou
     df = 1.0 + (fabs(Q_cur) * Q_cur / trt_pow64_det(conv_cur, 3.0)) * dxi * topw_cur * dKdA_cur;
 }
 
-/* rtsafe :1555-1662 for node i of reach j (the node upstream of the one whose depth y_ds is known) */
+/* The part of rtsafe (:1583-1594) that does not depend on the downstream depth: normal depth of the node for its new
+ * discharge, the bracket [x1, x2] around the mean of normal and previous depth, and the friction slope of the node at both
+ * ends.  Evaluated for every node at once (thread per node) before the water-surface chain starts. */
+TRT_HD void dw_bracket(Dom& D, int i, int j)
+{
+    const double y_ulm_multi = 2.0, y_llm_multi = DW_F(0.1);
+    const double Q_cur = DW_A2(D.qp, i, j), z_cur = DW_A2(D.z, i, j);
+    const double y_norm = dw_normal_elev(D, i, j, fabs(Q_cur)) - z_cur;
+    const double y_old = DW_A2(D.oldY, i, j) - z_cur;
+    const double x1 = 0.5 * (y_norm + y_old) * y_llm_multi;
+    const double x2 = 0.5 * (y_norm + y_old) * y_ulm_multi;
+    const double* elev = dw_col(D, i, j, C_ELEV);
+    const double* conv = dw_col(D, i, j, C_CONV);
+    const double e1 = x1 + z_cur, e2 = x2 + z_cur;
+    const double c1 = dw_interp_row(elev, conv, dw_row_of_elev(elev, e1), e1);
+    const double c2 = dw_interp_row(elev, conv, dw_row_of_elev(elev, e2), e2);
+    DW_A2(D.b_ynorm, i, j) = y_norm;
+    DW_A2(D.b_x1, i, j) = x1;
+    DW_A2(D.b_x2, i, j) = x2;
+    DW_A2(D.b_sf1, i, j) = fabs(Q_cur) * Q_cur / (c1 * c1);
+    DW_A2(D.b_sf2, i, j) = fabs(Q_cur) * Q_cur / (c2 * c2);
+}
+
+/* rtsafe :1555-1662 for node i of reach j (the node upstream of the one whose depth y_ds is known), from the bracket of
+ * dw_bracket.  The function values at the bracket ends (:1591-1592) are completed here with the downstream terms; their
+ * derivatives are never read by the Fortran. */
 TRT_HD double dw_rtsafe(const Dom& D, int i, int j, double Q_cur, double Q_ds, double z_cur, double z_ds, double y_ds)
 {
     const int maxit = 40;
     const double xacc = DW_F(1e-4);
-    const double y_ulm_multi = 2.0, y_llm_multi = DW_F(0.1);
-    double df, dxx, dxold, f, fh, fl, temp, xh, xl, r;
-    /* normal elevation: uniform-flow column searched from the row found for this node at the previous step */
-    const double* qn = dw_col(D, i, j, C_QNRM);
-    int* hint = &D.hint_q[(i - 1) + (size_t)(j - 1) * D.mx];
-    int irow = dw_locate_hint(qn, NEL, fabs(Q_cur), *hint);
-    if (irow == 0) irow = 1;
-    if (irow == NEL) irow = NEL - 1;
-    *hint = irow;
-    const double elv_norm = dw_interp_row(qn, dw_col(D, i, j, C_ELEV), irow, fabs(Q_cur));
-    const double y_norm = elv_norm - DW_A2(D.z, i, j);
-    const double y_old = DW_A2(D.oldY, i, j) - DW_A2(D.z, i, j);
-    const double x1 = 0.5 * (y_norm + y_old) * y_llm_multi;
-    const double x2 = 0.5 * (y_norm + y_old) * y_ulm_multi;
+    double df, dxx, dxold, f, temp, xh, xl, r;
+    const double y_norm = DW_A2(D.b_ynorm, i, j), x1 = DW_A2(D.b_x1, i, j), x2 = DW_A2(D.b_x2, i, j);
     /* loop-invariant parts of funcd_diffdepth: downstream friction slope (:1689-1692) and bed-slope term (:1699-1700) */
     const double elv_ds = y_ds + z_ds;
     const double* elev_ds = dw_col(D, i + 1, j, C_ELEV);
@@ -434,8 +471,8 @@ TRT_HD double dw_rtsafe(const Dom& D, int i, int j, double Q_cur, double Q_ds, d
     double slope = (DW_A2(D.z, i, j) - DW_A2(D.z, i + 1, j)) / dxi;
     slope = fmax(slope, D.so_llm);
     const double slope_dx = slope * dxi;
-    dw_funcd(D, i, j, Q_cur, sf_ds, z_cur, x1, y_ds, slope_dx, dxi, fl, df);
-    dw_funcd(D, i, j, Q_cur, sf_ds, z_cur, x2, y_ds, slope_dx, dxi, fh, df);
+    const double fl = x1 - y_ds + slope_dx - 0.50 * (DW_A2(D.b_sf1, i, j) + sf_ds) * dxi;
+    const double fh = x2 - y_ds + slope_dx - 0.50 * (DW_A2(D.b_sf2, i, j) + sf_ds) * dxi;
     if ((fl > 0.0 && fh > 0.0) || (fl < 0.0 && fh < 0.0)) return y_norm;
     if (fl == 0.0) return x1;
     else if (fh == 0.0) return x2;
@@ -617,18 +654,6 @@ TRT_HD void dw_forward_head(Dom& D, int j, double t, double dtini, const double*
     DW_A2(D.newQ, 1, j) = q;
 }
 
-/* intp_xsec_tab(i, j, nel, 10, 1, q): elevation at which node (i, j) carries q as uniform flow */
-TRT_HD double dw_normal_elev(const Dom& D, int i, int j, double q)
-{
-    const double* qn = dw_col(D, i, j, C_QNRM);
-    int* hint = &D.hint_q[(i - 1) + (size_t)(j - 1) * D.mx];
-    int irow = dw_locate_hint(qn, NEL, q, *hint);
-    if (irow == 0) irow = 1;
-    if (irow == NEL) irow = NEL - 1;
-    *hint = irow;
-    return dw_interp_row(qn, dw_col(D, i, j, C_ELEV), irow, q);
-}
-
 /* lateral inflow of segment i of reach j at time t (:660-666): the series is shifted by one row (varr_ql(1) = varr_ql(2)) */
 TRT_HD double dw_lateral(const Dom& D, int i, int j, double t)
 {
@@ -683,6 +708,11 @@ TRT_HD void dw_time_loop(Dom& D)
 {
     const int nm = D.nm, mx = D.mx, nl = D.nl;
     const double TOL = DW_F(1e-8);
+    /* Upper bound on the time steps of a run: the celerity cap (:1484-1492) keeps the CFL step >= dtini_min, the save
+     * interval adds at most one clipped step per row.  Exceeding it means the clock has stopped advancing (NaN forcing,
+     * dtini far below the resolution of t): the reference would spin forever, here the run ends with status -5. */
+    const double span = (D.tfin - D.t0) * 3600.0;
+    const long max_steps = (long)fmin(4.0e7, 64.0 * (span / D.dtini_min + span / D.saveInterval) + 1000.0);
     /* ---- initial water surface, tailwater to heads (:550-606); one-off, one thread */
     if (DW_TID == 0) {
         for (int jm = nm; jm >= 1; --jm) {
@@ -703,6 +733,7 @@ TRT_HD void dw_time_loop(Dom& D)
             }
             const double wdepth = DW_A2(D.newY, ncomp, j) - DW_A2(D.z, ncomp, j);
             for (int i = 1; i <= ncomp - 1; ++i) DW_A2(D.oldY, i, j) = wdepth + DW_A2(D.z, i, j);
+            for (int i = 1; i <= ncomp - 1; ++i) dw_bracket(D, i, j);
             dw_backward_chain(D, j);
             for (int i = 1; i <= ncomp; ++i) dw_node_props(D, i, j);
             dw_reach_means(D, j);
@@ -718,7 +749,8 @@ TRT_HD void dw_time_loop(Dom& D)
         int ts_ev = 1;
         double t = D.t0 * 60.0;
         const int ncomp = DW_FRNW(j, 1);
-        while (t <= D.tfin * 60.0) {
+        long walk = 0;
+        while (t <= D.tfin * 60.0 && ++walk <= max_steps) {
             if ((fmod((t - D.t0 * 60.) * 60., D.saveInterval) <= TOL) || (t == D.tfin * 60.)) {
                 if (ts_ev <= D.nev) {
                     const double q = dw_intp_y(D.nqt, D.tarr_qtrib, D.qtrib + (size_t)(j - 1) * D.nqt, 1, t, ts_ev);
@@ -746,7 +778,7 @@ TRT_HD void dw_time_loop(Dom& D)
             if (b > a) dtini = (a + 1) * (D.saveInterval) - (t - D.t0 * 60.) * 60.;
             if (t + dtini / 60. > D.tfin * 60.) dtini = (D.tfin * 60. - t) * 60.;
         }
-        if (!(dtini > 0.0) || ++guard > 50000000L) {          /* the reference would never leave the loop */
+        if (!(dtini > 0.0) || ++guard > max_steps) {          /* the reference would never leave the loop */
             if (DW_TID == 0) *D.status = -5;
             break;
         }
@@ -763,15 +795,24 @@ TRT_HD void dw_time_loop(Dom& D)
         /* phase 3: node 1 of every reach takes the junction inflow of this step */
         for (int jm = DW_TID; jm < nm; jm += DW_NT) dw_forward_head(D, D.mstem[jm], t, dtini, D.tarr_qtrib);
         DW_SYNC();
-        /* water-surface sweep: ONE dependency chain from the tailwater to the heads */
-        if (DW_TID == 0) {
-            for (int jm = nm; jm >= 1; --jm) {
-                const int j = D.mstem[jm - 1];
-                dw_downstream_stage(D, j, t + dtini / 60.);
-                dw_backward_chain(D, j);
-            }
+        /* water-surface sweep.  First what does not depend on the downstream depth, thread per node ... */
+        for (int idx = DW_TID; idx < nm * mx; idx += DW_NT) {
+            const int j = D.mstem[idx / mx], i = idx % mx + 1;
+            if (i <= DW_FRNW(j, 1) - 1) dw_bracket(D, i, j);
         }
         DW_SYNC();
+        /* ... then the dependency chain from the tailwater to the heads: reaches of equal distance from the tailwater
+         * (the arms above a confluence) are independent and go to different warps, one lane each */
+        for (int lev = 0; lev < D.nlev; ++lev) {
+            for (int k = D.lvl_ptr[lev] + DW_WARP; k < D.lvl_ptr[lev + 1]; k += DW_NWARP) {
+                if (DW_LANE == 0) {
+                    const int j = D.lvl_reach[k];
+                    dw_downstream_stage(D, j, t + dtini / 60.);
+                    dw_backward_chain(D, j);
+                }
+            }
+            DW_SYNC();
+        }
         /* ... and everything off the chain: hydraulic properties, celerity, diffusivity of every node */
         for (int idx = DW_TID; idx < nm * mx; idx += DW_NT) {
             const int j = D.mstem[idx / mx], i = idx % mx + 1;

@@ -62,13 +62,15 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     H.n_nodes = n2; H.n_out = (size_t)D.nev * n2;
     /* ---- ints: frnw (as given), mstem, hint_q; bytes: is_main */
     const size_t nfr = (size_t)nl * D.frnw_col;
-    H.ipool.assign(nfr + (size_t)nl + n2 + 1, 0);
+    H.ipool.assign(nfr + (size_t)nl + n2 + 1 + (size_t)nl + 2 + (size_t)nl, 0);
     int* ip = H.ipool.data();
     std::memcpy(ip, a.frnw_ar_g, nfr * sizeof(int));
     D.frnw = ip; ip += nfr;
     int* mstem = ip; ip += nl;
     int* hint = ip; ip += n2;
-    D.status = ip;
+    D.status = ip; ip += 1;
+    int* lvl_ptr = ip; ip += (size_t)nl + 2;
+    int* lvl_reach = ip; ip += nl;
     for (size_t k = 0; k < n2; ++k) hint[k] = NEL / 2;
     H.bpool.assign((size_t)nl + 1, 0);
     int nm = 0;
@@ -86,11 +88,31 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     }
     if (nm == 0) return "no mainstem reach (flag 555) in frnw_g";
     D.nm = nm; D.mstem = mstem; D.hint_q = hint; D.is_main = H.bpool.data();
+    {
+        /* distance of every mainstem reach from the tailwater, counted in mainstem reaches; a reach drains into a reach
+         * with a larger index (fp_network_map numbers reaches upstream to downstream, diffusive_utils_v02.py:90-101) */
+        std::vector<int> lev((size_t)nl + 1, -1);
+        int nlev = 0;
+        for (int jm = nm - 1; jm >= 0; --jm) {
+            const int j = mstem[jm], ds = DW_FRNW(j, 2);
+            if (ds >= 1) {
+                if (ds <= j) return "frnw_g: a reach must drain into a reach with a larger index";
+                if (!H.bpool[(size_t)ds]) return "frnw_g: a mainstem reach drains into a tributary reach";
+                lev[(size_t)j] = lev[(size_t)ds] + 1;
+            } else lev[(size_t)j] = 0;
+            if (lev[(size_t)j] + 1 > nlev) nlev = lev[(size_t)j] + 1;
+        }
+        for (int jm = 0; jm < nm; ++jm) lvl_ptr[lev[(size_t)mstem[jm]] + 1]++;
+        for (int l = 0; l < nlev; ++l) lvl_ptr[l + 1] += lvl_ptr[l];
+        std::vector<int> fill(lvl_ptr, lvl_ptr + nlev);
+        for (int jm = nm - 1; jm >= 0; --jm) lvl_reach[fill[(size_t)lev[(size_t)mstem[jm]]]++] = mstem[jm];
+        D.nlev = nlev; D.lvl_ptr = lvl_ptr; D.lvl_reach = lvl_reach;
+    }
 
     /* ---- doubles */
     const size_t nq = (size_t)D.nql * n2, nt = (size_t)D.nqt * nl;
     const size_t total = 8 * n2 /*geometry in*/ + nq + nt + (size_t)D.ndb + n2 /*iniq*/ + (size_t)(D.nql + 1) + D.nqt + D.ndb /*time axes*/
-                         + (size_t)nl /*rmax*/ + 28 * n2 /*state*/ + (size_t)D.ndb /*varr_db*/ + 8 /*scal*/;
+                         + (size_t)nl /*rmax*/ + 33 * n2 /*state*/ + (size_t)D.ndb /*varr_db*/ + 8 /*scal*/;
     H.dpool.assign(total, 0.0);
     double* p = H.dpool.data();
     auto take_in = [&](const double* src, size_t cnt) { double* q = p; if (cnt) std::memcpy(q, src, cnt * sizeof(double)); p += cnt; return (const double*)q; };
@@ -109,7 +131,8 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     D.rmax = take((size_t)nl);
     double** state[] = {&D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
                         &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
-                        &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi};
+                        &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.b_ynorm, &D.b_x1, &D.b_x2,
+                        &D.b_sf1, &D.b_sf2};
     for (double** s : state) *s = take(n2);
     D.varr_db = take((size_t)D.ndb);
     D.scal = take(8);
