@@ -58,7 +58,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="conus", choices=["conus", "tree"])
+    ap.add_argument("--workload", default="conus", choices=["conus", "tree", "diffusive"],
+                    help="conus / tree: Muskingum-Cunge routing (BASELINE configs[2] / configs[1]); diffusive: a batch of "
+                         "diffusive-wave mainstem domains (configs[3] kernel, see run_diffusive)")
+    ap.add_argument("--domains", type=int, default=296, help="diffusive: independent tailwater domains per call")
+    ap.add_argument("--mainstem", type=int, default=24, help="diffusive: mainstem reaches per domain")
     ap.add_argument("--style", default="nhd", choices=["nhd", "hack"],
                     help="basin generator of the conus workload: nhd = NHD-like confluences (SURVEY.md 8d in-degree mix), "
                          "hack = main stems with dozens of tributaries per node (gather stress case)")
@@ -419,6 +423,98 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# diffusive-wave mainstem domains (BASELINE configs[3]): one CTA per domain, whole time loop on the device
+# ---------------------------------------------------------------------------------------------------
+def run_diffusive(args, rank, world):
+    """`--workload diffusive`: `--domains` synthetic tailwater domains of `--mainstem` reaches (plus tributaries and a
+    second arm), `--nsteps` x 300 s.  A step = one compute_diffusive_batch call (host dicts in, host arrays out: that is the
+    only API, so `value` uses the device time of the time-loop kernel and `e2e` the wall time of the call).  Unit =
+    mainstem segment-timesteps (segments x output rows) per second, the unit of the Muskingum-Cunge line."""
+    if rank != 0:
+        return
+    from troute_b200 import synth_diffusive as sd
+    doms = [sd.diffusive_domain(n_mainstem=args.mainstem, nodes=(5, 12), n_branch=max(0, args.mainstem // 6), nsteps=args.nsteps,
+                                seed=1000 + k) for k in range(args.domains if args.impl == "ours" else min(args.domains, 8))]
+    segs = sum(int(sum(d["frnw_g"][j, 0] - 1 for j in d["mainstem"])) for d in doms)
+    units = float(segs * args.nsteps)
+    name = (f"{len(doms)} synthetic diffusive-wave domains x {args.mainstem} mainstem reaches "
+            f"({segs} mainstem segments), {args.nsteps} x 300 s, normal-depth tailwater")
+    if args.impl == "reference":
+        from oracle import diffusive as od
+        od.build()
+        vals = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            for d in doms:
+                od.compute_diffusive(d, od.POW_LIBM)
+            if i >= args.warmup:
+                vals.append(units / (time.perf_counter() - t0))
+        v = float(np.mean(vals))
+        print(json.dumps({"impl": "reference", "metric": "routed segment-timesteps/sec", "value": v,
+                          "unit": "segment-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * units / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": name},
+                          "cpu_baseline": {"value": v, "unit": "segment-timesteps/s", "cores": 1, "kind": "port",
+                                           "sample": f"{len(doms)} domains, serial loop over domains as compute.py:1764"},
+                          "e2e": {"value": v, "unit": "segment-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    from troute_b200 import _lib
+    from troute_b200.routing.fast_reach import diffusive
+    _lib.lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the diffusive path has no CPU fallback")
+    clocks = Clocks(0)
+    for _ in range(args.warmup):
+        diffusive.compute_diffusive_batch(doms)
+    clocks.start()
+    loop_ms, table_ms, wall = [], [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = diffusive.compute_diffusive_batch(doms)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        a, b, _n = diffusive.last_run()
+        table_ms.append(a); loop_ms.append(b)
+    clk = clocks.stop()
+    h2d = sum(sum(np.asarray(v).nbytes for v in d.values() if isinstance(v, np.ndarray)) for d in doms)
+    d2h = sum(sum(o.nbytes for o in res) for res in out)
+    dev_ms = float(np.mean(loop_ms) + np.mean(table_ms))
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import diffusive as od
+        od.build()
+        t0 = time.perf_counter(); k = 0
+        while k < len(doms) and time.perf_counter() - t0 < args.cpu_sample_seconds:
+            od.compute_diffusive(doms[k], od.POW_LIBM); k += 1
+        cs = sum(int(sum(d["frnw_g"][j, 0] - 1 for j in d["mainstem"])) for d in doms[:k])
+        cpu = {"value": cs * args.nsteps / (time.perf_counter() - t0), "unit": "segment-timesteps/s", "cores": 1,
+               "kind": "port", "sample": f"first {k} of {len(doms)} domains, serial (compute.py:1764 loops over domains)"}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    # algorithmic bytes of the time-loop kernel per mainstem node and OUTPUT step: 24 B of results + one pass over the 33
+    # state arrays (264 B); the adaptive step makes the real count a small multiple.  The kernel is a dependency chain
+    # of Newton solves per domain (latency-bound), so this fraction is reported because the contract asks for it.
+    nodes = sum(int(sum(d["frnw_g"][j, 0] for j in d["mainstem"])) for d in doms)
+    abytes = 288.0 * nodes * args.nsteps
+    ach = abytes / (float(np.mean(loop_ms)) * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "routed segment-timesteps/sec", "value": units / (dev_ms * 1e-3), "unit": "segment-timesteps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "l2": "tables (32 KB per node) are rebuilt by every call; inputs re-uploaded",
+                   "schedule": "one CTA per domain, whole time loop in one launch"},
+        "e2e": {"value": units / (float(np.mean(wall)) * 1e-3), "unit": "segment-timesteps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(np.mean(wall))},
+        "gpu_launches": 4 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "time_loop_kernel", "kernel_ms": float(np.mean(loop_ms)), "table_kernels_ms": float(np.mean(table_ms)),
+                     "algorithmic_bytes_per_launch": abytes,
+                     "note": "latency-bound: per domain one dependency chain of Newton solves per time step; see DESIGN.md"},
+        "cpu_baseline": cpu, "clocks": clk}), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -429,7 +525,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29513", os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    if args.impl == "reference":
+    if args.workload == "diffusive":
+        run_diffusive(args, rank, world)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
