@@ -94,15 +94,6 @@ struct DevDomain {
         }                                                                                                         \
     } while (0)
 
-/* move every pointer of `D` from the host pools to their device copies */
-template <class T>
-void rebase(T*& p, const void* hbase, size_t hbytes, void* dbase)
-{
-    if (!p) return;
-    const char* c = (const char*)p;
-    if (c >= (const char*)hbase && c < (const char*)hbase + hbytes) p = (T*)((char*)dbase + (c - (const char*)hbase));
-}
-
 int upload_domain(DevDomain& V, Dom& out)
 {
     DomHost& H = V.H;
@@ -119,23 +110,7 @@ int upload_domain(DevDomain& V, Dom& out)
     CUD(cudaMemset(V.d_tab, 0, H.n_nodes * NCOL * LD * sizeof(double)));
     CUD(cudaMemset(V.d_tabmin, 0, H.n_nodes * NCOL * sizeof(double)));
     CUD(cudaMemset(V.d_out, 0, 3 * H.n_out * sizeof(double)));        /* q_ev_g = elv_ev_g = depth_ev_g = 0 (:391-393) */
-    Dom D = H.d;
-    const void* hd = H.dpool.data();
-    const double** cdp[] = {&D.z_in, &D.bo_in, &D.traps_in, &D.tw_in, &D.twcc_in, &D.mann_in, &D.manncc_in, &D.dx_in, &D.qlat,
-                            &D.qtrib, &D.dbcd, &D.iniq, &D.tarr_ql, &D.tarr_qtrib, &D.tarr_db};
-    for (const double** q : cdp) rebase(*q, hd, db, V.d_pool);
-    double** dp[] = {&D.rmax, &D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
-                     &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
-                     &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.b_ynorm, &D.b_x1, &D.b_x2, &D.b_sf1,
-                     &D.b_sf2, &D.varr_db, &D.scal};
-    for (double** q : dp) rebase(*q, hd, db, V.d_pool);
-    rebase(D.frnw, H.ipool.data(), ib, V.i_pool);
-    rebase(D.mstem, H.ipool.data(), ib, V.i_pool);
-    rebase(D.hint_q, H.ipool.data(), ib, V.i_pool);
-    rebase(D.status, H.ipool.data(), ib, V.i_pool);
-    rebase(D.lvl_ptr, H.ipool.data(), ib, V.i_pool);
-    rebase(D.lvl_reach, H.ipool.data(), ib, V.i_pool);
-    rebase(D.is_main, H.bpool.data(), bb, V.b_pool);
+    Dom D = dw_rebase(H, V.d_pool, V.i_pool, V.b_pool);
     D.tab = V.d_tab; D.tabmin = V.d_tabmin;
     D.q_ev = V.d_out; D.elv_ev = V.d_out + H.n_out; D.depth_ev = V.d_out + 2 * H.n_out;
     out = D;

@@ -155,4 +155,38 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     return "";
 }
 
+/* Re-point every pool pointer of `D` (built by dw_build_host over H's pools) at copies of the pools that start at
+ * dd / di / db: what the CUDA library does after uploading the pools (diffusive.cu), testable on the host. */
+template <class T>
+inline void dw_rebase_ptr(T*& p, const void* hbase, size_t hbytes, void* dbase)
+{
+    if (!p) return;
+    const char* c = (const char*)p;
+    if (c >= (const char*)hbase && c < (const char*)hbase + hbytes) p = (T*)((char*)dbase + (c - (const char*)hbase));
+}
+
+inline Dom dw_rebase(const DomHost& H, double* dd, int* di, unsigned char* db)
+{
+    Dom D = H.d;
+    const void* hd = H.dpool.data(); const size_t nd = H.dpool.size() * sizeof(double);
+    const void* hi = H.ipool.data(); const size_t ni = H.ipool.size() * sizeof(int);
+    const void* hb = H.bpool.data(); const size_t nb = H.bpool.size();
+    const double** cdp[] = {&D.z_in, &D.bo_in, &D.traps_in, &D.tw_in, &D.twcc_in, &D.mann_in, &D.manncc_in, &D.dx_in, &D.qlat,
+                            &D.qtrib, &D.dbcd, &D.iniq, &D.tarr_ql, &D.tarr_qtrib, &D.tarr_db};
+    for (const double** q : cdp) dw_rebase_ptr(*q, hd, nd, dd);
+    double** dp[] = {&D.rmax, &D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
+                     &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
+                     &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.b_ynorm, &D.b_x1, &D.b_x2, &D.b_sf1,
+                     &D.b_sf2, &D.varr_db, &D.scal};
+    for (double** q : dp) dw_rebase_ptr(*q, hd, nd, dd);
+    dw_rebase_ptr(D.frnw, hi, ni, di);
+    dw_rebase_ptr(D.mstem, hi, ni, di);
+    dw_rebase_ptr(D.hint_q, hi, ni, di);
+    dw_rebase_ptr(D.status, hi, ni, di);
+    dw_rebase_ptr(D.lvl_ptr, hi, ni, di);
+    dw_rebase_ptr(D.lvl_reach, hi, ni, di);
+    dw_rebase_ptr(D.is_main, hb, nb, db);
+    return D;
+}
+
 }  // namespace trtdw

@@ -33,7 +33,15 @@ extern "C" int trt_replica_diffnw(
     DomHost H;
     const std::string err = dw_build_host(a, H);
     if (!err.empty()) return -1;
-    Dom& D = H.d;
+    /* Same steps as the CUDA library's upload (diffusive.cu upload_domain): the pools are COPIED, the pointers re-pointed
+     * at the copies with dw_rebase, and the originals poisoned -- a pointer that dw_rebase forgets reads NaN / garbage here. */
+    std::vector<double> dd(H.dpool);
+    std::vector<int> di(H.ipool);
+    std::vector<unsigned char> db(H.bpool);
+    Dom D = dw_rebase(H, dd.data(), di.data(), db.data());
+    for (double& v : H.dpool) v = trt64_from_bits(0x7ff8dead0000beefULL);
+    for (int& v : H.ipool) v = 0x40000000;
+    for (unsigned char& v : H.bpool) v = 0xff;
     std::vector<double> tab(H.n_nodes * NCOL * LD, 0.0), tabmin(H.n_nodes * NCOL, 0.0);
     D.tab = tab.data(); D.tabmin = tabmin.data();
     D.q_ev = q_ev_g; D.elv_ev = elv_ev_g; D.depth_ev = depth_ev_g;

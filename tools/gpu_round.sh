@@ -1,5 +1,6 @@
 #!/bin/bash
 # One GPU-box session: first light, GPU tests, bench, ncu launch list + full capture.  Everything lands in gpurun_out/.
+# Stages: light smoke test open diffusive bench ncu (default: all).  Round 2 starts with: gpu_round.sh "diffusive open"
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
@@ -14,6 +15,24 @@ if has smoke; then
 fi
 if has test; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/box.txt
+fi
+if has open; then
+  # open issues (skipped by default): full tracebacks, so that the failure of the sharded-nudging test can be read
+  TRT_TEST_OPEN_ISSUES=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -rA --tb=long -k sharded_nudging \
+      > gpurun_out/pytest_open_issues.log 2>&1; echo "open issues rc=$?" >> gpurun_out/box.txt
+fi
+if has diffusive; then
+  # first GPU run of the diffusive-wave solver: its own tests with full tracebacks, then its bench lines
+  timeout 900 python -m pytest tests/test_zz_gpu_diffusive.py -m gpu -q -rA --tb=long > gpurun_out/pytest_diffusive.log 2>&1
+  echo "diffusive tests rc=$?" >> gpurun_out/box.txt
+  timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_zz_gpu_diffusive.py -m gpu -q -x -k "small or uniform" \
+      > gpurun_out/sanitizer_diffusive.log 2>&1; echo "diffusive memcheck rc=$?" >> gpurun_out/box.txt
+  timeout 900 python bench.py --workload diffusive --steps 3 --warmup 1 > gpurun_out/bench_diffusive.json 2> gpurun_out/bench_diffusive.err
+  echo "bench diffusive rc=$?" >> gpurun_out/box.txt
+  timeout 600 python bench.py --workload diffusive --impl reference --steps 1 --warmup 0 > gpurun_out/bench_diffusive_ref.json 2>> gpurun_out/bench_diffusive.err
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"time_loop_kernel" -c 1 -f -o gpurun_out/prof_diffusive \
+      python bench.py --workload diffusive --domains 148 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_diffusive.log 2>&1
+  echo "ncu diffusive rc=$?" >> gpurun_out/box.txt
 fi
 if has bench; then
   timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/box.txt
