@@ -249,8 +249,10 @@ int trt_host_free(void* ptr);
  * (42 arguments, every one by reference, arrays in Fortran column-major order: node arrays (mxncomp_g, nrch_g), time series
  * with time first, outputs (ntss_ev_g, mxncomp_g, nrch_g)).  The only difference is the int return value (the Fortran
  * subroutine returns nothing): 0 or a negative trt_status with trt_last_error().
- * Unsupported inputs fail with TRT_ERR_INVALID instead of computing something else: natural cross sections
- * (mxnbathy_g > 0) and the refactored-hydrofabric crosswalk (cwnrow_g > 0).
+ * Both cross-section kinds of the reference are supported: synthetic trapezoid + floodplain (mxnbathy_g = 0, readXsection)
+ * and surveyed vertices (mxnbathy_g > 0, readXsection_natural_mann_vertices).  Unsupported inputs fail with TRT_ERR_INVALID
+ * instead of computing something else: the refactored-hydrofabric crosswalk (cwnrow_g > 0; the reference's own input
+ * builder no longer produces one, diffusive_utils_v02.py:1036-1041).  Array extents are trusted as in the Fortran.
  *
  * trt_diffnw_batch runs n_domains independent tailwater domains in ONE launch sequence, one CTA per domain (the reference
  * loops over them serially, compute.py:1764): argv holds n_domains x 42 pointers, the argument lists of c_diffnw one after

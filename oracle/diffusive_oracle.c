@@ -22,8 +22,8 @@
  * entered through c_diffnw (/root/reference/src/kernel/diffusive/pydiffusive.f90:8-52): every argument by reference,
  * arrays in Fortran (column-major) order.
  *
- * Not restated: natural cross sections (readXsection_natural_mann_vertices :1756-2091, taken when mxnbathy_g > 0) --
- * returns -2; the data-assimilation branch is commented out in the Fortran itself (:1283-1306).
+ *   readXsection_natural_mann_vertices :1756-2091  tables of a surveyed cross section (taken when mxnbathy_g > 0)
+ * Not restated: the data-assimilation branch, which is commented out in the Fortran itself (:1283-1306).
  *
  * Conventions frozen here (the Fortran leaves them open):
  *   * single-precision literals: `0.3`, `0.1`, `1e-4` ... in a double-precision expression are REAL(4) constants
@@ -321,6 +321,124 @@ static void read_xsection(Dw* S, int k, double lftBnkMann, double rmanning_main,
     A2(S->z, k, num_reach) = el_min;                               /* :2428 */
 }
 
+/* ---- readXsection_natural_mann_vertices :1756-2091 ------------------------------------------------------------------ */
+/* surveyed cross section: size_bathy(node, reach) vertices (x, z, Manning n), closed by a vertical wall on either side */
+static int read_xsection_natural(Dw* S, int idx_node, int idx_reach, double timesDepth, const double* x_bathy,
+                                 const double* z_bathy, const double* mann_bathy, const int* size_bathy, int mxnbathy)
+{
+    static const double TOL = (double)1e-8f;
+    const int nb = size_bathy[(idx_node - 1) + (size_t)(idx_reach - 1) * (size_t)S->mxncomp];
+    if (nb < 2 || nb > mxnbathy) return -6;
+#define BATHY(p, ic) (p)[((ic) - 1) + (size_t)mxnbathy * ((size_t)(idx_node - 1) + (size_t)S->mxncomp * (size_t)(idx_reach - 1))]
+    const int mt = nb + 2, num = mt;
+    double* buf = (double*)malloc(sizeof(double) * (size_t)(3 * (mt + 1) + 8 * (NEL + 1)));
+    if (!buf) return -3;
+    double *xcs = buf, *ycs = xcs + (mt + 1), *manncs = ycs + (mt + 1);                      /* 1-based */
+    double *el1 = manncs + (mt + 1), *a1 = el1 + (NEL + 1), *peri1 = a1 + (NEL + 1), *conv1 = peri1 + (NEL + 1),
+           *tpW1 = conv1 + (NEL + 1), *newdKdA = tpW1 + (NEL + 1), *skk = newdKdA + (NEL + 1), *redi1 = skk + (NEL + 1);
+    const double f2m = 1.0;
+    for (int ic = 2; ic <= nb + 1; ++ic) {                                                   /* :1799-1815 */
+        const double x1 = -BATHY(x_bathy, 1) + BATHY(x_bathy, ic - 1);
+        xcs[ic] = x1 * f2m;
+        ycs[ic] = BATHY(z_bathy, ic - 1) * f2m;
+        manncs[ic] = BATHY(mann_bathy, ic - 1);
+        if (manncs[ic] > (double)0.15f) manncs[ic] = (double)0.15f;
+    }
+    double el_min = 99999., el_max = -99999.;
+    for (int ic = 2; ic <= num - 1; ++ic) {
+        if (ycs[ic] < el_min) el_min = ycs[ic];
+        if (ycs[ic] > el_max) el_max = ycs[ic];
+    }
+    const double el_range = (el_max - el_min) * timesDepth;
+    const double el_incr = el_range / (double)(float)(NEL - 1.0f);
+    xcs[1] = xcs[2]; ycs[1] = el_min + el_range + 1.0;
+    xcs[num] = xcs[num - 1]; ycs[num] = el_min + el_range + 1.0;
+    manncs[1] = 0.0; manncs[num - 1] = 0.0; manncs[num] = 0.0;
+    for (int iel = 1; iel <= NEL; ++iel) {                                                   /* :1840-1925 */
+        double el_now = el_min + (double)(float)(iel - 1) * el_incr;
+        if (fabs(el_now - el_min) < TOL) el_now = el_now + (double)0.00001f;
+        double cal_area = 0.0, cal_peri = 0.0, cal_topW = 0.0, cal_equiv_mann = 0.0;
+        int i_find = 0, i_start = -999;
+        for (int ic = 1; ic <= num - 1; ++ic) {
+            const double ya = ycs[ic], yb = ycs[ic + 1];
+            if ((el_now <= ya) && (el_now > yb) && (i_find == 0)) { i_find = 1; i_start = ic; }
+            if ((el_now > ya) && (el_now <= yb) && (i_find == 1)) {
+                /* the Fortran first lists the wetted pockets (i_start, i_end) and then sums them in the same order */
+                i_find = 0;
+                const int i1 = i_start, i2 = ic;
+                double x1 = xcs[i1], x2 = xcs[i1 + 1], y1 = ycs[i1], y2 = ycs[i1 + 1];
+                const double x_start = (y1 == y2) ? x1 : x1 + (el_now - y1) / (y2 - y1) * (x2 - x1);
+                x1 = xcs[i2]; x2 = xcs[i2 + 1]; y1 = ycs[i2]; y2 = ycs[i2 + 1];
+                const double x_end = (y1 == y2) ? x1 : x1 + (el_now - y1) / (y2 - y1) * (x2 - x1);
+                cal_topW = x_end - x_start + cal_topW;
+                cal_area = cal_area + cal_tri_area(el_now, x_start, xcs[i1 + 1], ycs[i1 + 1])
+                         + cal_multi_area(el_now, xcs + 1, ycs + 1, i1 + 1, i2)
+                         + cal_tri_area(el_now, x_end, xcs[i2], ycs[i2]);
+                cal_peri = cal_peri + cal_dist(x_start, el_now, xcs[i1 + 1], ycs[i1 + 1])
+                         + cal_perimeter(xcs + 1, ycs + 1, i1 + 1, i2)
+                         + cal_dist(x_end, el_now, xcs[i2], ycs[i2]);
+                double pxm = 0.0;                                                            /* cal_peri_x_mann :2060-2089 */
+                for (int i = i1 + 1; i <= i2 - 1; ++i) pxm = pxm + cal_dist(xcs[i], ycs[i], xcs[i + 1], ycs[i + 1]) * P(manncs[i], 1.50);
+                cal_equiv_mann = cal_equiv_mann + cal_dist(x_start, el_now, xcs[i1 + 1], ycs[i1 + 1]) * P(manncs[i1], 1.50)
+                               + pxm + cal_dist(x_end, el_now, xcs[i2], ycs[i2]) * P(manncs[i2], 1.50);
+                if (i1 == 1) cal_peri = cal_peri - cal_dist(x_start, el_now, xcs[i1 + 1], ycs[i1 + 1]);
+                if (i2 == (num - 1)) cal_peri = cal_peri - cal_dist(x_end, el_now, xcs[i2], ycs[i2]);
+            }
+        }
+        el1[iel] = el_now; a1[iel] = cal_area; peri1[iel] = cal_peri; tpW1[iel] = cal_topW;
+        redi1[iel] = a1[iel] / peri1[iel];
+        const double equiv_mann = P(cal_equiv_mann / cal_peri, (double)(2.0f / 3.0f));
+        conv1[iel] = (1.0 / equiv_mann) * a1[iel] * P(redi1[iel], (double)(2.0f / 3.0f));
+        if (peri1[iel] <= TOL) { redi1[iel] = 0.0; conv1[iel] = 0.0; }
+        if (iel == 1) newdKdA[iel] = conv1[iel] / a1[iel];
+        else newdKdA[iel] = (conv1[iel] - conv1[iel - 1]) / (a1[iel] - a1[iel - 1]);
+        skk[iel] = 1.0 / equiv_mann;
+    }
+    /* conveyance made monotone in elevation :1951-1986 */
+    const double incr_rate = (double)0.01f;
+    int iel_start = 2;
+    for (int iel = iel_start; iel <= NEL; ++iel) {
+        /* NB: the Fortran's `iel_start = iel_incr_start` inside the loop does not change the do-loop's bounds */
+        if (conv1[iel] <= conv1[iel - 1]) {
+            int ii = iel;
+            while ((conv1[ii] < conv1[iel - 1]) && (ii < NEL)) ii = ii + 1;
+            const int inc0 = ii;
+            if ((inc0 >= NEL) && (conv1[inc0] < conv1[iel - 1])) conv1[inc0] = (1.0 + incr_rate) * conv1[iel - 1];
+            const double pos_slope = (conv1[inc0] - conv1[iel - 1]) / (el1[inc0] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) conv1[ii] = conv1[iel - 1] + pos_slope * (el1[ii] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) {
+                if (ii == 1) newdKdA[ii] = conv1[ii] / a1[ii];
+                else newdKdA[ii] = (conv1[ii] - conv1[ii - 1]) / (a1[ii] - a1[ii - 1]);
+            }
+        }
+    }
+    /* dK/dA made monotone :1988-2008 */
+    for (int iel = 2; iel <= NEL; ++iel) {
+        if (newdKdA[iel] <= newdKdA[iel - 1]) {
+            int ii = iel;
+            while ((newdKdA[ii] < newdKdA[iel - 1]) && (ii < NEL)) ii = ii + 1;
+            const int inc0 = ii;
+            if ((inc0 >= NEL) && (newdKdA[inc0] < newdKdA[iel - 1])) newdKdA[inc0] = (1.0 + incr_rate) * newdKdA[iel - 1];
+            const double pos_slope = (newdKdA[inc0] - newdKdA[iel - 1]) / (el1[inc0] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) newdKdA[ii] = newdKdA[iel - 1] + pos_slope * (el1[ii] - el1[iel - 1]);
+        }
+    }
+    for (int iel = 1; iel <= NEL; ++iel) {                                                   /* :2010-2019 */
+        TAB(1, iel, idx_node, idx_reach) = el1[iel];
+        TAB(2, iel, idx_node, idx_reach) = a1[iel];
+        TAB(3, iel, idx_node, idx_reach) = peri1[iel];
+        TAB(4, iel, idx_node, idx_reach) = redi1[iel];
+        TAB(5, iel, idx_node, idx_reach) = conv1[iel];
+        TAB(6, iel, idx_node, idx_reach) = tpW1[iel];
+        TAB(9, iel, idx_node, idx_reach) = newdKdA[iel];
+        TAB(11, iel, idx_node, idx_reach) = skk[iel];
+    }
+    A2(S->z, idx_node, idx_reach) = el_min;                                                  /* :2021 */
+    free(buf);
+    return 0;
+#undef BATHY
+}
+
 /* ---- funcd_diffdepth :1664-1711, rtsafe :1555-1662 ------------------------------------------------------------------ */
 static void funcd_diffdepth(const Dw* S, int i, int j, double Q_cur, double Q_ds, double z_cur, double z_ds, double y_cur,
                             double y_ds, double* f, double* df)
@@ -517,13 +635,12 @@ int trt_oracle_diffnw(const double* timestep_ar_g, const int* nts_ql_g, const in
                       const double* crosswalk_g, const double* z_thalweg_g, double* q_ev_g, double* elv_ev_g,
                       double* depth_ev_g)
 {
-    (void)nts_ub_g; (void)so_ar_g; (void)ubcd_g; (void)paradim; (void)x_bathy_g; (void)z_bathy_g; (void)mann_bathy_g;
-    (void)size_bathy_g; (void)usgs_da_g; (void)usgs_da_reach_g; (void)nts_da_g;
+    (void)nts_ub_g; (void)so_ar_g; (void)ubcd_g; (void)paradim; (void)usgs_da_g; (void)usgs_da_reach_g; (void)nts_da_g;
     static const double TOL = (double)1e-8f;
     Dw Sv, *S = &Sv;
     memset(S, 0, sizeof *S);
     const int mx = *mxncomp_g, nl = *nrch_g, nql = *nts_ql_g, ndb = *nts_db_g, nev = *ntss_ev_g, nqt = *nts_qtrib_g;
-    if (*mxnbathy_g != 0) return -2;                               /* natural cross sections: not restated */
+    const int mxnbathy = *mxnbathy_g;                              /* > 0: natural cross sections (:433-454) */
     if (mx < 2 || nl < 1) return -1;
     S->mxncomp = mx; S->nlinks = nl; S->nel = NEL; S->frnw = frnw_ar_g; S->frnw_col = *frnw_col;
     double dtini = timestep_ar_g[0];
@@ -583,7 +700,14 @@ int trt_oracle_diffnw(const double* timestep_ar_g, const int* nts_ql_g, const in
             if (A2(S->dx, i, j) < minDx) minDx = A2(S->dx, i, j);
         }
     }
-    for (int jm = 0; jm < nm; ++jm) {                              /* synthetic cross sections :456-483 */
+    for (int jm = 0; jm < nm && mxnbathy != 0; ++jm) {             /* natural cross sections :441-454 */
+        const int j = mstem[jm];
+        for (int i = 1; i <= FRNW(j, 1); ++i) {
+            const int rc = read_xsection_natural(S, i, j, timesDepth, x_bathy_g, z_bathy_g, mann_bathy_g, size_bathy_g, mxnbathy);
+            if (rc != 0) { free(pool); free(mstem); free(tarr_ql); free(tarr_qtrib); free(tarr_db); return rc; }
+        }
+    }
+    for (int jm = 0; jm < nm && mxnbathy == 0; ++jm) {             /* synthetic cross sections :456-483 */
         const int j = mstem[jm], ncomp = FRNW(j, 1);
         for (int i = 1; i <= ncomp; ++i) {
             const double leftBank = (A2(twcc_ar_g, i, j) - A2(tw_ar_g, i, j)) / 2.0;

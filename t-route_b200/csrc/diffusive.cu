@@ -40,7 +40,33 @@ __global__ void __launch_bounds__(256) table1_kernel(const Dom* __restrict__ dom
     const int row = (int)(idx % NEL) + 1;
     const int node = (int)(idx / NEL);
     const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
-    if (i <= DW_FRNW(j, 1)) dw_table_pass1(D, i, j, row);
+    if (i <= DW_FRNW(j, 1)) {
+        if (D.mxnbathy == 0) dw_table_pass1(D, i, j, row);
+        else dw_nat_pass1(D, i, j, row);
+    }
+}
+
+/* surveyed cross sections: thread per (node, vertex) before table1_kernel, thread per node after it */
+__global__ void __launch_bounds__(256) natprep_kernel(const Dom* __restrict__ doms)
+{
+    Dom D = doms[blockIdx.y];
+    if (D.mxnbathy == 0) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D.nm * D.mx * D.mxnbathy) return;
+    const int ic = (int)(idx % D.mxnbathy) + 1;
+    const int node = (int)(idx / D.mxnbathy);
+    const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
+    if (i <= DW_FRNW(j, 1) && ic <= D.size_bathy[(i - 1) + (size_t)(j - 1) * D.mx]) dw_nat_prep(D, i, j, ic);
+}
+
+__global__ void __launch_bounds__(128) natsmooth_kernel(const Dom* __restrict__ doms)
+{
+    Dom D = doms[blockIdx.y];
+    if (D.mxnbathy == 0) return;
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= D.nm * D.mx) return;
+    const int j = D.mstem[node / D.mx], i = node % D.mx + 1;
+    if (i <= DW_FRNW(j, 1)) dw_nat_smooth(D, i, j);
 }
 
 __global__ void __launch_bounds__(256) table2_kernel(const Dom* __restrict__ doms)
@@ -167,13 +193,15 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     }
     CUD(cudaSetDevice(g_device));
     std::vector<Dom> hdoms((size_t)n_domains);
-    long long max_rows = 0, max_cols = 0;
+    long long max_rows = 0, max_cols = 0, max_verts = 0, max_nodes = 0;
     for (int d = 0; d < n_domains; ++d) {
         const int rc = upload_domain(doms[(size_t)d], hdoms[(size_t)d]);
         if (rc != TRT_OK) return rc;
         const long long nodes = (long long)hdoms[(size_t)d].nm * hdoms[(size_t)d].mx;
         max_rows = std::max(max_rows, nodes * NEL);
         max_cols = std::max(max_cols, nodes * NCOL);
+        max_nodes = std::max(max_nodes, nodes);
+        max_verts = std::max(max_verts, nodes * hdoms[(size_t)d].mxnbathy);
     }
     Dom* d_doms = nullptr;
     CUD(cudaMalloc((void**)&d_doms, sizeof(Dom) * (size_t)n_domains));
@@ -183,7 +211,15 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     CUD(cudaEventCreate(&e0)); CUD(cudaEventCreate(&e1)); CUD(cudaEventCreate(&e2));
     CUD(cudaEventRecord(e0));
     const dim3 g1((unsigned)((max_rows + 255) / 256), (unsigned)n_domains), gm((unsigned)((max_cols + 255) / 256), (unsigned)n_domains);
+    if (max_verts > 0) {
+        const dim3 gv((unsigned)((max_verts + 255) / 256), (unsigned)n_domains);
+        natprep_kernel<<<gv, 256>>>(d_doms);
+    }
     table1_kernel<<<g1, 256>>>(d_doms);
+    if (max_verts > 0) {
+        const dim3 gn((unsigned)((max_nodes + 127) / 128), (unsigned)n_domains);
+        natsmooth_kernel<<<gn, 128>>>(d_doms);
+    }
     table2_kernel<<<g1, 256>>>(d_doms);
     tablemin_kernel<<<gm, 256>>>(d_doms);
     CUD(cudaGetLastError());
@@ -196,7 +232,7 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_table_ms = ms;
     if (cudaEventElapsedTime(&ms, e1, e2) == cudaSuccess) g_loop_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    g_launches = 4;
+    g_launches = max_verts > 0 ? 6 : 4;
     for (int d = 0; d < n_domains; ++d) {
         DevDomain& V = doms[(size_t)d];
         const size_t nb = V.H.n_out * sizeof(double);

@@ -86,6 +86,11 @@ struct Dom {
     const unsigned char* is_main; /* [nl + 1] */
     /* node geometry as given (mx, nl) */
     const double *z_in, *bo_in, *traps_in, *tw_in, *twcc_in, *mann_in, *manncc_in, *dx_in;
+    /* surveyed ("natural") cross sections, mxnbathy > 0: vertices (mxnbathy, mx, nl), counts (mx, nl) */
+    int mxnbathy;
+    const double *x_bathy, *z_bathy, *mann_bathy;
+    const int* size_bathy;
+    double* mann15;             /* (mxnbathy, mx, nl) min(n, 0.15)**1.5 of every vertex (dw_nat_prep) */
     /* forcing */
     const double* qlat;         /* (nql, mx, nl) */
     const double* qtrib;        /* (nqt, nl) */
@@ -381,16 +386,157 @@ TRT_HD void dw_table_pass2(Dom& D, int i, int j, int row)
 {
     const double* A = dw_col(D, i, j, C_AREA);
     const double* K = dw_col(D, i, j, C_CONV);
-    double dkda;
-    if (row == 1) dkda = K[0] / A[0];
-    else dkda = (K[row - 1] - K[row - 2]) / (A[row - 1] - A[row - 2]);
-    dw_col_w(D, i, j, C_DKDA)[row - 1] = dkda;
+    if (D.mxnbathy == 0) {                 /* surveyed sections: dw_nat_smooth has written the column */
+        double dkda;
+        if (row == 1) dkda = K[0] / A[0];
+        else dkda = (K[row - 1] - K[row - 2]) / (A[row - 1] - A[row - 2]);
+        dw_col_w(D, i, j, C_DKDA)[row - 1] = dkda;
+    }
     const int ncomp = DW_FRNW(j, 1);
     double slope;
     if (i < ncomp) slope = (DW_A2(D.z, i, j) - DW_A2(D.z, i + 1, j)) / DW_A2(D.dx, i, j);
     else slope = (DW_A2(D.z, i - 1, j) - DW_A2(D.z, i, j)) / DW_A2(D.dx, i - 1, j);
     if (slope <= D.so_llm) slope = D.so_llm;
     dw_col_w(D, i, j, C_QNRM)[row - 1] = K[row - 1] * trt_pow64_det(slope, 0.50);
+}
+
+/* ---- surveyed cross sections: readXsection_natural_mann_vertices :1756-2091 ------------------------------------------ */
+#define DW_BATHY(p, ic, i, j) ((p)[((ic) - 1) + (size_t)D.mxnbathy * ((size_t)((i) - 1) + (size_t)D.mx * (size_t)((j) - 1))])
+
+/* vertex ic (1-based) of the closed polygon of node (i, j): the surveyed points 2..nb+1 between two vertical walls */
+struct NatXs { int nb; double x0, el_min, el_range, el_incr, wall; };
+
+TRT_HD void dw_nat_setup(const Dom& D, int i, int j, NatXs& S)
+{
+    const double timesDepth = 4.0;
+    S.nb = D.size_bathy[(i - 1) + (size_t)(j - 1) * D.mx];
+    S.x0 = DW_BATHY(D.x_bathy, 1, i, j);
+    double el_min = 99999., el_max = -99999.;                                 /* :1818-1823 */
+    for (int ic = 1; ic <= S.nb; ++ic) {
+        const double y = DW_BATHY(D.z_bathy, ic, i, j) * 1.0;
+        if (y < el_min) el_min = y;
+        if (y > el_max) el_max = y;
+    }
+    S.el_min = el_min;
+    S.el_range = (el_max - el_min) * timesDepth;
+    S.el_incr = S.el_range / (double)(float)(NEL - 1.0f);
+    S.wall = el_min + S.el_range + 1.0;
+}
+/* coordinates and n**1.5 of polygon vertex k = 1 .. nb + 2 (:1799-1835) */
+TRT_HD double dw_nat_x(const Dom& D, const NatXs& S, int i, int j, int k)
+{
+    const int ic = k <= 1 ? 1 : (k >= S.nb + 2 ? S.nb : k - 1);
+    return (-S.x0 + DW_BATHY(D.x_bathy, ic, i, j)) * 1.0;
+}
+TRT_HD double dw_nat_y(const Dom& D, const NatXs& S, int i, int j, int k)
+{
+    if (k <= 1 || k >= S.nb + 2) return S.wall;
+    return DW_BATHY(D.z_bathy, k - 1, i, j) * 1.0;
+}
+TRT_HD double dw_nat_m15(const Dom& D, const NatXs& S, int i, int j, int k)
+{
+    if (k <= 1 || k >= S.nb + 1) return 0.0;      /* manncs(1) = manncs(num-1) = manncs(num) = 0 and 0**1.5 = 0 */
+    return DW_BATHY(D.mann15, k - 1, i, j);
+}
+
+/* thread per (node, vertex): the roughness term of every polygon side, min(n, 0.15)**1.5 (:1811-1814, :2047, :2084) */
+TRT_HD void dw_nat_prep(Dom& D, int i, int j, int ic)
+{
+    double m = DW_BATHY(D.mann_bathy, ic, i, j);
+    if (m > DW_F(0.15)) m = DW_F(0.15);
+    DW_BATHY(D.mann15, ic, i, j) = trt_pow64_det(m, 1.50);
+}
+
+/* thread per (node, table row): one elevation of the surveyed section (:1840-1925), conveyance not yet made monotone */
+TRT_HD void dw_nat_pass1(Dom& D, int i, int j, int row)
+{
+    NatXs S;
+    dw_nat_setup(D, i, j, S);
+    const int num = S.nb + 2;
+    double el_now = S.el_min + (double)(float)(row - 1) * S.el_incr;
+    if (fabs(el_now - S.el_min) < DW_F(1e-8)) el_now = el_now + DW_F(0.00001);
+    double cal_area = 0.0, cal_peri = 0.0, cal_topW = 0.0, cal_equiv_mann = 0.0;
+    int i_find = 0, i_start = -999;
+    double ya = dw_nat_y(D, S, i, j, 1);
+    for (int ic = 1; ic <= num - 1; ++ic) {
+        const double yb = dw_nat_y(D, S, i, j, ic + 1);
+        if ((el_now <= ya) && (el_now > yb) && (i_find == 0)) { i_find = 1; i_start = ic; }
+        if ((el_now > ya) && (el_now <= yb) && (i_find == 1)) {
+            i_find = 0;
+            const int i1 = i_start, i2 = ic;
+            double x1 = dw_nat_x(D, S, i, j, i1), x2 = dw_nat_x(D, S, i, j, i1 + 1), y1 = dw_nat_y(D, S, i, j, i1),
+                   y2 = dw_nat_y(D, S, i, j, i1 + 1);
+            const double x_start = (y1 == y2) ? x1 : x1 + (el_now - y1) / (y2 - y1) * (x2 - x1);
+            const double xs1 = x2, ys1 = y2;                                  /* vertex i1 + 1 */
+            x1 = dw_nat_x(D, S, i, j, i2); x2 = dw_nat_x(D, S, i, j, i2 + 1); y1 = dw_nat_y(D, S, i, j, i2);
+            y2 = dw_nat_y(D, S, i, j, i2 + 1);
+            const double x_end = (y1 == y2) ? x1 : x1 + (el_now - y1) / (y2 - y1) * (x2 - x1);
+            const double xe2 = x1, ye2 = y1;                                  /* vertex i2 */
+            cal_topW = x_end - x_start + cal_topW;
+            double multi_area = 0.0, perim = 0.0, pxm = 0.0;
+            double xk = xs1, yk = ys1;
+            for (int k = i1 + 1; k <= i2 - 1; ++k) {
+                const double xn = dw_nat_x(D, S, i, j, k + 1), yn = dw_nat_y(D, S, i, j, k + 1);
+                multi_area = multi_area + fabs(0.5 * (xn - xk) * (el_now - yk + el_now - yn));
+                const double dk = dw_dist(xk, yk, xn, yn);
+                perim = perim + dk;
+                pxm = pxm + dk * dw_nat_m15(D, S, i, j, k);
+                xk = xn; yk = yn;
+            }
+            const double d_s = dw_dist(x_start, el_now, xs1, ys1), d_e = dw_dist(x_end, el_now, xe2, ye2);
+            cal_area = cal_area + fabs(0.5 * (xs1 - x_start) * (el_now - ys1)) + multi_area + fabs(0.5 * (xe2 - x_end) * (el_now - ye2));
+            cal_peri = cal_peri + d_s + perim + d_e;
+            cal_equiv_mann = cal_equiv_mann + d_s * dw_nat_m15(D, S, i, j, i1) + pxm + d_e * dw_nat_m15(D, S, i, j, i2);
+            if (i1 == 1) cal_peri = cal_peri - d_s;
+            if (i2 == (num - 1)) cal_peri = cal_peri - d_e;
+        }
+        ya = yb;
+    }
+    const double redi = cal_area / cal_peri;
+    const double equiv_mann = trt_pow64_det(cal_equiv_mann / cal_peri, (double)(2.0f / 3.0f));
+    double conv = (1.0 / equiv_mann) * cal_area * trt_pow64_det(redi, (double)(2.0f / 3.0f));
+    if (cal_peri <= DW_F(1e-8)) conv = 0.0;
+    dw_col_w(D, i, j, C_ELEV)[row - 1] = el_now;
+    dw_col_w(D, i, j, C_AREA)[row - 1] = cal_area;
+    dw_col_w(D, i, j, C_PERI)[row - 1] = cal_peri;
+    dw_col_w(D, i, j, C_CONV)[row - 1] = conv;
+    dw_col_w(D, i, j, C_TOPW)[row - 1] = cal_topW;
+    dw_col_w(D, i, j, C_SKK)[row - 1] = 1.0 / equiv_mann;
+    if (row == 1) DW_A2(D.z, i, j) = S.el_min;                                /* :2021 */
+}
+
+/* thread per node: dK/dA of the raw table, then conveyance and dK/dA made monotone in elevation (:1919-1924, :1951-2008);
+ * sequential over the 501 rows by construction */
+TRT_HD void dw_nat_smooth(Dom& D, int i, int j)
+{
+    const double* el1 = dw_col(D, i, j, C_ELEV) - 1;          /* 1-based views */
+    const double* a1 = dw_col(D, i, j, C_AREA) - 1;
+    double* conv1 = dw_col_w(D, i, j, C_CONV) - 1;
+    double* dkda = dw_col_w(D, i, j, C_DKDA) - 1;
+    const double incr_rate = DW_F(0.01);
+    dkda[1] = conv1[1] / a1[1];
+    for (int iel = 2; iel <= NEL; ++iel) dkda[iel] = (conv1[iel] - conv1[iel - 1]) / (a1[iel] - a1[iel - 1]);
+    for (int iel = 2; iel <= NEL; ++iel) {
+        if (conv1[iel] <= conv1[iel - 1]) {
+            int ii = iel;
+            while ((conv1[ii] < conv1[iel - 1]) && (ii < NEL)) ii = ii + 1;
+            const int inc0 = ii;
+            if ((inc0 >= NEL) && (conv1[inc0] < conv1[iel - 1])) conv1[inc0] = (1.0 + incr_rate) * conv1[iel - 1];
+            const double pos_slope = (conv1[inc0] - conv1[iel - 1]) / (el1[inc0] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) conv1[ii] = conv1[iel - 1] + pos_slope * (el1[ii] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) dkda[ii] = (conv1[ii] - conv1[ii - 1]) / (a1[ii] - a1[ii - 1]);
+        }
+    }
+    for (int iel = 2; iel <= NEL; ++iel) {
+        if (dkda[iel] <= dkda[iel - 1]) {
+            int ii = iel;
+            while ((dkda[ii] < dkda[iel - 1]) && (ii < NEL)) ii = ii + 1;
+            const int inc0 = ii;
+            if ((inc0 >= NEL) && (dkda[inc0] < dkda[iel - 1])) dkda[inc0] = (1.0 + incr_rate) * dkda[iel - 1];
+            const double pos_slope = (dkda[inc0] - dkda[iel - 1]) / (el1[inc0] - el1[iel - 1]);
+            for (ii = iel; ii <= inc0 - 1; ++ii) dkda[ii] = dkda[iel - 1] + pos_slope * (el1[ii] - el1[iel - 1]);
+        }
+    }
 }
 
 /* minimum of one column of one node (what r_interpol returns below the table) */

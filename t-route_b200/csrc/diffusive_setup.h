@@ -43,7 +43,8 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     if (!a.mxncomp_g || !a.nrch_g || !a.timestep_ar_g || !a.para_ar_g || !a.frnw_ar_g || !a.frnw_col) return "NULL scalar argument";
     const int mx = *a.mxncomp_g, nl = *a.nrch_g;
     if (mx < 2 || nl < 1) return "mxncomp_g must be >= 2 and nrch_g >= 1";
-    if (*a.mxnbathy_g != 0) return "natural cross sections (mxnbathy_g > 0, readXsection_natural_mann_vertices) are not supported";
+    if (*a.mxnbathy_g < 0) return "mxnbathy_g < 0";
+    D.mxnbathy = *a.mxnbathy_g;
     if (*a.cwnrow_g > 0) return "refactored-hydrofabric crosswalk (cwnrow_g > 0, diffusive.f90:837-903) is not supported";
     if (*a.paradim < 11) return "para_ar_g needs 11 entries";
     D.mx = mx; D.nl = nl; D.nev = *a.ntss_ev_g; D.nql = *a.nts_ql_g; D.nqt = *a.nts_qtrib_g; D.ndb = *a.nts_db_g;
@@ -62,7 +63,7 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     H.n_nodes = n2; H.n_out = (size_t)D.nev * n2;
     /* ---- ints: frnw (as given), mstem, hint_q; bytes: is_main */
     const size_t nfr = (size_t)nl * D.frnw_col;
-    H.ipool.assign(nfr + (size_t)nl + n2 + 1 + (size_t)nl + 2 + (size_t)nl, 0);
+    H.ipool.assign(nfr + (size_t)nl + n2 + 1 + (size_t)nl + 2 + (size_t)nl + n2, 0);
     int* ip = H.ipool.data();
     std::memcpy(ip, a.frnw_ar_g, nfr * sizeof(int));
     D.frnw = ip; ip += nfr;
@@ -71,6 +72,9 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     D.status = ip; ip += 1;
     int* lvl_ptr = ip; ip += (size_t)nl + 2;
     int* lvl_reach = ip; ip += nl;
+    int* size_bathy = ip; ip += n2;
+    if (D.mxnbathy > 0) std::memcpy(size_bathy, a.size_bathy_g, n2 * sizeof(int));
+    D.size_bathy = size_bathy;
     for (size_t k = 0; k < n2; ++k) hint[k] = NEL / 2;
     H.bpool.assign((size_t)nl + 1, 0);
     int nm = 0;
@@ -87,6 +91,12 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
         }
     }
     if (nm == 0) return "no mainstem reach (flag 555) in frnw_g";
+    if (D.mxnbathy > 0)
+        for (int jm = 0; jm < nm; ++jm)
+            for (int i = 1; i <= DW_FRNW(mstem[jm], 1); ++i) {
+                const int nb = size_bathy[(i - 1) + (size_t)(mstem[jm] - 1) * mx];
+                if (nb < 2 || nb > D.mxnbathy) return "size_bathy_g: a mainstem node needs 2 .. mxnbathy_g cross-section vertices";
+            }
     D.nm = nm; D.mstem = mstem; D.hint_q = hint; D.is_main = H.bpool.data();
     {
         /* distance of every mainstem reach from the tailwater, counted in mainstem reaches; a reach drains into a reach
@@ -111,7 +121,8 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
 
     /* ---- doubles */
     const size_t nq = (size_t)D.nql * n2, nt = (size_t)D.nqt * nl;
-    const size_t total = 8 * n2 /*geometry in*/ + nq + nt + (size_t)D.ndb + n2 /*iniq*/ + (size_t)(D.nql + 1) + D.nqt + D.ndb /*time axes*/
+    const size_t nbathy = (size_t)D.mxnbathy * n2;
+    const size_t total = 4 * nbathy /*vertices + mann15*/ + 8 * n2 /*geometry in*/ + nq + nt + (size_t)D.ndb + n2 /*iniq*/ + (size_t)(D.nql + 1) + D.nqt + D.ndb /*time axes*/
                          + (size_t)nl /*rmax*/ + 33 * n2 /*state*/ + (size_t)D.ndb /*varr_db*/ + 8 /*scal*/;
     H.dpool.assign(total, 0.0);
     double* p = H.dpool.data();
@@ -122,6 +133,8 @@ inline std::string dw_build_host(const DiffnwArgs& a, DomHost& H)
     D.manncc_in = take_in(a.manncc_ar_g, n2); D.dx_in = take_in(a.dx_ar_g, n2);
     D.qlat = take_in(a.qlat_g, nq); D.qtrib = take_in(a.qtrib_g, nt); D.dbcd = take_in(a.dbcd_g, (size_t)D.ndb);
     D.iniq = take_in(a.iniq, n2);
+    D.x_bathy = take_in(a.x_bathy_g, nbathy); D.z_bathy = take_in(a.z_bathy_g, nbathy); D.mann_bathy = take_in(a.mann_bathy_g, nbathy);
+    D.mann15 = take(nbathy);
     double* tql = take((size_t)D.nql + 1); double* tqt = take((size_t)D.nqt); double* tdb = take((size_t)D.ndb);
     for (int n = 1; n <= D.nql; ++n) tql[n] = D.t0 * 60.0 + D.dt_ql * (double)n / 60.0;          /* :512-516 */
     tql[0] = D.t0 * 60;
@@ -172,8 +185,10 @@ inline Dom dw_rebase(const DomHost& H, double* dd, int* di, unsigned char* db)
     const void* hi = H.ipool.data(); const size_t ni = H.ipool.size() * sizeof(int);
     const void* hb = H.bpool.data(); const size_t nb = H.bpool.size();
     const double** cdp[] = {&D.z_in, &D.bo_in, &D.traps_in, &D.tw_in, &D.twcc_in, &D.mann_in, &D.manncc_in, &D.dx_in, &D.qlat,
-                            &D.qtrib, &D.dbcd, &D.iniq, &D.tarr_ql, &D.tarr_qtrib, &D.tarr_db};
+                            &D.qtrib, &D.dbcd, &D.iniq, &D.tarr_ql, &D.tarr_qtrib, &D.tarr_db, &D.x_bathy, &D.z_bathy, &D.mann_bathy};
     for (const double** q : cdp) dw_rebase_ptr(*q, hd, nd, dd);
+    dw_rebase_ptr(D.mann15, hd, nd, dd);
+    dw_rebase_ptr(D.size_bathy, hi, ni, di);
     double** dp[] = {&D.rmax, &D.z, &D.dx, &D.bo, &D.pere, &D.qp, &D.qpx, &D.sk, &D.co, &D.oldQ, &D.newQ, &D.oldArea, &D.newArea,
                      &D.oldY, &D.newY, &D.lateralFlow, &D.celerity, &D.diffusivity, &D.celerity2, &D.diffusivity2, &D.eei,
                      &D.ffi, &D.exi, &D.fxi, &D.c_ppi, &D.c_qqi, &D.c_rri, &D.c_ssi, &D.c_sxi, &D.b_ynorm, &D.b_x1, &D.b_x2, &D.b_sf1,

@@ -159,3 +159,35 @@ def uniform_channel(n_reaches=3, ncomp=6, q=60.0, nsteps=48, dt=300.0, slope=8e-
     d["iniq"][:] = q
     d["qtrib_g"][:, 0] = q          # reach 0 is the head tributary carrying the constant inflow
     return d
+
+
+def with_natural_sections(d, mxnbathy=24, seed=5):
+    """Replace the synthetic trapezoids of a domain by surveyed ("natural") cross sections: per mainstem node 9..mxnbathy
+    vertices (x, z, Manning n) -- levee / floodplain / bank / irregular bed / bank / floodplain / levee -- in the arrays
+    fp_naturalxsec_map builds from the topobathy table (diffusive_utils_v02.py:394-510): x_bathy_g, z_bathy_g, mann_bathy_g
+    (mxnbathy_g, mxncomp_g, nrch_g) and size_bathy_g (mxncomp_g, nrch_g).  The lowest vertex sits on the node's z_ar_g.
+    Some floodplain roughness values exceed 0.15 (the solver caps them, diffusive.f90:1811-1814)."""
+    rng = np.random.default_rng(seed)
+    d = dict(d)
+    mx, nrch = d["mxncomp_g"], d["nrch_g"]
+    xb = np.zeros((mxnbathy, mx, nrch)); zb = np.zeros_like(xb); mb = np.zeros_like(xb)
+    size = np.zeros((mx, nrch), dtype=np.int32)
+    for j in d["mainstem"]:
+        for i in range(d["frnw_g"][j, 0]):
+            nb = int(rng.integers(9, mxnbathy + 1))
+            nbed = nb - 6
+            bw, tw, twcc = d["bo_ar_g"][i, j], d["tw_ar_g"][i, j], d["twcc_ar_g"][i, j]
+            hbf = (tw - bw) / (2.0 * d["traps_ar_g"][i, j])
+            z0 = d["z_ar_g"][i, j]
+            fp = (twcc - tw) / 2.0
+            bed_x = fp + (tw - bw) / 2.0 + np.sort(rng.uniform(0.0, bw, nbed))
+            bed_z = z0 + rng.uniform(0.0, 0.25 * hbf, nbed)
+            bed_z[rng.integers(0, nbed)] = z0
+            x = np.concatenate([[0.0, 0.05 * fp, fp], bed_x, [fp + tw, fp + tw + 0.95 * fp, twcc]])
+            z = np.concatenate([[z0 + 3.5 * hbf, z0 + 1.3 * hbf, z0 + hbf], bed_z, [z0 + hbf, z0 + 1.2 * hbf, z0 + 3.2 * hbf]])
+            n = np.concatenate([[0.2, 0.12, 0.09], rng.uniform(0.03, 0.05, nbed), [0.09, 0.16, 0.1]])
+            x += rng.uniform(100.0, 5000.0)                          # surveys do not start at x = 0 (:1804-1806)
+            xb[:nb, i, j], zb[:nb, i, j], mb[:nb, i, j] = x, z, n
+            size[i, j] = nb
+    d.update(mxnbathy_g=mxnbathy, x_bathy_g=xb, z_bathy_g=zb, mann_bathy_g=mb, size_bathy_g=size)
+    return d

@@ -48,8 +48,15 @@ extern "C" int trt_replica_diffnw(
     for (size_t k = 0; k < H.n_out; ++k) { q_ev_g[k] = 0.0; elv_ev_g[k] = 0.0; depth_ev_g[k] = 0.0; }
     for (int jm = 0; jm < D.nm; ++jm) {
         const int j = D.mstem[jm];
-        for (int i = 1; i <= DW_FRNW(j, 1); ++i)
-            for (int row = 1; row <= NEL; ++row) dw_table_pass1(D, i, j, row);
+        for (int i = 1; i <= DW_FRNW(j, 1); ++i) {
+            if (D.mxnbathy == 0) {
+                for (int row = 1; row <= NEL; ++row) dw_table_pass1(D, i, j, row);
+            } else {
+                for (int ic = 1; ic <= D.size_bathy[(i - 1) + (size_t)(j - 1) * D.mx]; ++ic) dw_nat_prep(D, i, j, ic);
+                for (int row = 1; row <= NEL; ++row) dw_nat_pass1(D, i, j, row);
+                dw_nat_smooth(D, i, j);
+            }
+        }
     }
     for (int jm = 0; jm < D.nm; ++jm) {
         const int j = D.mstem[jm];
@@ -78,3 +85,23 @@ extern "C" int trt_replica_table(const double* z_ar_g, const double* bo_ar_g, co
 
 /* probe of dw_locate_hint for tests/test_diffusive_replica.py */
 extern "C" int trt_replica_locate(const double* xx, int n, double x, int hint) { return dw_locate_hint(xx, n, x, hint); }
+
+/* look-up table of ONE surveyed cross section (nb vertices): out = [NCOL][501] columns C_ELEV, C_AREA, C_PERI, C_CONV, C_TOPW,
+ * C_DKDA, (unused), C_SKK after the monotone smoothing; returns the bed elevation in *z_out */
+extern "C" int trt_replica_table_natural(int nb, const double* x, const double* z, const double* mann, double* out8x501, double* z_out)
+{
+    Dom D;
+    std::memset(&D, 0, sizeof D);
+    D.mx = 1; D.nl = 1; D.nm = 1; D.mxnbathy = nb;
+    std::vector<double> tab((size_t)NCOL * LD, 0.0), m15((size_t)nb, 0.0), zz(1, 0.0);
+    int size = nb;
+    D.x_bathy = x; D.z_bathy = z; D.mann_bathy = mann; D.size_bathy = &size; D.mann15 = m15.data();
+    D.tab = tab.data(); D.z = zz.data();
+    for (int ic = 1; ic <= nb; ++ic) dw_nat_prep(D, 1, 1, ic);
+    for (int row = 1; row <= NEL; ++row) dw_nat_pass1(D, 1, 1, row);
+    dw_nat_smooth(D, 1, 1);
+    for (int c = 0; c < NCOL; ++c)
+        for (int r = 0; r < NEL; ++r) out8x501[(size_t)c * NEL + r] = tab[(size_t)c * LD + r];
+    *z_out = zz[0];
+    return 0;
+}

@@ -89,10 +89,10 @@ def test_libm_and_bit_specified_pow_builds_agree(od):
         assert rel.max() < 1e-9, rel.max()
 
 
-def test_unsupported_inputs_are_refused(od):
+def test_inconsistent_cross_section_counts_are_refused(od):
     from troute_b200 import synth_diffusive as sd
     d = sd.diffusive_domain()
-    d["mxnbathy_g"] = 4
+    d["mxnbathy_g"] = 4                                                 # surveyed sections announced, none given
     with pytest.raises(RuntimeError):
         od.compute_diffusive(d)
 

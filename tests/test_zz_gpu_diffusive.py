@@ -59,6 +59,19 @@ def test_gpu_within_tolerance_of_the_libm_build(gpu, od, case):
         assert rel.max() < REL_TOL, rel.max()
 
 
+@pytest.mark.parametrize("case", ["small", "branched", "tailwater-depth"])
+def test_surveyed_cross_sections_on_gpu(gpu, od, case):
+    """mxnbathy_g > 0 (what the reference's LowerColorado hybrid configuration uses, use_natl_xsections: True): the vertex
+    roughness, table and smoothing kernels, then the same time loop -- bit-equal to the oracle."""
+    from troute_b200 import synth_diffusive as sd
+    d = sd.with_natural_sections(sd.diffusive_domain(**HD.CASES[case]))
+    ref = od.compute_diffusive(d, od.POW_DET)
+    got = gpu.compute_diffusive(d)
+    for name, a, b in zip(("q_ev_g", "elv_ev_g", "depth_ev_g"), ref, got):
+        HD.assert_bits64(b, a, f"{case}: {name}")
+    assert gpu.last_run()[2] == 6
+
+
 def test_uniform_flow_on_gpu(gpu):
     from troute_b200 import synth_diffusive as sd
     d = sd.uniform_channel(q=60.0)
