@@ -170,3 +170,54 @@ def compute_nhd_routing_v02(
     LOG.debug("B200 routing of %d segments x %d steps complete in %s seconds.", len(param_df_sub), nts,
               time.time() - start_time)
     return [result], subnetwork_list
+
+
+def compute_diffusive_routing(
+    results, diffusive_network_data, cpu_pool, t0, dt, nts, q0, qlats, qts_subdivisions, usgs_df, lastobs_df,
+    da_parameter_dict, waterbodies_df, topobathy, refactored_diffusive_domain, refactored_reaches,
+    coastal_boundary_depth_df, unrefactored_topobathy,
+):
+    """Mirror of troute.routing.compute.compute_diffusive_routing (compute.py:1740-1884): diffusive-wave routing of the
+    mainstem of every tailwater domain, fed at its junctions by the Muskingum-Cunge flows already in `results`.
+
+    Same arguments, same list of 10-tuples (ids, [q, NaN, depth] x nts per segment, 0, placeholders ...).  The reference
+    loops over the tailwaters and calls the Fortran solver once per domain (":1764 TODO by-network parallel loop"); here all
+    domains are packed first and routed by ONE trt_diffnw_batch call, one CTA per domain."""
+    from . import diffusive_utils as diff_utils
+    from .fast_reach import diffusive
+    if refactored_diffusive_domain:
+        raise NotImplementedError("refactored hydrofabric (see diffusive_utils.diffusive_input_data_v02)")
+    packed = []
+    for tw in diffusive_network_data:
+        net = diffusive_network_data[tw]
+        # junction inflows: the flow series of the tributary segments out of the MC results (:1764-1781)
+        segs, flows = [], []
+        for r in results:
+            x = np.isin(r[0], net["tributary_segments"])
+            if x.any():
+                segs.append(np.asarray(r[0])[x]); flows.append(np.asarray(r[1])[x, ::3])
+        junction_inflows = pd.DataFrame(data=np.concatenate(flows) if flows else None,
+                                        index=np.concatenate(segs) if segs else None)
+        topobathy_bytw = pd.DataFrame()
+        if topobathy is not None and not topobathy.empty:
+            topobathy_bytw = topobathy.loc[net["mainstem_segs"]]                                  # :1786-1796
+        diffusive_usgs_df = usgs_df if "diffusive_streamflow_nudging" in (da_parameter_dict or {}) else pd.DataFrame()
+        coastal_bytw = pd.DataFrame()
+        if coastal_boundary_depth_df is not None and not coastal_boundary_depth_df.empty and tw in coastal_boundary_depth_df.index:
+            coastal_bytw = coastal_boundary_depth_df.loc[tw].to_frame().T                         # :1816-1819
+        diffusive_qlats = qlats.copy()
+        diffusive_qlats.columns = range(diffusive_qlats.shape[1])                                 # :1823-1824
+        packed.append(diff_utils.diffusive_input_data_v02(
+            tw, net["connections"], net["rconn"], net["reaches"], net["mainstem_segs"], net["tributary_segments"], None,
+            net["param_df"], diffusive_qlats, q0, junction_inflows, qts_subdivisions, t0, nts, dt, waterbodies_df,
+            topobathy_bytw, diffusive_usgs_df, None, None, coastal_bytw, pd.DataFrame()))
+    outputs = diffusive.compute_diffusive_batch(packed)
+    results_diffusive = []
+    e = np.asarray([])
+    for tw, ins, (out_q, out_elv, out_depth) in zip(diffusive_network_data, packed, outputs):
+        rch_list, dat_all = diff_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], out_q, out_depth)
+        x = np.isin(rch_list, diffusive_network_data[tw]["tributary_segments"])                   # MC segments: keep MC's answer
+        results_diffusive.append((
+            rch_list[~x], dat_all[~x, 3:], 0, (e, e, e), (e, e, e, e, e), (e, e, e, e, e), np.zeros(dat_all[~x, 3::3].shape),
+            (e, e, e), np.empty(shape=(0, nts + 1), dtype="float32"), (e, e, e, e)))
+    return results_diffusive

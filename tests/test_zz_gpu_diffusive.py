@@ -105,3 +105,34 @@ def test_repeated_calls_are_deterministic(gpu):
     b = gpu.compute_diffusive(d)
     for x, y in zip(a, b):
         HD.assert_bits64(x, y, "second call")
+
+
+def test_compute_diffusive_routing_on_gpu(gpu, od):
+    """The reference-level entry point (compute.py:1740-1884 mirrored): two tailwater domains recorded from the reference's
+    own packer tests, junction inflows taken from Muskingum-Cunge style results, packed by
+    troute_b200.routing.diffusive_utils, routed in one trt_diffnw_batch launch, unpacked -- equal to the oracle run on the
+    same packed inputs."""
+    import datetime
+    import pandas as pd
+    import test_diffusive_packer as TP
+    from troute_b200.routing import compute, diffusive_utils
+    gold = np.load(TP.GOLD)
+    dnd, results, q0, qlats, nsteps = TP.hybrid_case(gold)
+    out = compute.compute_diffusive_routing(results, dnd, None, datetime.datetime(2023, 4, 2), 300.0, nsteps, q0, qlats, 12,
+                                            pd.DataFrame(), pd.DataFrame(), {}, pd.DataFrame(), pd.DataFrame(), None, None,
+                                            pd.DataFrame(), pd.DataFrame())
+    assert len(out) == len(dnd)
+    for (tw, net), tup in zip(dnd.items(), out):
+        fvd = np.zeros((len(net["tributary_segments"]), 3 * nsteps), dtype=np.float32)
+        ji = pd.DataFrame(np.concatenate([r[1][np.isin(r[0], net["tributary_segments"])][:, ::3] for r in results]),
+                          index=np.concatenate([r[0][np.isin(r[0], net["tributary_segments"])] for r in results]))
+        dq = qlats.copy(); dq.columns = range(dq.shape[1])
+        ins = diffusive_utils.diffusive_input_data_v02(
+            tw, net["connections"], net["rconn"], net["reaches"], net["mainstem_segs"], net["tributary_segments"], None,
+            net["param_df"], dq, q0, ji, 12, datetime.datetime(2023, 4, 2), nsteps, 300.0, pd.DataFrame(), pd.DataFrame(),
+            pd.DataFrame(), None, None, pd.DataFrame(), pd.DataFrame())
+        ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
+        ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
+        keep = ~np.isin(ids, net["tributary_segments"])
+        assert ids[keep].tolist() == tup[0].tolist()
+        assert np.array_equal(dat[keep][:, 3:], tup[1], equal_nan=True)
