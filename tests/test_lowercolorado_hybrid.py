@@ -1,0 +1,90 @@
+"""BASELINE config 3 -- LowerColorado_TX hybrid: Muskingum-Cunge everywhere, diffusive wave on the coastal mainstem domain
+of test/LowerColorado_TX_v4/domain/coastal_domain_tw.yaml (tailwater 2421105, "walk upstream until the listed headwaters").
+Real hydrofabric (fixture tests/golden/lowercolorado_v4.npz), the reference's forcing, synthetic cross sections from the
+channel parameters (the `MCwithDiffusive` routing type, hybrid without topobathy).
+
+CPU: the domain builder, the packer, the oracle and the host build of the product's solver source on the real domain.
+GPU (test_zz_gpu_diffusive.py imports this module): the same through compute_diffusive_routing on the device."""
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import helpers_diffusive as HD
+import test_lowercolorado as LC
+
+TW = 2421105
+HEADS = [999999, 2427700, 2427743, 2427640, 2421022, 2421503]          # coastal_domain_tw.yaml:13-20
+NTS = 72                                                              # 6 h of the 24 h forcing: keeps the CPU test short
+
+
+def hybrid_inputs(oracle):
+    """(diffusive_network_data, MC `results`, q0, qlats) the way nwm_route holds them before compute_diffusive_routing
+    (__main__.py:1215-1290): the MC results here come from the CPU oracle routing the whole network."""
+    from troute_b200.routing import diffusive_domain
+    c = LC._load()
+    ids = c["ids"]
+    param_df = pd.DataFrame(c["params"].astype(np.float64), index=pd.Index(ids.tolist()), columns=c["cols"])
+    dnd, df_mc, conn_mc = diffusive_domain.build_diffusive_network_data({TW: {"headwater": list(HEADS)}}, c["connections"], param_df)
+    mc = LC._oracle_call(oracle, c, True)
+    fvd = mc[1].reshape(ids.shape[0], LC.NTS, 3)[:, :NTS, :].reshape(ids.shape[0], -1)
+    results = [(ids.copy(), fvd.astype(np.float32), 0)]
+    q0 = pd.DataFrame(np.full((ids.shape[0], 3), 0.5), index=pd.Index(ids.tolist()), columns=["qu0", "qd0", "h0"])
+    qlats = pd.DataFrame(c["qlat"].astype(np.float64), index=pd.Index(ids.tolist()))
+    return c, dnd, results, q0, qlats, df_mc, conn_mc
+
+
+def pack(dnd, results, q0, qlats):
+    from troute_b200.routing import diffusive_utils
+    net = dnd[TW]
+    r = results[0]
+    x = np.isin(r[0], net["tributary_segments"])
+    ji = pd.DataFrame(r[1][x, ::3], index=r[0][x])
+    dq = qlats.copy(); dq.columns = range(dq.shape[1])
+    return diffusive_utils.diffusive_input_data_v02(
+        TW, net["connections"], net["rconn"], net["reaches"], net["mainstem_segs"], net["tributary_segments"], None,
+        net["param_df"], dq, q0, ji, 12, datetime(2023, 4, 2), NTS, 300.0, pd.DataFrame(), pd.DataFrame(), pd.DataFrame(), None,
+        None, pd.DataFrame(), pd.DataFrame())
+
+
+def test_domain_builder_on_the_real_network(oracle):
+    c, dnd, results, q0, qlats, df_mc, conn_mc = hybrid_inputs(oracle)
+    net = dnd[TW]
+    main, tribs = net["mainstem_segs"], net["tributary_segments"]
+    assert TW in main and len(main) > 300 and len(tribs) >= 5
+    assert set(h for h in HEADS if h != 999999) <= set(main) | set(tribs)
+    assert not set(main) & set(tribs)
+    # every tributary drains into the mainstem; the MC network lost the mainstem and ends at the tributaries
+    for t in tribs:
+        assert c["connections"][t][0] in main and conn_mc[t] == []
+    assert not set(main) & set(conn_mc) and not set(main) & set(df_mc.index)
+    # the reaches partition mainstem + tributaries; inside a reach each segment drains into the next one
+    assert sorted(s for r in net["reaches"] for s in r) == sorted(main + tribs)
+    for r in net["reaches"]:
+        for a, b in zip(r[:-1], r[1:]):
+            assert net["connections"][a] == [b]
+
+
+def test_real_domain_oracle_and_solver_source_agree(oracle):
+    from oracle import diffusive as od
+    from troute_b200.routing import diffusive_utils
+    od.build()
+    c, dnd, results, q0, qlats, _, _ = hybrid_inputs(oracle)
+    ins = pack(dnd, results, q0, qlats)
+    assert ins["nrch_g"] == len(dnd[TW]["reaches"]) and ins["mxnbathy_g"] == 0
+    ref = od.compute_diffusive(ins, od.POW_DET)
+    got = HD.replica_compute_diffusive(ins)
+    for name, a, b in zip(("q_ev_g", "elv_ev_g", "depth_ev_g"), ref, got):
+        HD.assert_bits64(b, a, name)
+    ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref[0], ref[2])
+    keep = np.isin(ids, dnd[TW]["mainstem_segs"])
+    q, depth = dat[keep][:, 3::3], dat[keep][:, 5::3]
+    assert np.isfinite(q).all() and np.isfinite(depth).all() and (depth > 0).all()
+    # a handful of slightly negative flows appear where flat reaches drain (0.02 % of the values, > -0.5 m3/s): the
+    # Crank-Nicolson sweep has no positivity guard beyond |q| >= q_llm (diffusive.f90:1320-1324)
+    assert (q <= 0).mean() < 1e-3 and q.min() > -1.0 and q.max() < 500.0
+    # the two arithmetic builds of the oracle (platform pow / pinned pow) agree on the real domain
+    lib = od.compute_diffusive(ins, od.POW_LIBM)
+    m = np.abs(ref[0]) > 1e-3
+    assert (np.abs(lib[0] - ref[0])[m] / np.abs(ref[0])[m]).max() < 1e-9
