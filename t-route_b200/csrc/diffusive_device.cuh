@@ -174,16 +174,25 @@ TRT_HD double dw_intp_y(int nrow, const double* xarr, const double* yarr, size_t
     return dw_linterpol(xarr[irow - 1], yarr[(size_t)(irow - 1) * ystride], xarr[irow], yarr[(size_t)irow * ystride], x);
 }
 
-/* arithmetic guess of the row of elevation `el` in a node's elevation column: rows 6..NEL are uniform (:2263-2266) */
-TRT_HD int dw_elev_guess(const double* elev, double el)
+/* arithmetic guess of the row of elevation `el` in a node's elevation column: rows 6..NEL are uniform (:2263-2266; surveyed
+ * sections: every row, :1826).  The two numbers that define the grid are read once per node and kept in registers. */
+struct ElevGrid { double e6, inc; };
+TRT_HD ElevGrid dw_grid(const double* elev)
 {
-    const double inc = elev[NEL - 1] - elev[NEL - 2];
-    if (!(inc > 0.0)) return NEL / 2;
-    const double r = (el - elev[5]) / inc;
+    ElevGrid g;
+    g.e6 = elev[5];
+    g.inc = elev[NEL - 1] - elev[NEL - 2];
+    return g;
+}
+TRT_HD int dw_guess(const ElevGrid& g, double el)
+{
+    if (!(g.inc > 0.0)) return NEL / 2;
+    const double r = (el - g.e6) / g.inc;
     if (!(r > -6.0)) return 1;
     if (r > (double)NEL) return NEL - 1;
     return 6 + (int)r;
 }
+TRT_HD int dw_elev_guess(const double* elev, double el) { return dw_guess(dw_grid(elev), el); }
 
 /* intp_xsec_tab(i, j, nel, 1, ycol, x) :1713-1748 for an elevation argument */
 TRT_HD int dw_row_of_elev(const double* elev, double el)
@@ -561,18 +570,33 @@ TRT_HD double dw_normal_elev(const Dom& D, int i, int j, double q)
 }
 
 /* ---- water-surface solve ------------------------------------------------------------------------------------------- */
-/* funcd_diffdepth :1664-1711 with the downstream friction slope (constant during a solve) passed in */
-TRT_HD void dw_funcd(const Dom& D, int i, int j, double Q_cur, double sf_ds, double z_cur, double y_cur, double y_ds,
-                     double slope_dx, double dxi, double& f, double& df)
+/* funcd_diffdepth :1664-1711 with the downstream friction slope (constant during a solve) passed in.
+ * Latency matters here (this runs on the water-surface dependency chain): the row is guessed arithmetically and the two
+ * bracketing rows of all four columns are loaded in ONE round of independent loads; the guess is then verified against the
+ * elevations just loaded, and only a wrong guess (first five rows, table ends) pays for the search.  Same row, same values,
+ * same arithmetic as intp_xsec_tab either way. */
+TRT_HD void dw_funcd(const Dom& D, int i, int j, const ElevGrid& grid, double Q_cur, double sf_ds, double z_cur, double y_cur,
+                     double y_ds, double slope_dx, double dxi, double& f, double& df)
 {
     const double* elev = dw_col(D, i, j, C_ELEV);
+    const double* convc = dw_col(D, i, j, C_CONV);
+    const double* dkdac = dw_col(D, i, j, C_DKDA);
+    const double* topwc = dw_col(D, i, j, C_TOPW);
     const double elv_cur = y_cur + z_cur;
-    const int irow = dw_row_of_elev(elev, elv_cur);
-    const double conv_cur = dw_interp_row(elev, dw_col(D, i, j, C_CONV), irow, elv_cur);
+    int irow = dw_guess(grid, elv_cur);
+    irow = irow < 1 ? 1 : (irow > NEL - 1 ? NEL - 1 : irow);
+    double x1 = elev[irow - 1], x2 = elev[irow];
+    double c1 = convc[irow - 1], c2 = convc[irow], k1 = dkdac[irow - 1], k2 = dkdac[irow], t1 = topwc[irow - 1], t2 = topwc[irow];
+    if (!(x1 <= elv_cur && elv_cur < x2)) {
+        irow = dw_row_of_elev(elev, elv_cur);
+        x1 = elev[irow - 1]; x2 = elev[irow];
+        c1 = convc[irow - 1]; c2 = convc[irow]; k1 = dkdac[irow - 1]; k2 = dkdac[irow]; t1 = topwc[irow - 1]; t2 = topwc[irow];
+    }
+    const double conv_cur = dw_linterpol(x1, c1, x2, c2, elv_cur);
     const double sf_cur = fabs(Q_cur) * Q_cur / (conv_cur * conv_cur);
     f = y_cur - y_ds + slope_dx - 0.50 * (sf_cur + sf_ds) * dxi;
-    const double dKdA_cur = dw_interp_row(elev, dw_col(D, i, j, C_DKDA), irow, elv_cur);
-    const double topw_cur = dw_interp_row(elev, dw_col(D, i, j, C_TOPW), irow, elv_cur);
+    const double dKdA_cur = dw_linterpol(x1, k1, x2, k2, elv_cur);
+    const double topw_cur = dw_linterpol(x1, t1, x2, t2, elv_cur);
     df = 1.0 + (fabs(Q_cur) * Q_cur / trt_pow64_det(conv_cur, 3.0)) * dxi * topw_cur * dKdA_cur;
 }
 
@@ -608,6 +632,7 @@ TRT_HD double dw_rtsafe(const Dom& D, int i, int j, double Q_cur, double Q_ds, d
     const double xacc = DW_F(1e-4);
     double df, dxx, dxold, f, temp, xh, xl, r;
     const double y_norm = DW_A2(D.b_ynorm, i, j), x1 = DW_A2(D.b_x1, i, j), x2 = DW_A2(D.b_x2, i, j);
+    const ElevGrid grid = dw_grid(dw_col(D, i, j, C_ELEV));
     /* loop-invariant parts of funcd_diffdepth: downstream friction slope (:1689-1692) and bed-slope term (:1699-1700) */
     const double elv_ds = y_ds + z_ds;
     const double* elev_ds = dw_col(D, i + 1, j, C_ELEV);
@@ -627,7 +652,7 @@ TRT_HD double dw_rtsafe(const Dom& D, int i, int j, double Q_cur, double Q_ds, d
     r = 0.50 * (x1 + x2);
     dxold = fabs(x2 - x1);
     dxx = dxold;
-    dw_funcd(D, i, j, Q_cur, sf_ds, z_cur, r, y_ds, slope_dx, dxi, f, df);
+    dw_funcd(D, i, j, grid, Q_cur, sf_ds, z_cur, r, y_ds, slope_dx, dxi, f, df);
     for (int iter = 1; iter <= maxit; ++iter) {
         if (((r - xh) * df - f) * ((r - xl) * df - f) > 0.0 || fabs(2.0 * f) > fabs(dxold * df)) {
             dxold = dxx;
@@ -642,7 +667,7 @@ TRT_HD double dw_rtsafe(const Dom& D, int i, int j, double Q_cur, double Q_ds, d
             if (temp == r) return r;
         }
         if (fabs(dxx) < xacc) return r;
-        dw_funcd(D, i, j, Q_cur, sf_ds, z_cur, r, y_ds, slope_dx, dxi, f, df);
+        dw_funcd(D, i, j, grid, Q_cur, sf_ds, z_cur, r, y_ds, slope_dx, dxi, f, df);
         if (f < 0.0) xl = r; else xh = r;
     }
     return y_norm;
