@@ -88,3 +88,49 @@ def test_real_domain_oracle_and_solver_source_agree(oracle):
     lib = od.compute_diffusive(ins, od.POW_LIBM)
     m = np.abs(ref[0]) > 1e-3
     assert (np.abs(lib[0] - ref[0])[m] / np.abs(ref[0])[m]).max() < 1e-9
+
+
+# ---- the whole hybrid flow: Muskingum-Cunge on what is left of the network, then the diffusive mainstem ----------------
+def reduced_mc_case(c, conn_mc, df_mc):
+    """The Muskingum-Cunge network after the diffusive mainstem was taken out (AbstractRouting.py:314-328): a `c`-style
+    dict for LC._oracle_call plus the arguments compute_nhd_routing_v02 needs (reaches by tail-water, independent networks)."""
+    from troute_b200.routing import diffusive_utils
+    keep = np.isin(c["ids"], np.asarray(sorted(conn_mc), dtype=np.int64))
+    ids = c["ids"][keep]
+    rconn = {k: [] for k in conn_mc}
+    for k, v in conn_mc.items():
+        for d in v:
+            rconn[d].append(k)
+    tws = [k for k, v in conn_mc.items() if not v]
+    reaches_bytw = {tw: [r for _, r in diffusive_utils._decompose(tw, rconn, set())] for tw in tws}
+    indep = {}
+    for tw, rl in reaches_bytw.items():
+        indep[tw] = {s: rconn[s] for r in rl for s in r}
+    sub = dict(ids=ids, cols=c["cols"], params=c["params"][keep], qlat=c["qlat"][keep],
+               reaches=[r for tw in tws for r in reaches_bytw[tw]], rconn=rconn, connections=conn_mc)
+    return sub, reaches_bytw, indep
+
+
+def test_hybrid_flow_on_the_cpu_side(oracle):
+    """MC (oracle) on the reduced network -> junction inflows -> packer -> diffusive oracle / solver source.  The GPU twin of
+    this test (test_zz_gpu_diffusive.py) runs both halves on the device through the reference-level entry points."""
+    from oracle import diffusive as od
+    od.build()
+    c, dnd, _, q0, qlats, df_mc, conn_mc = hybrid_inputs(oracle)
+    sub, reaches_bytw, indep = reduced_mc_case(c, conn_mc, df_mc)
+    assert len(reaches_bytw) == len(dnd[TW]["tributary_segments"])              # every tributary became a tail-water
+    assert sub["ids"].shape[0] + len(dnd[TW]["mainstem_segs"]) == c["ids"].shape[0]
+    mc = LC._oracle_call(oracle, sub, True)
+    fvd = mc[1].reshape(sub["ids"].shape[0], LC.NTS, 3)[:, :NTS, :].reshape(sub["ids"].shape[0], -1)
+    results = [(mc[0], fvd, 0)]
+    ins = pack(dnd, results, q0, qlats)
+    ref = od.compute_diffusive(ins, od.POW_DET)
+    got = HD.replica_compute_diffusive(ins)
+    for a, b in zip(ref, got):
+        HD.assert_bits64(b, a, "hybrid: diffusive half")
+    # cutting the mainstem out does not change what the tributaries deliver (their sub-networks are upstream of it)
+    full = LC._oracle_call(oracle, c, True)
+    for t in dnd[TW]["tributary_segments"]:
+        a = full[1][int(np.searchsorted(full[0], t))][: 3 * NTS]
+        b = fvd[int(np.searchsorted(mc[0], t))]
+        assert np.array_equal(a, b)

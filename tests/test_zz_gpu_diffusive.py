@@ -155,3 +155,48 @@ def test_lowercolorado_hybrid_domain_on_gpu(gpu, od, oracle):
     keep = ~np.isin(ids, dnd[LH.TW]["tributary_segments"])
     assert ids[keep].tolist() == out[0][0].tolist()
     assert np.array_equal(dat[keep][:, 3:], out[0][1], equal_nan=True)
+
+
+def test_lowercolorado_hybrid_end_to_end_on_gpu(gpu, od, oracle):
+    """BASELINE configs[3], both halves on the device through the reference-level entry points, the way nwm_route chains
+    them (__main__.py:1215-1290): compute_nhd_routing_v02 on the network without the diffusive mainstem, then
+    compute_diffusive_routing fed by its results.  MC half bit-equal to the MC oracle, diffusive half equal to the diffusive
+    oracle run on the same junction inflows."""
+    import datetime
+    import pandas as pd
+    import test_lowercolorado as LC
+    import test_lowercolorado_hybrid as LH
+    from troute_b200.routing import compute, diffusive_utils
+    from troute_b200.routing.fast_reach.mc_reach import clear_network_cache
+    c, dnd, _, q0, qlats, df_mc, conn_mc = LH.hybrid_inputs(oracle)
+    sub, reaches_bytw, indep = LH.reduced_mc_case(c, conn_mc, df_mc)
+    ids = sub["ids"]
+    param_df = pd.DataFrame(sub["params"][:, 1:], index=ids, columns=sub["cols"][1:])
+    mc_qlats = pd.DataFrame(sub["qlat"], index=ids)
+    mc_q0 = pd.DataFrame(np.zeros((ids.shape[0], 3), np.float32), index=ids, columns=["qu0", "qd0", "h0"])
+    empty = pd.DataFrame()
+    t0 = datetime.datetime(2023, 4, 2)
+    try:
+        results, _ = compute.compute_nhd_routing_v02(
+            sub["connections"], sub["rconn"], {}, reaches_bytw, "V02-structured", "by-network", 10000, 1, t0, 300.0, LH.NTS, 12,
+            indep, param_df, mc_q0, mc_qlats, empty, empty, empty, empty, empty, empty, empty, empty, empty, empty, empty, {},
+            True, False, empty, {}, empty, False, [None, None])
+    finally:
+        clear_network_cache()
+    # MC half vs the MC oracle (same reduced network, first LH.NTS steps)
+    sub72 = dict(sub); sub72["qlat"] = sub["qlat"]
+    ref_mc = LC._oracle_call(oracle, sub, True)
+    ref_fvd = ref_mc[1].reshape(ids.shape[0], LC.NTS, 3)[:, :LH.NTS, :].reshape(ids.shape[0], -1)
+    got_ids = np.concatenate([r[0] for r in results]); got_fvd = np.concatenate([r[1] for r in results])
+    order = np.argsort(got_ids)
+    assert np.array_equal(got_ids[order], ref_mc[0])
+    assert np.array_equal(got_fvd[order].view(np.int32), ref_fvd.view(np.int32))
+    # diffusive half
+    out = compute.compute_diffusive_routing(results, dnd, None, t0, 300.0, LH.NTS, q0, qlats, 12, empty, empty, {}, empty, empty,
+                                            None, None, empty, empty)
+    ins = LH.pack(dnd, [(ref_mc[0], ref_fvd, 0)], q0, qlats)
+    ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
+    seg_ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
+    keep = ~np.isin(seg_ids, dnd[LH.TW]["tributary_segments"])
+    assert seg_ids[keep].tolist() == out[0][0].tolist()
+    assert np.array_equal(dat[keep][:, 3:], out[0][1], equal_nan=True)
