@@ -52,6 +52,18 @@
 #define DW_WARP ((int)(threadIdx.x >> 5))
 #define DW_NWARP ((int)(blockDim.x >> 5))
 #define DW_LANE ((int)(threadIdx.x & 31))
+#elif defined(DW_EMULATE_CTA)
+/* tests only (tests/native/diffusive_cta_main.cpp): a CTA emulated by host threads that meet at a barrier, to run the SPMD
+ * phase structure of dw_time_loop under ThreadSanitizer -- a missing DW_SYNC() shows up as a data race */
+extern thread_local int dw_emu_tid;
+extern int dw_emu_nt;
+void dw_emu_sync();
+#define DW_TID dw_emu_tid
+#define DW_NT dw_emu_nt
+#define DW_SYNC() dw_emu_sync()
+#define DW_WARP (dw_emu_tid >> 5)
+#define DW_NWARP (dw_emu_nt >> 5)
+#define DW_LANE (dw_emu_tid & 31)
 #else
 #define DW_TID 0
 #define DW_NT 1
