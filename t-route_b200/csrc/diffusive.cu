@@ -99,14 +99,31 @@ __global__ void __launch_bounds__(kLoopThreads) time_loop_kernel(const Dom* __re
     dw_time_loop(D);
 }
 
+/* One device allocation per call for every domain: pools, look-up tables and outputs are carved out of it at 256-byte
+ * alignment (a cudaMalloc / cudaFree pair per array and domain would cost more than the kernels for small domains). */
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, off = 0;
+    ~Arena() { cudaFree(base); }
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    void* take(size_t bytes)
+    {
+        void* p = base + off;
+        off += pad(bytes);
+        return p;
+    }
+};
+
 struct DevDomain {
     DomHost H;
     double *d_pool = nullptr, *d_tab = nullptr, *d_tabmin = nullptr, *d_out = nullptr;
     int* i_pool = nullptr;
     unsigned char* b_pool = nullptr;
-    ~DevDomain()
+    size_t bytes() const
     {
-        cudaFree(d_pool); cudaFree(d_tab); cudaFree(d_tabmin); cudaFree(d_out); cudaFree(i_pool); cudaFree(b_pool);
+        return Arena::pad(H.dpool.size() * sizeof(double)) + Arena::pad(H.ipool.size() * sizeof(int)) + Arena::pad(H.bpool.size()) +
+               Arena::pad(H.n_nodes * NCOL * LD * sizeof(double)) + Arena::pad(H.n_nodes * NCOL * sizeof(double)) +
+               Arena::pad(3 * H.n_out * sizeof(double));
     }
 };
 
@@ -120,22 +137,21 @@ struct DevDomain {
         }                                                                                                         \
     } while (0)
 
-int upload_domain(DevDomain& V, Dom& out)
+/* carve the arrays of one domain out of the (zero-filled) arena and copy its host pools in */
+int upload_domain(DevDomain& V, Arena& A, Dom& out)
 {
     DomHost& H = V.H;
     const size_t db = H.dpool.size() * sizeof(double), ib = H.ipool.size() * sizeof(int), bb = H.bpool.size();
-    CUD(cudaMalloc((void**)&V.d_pool, db));
-    CUD(cudaMalloc((void**)&V.i_pool, ib));
-    CUD(cudaMalloc((void**)&V.b_pool, bb));
-    CUD(cudaMalloc((void**)&V.d_tab, H.n_nodes * NCOL * LD * sizeof(double)));
-    CUD(cudaMalloc((void**)&V.d_tabmin, H.n_nodes * NCOL * sizeof(double)));
-    CUD(cudaMalloc((void**)&V.d_out, 3 * H.n_out * sizeof(double)));
+    V.d_pool = (double*)A.take(db);
+    V.i_pool = (int*)A.take(ib);
+    V.b_pool = (unsigned char*)A.take(bb);
+    V.d_tab = (double*)A.take(H.n_nodes * NCOL * LD * sizeof(double));
+    V.d_tabmin = (double*)A.take(H.n_nodes * NCOL * sizeof(double));
+    V.d_out = (double*)A.take(3 * H.n_out * sizeof(double));          /* q_ev_g = elv_ev_g = depth_ev_g = 0 (:391-393) */
+    if (A.off > A.size) return trt_internal_fail(TRT_ERR_STATE, "diffusive arena overflow");
     CUD(cudaMemcpy(V.d_pool, H.dpool.data(), db, cudaMemcpyHostToDevice));
     CUD(cudaMemcpy(V.i_pool, H.ipool.data(), ib, cudaMemcpyHostToDevice));
     CUD(cudaMemcpy(V.b_pool, H.bpool.data(), bb, cudaMemcpyHostToDevice));
-    CUD(cudaMemset(V.d_tab, 0, H.n_nodes * NCOL * LD * sizeof(double)));
-    CUD(cudaMemset(V.d_tabmin, 0, H.n_nodes * NCOL * sizeof(double)));
-    CUD(cudaMemset(V.d_out, 0, 3 * H.n_out * sizeof(double)));        /* q_ev_g = elv_ev_g = depth_ev_g = 0 (:391-393) */
     Dom D = dw_rebase(H, V.d_pool, V.i_pool, V.b_pool);
     D.tab = V.d_tab; D.tabmin = V.d_tabmin;
     D.q_ev = V.d_out; D.elv_ev = V.d_out + H.n_out; D.depth_ev = V.d_out + 2 * H.n_out;
@@ -194,8 +210,13 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     CUD(cudaSetDevice(g_device));
     std::vector<Dom> hdoms((size_t)n_domains);
     long long max_rows = 0, max_cols = 0, max_verts = 0, max_nodes = 0;
+    Arena arena;
+    for (int d = 0; d < n_domains; ++d) arena.size += doms[(size_t)d].bytes();
+    arena.size += Arena::pad(sizeof(Dom) * (size_t)n_domains);
+    CUD(cudaMalloc((void**)&arena.base, arena.size));
+    CUD(cudaMemset(arena.base, 0, arena.size));
     for (int d = 0; d < n_domains; ++d) {
-        const int rc = upload_domain(doms[(size_t)d], hdoms[(size_t)d]);
+        const int rc = upload_domain(doms[(size_t)d], arena, hdoms[(size_t)d]);
         if (rc != TRT_OK) return rc;
         const long long nodes = (long long)hdoms[(size_t)d].nm * hdoms[(size_t)d].mx;
         max_rows = std::max(max_rows, nodes * NEL);
@@ -203,9 +224,8 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
         max_nodes = std::max(max_nodes, nodes);
         max_verts = std::max(max_verts, nodes * hdoms[(size_t)d].mxnbathy);
     }
-    Dom* d_doms = nullptr;
-    CUD(cudaMalloc((void**)&d_doms, sizeof(Dom) * (size_t)n_domains));
-    struct Guard { Dom* p; ~Guard() { cudaFree(p); } } guard{d_doms};
+    Dom* d_doms = (Dom*)arena.take(sizeof(Dom) * (size_t)n_domains);
+    if (arena.off > arena.size) return trt_internal_fail(TRT_ERR_STATE, "diffusive arena overflow");
     CUD(cudaMemcpy(d_doms, hdoms.data(), sizeof(Dom) * (size_t)n_domains, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1, e2;
     CUD(cudaEventCreate(&e0)); CUD(cudaEventCreate(&e1)); CUD(cudaEventCreate(&e2));
