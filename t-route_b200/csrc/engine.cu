@@ -181,7 +181,7 @@ int trt_internal_fail(int code, const char* msg) { return fail(code, "%s", msg);
 extern "C" {
 
 const char* trt_last_error(void) { return g_err.c_str(); }
-int trt_version(void) { return 100; }
+int trt_version(void) { return 110; }   /* 1.1: diffusive-wave entry points */
 
 int trt_device_count(void)
 {
