@@ -134,3 +134,45 @@ def test_hybrid_flow_on_the_cpu_side(oracle):
         a = full[1][int(np.searchsorted(full[0], t))][: 3 * NTS]
         b = fvd[int(np.searchsorted(mc[0], t))]
         assert np.array_equal(a, b)
+
+
+def test_nwm_route_chains_both_halves(oracle, monkeypatch):
+    """troute_b200.nwm_routing.nwm_route (nwm_routing/__main__.py:1122-1300 mirrored) with both device calls replaced by
+    CPU stand-ins (the MC oracle, the host build of the diffusive solver source): one call returns the MC tuples followed
+    by one tuple per diffusive domain, each equal to its half computed separately."""
+    from oracle import diffusive as od
+    from troute_b200 import nwm_routing
+    from troute_b200.routing import compute, diffusive_utils
+    from troute_b200.routing.fast_reach import diffusive
+    od.build()
+
+    def mc_stand_in(*a, **k):
+        k.pop("device", None)
+        return oracle.compute_network_structured(*a, **k)
+    monkeypatch.setitem(compute._compute_func_map, "V02-structured", mc_stand_in)
+    monkeypatch.setattr(diffusive, "compute_diffusive_batch", lambda L: [HD.replica_compute_diffusive(d) for d in L])
+    c, dnd, _, q0, qlats, df_mc, conn_mc = hybrid_inputs(oracle)
+    sub, reaches_bytw, indep = reduced_mc_case(c, conn_mc, df_mc)
+    ids = sub["ids"]
+    param_df = pd.DataFrame(sub["params"][:, 1:], index=ids, columns=sub["cols"][1:])
+    q0 = q0.copy()
+    q0.loc[ids.tolist()] = 0.0                                  # cold start on the MC network, 0.5 m3/s on the mainstem
+    e = pd.DataFrame()
+    t0 = datetime(2023, 4, 2)
+    both, sl = nwm_routing.nwm_route(
+        sub["connections"], sub["rconn"], {}, reaches_bytw, "by-network", "V02-structured", 10000, 1, t0, 300.0, NTS, 12, indep,
+        param_df, q0.astype(np.float32), qlats, e, e, e, e, e, e, e, e, e, e, e, {}, True, False, e, {}, e, False, dnd, e, None, None,
+        [None, None], e, e)
+    assert sl == [None, None] and len(both) == 2
+    mc, dw = both
+    ref_mc = LC._oracle_call(oracle, sub, True)
+    ref_fvd = ref_mc[1].reshape(ids.shape[0], LC.NTS, 3)[:, :NTS, :].reshape(ids.shape[0], -1)
+    order = np.argsort(mc[0])
+    assert np.array_equal(mc[0][order], ref_mc[0]) and np.array_equal(mc[1][order].view(np.int32), ref_fvd.view(np.int32))
+    ins = pack(dnd, [(ref_mc[0], ref_fvd, 0)], q0, qlats)
+    ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
+    seg_ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
+    keep = ~np.isin(seg_ids, dnd[TW]["tributary_segments"])
+    assert seg_ids[keep].tolist() == dw[0].tolist() and np.array_equal(dat[keep][:, 3:], dw[1], equal_nan=True)
+    # together the two halves cover every flowpath of the hydrofabric exactly once
+    assert sorted(mc[0].tolist() + dw[0].tolist()) == c["ids"].tolist()

@@ -172,19 +172,23 @@ def test_lowercolorado_hybrid_end_to_end_on_gpu(gpu, od, oracle):
     sub, reaches_bytw, indep = LH.reduced_mc_case(c, conn_mc, df_mc)
     ids = sub["ids"]
     param_df = pd.DataFrame(sub["params"][:, 1:], index=ids, columns=sub["cols"][1:])
-    mc_qlats = pd.DataFrame(sub["qlat"], index=ids)
-    mc_q0 = pd.DataFrame(np.zeros((ids.shape[0], 3), np.float32), index=ids, columns=["qu0", "qd0", "h0"])
+    # one initial-condition frame for both halves: cold start on the MC network, 0.5 m3/s on the diffusive mainstem
+    q0 = q0.copy()
+    q0.loc[ids.tolist()] = 0.0
     empty = pd.DataFrame()
     t0 = datetime.datetime(2023, 4, 2)
+    # one call of the driver-level entry point routes both halves; the diffusive half needs forcing / initial state of the
+    # mainstem segments too, so the full-network frames are passed (rows outside the MC network are ignored by the MC half)
+    from troute_b200.nwm_routing import nwm_route
     try:
-        results, _ = compute.compute_nhd_routing_v02(
-            sub["connections"], sub["rconn"], {}, reaches_bytw, "V02-structured", "by-network", 10000, 1, t0, 300.0, LH.NTS, 12,
-            indep, param_df, mc_q0, mc_qlats, empty, empty, empty, empty, empty, empty, empty, empty, empty, empty, empty, {},
-            True, False, empty, {}, empty, False, [None, None])
+        both, _ = nwm_route(
+            sub["connections"], sub["rconn"], {}, reaches_bytw, "by-network", "V02-structured", 10000, 1, t0, 300.0, LH.NTS, 12,
+            indep, param_df, q0.astype(np.float32), qlats, empty, empty, empty, empty, empty, empty, empty, empty, empty, empty,
+            empty, {}, True, False, empty, {}, empty, False, dnd, empty, None, None, [None, None], empty, empty)
     finally:
         clear_network_cache()
+    results, out = both[:-1], both[-1:]
     # MC half vs the MC oracle (same reduced network, first LH.NTS steps)
-    sub72 = dict(sub); sub72["qlat"] = sub["qlat"]
     ref_mc = LC._oracle_call(oracle, sub, True)
     ref_fvd = ref_mc[1].reshape(ids.shape[0], LC.NTS, 3)[:, :LH.NTS, :].reshape(ids.shape[0], -1)
     got_ids = np.concatenate([r[0] for r in results]); got_fvd = np.concatenate([r[1] for r in results])
@@ -192,8 +196,6 @@ def test_lowercolorado_hybrid_end_to_end_on_gpu(gpu, od, oracle):
     assert np.array_equal(got_ids[order], ref_mc[0])
     assert np.array_equal(got_fvd[order].view(np.int32), ref_fvd.view(np.int32))
     # diffusive half
-    out = compute.compute_diffusive_routing(results, dnd, None, t0, 300.0, LH.NTS, q0, qlats, 12, empty, empty, {}, empty, empty,
-                                            None, None, empty, empty)
     ins = LH.pack(dnd, [(ref_mc[0], ref_fvd, 0)], q0, qlats)
     ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
     seg_ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
