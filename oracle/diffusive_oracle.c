@@ -176,7 +176,7 @@ static void read_xsection(Dw* S, int k, double lftBnkMann, double rmanning_main,
     double xcs[MT + 1], ycs[MT + 1];                               /* 1-based */
     double allX[MT + 1][4], allY[MT + 1][4];
     static double el1[NEL + 1][4], a1[NEL + 1][4], peri1[NEL + 1][4], redi1[NEL + 1][4], conv1[NEL + 1][4], tpW1[NEL + 1][4],
-        diffArea[NEL + 1][4], newI1[NEL + 1][4], diffPere[NEL + 1][4];
+        diffArea[NEL + 1][4], newI1[NEL + 1][4];
     double elev[NEL + 1];
     int i_start[NEL + 1], i_end[NEL + 1];
     const int totalNodes[4] = {0, 5, 7, 5};
@@ -283,9 +283,10 @@ static void read_xsection(Dw* S, int k, double lftBnkMann, double rmanning_main,
             conv1[j][kkk] = 1. / rmanning * a1[j][kkk] * P(redi1[j][kkk], (double)(2.f / 3.f));
             if (peri1[j][kkk] <= TOL) { redi1[j][kkk] = 0.0; conv1[j][kkk] = 0.0; }
             tpW1[j][kkk] = cal_topW;
-            if (j == 1) { diffArea[j][kkk] = a1[j][kkk]; diffPere[j][kkk] = peri1[j][kkk]; }
-            else if (el_now <= ymin_nodes) { diffArea[j][kkk] = a1[j][kkk]; diffPere[j][kkk] = peri1[j][kkk]; }
-            else { diffArea[j][kkk] = a1[j][kkk] - a1[j - 1][kkk]; diffPere[j][kkk] = peri1[j][kkk] - peri1[j - 1][kkk]; }
+            /* (diffPere :2367-2377 is computed by the Fortran and never read) */
+            if (j == 1) diffArea[j][kkk] = a1[j][kkk];
+            else if (el_now <= ymin_nodes) diffArea[j][kkk] = a1[j][kkk];
+            else diffArea[j][kkk] = a1[j][kkk] - a1[j - 1][kkk];
             const double waterElev = el1[j][kkk];
             for (int jj = 2; jj <= j; ++jj) {
                 const double diffAreaCenter = el1[jj][kkk] - (el1[jj][kkk] - el1[jj - 1][kkk]) * 0.5;
@@ -646,7 +647,7 @@ int trt_oracle_diffnw(const double* timestep_ar_g, const int* nts_ql_g, const in
     double dtini = timestep_ar_g[0];
     const double t0 = timestep_ar_g[1], tfin = timestep_ar_g[2], saveInterval = timestep_ar_g[3], dt_ql = timestep_ar_g[4],
                  dt_db = timestep_ar_g[6], dt_qtrib = timestep_ar_g[7];
-    const double dtini_given = dtini, dtini_divisor = timestep_ar_g[9];
+    const double dtini_divisor = timestep_ar_g[9];
     S->dtini = dtini; S->dtini_min = dtini / dtini_divisor;
     const double timesDepth = 4.0;
     S->cfl = para_ar_g[0]; S->C_llm = para_ar_g[1]; S->D_llm = para_ar_g[2]; S->D_ulm = para_ar_g[3];
