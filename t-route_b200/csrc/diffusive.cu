@@ -227,8 +227,12 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     Dom* d_doms = (Dom*)arena.take(sizeof(Dom) * (size_t)n_domains);
     if (arena.off > arena.size) return trt_internal_fail(TRT_ERR_STATE, "diffusive arena overflow");
     CUD(cudaMemcpy(d_doms, hdoms.data(), sizeof(Dom) * (size_t)n_domains, cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1, e2;
-    CUD(cudaEventCreate(&e0)); CUD(cudaEventCreate(&e1)); CUD(cudaEventCreate(&e2));
+    struct Events {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } ev;
+    for (cudaEvent_t& x : ev.e) CUD(cudaEventCreate(&x));
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
     CUD(cudaEventRecord(e0));
     const dim3 g1((unsigned)((max_rows + 255) / 256), (unsigned)n_domains), gm((unsigned)((max_cols + 255) / 256), (unsigned)n_domains);
     if (max_verts > 0) {
@@ -251,7 +255,6 @@ int trt_diffnw_batch(int n_domains, const void* const* argv)
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_table_ms = ms;
     if (cudaEventElapsedTime(&ms, e1, e2) == cudaSuccess) g_loop_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     g_launches = max_verts > 0 ? 6 : 4;
     for (int d = 0; d < n_domains; ++d) {
         DevDomain& V = doms[(size_t)d];
