@@ -1,0 +1,103 @@
+"""The product's per-lane Muskingum-Cunge / level-pool device source (t-route_b200/csrc/mc_device.cuh) compiled for the
+HOST (tests/native/mc_replica.cpp) against the oracle's bit-specified-powf build: bit equality on the reference's 5000-row
+randomized suite, on random rows over the CONUS parameter ranges and on the level-pool known-answer fixtures -- both as the
+one-call solve the dataflow kernel uses and as the prepare / begin / iterate / outflow / velocity pieces the marching
+kernel interleaves.  This is the no-GPU gate for changes to the device physics; the GPU tests repeat it on the device."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "native", "mc_replica.cpp")
+LIB = os.path.join(HERE, "native", "libmc_replica.so")
+DEPS = [SRC, os.path.join(HERE, "native", "shim", "cuda_runtime.h"), os.path.join(ROOT, "t-route_b200", "csrc", "mc_device.cuh"),
+        os.path.join(ROOT, "include", "trt_detmath.h"), os.path.join(ROOT, "include", "trt_detmath_tables.h")]
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def rep():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        flags = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
+        cmd = ["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-I", os.path.join(HERE, "native", "shim"),
+               "-shared", "-fPIC", "-o", LIB, SRC]
+        if " fma" in flags:
+            cmd.insert(1, "-mfma")
+        subprocess.run(cmd, check=True)
+    return C.CDLL(LIB)
+
+
+def run_rows(rep, rows, resumable):
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 15)
+    out = np.zeros((rows.shape[0], 6), dtype=np.float32)
+    iters = np.zeros(rows.shape[0], dtype=np.int32)
+    rep.trt_replica_mc_segment_batch(C.c_long(rows.shape[0]), rows.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                     iters.ctypes.data_as(C.c_void_p), C.c_int(1 if resumable else 0))
+    return out, iters
+
+
+def random_rows(n, seed):
+    """dt,qup,quc,qdp,ql,dx,bw,tw,twcc,n,ncc,cs,s0,velp,depthp over the ranges of test_suite_parameters.py:4-13, with dry
+    segments, zero side slope, bw >= tw and flat beds mixed in"""
+    rng = np.random.default_rng(seed)
+    r = np.empty((n, 15), dtype=np.float32)
+    r[:, 0] = 300.0
+    r[:, 1:4] = np.exp(rng.uniform(np.log(1e-4), np.log(3e3), (n, 3)))
+    r[:, 4] = np.exp(rng.uniform(np.log(1e-6), np.log(50.0), n))
+    r[:, 5] = np.exp(rng.uniform(np.log(1.0), np.log(9.5e4), n))
+    r[:, 6] = np.exp(rng.uniform(np.log(0.135), np.log(230.0), n))
+    r[:, 7] = r[:, 6] / 0.6
+    r[:, 8] = 3 * r[:, 7]
+    r[:, 9] = rng.uniform(0.04, 0.06, n); r[:, 10] = 2 * r[:, 9]
+    r[:, 11] = rng.uniform(0.085, 2.25, n)
+    r[:, 12] = np.exp(rng.uniform(np.log(1e-5), np.log(0.5), n))
+    r[:, 13] = 0.0
+    r[:, 14] = np.exp(rng.uniform(np.log(1e-3), np.log(12.0), n))
+    k = n // 20
+    r[0 * k:1 * k, 1:5] = 0.0                    # no flow at all (:171-178)
+    r[1 * k:2 * k, 11] = 0.0                     # cs = 0 -> z = 1 (:49-53)
+    r[2 * k:3 * k, 7] = r[2 * k:3 * k, 6] * 0.5  # bw > tw (:55-57)
+    r[3 * k:4 * k, 7] = r[3 * k:4 * k, 6]        # bw == tw
+    r[4 * k:5 * k, 8] = 0.0                      # no floodplain width (:400-403)
+    r[5 * k:6 * k, 14] = 0.0                     # dry start
+    return r
+
+
+@pytest.mark.parametrize("resumable", [False, True])
+def test_reference_suite_rows(rep, oracle, resumable):
+    rows = np.load(os.path.join(GOLD, "mc_suite_seed16.npy"))
+    want, wi = oracle.mc_segment_batch(rows, oracle.POW_DET)
+    got, gi = run_rows(rep, rows, resumable)
+    cols = [0, 1, 2, 5] if resumable else [0, 1, 2, 3, 4, 5]        # the marching pieces never evaluate the Courant diagnostics
+    assert np.array_equal(got[:, cols].view(np.int32), want[:, cols].view(np.int32))
+    assert np.array_equal(gi, wi)
+
+
+@pytest.mark.parametrize("resumable", [False, True])
+def test_random_rows_over_the_parameter_ranges(rep, oracle, resumable):
+    rows = random_rows(200_000, 7)
+    want, wi = oracle.mc_segment_batch(rows, oracle.POW_DET)
+    got, gi = run_rows(rep, rows, resumable)
+    cols = [0, 1, 2, 5] if resumable else [0, 1, 2, 3, 4, 5]
+    bad = (got[:, cols].view(np.int32) != want[:, cols].view(np.int32)).any(axis=1)
+    assert not bad.any(), (int(bad.sum()), rows[bad][0].tolist(), got[bad][0].tolist(), want[bad][0].tolist())
+    assert np.array_equal(gi, wi) and wi.max() > 5               # the retry ladder is reached
+
+
+def test_levelpool_kats(rep, oracle):
+    k = json.load(open(os.path.join(GOLD, "levelpool_kats.json")))
+    for c in k["cases"]:
+        a = np.ascontiguousarray(c["wbody_row"], dtype=np.float64)
+        inflow = np.ascontiguousarray(c["inflow"], dtype=np.float32)
+        q = np.zeros_like(inflow); h = np.zeros_like(inflow)
+        rep.trt_replica_levelpool_series(a.ctypes.data_as(C.c_void_p), C.c_long(inflow.size), inflow.ctypes.data_as(C.c_void_p),
+                                         C.c_float(0.0), C.c_float(c["routing_period"]), q.ctypes.data_as(C.c_void_p),
+                                         h.ctypes.data_as(C.c_void_p))
+        wq, wh = oracle.levelpool_series(c["wbody_row"], c["inflow"], 0.0, c["routing_period"], pow_mode=oracle.POW_DET)
+        assert np.array_equal(q.view(np.int32), wq.view(np.int32)) and np.array_equal(h.view(np.int32), wh.view(np.int32))
+        assert q[-1] == np.float32(c["expected_final_outflow"]) and h[-1] == np.float32(c["expected_final_water_elevation"])
