@@ -462,6 +462,12 @@ def test_sharded_nudging_on_one_gpu(eng, oracle, P):
                                                 pieces_per_shard=6, level=level)
     assert stats["n_cut_edges"] > 0
     deep = multigpu.global_deep_level(level, shard, P, 2000)
+    # A gage with an observation at step 0 replaces the INITIAL flow of its segment (mc_reach.pyx:403-411).  The owning
+    # shard does that on the device (reset_gages_kernel); a shard that imports the segment reads q[u, 0] from its own
+    # import row, which is initialised from the q0 it was given -- so the planner hands every shard the replaced value.
+    q0_eff = case["q0"].copy()
+    obs0 = ~np.isnan(usgs[:, 0])
+    q0_eff[grow[obs0], 0] = usgs[obs0, 0]
     nets, gsel = [], []
     for p in plans:
         net = RoutingNetwork(p.up_ptr, p.up_rows, p.kind, case["params"][p.rows], case["cols"], levels=p.levels)
@@ -475,7 +481,7 @@ def test_sharded_nudging_on_one_gpu(eng, oracle, P):
                            usgs_positions_gage=np.arange(sel.size, dtype=np.int32), lastobs_values_init=lastobs[sel],
                            time_since_lastobs_init=since[sel], da_decay_coefficient=120.0,
                            reach_len=np.ones(nloc, dtype=np.int64), seg_rows=np.arange(nloc)), T, routing_period=300.0)
-        net.upload(T, 12, case["qlat"][p.rows], case["q0"][p.rows])
+        net.upload(T, 12, case["qlat"][p.rows], q0_eff[p.rows])
         nets.append(net); gsel.append(sel)
     assert sum(s.size for s in gsel) == G
     pos = [net.positions() for net in nets]
