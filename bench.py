@@ -78,6 +78,8 @@ def parse():
                          "warp: the main stem is the critical path once the wide levels are spread over many GPUs)")
     ap.add_argument("--no-trip-order", action="store_true",
                     help="skip the calibration call that orders the segments of a level by their secant trip counts")
+    ap.add_argument("--trip-buckets", type=int, default=0,
+                    help="time slices of the calibration call's trip counts (0 = network.TRIP_BUCKETS, 1 = totals only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
@@ -313,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
     engine_opts = {"deep_lanes": deep_lanes_for(args, world)}
     engine_opts.update({kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
     if world == 1 and not args.no_trip_order and args.mode in (2, 4):
-        runner.reorder_by_trip_history(engine_opts)            # set-up, not timed: once per network in production
+        runner.reorder_by_trip_history(engine_opts, args.trip_buckets or None)   # set-up, not timed: once per network in production
     for _ in range(args.warmup):
         runner.run_resident()
     barrier()
@@ -413,8 +415,8 @@ def run_ours(args, rank, world, local_rank):
                                     5: "time-blocked marching lanes over the wide shallow levels (stage = level + "
                                        "block), marching lanes over the deep levels, one persistent kernel"}[args.mode],
                        "l2": "inputs larger than L2 (38 GB working set), no flush", "sharding": stats["sharding"],
-                       "within_level_order": "secant trip counts of one calibration call" if getattr(runner, "reordered", False)
-                       else "caller row order"},
+                       "within_level_order": getattr(runner, "order_source", "secant trip counts of one calibration call")
+                       if getattr(runner, "reordered", False) else "caller row order"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         }
         print(json.dumps(line), flush=True)

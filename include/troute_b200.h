@@ -81,6 +81,11 @@ int trt_network_create_ordered(int device, int64_t n_rows, const int64_t* up_ptr
 /* option "collect_trips" = 1 before a run: secant trips of every row summed over the steps of that run (rows routed by the
  * marching kernel report 0) */
 int trt_trip_counts(trt_network* net, int32_t* trips_of_row /* [n_rows] */);
+/* Same, resolved in time: option "trip_buckets" = B (1..64, default 1) before the collecting run sums the trips of step t
+ * into slice (t - 1) * B / nsteps.  Segments whose trip counts move together through the storm belong into the same warp;
+ * troute_b200.network.order_key_from_trips turns this table into an order_key (tools/trip_order_study.py: 28.0 instead of
+ * 25.9 busy lanes out of 32 on the bench network, against 22.4 in the caller's row order). */
+int trt_trip_counts_bucketed(trt_network* net, int32_t buckets, int32_t* trips /* [buckets][n_rows] */);
 int trt_network_destroy(trt_network* net);
 
 /* topology queries: number of wavefront levels; level of every row; engine position of every row */

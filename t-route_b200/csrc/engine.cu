@@ -149,7 +149,9 @@ struct trt_network {
     DevBuf<float> d_usgs, d_lastobs, d_lastobs_init, d_nudge;
 
     bool collect_trips = false;                               // sum the secant trips of every segment over a run
-    DevBuf<int> d_trip_sum;                                   // [n] by position
+    int trip_buckets = 1;                                     // ... separately for this many equal time slices of the call
+    int trip_buckets_ran = 0;                                 // layout of d_trip_sum after the last collecting run
+    DevBuf<int> d_trip_sum;                                   // [trip_buckets][n] by position
 
     // options / stats
     int mode = 4;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow,
@@ -170,6 +172,7 @@ struct trt_network {
         RunDev r;
         r.T = T; r.t_off = 0; r.Tc = T; r.qts = qts; r.nq = nq; r.short_ts = short_ts; r.qlat_t = d_qlat_t.p; r.S = d_S.p;
         r.trip_sum = collect_trips ? d_trip_sum.p : nullptr;
+        r.trip_buckets = trip_buckets;
         r.gage.n_gages = (int)n_gages; r.gage.gmax = gage_max; r.gage.dt = gage_dt; r.gage.decay = gage_decay;
         r.gage.slot = d_gage_slot.p; r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
         return r;
@@ -640,14 +643,17 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         RunDev rg = net->rundev(0);
         CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
     }
-    if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1)));
+    if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1) * (size_t)net->trip_buckets));
     const NetDev nd = net->netdev();
     RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
     rd.t_off = t_off; rd.Tc = Tc;
     const int T = Tc;                          // steps this launch schedules
     const int L = assume_short_ts ? 1 : net->nlevels;
     if (first) { net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0; }
-    if (first && net->collect_trips && net->n > 0) CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * sizeof(int), st));
+    if (first && net->collect_trips && net->n > 0) {
+        CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * (size_t)net->trip_buckets * sizeof(int), st));
+        net->trip_buckets_ran = net->trip_buckets;
+    }
 
     if (first) CU(cudaEventRecord(net->ev0, st));
     if (net->n > 0 && T > 0 && L > 0) {
@@ -1220,6 +1226,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         net->sched_T = -1;
     } else if (!strcmp(key, "collect_trips")) {
         net->collect_trips = value != 0;
+    } else if (!strcmp(key, "trip_buckets")) {
+        if (value < 1 || value > 64) return fail(TRT_ERR_INVALID, "trip_buckets must be in 1..64");
+        net->trip_buckets = (int)value;
     } else if (!strcmp(key, "route_chunks")) {
         if (value < 1 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 1..1024");
         net->route_chunks = (int)value;
@@ -1276,16 +1285,43 @@ int trt_stage_profile(const trt_network* net, int64_t capacity, float* stage_ms,
     return TRT_OK;
 }
 
-int trt_trip_counts(trt_network* net, int32_t* trips_of_row)
+static int download_trip_sums(trt_network* net, std::vector<int32_t>& h)
 {
-    if (!net || !trips_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
-    if (!net->collect_trips || !net->d_trip_sum.p || !net->ran)
+    if (!net->collect_trips || !net->d_trip_sum.p || !net->ran || net->trip_buckets_ran < 1)
         return fail(TRT_ERR_STATE, "no trip counts: set option collect_trips = 1 before trt_run");
     CU(cudaSetDevice(net->device));
     CU(cudaStreamSynchronize(net->stream));
-    std::vector<int32_t> h((size_t)net->n);
-    CU(cudaMemcpy(h.data(), net->d_trip_sum.p, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    for (int64_t r = 0; r < net->n; ++r) trips_of_row[r] = h[(size_t)net->pos_of_row[(size_t)r]];
+    h.resize((size_t)net->n * (size_t)net->trip_buckets_ran);
+    if (!h.empty()) CU(cudaMemcpy(h.data(), net->d_trip_sum.p, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return TRT_OK;
+}
+
+int trt_trip_counts(trt_network* net, int32_t* trips_of_row)
+{
+    if (!net || !trips_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::vector<int32_t> h;
+    const int rc = download_trip_sums(net, h);
+    if (rc != TRT_OK) return rc;
+    const size_t n = (size_t)net->n;
+    for (size_t r = 0; r < n; ++r) {
+        int32_t sum = 0;
+        for (int b = 0; b < net->trip_buckets_ran; ++b) sum += h[(size_t)b * n + (size_t)net->pos_of_row[r]];
+        trips_of_row[r] = sum;
+    }
+    return TRT_OK;
+}
+
+int trt_trip_counts_bucketed(trt_network* net, int32_t buckets, int32_t* trips /* [buckets][n_rows] */)
+{
+    if (!net || !trips) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::vector<int32_t> h;
+    const int rc = download_trip_sums(net, h);
+    if (rc != TRT_OK) return rc;
+    if (buckets != net->trip_buckets_ran)
+        return fail(TRT_ERR_INVALID, "the last collecting run used trip_buckets = %d, not %d", net->trip_buckets_ran, buckets);
+    const size_t n = (size_t)net->n;
+    for (int b = 0; b < buckets; ++b)
+        for (size_t r = 0; r < n; ++r) trips[(size_t)b * n + r] = h[(size_t)b * n + (size_t)net->pos_of_row[r]];
     return TRT_OK;
 }
 

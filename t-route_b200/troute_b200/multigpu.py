@@ -51,15 +51,26 @@ class SingleRouter:
     def upload(self):
         self.net.upload(self.T, self.qts, self.wl["qlat"], self.wl["q0"])
 
-    def reorder_by_trip_history(self, options=None):
+    def reorder_by_trip_history(self, options=None, buckets=None):
         """One calibration call that records how many secant trips every segment needed, then the network is rebuilt
-        with the segments of every wavefront level ordered by that count: a segment's trip count repeats from step to
-        step (p = 0.82), so the 32 lanes of a warp -- which run in lockstep -- now mostly need the same number of trips.
+        with the segments of every wavefront level ordered by that history (network.order_key_from_trips: the trips of
+        16 time slices of the call): a segment's trip count repeats from step to step (p = 0.82) and moves with the storm
+        pulse, so the 32 lanes of a warp -- which run in lockstep -- now mostly need the same number of trips.
         What an operational deployment would do once per network (the handle is cached across calls); the results do
         not depend on the order."""
-        self.net.set_option("collect_trips", 1)
+        from ._lib import TrouteB200Error
+        from .network import TRIP_BUCKETS
+        buckets = TRIP_BUCKETS if buckets is None else int(buckets)
+        self.net.collect_trips(buckets)
         self.net.run(self.short_ts)
-        key = self.net.trip_counts()
+        try:
+            if buckets <= 1:
+                raise TrouteB200Error("totals requested")
+            key = self.net.trip_order_key(buckets)
+            self.order_source = f"secant trip counts of {buckets} time slices of one calibration call"
+        except TrouteB200Error:                      # the time-resolved table is an optimisation: the totals still order
+            key = self.net.trip_counts()
+            self.order_source = "secant trip counts of one calibration call"
         wl = self.wl
         self.net.close()
         self.net = RoutingNetwork(wl["up_ptr"], wl["up_rows"], wl["kind"], wl["params"], wl["cols"], device=self.device,

@@ -149,7 +149,7 @@ def _get_network(reaches_wTypes, upstream_connections, data_idx, data_cols, data
         net.set_option(k, v)
     entry = dict(net=net, kind=kind, seg_rows=seg_rows, reach_len=reach_len, reach_type=reach_type, ordered=True)
     if REORDER_MIN_ROWS is not None and kind.shape[0] >= REORDER_MIN_ROWS:
-        net.set_option("collect_trips", 1)
+        net.collect_trips()
         entry.update(ordered=False, flat=(up_ptr, up_rows, vals, cols, device))
     _NET_CACHE[key] = entry
     while len(_NET_CACHE) > _NET_CACHE_MAX:
@@ -272,7 +272,7 @@ def compute_network_structured(
     if not entry["ordered"]:
         # first call on this network: rebuild it with every level ordered by the trip counts just collected
         up_ptr_f, up_rows_f, vals_f, cols_f, dev_f = entry.pop("flat")
-        ordered = RoutingNetwork(up_ptr_f, up_rows_f, kind, vals_f, cols_f, device=dev_f, order_key=net.trip_counts())
+        ordered = RoutingNetwork(up_ptr_f, up_rows_f, kind, vals_f, cols_f, device=dev_f, order_key=net.trip_order_key())
         for k, v in DEFAULT_OPTIONS.items():
             ordered.set_option(k, v)
         net.close()

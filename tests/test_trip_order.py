@@ -1,0 +1,101 @@
+"""Within-level ordering of the segments by their secant trip history (troute_b200.network.order_key_from_trips,
+trt_trip_counts_bucketed): host logic and the warp-occupancy model of tools/trip_order_study.py on the CPU; the device
+counters against the oracle's per-step trip counts on the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+def _bucketed(trips, B):
+    T = trips.shape[1]
+    b = (np.arange(T) * B) // T
+    return np.stack([trips[:, b == k].sum(axis=1) for k in range(B)], axis=0).astype(np.int32)
+
+
+def test_order_key_is_a_ranking_and_total_breaks_ties():
+    from troute_b200.network import order_key_from_trips
+    total = np.array([5, 1, 3, 3], dtype=np.int32)
+    assert order_key_from_trips(total).tolist() == total.tolist()            # 1-D: the totals are the key
+    # two slices of 4 steps; rows 0 and 1 are slow early, rows 2 and 3 late; the second slice spreads more
+    t = np.array([[12, 12, 8, 8], [8, 9, 16, 20]], dtype=np.int32)
+    key = order_key_from_trips(t, nsteps=8)
+    assert sorted(key.tolist()) == [0, 1, 2, 3]
+    assert key[0] < key[1] < key[2] < key[3]                                 # slice 2 first (8 < 9 < 16 < 20)
+    same = np.array([[4, 4, 4], [4, 4, 4]], dtype=np.int32)
+    assert order_key_from_trips(same, nsteps=2).tolist() == [0, 1, 2]        # stable for equal rows
+    # quantisation: means 2.0 and 2.1 trips per step fall into one class, the total then decides
+    t = np.array([[20, 21, 20], [30, 20, 20]], dtype=np.int32)
+    key = order_key_from_trips(t, nsteps=20)
+    assert key[1] < key[0] and key[2] < key[0]
+
+
+def test_time_resolved_key_fills_the_warps_better_than_the_total(oracle):
+    """The cost model of the dataflow kernel (32 lanes wait for the slowest) on the trip counts the oracle produces for an
+    NHD-like network: caller order < total-trips order < time-resolved order."""
+    import trip_order_study as S
+    from troute_b200 import synth, hostgraph
+    from troute_b200.network import order_key_from_trips, TRIP_BUCKETS
+    n, T = 12000, 96
+    down = synth.conus_like(n_total=n, n_basins=60, seed=16, style="nhd")
+    case = H.make_case(down, nsteps=T)
+    fvd, _, extras = H.oracle_route(oracle, case, False)
+    trips = S.trip_matrix(oracle, case, fvd)
+    hist = extras["iter_hist"]
+    # the tool sees the oracle's trips: histogram slots 0..7 are exact counts, the rest hold 8-15, 16-31, ... (troute_oracle.c)
+    assert np.bincount(trips.ravel().astype(np.int64), minlength=8)[:8].tolist() == hist[:8].tolist()
+    assert int((trips >= 8).sum()) == int(hist[8:].sum())
+    level = hostgraph.levels(down, case["up_ptr"]).astype(np.int64)
+
+    def lanes(key):
+        u, c = S.efficiency(trips, level, key)
+        return 32.0 * u / c
+
+    rows = lanes(np.arange(n))
+    total = lanes(order_key_from_trips(trips.sum(axis=1)))
+    resolved = lanes(order_key_from_trips(_bucketed(trips, TRIP_BUCKETS), nsteps=T))
+    assert rows < total < resolved, (rows, total, resolved)
+    assert resolved > 1.03 * total, (total, resolved)
+
+
+@pytest.mark.gpu
+@pytest.mark.first_light
+@pytest.mark.parametrize("mode,chunks", [(2, 1), (4, 3)])
+def test_device_trip_counters_equal_the_oracle_per_time_slice(oracle, mode, chunks):
+    """trt_trip_counts_bucketed == the oracle's trip count of every (segment, step) summed per slice, exactly (same
+    arithmetic); the totals are their sum; a network rebuilt in that order gives the same bits."""
+    import __graft_entry__ as g
+    g.build()
+    import trip_order_study as S
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    n, T, B = 20000, 50, 8
+    case = H.make_case(synth.conus_like(n_total=n, n_basins=30, seed=9, style="nhd"), nsteps=T, warm=True)
+    ref, _, _ = H.oracle_route(oracle, case, False)
+    want = _bucketed(S.trip_matrix(oracle, case, ref), B)
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+    net.set_option("mode", mode); net.set_option("route_chunks", chunks); net.set_option("deep_lanes", 0 if mode == 2 else 2000)
+    net.collect_trips(B)
+    out, _ = net.route_call(T, 12, case["qlat"], case["q0"])
+    got = net.trip_counts(B)
+    tot = net.trip_counts()
+    key = net.trip_order_key(B)
+    levels = net.levels()
+    first_marching = net.last_run_stats()["first_marching_level"] if mode == 4 else levels.max() + 1
+    net.close()
+    H.assert_bit_equal(out, ref, "collecting run")
+    assert np.array_equal(tot, got.sum(axis=0))
+    wide = levels < first_marching                      # rows routed by the marching kernel report 0
+    assert wide.sum() > 0.5 * n
+    assert np.array_equal(got[:, wide], want[:, wide])
+    assert (got[:, ~wide] == 0).all()
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"], order_key=key)
+    net.set_option("mode", mode)
+    out, _ = net.route(T, 12, case["qlat"], case["q0"])
+    net.close()
+    H.assert_bit_equal(out, ref, "network ordered by the time-resolved key")
