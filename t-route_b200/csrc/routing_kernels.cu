@@ -275,7 +275,12 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
 // ---------------------------------------------------------------------------------------------------------
 // dataflow schedule (see kernels.cuh): persistent warps claim units in stage order, lanes wait on their own inputs
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 4) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
+// 4 CTAs per SM = 64 registers per thread (60 bytes of spill stores, 32 warps per SM); 3 would give 80 registers, no spills
+// and 24 warps -- an A/B for a GPU session: make EXTRA=-DTRT_DATAFLOW_MIN_BLOCKS=3
+#ifndef TRT_DATAFLOW_MIN_BLOCKS
+#define TRT_DATAFLOW_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
 {
     __shared__ SmemTabs smem;
     const PowTabs tabs = stage_tables(smem);
