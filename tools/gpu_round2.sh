@@ -1,0 +1,45 @@
+#!/bin/bash
+# First GPU session of round 2, one gpurun call (~25 min of box time):
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round2.sh'
+# 1. everything that has never run on a device (tools/gpu_round.sh "diffusive open": diffusive tests with tracebacks,
+#    compute-sanitizer, its bench lines and ncu capture; the sharded-nudging test with its error text), then the strict
+#    first-light tests (warm restart, time-resolved trip counters);
+# 2. the Muskingum-Cunge A/Bs of DESIGN.md "Order of work" (one bench line each, resident number only);
+# 3. the default bench + reference arm, and the GPU test suite as the driver runs it.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+export TRT_TEST_STRICT=1
+bash tools/gpu_round.sh "diffusive open"
+timeout 900 python -m pytest tests/test_restart_continuity.py tests/test_trip_order.py -m gpu -q -rA --tb=long \
+    > gpurun_out/pytest_first_light.log 2>&1; echo "first-light tests rc=$?" >> gpurun_out/box.txt
+
+ab() {   # name, bench arguments...
+  local name=$1; shift
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e "$@" > "gpurun_out/ab_${name}.json" 2> "gpurun_out/ab_${name}.err"
+  echo "ab ${name} rc=$? $(python - "gpurun_out/ab_${name}.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r = d["roofline"]
+    print(f"ms_per_step={d['ms_per_step']:.2f} dataflow_ms={r['kernel_ms']:.2f} march_ms={r['marching_kernel_ms']:.2f}")
+except Exception as e:
+    print("unreadable:", e)
+PY
+)" >> gpurun_out/box.txt
+}
+ab default
+ab trip_totals --trip-buckets 1
+ab no_trip_order --no-trip-order
+ab march_group1 --opt march_group=1
+ab march_group2 --opt march_group=2
+ab march_group1_deep4096 --opt march_group=1 --deep-lanes 4096
+# 80-register dataflow kernel (no spills, 24 warps per SM); rebuilt in place, default build restored afterwards
+make -C t-route_b200/csrc -B EXTRA=-DTRT_DATAFLOW_MIN_BLOCKS=3 > gpurun_out/build_minblocks3.log 2>&1 && ab dataflow_minblocks3
+make -C t-route_b200/csrc -B > gpurun_out/build_default.log 2>&1; echo "rebuild default rc=$?" >> gpurun_out/box.txt
+
+unset TRT_TEST_STRICT
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest (driver style) rc=$?" >> gpurun_out/box.txt
+timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/box.txt
+timeout 600 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench_ref rc=$?" >> gpurun_out/box.txt
+cat gpurun_out/box.txt
