@@ -100,6 +100,7 @@ struct trt_network {
     DevBuf<unsigned char> d_unit_shift;
     DevBuf<unsigned long long> d_stage_time;                  // mode 2 + profile_stages: completion time of every stage
     int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0, sched_lw = -1;
+    int warp_resync = 0;                                      // dataflow kernel: __syncwarp between input polls and solve
     int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
     int gate_min = 12;
     int64_t gate_lanes = 16384;
@@ -784,6 +785,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             sd.claim = (unsigned int*)net->d_ctrl.p; sd.frontier = net->d_ctrl.p + 1; sd.abort_flag = net->d_ctrl.p + 2;
             sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
             sd.stage_time = nullptr;
+            sd.resync = net->warp_resync;
             if (net->profile_stages && nstages > 0) {
                 CU(net->d_stage_time.reserve((size_t)nstages + 1));
                 CU(cudaMemsetAsync(net->d_stage_time.p, 0, ((size_t)nstages + 1) * sizeof(unsigned long long), st));
@@ -1224,6 +1226,8 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
+    } else if (!strcmp(key, "warp_resync")) {
+        net->warp_resync = value != 0;
     } else if (!strcmp(key, "collect_trips")) {
         net->collect_trips = value != 0;
     } else if (!strcmp(key, "trip_buckets")) {

@@ -92,6 +92,8 @@ struct SchedDev {
                                       // the last non-empty stage <= k - gate (0 = no wait)
     unsigned long long* stage_time;   // [nstages + 1] or NULL: %globaltimer (ns) when stage k completed, in slot k;
                                       // slot 0 = kernel start ("profile_stages" option)
+    int resync;                       // 1: the lanes of a unit meet at a __syncwarp between their input polls and the solve
+                                      // ("warp_resync" option, see dataflow_kernel)
 };
 
 // cut edges to other shards: lane s with (kind & TRT_KIND_EXPORT_FLAG) stores q also to peer memory

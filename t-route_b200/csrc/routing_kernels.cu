@@ -159,10 +159,12 @@ __device__ __forceinline__ float apply_nudging(const RunDev& run, int s, int t, 
     return replacement_val;
 }
 
-// route segment `s` (engine position) at step `t`
+// route segment `s` (engine position) at step `t`.  sync_mask != 0 (polling schedules only): the lanes named in it -- exactly
+// the lanes of the warp that call this function for a routed (non-boundary) segment -- meet at a __syncwarp after their
+// inputs have arrived and before the solve.
 template <bool WAIT>
 __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs,
-                                           const PeerDev* peers, int* abort_flag)
+                                           const PeerDev* peers, int* abort_flag, unsigned sync_mask = 0)
 {
     const unsigned kflags = net.kind[s];
     const unsigned kind = kflags & 0x0F;
@@ -196,6 +198,15 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
     }
     // depth (MC) / water elevation (level pool) at t-1
     const float statep = ld_state<WAIT>(own - 1, abort_flag);
+    float ql = 0.0f, qdp = 0.0f;
+    if (kind != TRT_KIND_LEVELPOOL) {
+        ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);              // :723
+        qdp = ld_state<WAIT>(own - 3, abort_flag);                                  // :733
+    }
+    // Every input is here.  The polls above are spin loops with a sleep in them; the warp does not reliably come back
+    // together behind them on its own (ncu, profiles/r01_v5_trip_order: 2.46e7 unit iterations but 3.12e7 executions of the
+    // code from here on, at 25 of 32 lanes -- a quarter of the warps run the whole solve in two pieces).
+    if (WAIT && sync_mask) __syncwarp(sync_mask);
 
     float o_q, o_v, o_d;
     bool write_v = true;
@@ -210,8 +221,6 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
         o_v = quc;      // velocity slot carries the reservoir inflow (upstream_array, :710); finalize writes 0 for v
         o_d = H;
     } else {
-        const float ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);   // :723
-        const float qdp = ld_state<WAIT>(own - 3, abort_flag);                       // :733
         // polling schedules (WAIT): the velocity slot keeps TRT_SENTINEL and the result pass fills it in from the depth
         const McResult r = trt_mc_segment<false, !WAIT>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
@@ -329,9 +338,20 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
             __syncwarp();
         }
 
-        for (int s = p0 + lane; s < p1; s += 32) {
-            const int t = (run.short_ts ? k : k - __ldg(net.level + s)) + run.t_off;
-            route_lane<true>(net, run, s, t, tabs, &peers, sc.abort_flag);
+        for (int base = p0; base < p1; base += 32) {
+            const int s = base + lane;
+            bool live = s < p1;
+            unsigned mask = 0;
+            if (sc.resync) {
+                // all 32 lanes are here together: name the ones that will route a segment for the __syncwarp in route_lane
+                live = live && (net.kind[s] & 0x0F) != TRT_KIND_BOUNDARY;
+                mask = __ballot_sync(0xffffffffu, live);
+            }
+            if (live) {
+                const int t = (run.short_ts ? k : k - __ldg(net.level + s)) + run.t_off;
+                route_lane<true>(net, run, s, t, tabs, &peers, sc.abort_flag, mask);
+            }
+            if (sc.resync) __syncwarp();
         }
         __syncwarp();
         if (lane == 0) {

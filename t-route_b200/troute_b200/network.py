@@ -9,6 +9,7 @@ once from CSR arrays in the caller's row order (rows = positions in the sorted s
 Only numpy and ctypes are used here; all arithmetic happens in libtroute_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -108,6 +109,11 @@ class RoutingNetwork:
         self._keep = None
         self.nsteps = 0
         self._lp_rows = np.zeros(0, dtype=np.int64)
+        # TRT_OPTIONS="key=value,...": engine options applied to every network of the process -- lets a whole test or
+        # bench run go through an alternative schedule knob (e.g. TRT_OPTIONS=warp_resync=1 pytest -m gpu)
+        for kv in filter(None, os.environ.get("TRT_OPTIONS", "").split(",")):
+            k, _, v = kv.partition("=")
+            self.set_option(k.strip(), int(v))
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):

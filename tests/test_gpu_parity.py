@@ -373,6 +373,27 @@ def test_gate_and_grid_options_do_not_change_results(eng, oracle):
         H.assert_bit_equal(out, ref, f"gate={gate} grid={grid}")
 
 
+@pytest.mark.first_light
+@pytest.mark.parametrize("short_ts", [False, True])
+@pytest.mark.parametrize("mode,chunks,grid", [(2, 1, 0), (2, 1, 2), (4, 1, 0), (4, 3, 0)])
+def test_warp_resync_option_does_not_change_results(eng, oracle, short_ts, mode, chunks, grid):
+    """Option warp_resync = 1: the lanes of a dataflow unit meet at a __syncwarp between their input polls and the solve
+    (route_lane).  A schedule knob like the others: same bits with level pools, tiny grids and time chunks.  (The whole GPU
+    suite -- shards, boundary rows, nudging -- runs under the option with TRT_OPTIONS=warp_resync=1, tools/gpu_round2.sh.)"""
+    from troute_b200 import synth
+    from troute_b200.network import RoutingNetwork
+    case = H.make_case(synth.conus_like(n_total=20000, n_basins=30, seed=9, style="nhd"), nsteps=30, n_lp=10, warm=True)
+    ref, upref, _ = H.oracle_route(oracle, case, short_ts)
+    net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
+    net.set_levelpools(case["lp_rows"], case["wbody"])
+    net.set_option("mode", mode); net.set_option("warp_resync", 1); net.set_option("route_chunks", chunks)
+    net.set_option("grid_blocks", grid); net.set_option("deep_lanes", 2000)
+    out, up = net.route_call(30, 12, case["qlat"], case["q0"], assume_short_ts=short_ts, want_upstream=True)
+    net.close()
+    H.assert_bit_equal(out, ref, f"warp_resync, mode {mode}, {chunks} chunks, grid {grid}")
+    H.assert_bit_equal(up[case["lp_rows"]], upref[case["lp_rows"]], "warp_resync: reservoir inflow")
+
+
 @pytest.mark.parametrize("P", [2, 3])
 @pytest.mark.parametrize("short_ts", [False, True])
 @pytest.mark.parametrize("split", ["all-march", "dataflow+march", "dataflow"])

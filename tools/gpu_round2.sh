@@ -11,8 +11,12 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export TRT_TEST_STRICT=1
 bash tools/gpu_round.sh "diffusive open"
-timeout 900 python -m pytest tests/test_restart_continuity.py tests/test_trip_order.py -m gpu -q -rA --tb=long \
+timeout 900 python -m pytest tests/test_restart_continuity.py tests/test_trip_order.py tests/test_gpu_parity.py -m gpu -k 'restart or trip or warp_resync' -q -rA --tb=long \
     > gpurun_out/pytest_first_light.log 2>&1; echo "first-light tests rc=$?" >> gpurun_out/box.txt
+
+# the Muskingum-Cunge parity suite once more with the warp re-synchronisation switched on for every network
+TRT_OPTIONS=warp_resync=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -m gpu -x -q \
+    > gpurun_out/pytest_warp_resync.log 2>&1; echo "parity suite under warp_resync rc=$?" >> gpurun_out/box.txt
 
 ab() {   # name, bench arguments...
   local name=$1; shift
@@ -29,6 +33,7 @@ PY
 )" >> gpurun_out/box.txt
 }
 ab default
+ab warp_resync --opt warp_resync=1
 ab trip_totals --trip-buckets 1
 ab no_trip_order --no-trip-order
 ab march_group1 --opt march_group=1
