@@ -80,6 +80,8 @@ def parse():
                     help="skip the calibration call that orders the segments of a level by their secant trip counts")
     ap.add_argument("--trip-buckets", type=int, default=0,
                     help="time slices of the calibration call's trip counts (0 = network.TRIP_BUCKETS, 1 = totals only)")
+    ap.add_argument("--sharded-trip-order", action="store_true",
+                    help="N > 1: calibrate and re-order every shard like the single-GPU run does (opt-in, unmeasured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
@@ -287,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
 
     for kv in args.opt:
         k, v = kv.split("=")
-        runner.net.set_option(k, int(v))
+        (runner.set_option if hasattr(runner, "set_option") else runner.net.set_option)(k, int(v))
 
     def barrier():
         if world > 1:
@@ -316,6 +318,8 @@ def run_ours(args, rank, world, local_rank):
     engine_opts.update({kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
     if world == 1 and not args.no_trip_order and args.mode in (2, 4):
         runner.reorder_by_trip_history(engine_opts, args.trip_buckets or None)   # set-up, not timed: once per network in production
+    if world > 1 and args.sharded_trip_order and not args.no_trip_order and args.mode in (2, 4):
+        runner.reorder_by_trip_history(args.trip_buckets or None)
     for _ in range(args.warmup):
         runner.run_resident()
     barrier()

@@ -139,24 +139,14 @@ class ShardedRouter:
         self.plan = plan = plans[rank]
         self.n = int(plan.rows.size)
         self.n_own = int(plan.own.sum())
-        self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
-                                  device=device, levels=plan.levels)
-        self.net.set_option("mode", mode)
-        lp_local = np.nonzero(plan.kind == 1)[0]
-        if lp_local.size:
-            # level pools of this shard: the rows of wl["wbody"] that belong to its reservoirs
-            lp_index = {int(r): i for i, r in enumerate(np.asarray(wl["lp_rows"]).tolist())}
-            rows = np.asarray([lp_index[int(g)] for g in plan.rows[lp_local]], dtype=np.int64)
-            self.net.set_levelpools(lp_local, np.asarray(wl["wbody"])[rows], routing_period=wl.get("dt", 300.0))
-        if mode >= 4:
-            # one split level for ALL shards: a dataflow (wide) kernel may wait only for values that other shards produce
-            # in THEIR dataflow kernels; the deepest levels (at most deep_lanes segments on any shard) march
-            self.deep_level = global_deep_level(level, self.shard, world, deep_lanes)
-            self.net.set_option("deep_level", self.deep_level)
+        # one split level for ALL shards: a dataflow (wide) kernel may wait only for values that other shards produce
+        # in THEIR dataflow kernels; the deepest levels (at most deep_lanes segments on any shard) march
+        self.deep_level = global_deep_level(level, self.shard, world, deep_lanes) if mode >= 4 else None
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
-        self.net.set_option("stream", self.tstream.cuda_stream)
-        self.net.set_imports(plan.imports)
+        self.options = {}
+        self.reordered = False
+        self._build_net(None)
         self.qlat = np.ascontiguousarray(wl["qlat"][plan.rows])
         self.q0 = np.ascontiguousarray(wl["q0"][plan.rows])
         self.nq = self.qlat.shape[1]
@@ -164,6 +154,51 @@ class ShardedRouter:
         self.d2h_bytes = self.n * 3 * nsteps * 4
         self._host = None
         self._wired = False
+
+    def _build_net(self, order_key):
+        """The shard's device network (again, in a new within-level order, for reorder_by_trip_history)."""
+        wl, plan = self.wl, self.plan
+        self.net = RoutingNetwork(plan.up_ptr, plan.up_rows, plan.kind, wl["params"][plan.rows], wl["cols"],
+                                  device=self.device, levels=plan.levels, order_key=order_key)
+        self.net.set_option("mode", self.mode)
+        lp_local = np.nonzero(plan.kind == 1)[0]
+        if lp_local.size:
+            # level pools of this shard: the rows of wl["wbody"] that belong to its reservoirs
+            lp_index = {int(r): i for i, r in enumerate(np.asarray(wl["lp_rows"]).tolist())}
+            rows = np.asarray([lp_index[int(g)] for g in plan.rows[lp_local]], dtype=np.int64)
+            self.net.set_levelpools(lp_local, np.asarray(wl["wbody"])[rows], routing_period=wl.get("dt", 300.0))
+        if self.deep_level is not None:
+            self.net.set_option("deep_level", self.deep_level)
+        self.net.set_option("stream", self.tstream.cuda_stream)
+        for k, v in self.options.items():
+            self.net.set_option(k, v)
+        self.net.set_imports(plan.imports)
+        self._wired = False
+
+    def set_option(self, key, value):
+        """Engine option that survives a rebuild of the shard's network."""
+        self.options[key] = int(value)
+        self.net.set_option(key, int(value))
+
+    def reorder_by_trip_history(self, buckets=None):
+        """SingleRouter.reorder_by_trip_history for a sharded run: every rank records the trips of its own segments in one
+        calibration call, rebuilds its network in that order and the shards are wired again (positions and flow arrays are
+        new).  Opt-in (bench.py --sharded-trip-order) until it has been measured."""
+        from .network import TRIP_BUCKETS
+        buckets = TRIP_BUCKETS if buckets is None else int(buckets)
+        self.net.collect_trips(buckets)
+        self.run_resident()
+        self.net.sync()
+        self.dist.barrier()
+        key = self.net.trip_order_key(buckets) if buckets > 1 else self.net.trip_counts()
+        self.order_source = (f"secant trip counts of {buckets} time slices of one calibration call" if buckets > 1
+                             else "secant trip counts of one calibration call")
+        self.dist.barrier()                         # nobody closes a flow array a peer may still be writing to
+        self.net.close_peers()
+        self.net.close()
+        self._build_net(key)
+        self.upload()
+        self.reordered = True
 
     def _wire(self):
         """After the first upload (the flow array exists): exchange IPC handles and import positions, open peers."""
