@@ -206,6 +206,10 @@ int trt_prepare(trt_network* net);
  *                 more segments resident at once
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
+ *   "warp_resync" mode 2 / 4: 1 = the lanes of a dataflow unit meet at a __syncwarp between their input polls and the
+ *                 solve (the spin loops of the polls leave a quarter of the warps split in two for the whole solve);
+ *                 0 (default until measured) = no explicit barrier.  Results do not depend on it
+ *   "collect_trips", "trip_buckets"  see trt_trip_counts / trt_trip_counts_bucketed
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
  *   "route_chunks" time chunks of trt_route / trt_run_download (default 4; 1 = compute everything, then copy)
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
