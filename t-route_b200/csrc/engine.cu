@@ -369,6 +369,7 @@ int trt_network_destroy(trt_network* net)
     if (net->ev1) cudaEventDestroy(net->ev1);
     if (net->ev_mid) cudaEventDestroy(net->ev_mid);
     for (cudaEvent_t ev : net->chunk_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : net->stage_events) cudaEventDestroy(ev);
     if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
     if (net->stream && net->own_stream) cudaStreamDestroy(net->stream);
     delete net;
