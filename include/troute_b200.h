@@ -86,6 +86,11 @@ int trt_trip_counts(trt_network* net, int32_t* trips_of_row /* [n_rows] */);
  * troute_b200.network.order_key_from_trips turns this table into an order_key (tools/trip_order_study.py: 28.0 instead of
  * 25.9 busy lanes out of 32 on the bench network, against 22.4 in the caller's row order). */
 int trt_trip_counts_bucketed(trt_network* net, int32_t buckets, int32_t* trips /* [buckets][n_rows] */);
+/* Collected by the same run: the number of steps every row ended above its bankfull depth in a compound channel, i.e. took
+ * the over-bank branch of the celerity (MCsingleSegStime_f2py_NOLOOP.f90:248-258, one more power) instead of the in-bank
+ * one.  A warp whose lanes disagree executes both; flooding lasts for hours, so ordering by this count first leaves 25 %
+ * of the warp-steps mixed instead of 55 % (tools/trip_order_study.py). */
+int trt_overbank_counts(trt_network* net, int32_t* steps_of_row /* [n_rows] */);
 int trt_network_destroy(trt_network* net);
 
 /* topology queries: number of wavefront levels; level of every row; engine position of every row */

@@ -152,7 +152,7 @@ struct trt_network {
     bool collect_trips = false;                               // sum the secant trips of every segment over a run
     int trip_buckets = 1;                                     // ... separately for this many equal time slices of the call
     int trip_buckets_ran = 0;                                 // layout of d_trip_sum after the last collecting run
-    DevBuf<int> d_trip_sum;                                   // [trip_buckets][n] by position
+    DevBuf<int> d_trip_sum;                                   // [trip_buckets + 1][n] by position (last row: over-bank steps)
 
     // options / stats
     int mode = 4;                  // 0 stage-per-launch, 1 persistent cooperative (grid.sync per stage), 2 dataflow,
@@ -645,7 +645,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         RunDev rg = net->rundev(0);
         CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
     }
-    if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1) * (size_t)net->trip_buckets));
+    if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1) * (size_t)(net->trip_buckets + 1)));
     const NetDev nd = net->netdev();
     RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
     rd.t_off = t_off; rd.Tc = Tc;
@@ -653,7 +653,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
     const int L = assume_short_ts ? 1 : net->nlevels;
     if (first) { net->launches = 0; net->stages = 0; net->lane_steps = 0; net->kernel_ms = 0.0; }
     if (first && net->collect_trips && net->n > 0) {
-        CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * (size_t)net->trip_buckets * sizeof(int), st));
+        CU(cudaMemsetAsync(net->d_trip_sum.p, 0, (size_t)net->n * (size_t)(net->trip_buckets + 1) * sizeof(int), st));
         net->trip_buckets_ran = net->trip_buckets;
     }
 
@@ -1296,7 +1296,7 @@ static int download_trip_sums(trt_network* net, std::vector<int32_t>& h)
         return fail(TRT_ERR_STATE, "no trip counts: set option collect_trips = 1 before trt_run");
     CU(cudaSetDevice(net->device));
     CU(cudaStreamSynchronize(net->stream));
-    h.resize((size_t)net->n * (size_t)net->trip_buckets_ran);
+    h.resize((size_t)net->n * (size_t)(net->trip_buckets_ran + 1));
     if (!h.empty()) CU(cudaMemcpy(h.data(), net->d_trip_sum.p, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return TRT_OK;
 }
@@ -1327,6 +1327,17 @@ int trt_trip_counts_bucketed(trt_network* net, int32_t buckets, int32_t* trips /
     const size_t n = (size_t)net->n;
     for (int b = 0; b < buckets; ++b)
         for (size_t r = 0; r < n; ++r) trips[(size_t)b * n + r] = h[(size_t)b * n + (size_t)net->pos_of_row[r]];
+    return TRT_OK;
+}
+
+int trt_overbank_counts(trt_network* net, int32_t* steps_of_row)
+{
+    if (!net || !steps_of_row) return fail(TRT_ERR_INVALID, "NULL argument");
+    std::vector<int32_t> h;
+    const int rc = download_trip_sums(net, h);
+    if (rc != TRT_OK) return rc;
+    const size_t n = (size_t)net->n, row = (size_t)net->trip_buckets_ran;
+    for (size_t r = 0; r < n; ++r) steps_of_row[r] = h[row * n + (size_t)net->pos_of_row[r]];
     return TRT_OK;
 }
 

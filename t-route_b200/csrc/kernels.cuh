@@ -56,8 +56,9 @@ struct GageDev {
 
 struct RunDev {
     GageDev gage;
-    int* trip_sum;  // NULL, or [trip_buckets][n]: secant trips of every position, summed over the steps of each of
-                    // trip_buckets equal slices of the call ("collect_trips"; step t falls into slice (t-1)*buckets/T)
+    int* trip_sum;  // NULL, or [trip_buckets + 1][n]: secant trips of every position, summed over the steps of each of
+                    // trip_buckets equal slices of the call ("collect_trips"; step t falls into slice (t-1)*buckets/T);
+                    // last row: number of steps the segment ended above bankfull depth
     int trip_buckets;
     int T;          // timesteps of the call (the flow state holds T + 1 columns)
     int t_off;      // this launch routes steps t_off + 1 .. t_off + Tc (a time chunk of the call; whole call: 0, T)

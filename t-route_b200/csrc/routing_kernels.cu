@@ -224,7 +224,10 @@ __device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run,
         // polling schedules (WAIT): the velocity slot keeps TRT_SENTINEL and the result pass fills it in from the depth
         const McResult r = trt_mc_segment<false, !WAIT>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
         o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
-        if (run.trip_sum) atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * n + s, r.iters);
+        if (run.trip_sum) {
+            atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * n + s, r.iters);
+            if (r.over) atomicAdd(run.trip_sum + (size_t)run.trip_buckets * n + s, 1);       // row trip_buckets: over-bank steps
+        }
         write_v = !WAIT || !(ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);   // no-flow branch: v = 0 (:171-178)
     }
     if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, s, t, o_q, tabs);    // mc_reach.pyx:761-796

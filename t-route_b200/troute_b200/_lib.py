@@ -45,6 +45,7 @@ SYMBOLS = [
     ("trt_network_create_ordered", C.c_int, [C.c_int, C.c_int64, _i64p, _i64p, _u8p, _f32p, C.c_int32, _i32p, _i32p, _i32p, C.POINTER(_net)]),
     ("trt_trip_counts", C.c_int, [_net, _i32p]),
     ("trt_trip_counts_bucketed", C.c_int, [_net, C.c_int32, _i32p]),
+    ("trt_overbank_counts", C.c_int, [_net, _i32p]),
     ("trt_network_destroy", C.c_int, [_net]),
     ("trt_network_num_levels", C.c_int, [_net, _i32p]),
     ("trt_network_get_levels", C.c_int, [_net, _i32p]),

@@ -18,6 +18,37 @@ def _bucketed(trips, B):
     return np.stack([trips[:, b == k].sum(axis=1) for k in range(B)], axis=0).astype(np.int32)
 
 
+def _overbank_steps(case, fvd):
+    """steps every segment ended above bankfull depth in a compound channel, with the float32 expressions of mc_channel
+    (MCsingleSegStime_f2py_NOLOOP.f90:49-61) -- what the device counts (McResult.over)"""
+    cols = list(case["cols"])
+    P = np.asarray(case["params"], dtype=np.float32)
+    bw, tw, cs, twcc, ncc = (P[:, cols.index(c)] for c in ("bw", "tw", "cs", "twcc", "ncc"))
+    one, two = np.float32(1.0), np.float32(2.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = np.where(cs == 0, one, one / cs).astype(np.float32)
+        bfd = np.where(bw > tw, bw / np.float32(0.00001), np.where(bw == tw, bw / (two * z), (tw - bw) / (two * z))).astype(np.float32)
+    depth = fvd[:, 2::3]
+    return ((depth > bfd[:, None]) & ((twcc > 0) & (ncc > 0))[:, None])
+
+
+def _mixed_fraction(over, level, key):
+    """share of warp-steps (32 consecutive segments of a level in `key` order) whose lanes disagree about being over bank"""
+    order = np.lexsort((key, level))
+    lv = level[order]
+    starts = np.flatnonzero(np.r_[True, lv[1:] != lv[:-1]])
+    ends = np.r_[starts[1:], lv.size]
+    mixed = total = 0
+    for a, b in zip(starts, ends):
+        m = (b - a) // 32 * 32
+        if m < 64:
+            continue
+        ov = over[order[a:a + m]].reshape(-1, 32, over.shape[1])
+        mixed += int((ov.any(axis=1) & ~ov.all(axis=1)).sum())
+        total += ov.shape[0] * over.shape[1]
+    return mixed / total
+
+
 def test_order_key_is_a_ranking_and_total_breaks_ties():
     from troute_b200.network import order_key_from_trips
     total = np.array([5, 1, 3, 3], dtype=np.int32)
@@ -58,9 +89,17 @@ def test_time_resolved_key_fills_the_warps_better_than_the_total(oracle):
 
     rows = lanes(np.arange(n))
     total = lanes(order_key_from_trips(trips.sum(axis=1)))
-    resolved = lanes(order_key_from_trips(_bucketed(trips, TRIP_BUCKETS), nsteps=T))
+    key_t = order_key_from_trips(_bucketed(trips, TRIP_BUCKETS), nsteps=T)
+    resolved = lanes(key_t)
     assert rows < total < resolved, (rows, total, resolved)
     assert resolved > 1.03 * total, (total, resolved)
+    # over-bank steps as the primary key: far fewer warps execute both branches of the celerity, the trips stay grouped
+    over = _overbank_steps(case, fvd)
+    assert 0.05 < over.mean() < 0.95                       # the storm pulse floods part of the network
+    key_o = order_key_from_trips(_bucketed(trips, TRIP_BUCKETS), nsteps=T, overbank=over.sum(axis=1))
+    assert sorted(key_o.tolist()) == list(range(n))
+    assert _mixed_fraction(over, level, key_o) < 0.75 * _mixed_fraction(over, level, key_t)
+    assert lanes(key_o) > 0.99 * resolved
 
 
 @pytest.mark.gpu
@@ -84,6 +123,7 @@ def test_device_trip_counters_equal_the_oracle_per_time_slice(oracle, mode, chun
     out, _ = net.route_call(T, 12, case["qlat"], case["q0"])
     got = net.trip_counts(B)
     tot = net.trip_counts()
+    over = net.overbank_counts()
     key = net.trip_order_key(B)
     levels = net.levels()
     first_marching = net.last_run_stats()["first_marching_level"] if mode == 4 else levels.max() + 1
@@ -94,6 +134,8 @@ def test_device_trip_counters_equal_the_oracle_per_time_slice(oracle, mode, chun
     assert wide.sum() > 0.5 * n
     assert np.array_equal(got[:, wide], want[:, wide])
     assert (got[:, ~wide] == 0).all()
+    want_over = _overbank_steps(case, ref).sum(axis=1)
+    assert np.array_equal(over[wide], want_over[wide]) and (over[~wide] == 0).all()
     net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"], order_key=key)
     net.set_option("mode", mode)
     out, _ = net.route(T, 12, case["qlat"], case["q0"])
