@@ -19,6 +19,7 @@ from itertools import chain
 
 import numpy as np
 
+from ..._lib import TrouteB200Error
 from ...network import RoutingNetwork, TRT_KIND_BOUNDARY, TRT_KIND_LEVELPOOL, TRT_KIND_MC
 
 
@@ -272,12 +273,18 @@ def compute_network_structured(
     if not entry["ordered"]:
         # first call on this network: rebuild it with every level ordered by the trip counts just collected
         up_ptr_f, up_rows_f, vals_f, cols_f, dev_f = entry.pop("flat")
-        ordered = RoutingNetwork(up_ptr_f, up_rows_f, kind, vals_f, cols_f, device=dev_f, order_key=net.trip_order_key())
-        for k, v in DEFAULT_OPTIONS.items():
-            ordered.set_option(k, v)
-        net.close()
-        entry["net"] = ordered
         entry["ordered"] = True
+        try:
+            order_key = net.trip_order_key()
+        except TrouteB200Error:            # the re-ordering is an optimisation: without the counters the network stays as it is
+            order_key = None
+            net.set_option("collect_trips", 0)
+        if order_key is not None:
+            ordered = RoutingNetwork(up_ptr_f, up_rows_f, kind, vals_f, cols_f, device=dev_f, order_key=order_key)
+            for k, v in DEFAULT_OPTIONS.items():
+                ordered.set_option(k, v)
+            net.close()
+            entry["net"] = ordered
 
     empty_f = np.zeros(0, dtype=np.float32)
     empty_i = np.zeros(0, dtype=np.int32)
