@@ -10,7 +10,8 @@ the oracle (pinned-pow build: the counts the device sees) and evaluates candidat
 
     python tools/trip_order_study.py [n_segments] [nsteps]
 
-Prints one line per candidate: lane efficiency = useful / cost, and the implied active lanes out of 32.
+Prints one line per candidate: lane efficiency = useful / cost, the implied active lanes out of 32, and the share of
+warp-steps whose lanes disagree about being above bankfull depth (such a warp executes both branches of the celerity).
 """
 import os
 import sys
@@ -81,6 +82,35 @@ def efficiency(trips, level, key, min_width=64):
     return useful, cost
 
 
+def overbank_steps(case, fvd):
+    """[n, T] bool: the segment ended the step above bankfull depth in a compound channel (what McResult.over counts)"""
+    cols = list(case["cols"])
+    P = np.asarray(case["params"], dtype=np.float32)
+    bw, tw, cs, twcc, ncc = (P[:, cols.index(c)] for c in ("bw", "tw", "cs", "twcc", "ncc"))
+    one, two = np.float32(1.0), np.float32(2.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = np.where(cs == 0, one, one / cs).astype(np.float32)
+        bfd = np.where(bw > tw, bw / np.float32(0.00001), np.where(bw == tw, bw / (two * z), (tw - bw) / (two * z)))
+    return (fvd[:, 2::3] > bfd.astype(np.float32)[:, None]) & ((twcc > 0) & (ncc > 0))[:, None]
+
+
+def mixed_fraction(over, level, key, min_width=64):
+    """share of warp-steps whose 32 lanes disagree about being over bank (such a warp executes both celerity branches)"""
+    order = np.lexsort((key, level))
+    lv = level[order]
+    starts = np.flatnonzero(np.r_[True, lv[1:] != lv[:-1]])
+    ends = np.r_[starts[1:], lv.size]
+    mixed = total = 0
+    for a, b in zip(starts, ends):
+        m = (b - a) // 32 * 32
+        if m < min_width:
+            continue
+        ov = over[order[a:a + m]].reshape(-1, 32, over.shape[1])
+        mixed += int((ov.any(axis=1) & ~ov.all(axis=1)).sum())
+        total += ov.shape[0] * over.shape[1]
+    return mixed / max(total, 1)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 288
@@ -99,9 +129,13 @@ def main():
     level = hostgraph.levels(down, case["up_ptr"]).astype(np.int64)
     tot = trips.sum(axis=1).astype(np.int64)
 
+    over = overbank_steps(case, fvd)
+    print(f"lane-steps above bankfull depth: {100 * over.mean():.1f} %", flush=True)
+
     def report(name, key):
         u, c = efficiency(trips, level, key)
-        print(f"{name:58s} efficiency {u / c:.4f}  ({32 * u / c:.2f} of 32 lanes)", flush=True)
+        print(f"{name:58s} efficiency {u / c:.4f}  ({32 * u / c:.2f} of 32 lanes), "
+              f"{100 * mixed_fraction(over, level, key):.1f} % of the warp-steps mixed in/over bank", flush=True)
 
     report("caller row order", np.arange(n))
     report("sum of trips over the call (what the engine does today)", tot)
@@ -114,6 +148,11 @@ def main():
         for j in sig:
             key = key * (int(bs.max()) + 1) + bs[:, j]
         report(f"lexicographic, {B} time buckets (largest spread first)", key)
+    from troute_b200.network import order_key_from_trips, TRIP_BUCKETS
+    bk = (np.arange(T) * TRIP_BUCKETS) // T
+    table = np.stack([trips[:, bk == k].sum(axis=1) for k in range(TRIP_BUCKETS)], axis=0)
+    report("engine key: time-resolved trips (order_key_from_trips)", order_key_from_trips(table, T))
+    report("engine key: over-bank class first, then trips", order_key_from_trips(table, T, overbank=over.sum(axis=1)))
     # 1-D embedding of the whole trip series: first principal component of the centred trip matrix
     x = trips.astype(np.float32)
     x -= x.mean(axis=0, keepdims=True)
