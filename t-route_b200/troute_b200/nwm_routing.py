@@ -3,9 +3,18 @@ function the CLI loop, the BMI model (troute_model.py:232) and the tests call to
 (+ level pools, nudging) on the network, then -- when diffusive_network_data is given -- the diffusive wave on every
 mainstem domain, fed by the MC results.  Same 41 positional arguments and keywords, same return value
 (results list, subnetwork_list); the run-log writers (compute_log_mc / compute_log_diff, firstRun) are not mirrored.
+
+Also here: the state hand-off between consecutive windows that the CLI loop (__main__.py:258-266) and the BMI model
+(troute_model.py:250-262) perform after every nwm_route call -- new_q0 / update_waterbody_water_elevation
+(AbstractNetwork.py:177-198), new_lastobs (DataAssimilation.py:1506-1551) -- and `route_windows`, that loop without its file
+I/O.  The device network stays resident across the windows (the handle cache of compute_network_structured); only the
+forcing of a window and its result cross PCIe.
 """
 import logging
 import time
+
+import numpy as np
+import pandas as pd
 
 from .routing.compute import compute_diffusive_routing, compute_nhd_routing_v02
 
@@ -41,3 +50,43 @@ def nwm_route(
         LOG.debug("Diffusive computation complete in %s seconds.", time.time() - t1)
     LOG.debug("ordered reach computation complete in %s seconds.", time.time() - start)
     return results, subnetwork_list
+
+
+def new_q0(run_results):
+    """Initial conditions of the next window: qu0 = qd0 = last flow, h0 = last depth of every segment
+    (AbstractNetwork.new_q0, AbstractNetwork.py:177-191)."""
+    return pd.concat([pd.DataFrame(r[1][:, [-3, -3, -1]], index=r[0], columns=["qu0", "qd0", "h0"]) for r in run_results])
+
+
+def update_waterbody_water_elevation(waterbodies_df, q0):
+    """Reservoirs start the next window from their last outflow and water elevation: the `qd0` / `h0` columns of the
+    waterbody table take the rows of q0 with the same (lake) id, in place (AbstractNetwork.py:193-198)."""
+    waterbodies_df.update(q0)
+    return waterbodies_df
+
+
+def new_lastobs(run_results, time_increment):
+    """Last-observation table of the next window from element [3] of every result tuple, times re-based to the start of
+    the next window (DataAssimilation.new_lastobs, DataAssimilation.py:1506-1551)."""
+    df = pd.concat([pd.DataFrame(np.array([rr[3][1], rr[3][2]]).T, index=rr[3][0],
+                                 columns=["time_since_lastobs", "lastobs_discharge"]) for rr in run_results])
+    df["time_since_lastobs"] = df["time_since_lastobs"] - time_increment
+    return df
+
+
+def route_windows(route_window, windows, q0, waterbodies_df, lastobs_df, dt, nts):
+    """The loop of nwm_routing.__main__.main_v04 (:150-330) / troute_model.run without file I/O.
+
+    route_window(window, q0, waterbodies_df, lastobs_df) -> (results, subnetwork_list) routes one window (normally a
+    closure over nwm_route with that window's qlats / usgs_df).  After every window the next initial state is derived from
+    its results exactly as the reference does.  Returns (list of per-window results, q0, waterbodies_df, lastobs_df)."""
+    out = []
+    for window in windows:
+        results, _ = route_window(window, q0, waterbodies_df, lastobs_df)
+        out.append(results)
+        q0 = new_q0(results)
+        if waterbodies_df is not None and not waterbodies_df.empty:
+            update_waterbody_water_elevation(waterbodies_df, q0)
+        if lastobs_df is not None and not lastobs_df.empty:
+            lastobs_df = new_lastobs(results, dt * nts)
+    return out, q0, waterbodies_df, lastobs_df
