@@ -54,24 +54,33 @@ def nwm_route(
 
 def new_q0(run_results):
     """Initial conditions of the next window: qu0 = qd0 = last flow, h0 = last depth of every segment
-    (AbstractNetwork.new_q0, AbstractNetwork.py:177-191)."""
-    return pd.concat([pd.DataFrame(r[1][:, [-3, -3, -1]], index=r[0], columns=["qu0", "qd0", "h0"]) for r in run_results])
+    (what AbstractNetwork.new_q0 derives, AbstractNetwork.py:177-191).  One frame over all (sub)networks, rows in result
+    order."""
+    ids = np.concatenate([np.asarray(r[0]) for r in run_results]) if run_results else np.zeros(0, dtype=np.int64)
+    last = [np.asarray(r[1]) for r in run_results]
+    flow = np.concatenate([a[:, -3] for a in last]) if last else np.zeros(0, dtype=np.float32)
+    depth = np.concatenate([a[:, -1] for a in last]) if last else np.zeros(0, dtype=np.float32)
+    return pd.DataFrame({"qu0": flow, "qd0": flow, "h0": depth}, index=ids)
 
 
 def update_waterbody_water_elevation(waterbodies_df, q0):
     """Reservoirs start the next window from their last outflow and water elevation: the `qd0` / `h0` columns of the
     waterbody table take the rows of q0 with the same (lake) id, in place (AbstractNetwork.py:193-198)."""
-    waterbodies_df.update(q0)
+    shared = waterbodies_df.index.intersection(q0.index)
+    for col in ("qd0", "h0"):
+        if col in waterbodies_df.columns:
+            waterbodies_df.loc[shared, col] = q0.loc[shared, col].to_numpy(dtype=waterbodies_df[col].dtype)
     return waterbodies_df
 
 
 def new_lastobs(run_results, time_increment):
-    """Last-observation table of the next window from element [3] of every result tuple, times re-based to the start of
+    """Last-observation table of the next window from element [3] of every result tuple -- (gage segment ids, seconds from
+    the start of the window to the last assimilated observation, its value) -- with the times re-based to the start of
     the next window (DataAssimilation.new_lastobs, DataAssimilation.py:1506-1551)."""
-    df = pd.concat([pd.DataFrame(np.array([rr[3][1], rr[3][2]]).T, index=rr[3][0],
-                                 columns=["time_since_lastobs", "lastobs_discharge"]) for rr in run_results])
-    df["time_since_lastobs"] = df["time_since_lastobs"] - time_increment
-    return df
+    ids = np.concatenate([np.asarray(rr[3][0]) for rr in run_results]) if run_results else np.zeros(0, dtype=np.int64)
+    when = np.concatenate([np.asarray(rr[3][1], dtype=np.float64) for rr in run_results]) if run_results else np.zeros(0)
+    value = np.concatenate([np.asarray(rr[3][2], dtype=np.float64) for rr in run_results]) if run_results else np.zeros(0)
+    return pd.DataFrame({"time_since_lastobs": when - time_increment, "lastobs_discharge": value}, index=ids)
 
 
 def route_windows(route_window, windows, q0, waterbodies_df, lastobs_df, dt, nts):
