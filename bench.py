@@ -205,10 +205,17 @@ def cpu_arm(wl, args, threads, budget_s):
     o.build()
     n = wl["n"]
     scols = np.asarray(o.column_mapper(wl["cols"]), dtype=np.int32)
-    reaches = hostgraph.segment_reaches_level_order(wl["down"], wl["up_ptr"], wl["up_rows"])
+    # the reach decomposition and the by-subnetwork job list are set-up (the reference builds them once per run), kept
+    # across the steps of this process
+    plan = wl.setdefault("_cpu_plan", {})
+    if "reaches" not in plan:
+        plan["reaches"] = hostgraph.segment_reaches_level_order(wl["down"], wl["up_ptr"], wl["up_rows"])
+    reaches = plan["reaches"]
     jobs = None
     if threads > 1:
-        jobs = hostgraph.subnetwork_jobs(wl["down"], wl["up_ptr"], wl["up_rows"], reaches["order"], target_size=10000)
+        if "jobs" not in plan:
+            plan["jobs"] = hostgraph.subnetwork_jobs(wl["down"], wl["up_ptr"], wl["up_rows"], reaches["order"], target_size=10000)
+        jobs = plan["jobs"]
 
     def run(ts):
         nq = max(1, int(np.ceil(ts / QTS)))
