@@ -21,16 +21,7 @@ TRT_OPTIONS=warp_resync=1 timeout 900 python -m pytest tests/test_gpu_parity.py 
 ab() {   # name, bench arguments...
   local name=$1; shift
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e "$@" > "gpurun_out/ab_${name}.json" 2> "gpurun_out/ab_${name}.err"
-  echo "ab ${name} rc=$? $(python - "gpurun_out/ab_${name}.json" <<'PY'
-import json, sys
-try:
-    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    r = d["roofline"]
-    print(f"ms_per_step={d['ms_per_step']:.2f} dataflow_ms={r['kernel_ms']:.2f} march_ms={r['marching_kernel_ms']:.2f}")
-except Exception as e:
-    print("unreadable:", e)
-PY
-)" >> gpurun_out/box.txt
+  echo "ab ${name} rc=$? $(python tools/ab_line.py "gpurun_out/ab_${name}.json")" >> gpurun_out/box.txt
 }
 ab default
 ab warp_resync --opt warp_resync=1
