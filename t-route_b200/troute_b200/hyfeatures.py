@@ -3,8 +3,9 @@
 The reference reads the GeoPackage with geopandas/fiona (troute/HYFeaturesNetwork.py:33-107 read_geopkg) and renames /
 re-indexes it in preprocess_network (:369-444).  A GeoPackage is an SQLite file, so the two attribute tables the
 routing path needs can be read with `sqlite3` -- no geometry, no GDAL.  This covers the MC-only plumbing configuration
-(BASELINE config 0: test/LowerColorado_TX_v4, waterbodies not broken out); lakes / gages / coastal boundaries are not
-read here.
+(BASELINE config 0: test/LowerColorado_TX_v4) and its level-pool reservoirs (the `lakes` layer: read_lakes,
+waterbody_connections, drop_inconsistent_lakes -- what preprocess_waterbodies :456-526 and bandaid :819-856 derive);
+gages / coastal boundaries are not read here.
 """
 import glob
 import os
@@ -80,3 +81,64 @@ def param_frame(df, dt):
     p = df[["bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"]].copy()
     p.insert(0, "dt", float(dt))
     return p.astype("float32")
+
+
+# ---- level-pool reservoirs of the hydrofabric -----------------------------------------------------------------------
+LAKE_COLUMNS = ["ifd", "LkArea", "LkMxE", "OrificeA", "OrificeC", "OrificeE", "WeirC", "WeirE", "WeirL"]
+
+
+def read_lakes(gpkg_path):
+    """The `lakes` layer as the waterbody table of the routing path: indexed by lake id (`hl_link`), the nine level-pool
+    parameters plus `id` = numeric id of the flowpath the lake outlet belongs to; duplicates and lakes with a missing
+    parameter dropped, sorted (HYFeaturesNetwork.preprocess_waterbodies :459-472)."""
+    con = sqlite3.connect(f"file:{gpkg_path}?mode=ro", uri=True)
+    try:
+        lk = pd.read_sql_query("SELECT hl_link, id, " + ", ".join(LAKE_COLUMNS) + " FROM lakes", con)
+    finally:
+        con.close()
+    lk = lk.dropna(subset=["hl_link"])
+    out = pd.DataFrame({c: lk[c].astype("float64") for c in LAKE_COLUMNS})
+    out["id"] = lk["id"].map(_numeric_id).astype("int64")
+    out.index = pd.Index(lk["hl_link"].astype(float).astype("int64"), name="lake_id")
+    out = out[~out.index.duplicated(keep="first")].dropna().sort_index()
+    return out[["ifd", "LkArea", "LkMxE", "OrificeA", "OrificeC", "OrificeE", "WeirC", "WeirE", "WeirL", "id"]]
+
+
+def waterbody_connections(df, waterbodies_df):
+    """{flowpath id: lake id} for every flowpath whose `waterbody` attribute (rl_NHDWaterbodyComID, possibly a
+    comma-separated list) names a lake of the table (preprocess_waterbodies :483-515).  When a flowpath lists several
+    known lakes the last one wins, as the reference's merge + to_dict does."""
+    known = set(int(x) for x in waterbodies_df.index)
+    out = {}
+    col = df["waterbody"] if "waterbody" in df.columns else pd.Series(dtype=object)
+    for key, val in col.dropna().items():
+        for tok in str(val).split(","):
+            tok = tok.strip()
+            if not tok:
+                continue
+            try:
+                lake = int(float(tok))
+            except ValueError:
+                continue
+            if lake in known:
+                out[int(key)] = lake
+    return out
+
+
+def drop_inconsistent_lakes(df, waterbodies_df, wbody_conn):
+    """Lakes whose flowpaths, collapsed into one node, would drain to more than one downstream node are not simulated as
+    reservoirs -- their flowpaths stay ordinary Muskingum-Cunge segments (HYFeaturesNetwork.bandaid :819-849: the
+    hydrofabric misses some of the flowpaths under such a lake).  Returns (waterbodies_df, wbody_conn) without them."""
+    index = set(int(k) for k in df.index)
+    outlets = {}
+    for key, down in df["downstream"].items():
+        key, down = int(key), int(down)
+        src = wbody_conn.get(key, key)
+        dst = wbody_conn.get(down, down) if down in index else down
+        if src != dst and key in wbody_conn:
+            outlets.setdefault(src, set()).add(dst)
+    bad = sorted(lake for lake, dsts in outlets.items() if len(dsts) > 1)
+    if not bad:
+        return waterbodies_df, dict(wbody_conn)
+    keep = waterbodies_df.drop(index=[b for b in bad if b in waterbodies_df.index])
+    return keep, {k: v for k, v in wbody_conn.items() if v not in set(bad)}

@@ -20,6 +20,7 @@ Writes
                           (src/troute-network/troute/network/reservoirs/test/test_compute_kernel.py:28-110,
                            :376-505, :508-637, :640-949)
   simple_da_kat.json      nudging known answer (src/troute-routing/troute/routing/test_compute.py:33-42)
+  lowercolorado_v4_lakes.npz  the same network with its 19 level-pool reservoirs collapsed to nodes by the reference's graph code
   lowercolorado_v4.npz    LowerColorado_TX NextGen hydrofabric (test/LowerColorado_TX_v4/domain/*.gpkg): ids, downstream
                           ids, channel parameters, 49 h of lateral inflow (channel_forcing/*.csv) and the reach lists
                           the reference's own nhd_network.dfs_decomposition yields for it (BASELINE config 0)
@@ -252,9 +253,62 @@ def lowercolorado_v4():
                 longest_reach=max(len(r) for r in reaches))
 
 
+def lowercolorado_v4_lakes():
+    """The same hydrofabric with its level-pool reservoirs broken out (break_network_at_waterbodies: True): lake table and
+    flowpath -> lake map read by troute_b200.hyfeatures (sqlite3), then the REFERENCE's own graph code collapses every
+    lake into one node and cuts the reaches at lakes and junctions: nhd_network.replace_waterbodies_connections
+    (HYFeaturesNetwork.py:520-524) -> reverse_network -> reachable_network ->
+    dfs_decomposition(split_at_waterbodies_and_junctions)  (AbstractNetwork.py:241-257 with break segments = lake ids)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(OUT)), "t-route_b200"))
+    from functools import partial
+    from troute_b200 import hyfeatures as hy
+    if "toolz" not in sys.modules:
+        tz = types.ModuleType("toolz")
+        tz.pluck = lambda ind, seqs: (s_[ind] for s_ in seqs)
+        sys.modules["toolz"] = tz
+    nn = _load(f"{REF}/src/troute-network/troute/nhd_network.py", "ref_nhd_network")
+    gpkg = f"{REF}/test/LowerColorado_TX_v4/domain/LowerColorado_NGEN_v201.gpkg"
+    df = hy.read_flowpaths(gpkg)
+    wb = hy.read_lakes(gpkg)
+    wbody_conn = hy.waterbody_connections(df, wb)
+    wb, wbody_conn = hy.drop_inconsistent_lakes(df, wb, wbody_conn)
+    terminal_codes = {0} | set(df[~df["downstream"].isin(df.index)]["downstream"].values.tolist())
+    conn = nn.extract_connections(df, "downstream", terminal_codes=terminal_codes)
+    new_conn, link_lake = nn.replace_waterbodies_connections(conn, wbody_conn)
+    new_conn = {int(k): [int(x) for x in v] for k, v in new_conn.items()}
+    rconn = nn.reverse_network(new_conn)
+    indep = nn.reachable_network(rconn)
+    lakes = set(wbody_conn.values())
+    reaches, tw_of_reach = [], []
+    for tw, net in indep.items():
+        for r in nn.dfs_decomposition(net, partial(nn.split_at_waterbodies_and_junctions, lakes, net)):
+            reaches.append([int(x) for x in r]); tw_of_reach.append(int(tw))
+    # Where one lake drains straight into another, replace_waterbodies_connections leaves the downstream lake's entry
+    # flowpath as the outlet of the upstream lake although that flowpath is no longer a key of the graph
+    # (reservoir_shore only excludes the lake's OWN flowpaths): reverse_network then makes it a node without a downstream
+    # neighbour and the reference routes it as a one-segment tail-water.  The fixture keeps what the reference does.
+    nodes = np.asarray(sorted(set(new_conn) | {x for v in new_conn.values() for x in v}), dtype=np.int64)
+    down = np.asarray([new_conn[int(k)][0] if new_conn.get(int(k)) else -1 for k in nodes], dtype=np.int64)
+    assert all(len(v) <= 1 for v in new_conn.values())
+    np.savez_compressed(
+        f"{OUT}/lowercolorado_v4_lakes.npz",
+        nodes=nodes, downstream=down,
+        reach_len=np.asarray([len(r) for r in reaches], dtype=np.int64),
+        reach_ids=np.asarray([x for r in reaches for x in r], dtype=np.int64),
+        reach_tw=np.asarray(tw_of_reach, dtype=np.int64),
+        wbody_seg=np.asarray(sorted(wbody_conn), dtype=np.int64),
+        wbody_lake=np.asarray([wbody_conn[k] for k in sorted(wbody_conn)], dtype=np.int64),
+        lake_ids=wb.index.values.astype(np.int64), lake_cols=np.array(wb.columns.tolist()), lake_table=wb.values.astype(np.float64),
+        link_lake_lake=np.asarray(sorted(link_lake), dtype=np.int64),
+        link_lake_seg=np.asarray([link_lake[k] for k in sorted(link_lake)], dtype=np.int64))
+    return dict(nodes=len(nodes), lakes=len(wb), lake_flowpaths=len(wbody_conn), reaches=len(reaches),
+                lake_reaches=sum(1 for r in reaches if set(r) & lakes))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lowercolorado":
         print("LowerColorado v4:", lowercolorado_v4())
+        print("LowerColorado v4 with lakes:", lowercolorado_v4_lakes())
         sys.exit(0)
     k = mc_demo_kat()
     print("mc demo KAT:", k["single"]["expected"])

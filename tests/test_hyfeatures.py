@@ -51,3 +51,37 @@ def test_read_channel_forcing(tmp_path):
     assert q.loc[2].tolist() == [0.0, 2.0] and q.loc[4].tolist() == [0.0, 0.0] and q.loc[3].tolist() == [1.5, 1.0]
     with pytest.raises(FileNotFoundError):
         hy.read_channel_forcing(str(tmp_path / "nothing"))
+
+
+def _add_lakes(path):
+    """two lakes: lake 900 covers flowpaths 4 and 3 (drains to 1: consistent), lake 901 covers 5 and 2 -- 5 drains into
+    lake 900, 2 drains to flowpath 1: two different downstream nodes, the hydrofabric defect bandaid() drops"""
+    con = sqlite3.connect(path)
+    con.execute("CREATE TABLE lakes (fid INTEGER, geom BLOB, id TEXT, toid TEXT, hl_id REAL, hl_reference TEXT, hl_link TEXT,"
+                " hl_uri TEXT, Dam_Length REAL, ifd REAL, LkArea REAL, LkMxE REAL, OrificeA REAL, OrificeC REAL,"
+                " OrificeE REAL, time REAL, WeirC REAL, WeirE REAL, WeirL REAL)")
+    rows = [(1, "nex-3", "wb-3", "900", 0.9, 4.5, 120.0, 1.0, 0.1, 100.0, 0.4, 118.0, 10.0),
+            (2, "nex-2", "wb-2", "901.0", 0.9, 2.5, 220.0, 1.0, 0.1, 200.0, 0.4, 218.0, 10.0),
+            (3, "nex-2", "wb-2", "901.0", 0.9, 2.5, 220.0, 1.0, 0.1, 200.0, 0.4, 218.0, 10.0),      # duplicate row
+            (4, "nex-9", "wb-9", "902", 0.9, None, 320.0, 1.0, 0.1, 300.0, 0.4, 318.0, 10.0)]        # missing parameter
+    for fid, nid, toid, link, ifd, area, mxe, oa, oc, oe, wc, we, wl in rows:
+        con.execute("INSERT INTO lakes VALUES (?, NULL, ?, ?, 1, 'WBOut', ?, 'x', 10.0, ?, ?, ?, ?, ?, ?, 0, ?, ?, ?)",
+                    (fid, nid, toid, link, ifd, area, mxe, oa, oc, oe, wc, we, wl))
+    for k, lake in ((4, "900"), (3, "900"), (5, "901,555"), (2, "901")):
+        con.execute("UPDATE flowpath_attributes SET rl_NHDWaterbodyComID = ? WHERE id = ?", (lake, f"wb-{k}"))
+    con.commit(); con.close()
+
+
+def test_read_lakes_and_waterbody_connections(tmp_path):
+    g = str(tmp_path / "toy.gpkg")
+    _make_gpkg(g)
+    _add_lakes(g)
+    df = hy.read_flowpaths(g)
+    wb = hy.read_lakes(g)
+    assert wb.index.tolist() == [900, 901] and wb.index.name == "lake_id"          # duplicate and incomplete rows dropped
+    assert wb.columns.tolist() == ["ifd", "LkArea", "LkMxE", "OrificeA", "OrificeC", "OrificeE", "WeirC", "WeirE", "WeirL", "id"]
+    assert wb.loc[900, "LkArea"] == 4.5 and wb.loc[901, "WeirE"] == 218.0 and wb.loc[900, "id"] == 3
+    wc = hy.waterbody_connections(df, wb)
+    assert wc == {2: 901, 3: 900, 4: 900, 5: 901}                                  # 555 is not a lake of the table
+    wb2, wc2 = hy.drop_inconsistent_lakes(df, wb, wc)
+    assert wb2.index.tolist() == [900] and wc2 == {3: 900, 4: 900}                 # lake 901 would have two outlets

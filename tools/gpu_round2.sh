@@ -11,7 +11,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export TRT_TEST_STRICT=1
 bash tools/gpu_round.sh "diffusive open"
-timeout 900 python -m pytest tests/test_restart_continuity.py tests/test_route_windows.py tests/test_trip_order.py tests/test_gpu_parity.py -m gpu -k 'restart or windows or trip or warp_resync' -q -rA --tb=long \
+timeout 900 python -m pytest tests/test_restart_continuity.py tests/test_route_windows.py tests/test_lowercolorado_lakes.py tests/test_trip_order.py tests/test_gpu_parity.py -m gpu -k 'restart or windows or reservoirs or trip or warp_resync' -q -rA --tb=long \
     > gpurun_out/pytest_first_light.log 2>&1; echo "first-light tests rc=$?" >> gpurun_out/box.txt
 
 # the Muskingum-Cunge parity suite once more with the warp re-synchronisation switched on for every network
