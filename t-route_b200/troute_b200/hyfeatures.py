@@ -4,8 +4,9 @@ The reference reads the GeoPackage with geopandas/fiona (troute/HYFeaturesNetwor
 re-indexes it in preprocess_network (:369-444).  A GeoPackage is an SQLite file, so the two attribute tables the
 routing path needs can be read with `sqlite3` -- no geometry, no GDAL.  This covers the MC-only plumbing configuration
 (BASELINE config 0: test/LowerColorado_TX_v4) and its level-pool reservoirs (the `lakes` layer: read_lakes,
-waterbody_connections, drop_inconsistent_lakes -- what preprocess_waterbodies :456-526 and bandaid :819-856 derive);
-gages / coastal boundaries are not read here.
+waterbody_connections, drop_inconsistent_lakes -- what preprocess_waterbodies :456-526 and bandaid :819-856 derive) and
+the surveyed cross sections of a diffusive domain (read_topobathy, complete_topobathy -- AbstractRouting.py:57-82, :390-428,
+:503-526; parquet through pandas / pyarrow); gages / coastal boundaries are not read here.
 """
 import glob
 import os
@@ -142,3 +143,48 @@ def drop_inconsistent_lakes(df, waterbodies_df, wbody_conn):
         return waterbodies_df, dict(wbody_conn)
     keep = waterbodies_df.drop(index=[b for b in bad if b in waterbodies_df.index])
     return keep, {k: v for k, v in wbody_conn.items() if v not in set(bad)}
+
+
+# ---- surveyed ("natural") cross sections of a diffusive domain ------------------------------------------------------
+def read_topobathy(parquet_path, links):
+    """Cross-section vertices of the given flowpaths from a hydrofabric cross-section table: rows (relative_dist, Z,
+    roughness, cs_id) indexed by the numeric flowpath id, incomplete rows dropped (AbstractRouting.read_parquet :57-82 and
+    the index handling of :396-400)."""
+    want = ["wb-" + str(int(s)) for s in links]
+    df = pd.read_parquet(parquet_path, columns=["hy_id", "relative_dist", "Z", "roughness", "cs_id"],
+                         filters=[("hy_id", "in", want)]).dropna()
+    df["hy_id"] = df["hy_id"].map(lambda x: int(str(x).split("-")[-1]))
+    return df.set_index("hy_id")
+
+
+def complete_topobathy(topobathy_df, links, dataframe):
+    """One cross section per flowpath of the domain (AbstractRouting.py:404-426, _fill_in_missing_topo_data :503-526).
+
+    A flowpath without data borrows the most downstream section (largest cs_id, relabelled 1) of the nearest flowpath
+    upstream of it ON THE SAME MAINSTEM that has data; flowpaths for which that fails are returned as `bad_links` -- the
+    domain builder ends the diffusive domain below them.  Where a flowpath has several sections the one with the smallest
+    cs_id is kept.  `dataframe`: flowpath table indexed by id with `downstream` and `mainstem` columns (read_flowpaths)."""
+    have = set(int(x) for x in topobathy_df.index.unique())
+    up_on_mainstem = {}
+    for key, (down, stem) in dataframe[["downstream", "mainstem"]].iterrows():
+        up_on_mainstem.setdefault((int(down), stem), []).append(int(key))
+    pieces, bad = [topobathy_df.reset_index()], []
+    for key in sorted(set(int(x) for x in links) - have):
+        stem = dataframe.loc[key, "mainstem"]
+        donor, cur, seen = None, key, set()
+        while donor is None and (cur, stem) in up_on_mainstem and cur not in seen:
+            seen.add(cur)
+            ups = up_on_mainstem[(cur, stem)]
+            donor = next((u for u in ups if u in have), None)
+            cur = ups[0]
+        if donor is None:
+            bad.append(key)
+            continue
+        rows = topobathy_df.loc[[donor]].reset_index()
+        rows = rows[rows["cs_id"] == rows["cs_id"].max()].copy()
+        rows["cs_id"] = 1.0
+        rows["hy_id"] = key
+        pieces.append(rows)
+    df = pd.concat(pieces, ignore_index=True)
+    df = df[df["cs_id"] == df.groupby("hy_id")["cs_id"].transform("min")]
+    return df.set_index("hy_id"), bad

@@ -3,7 +3,7 @@ what is left for the Muskingum-Cunge engine.  Mirror of MCwithDiffusive.update_r
 (/root/reference/src/troute-network/troute/AbstractRouting.py:209-328) on plain dicts and one DataFrame; the reference
 version lives in the hydrofabric classes (xarray / geopandas), this one only needs the connection dicts.
 
-    build_diffusive_network_data(diffusive_domain, connections, dataframe, waterbody_ids=())
+    build_diffusive_network_data(diffusive_domain, connections, dataframe, waterbody_ids=(), bad_topobathy_links=())
         -> (diffusive_network_data, dataframe_mc, connections_mc)
 
 `diffusive_domain` is the content of the domain file (:14-35): {tailwater id: {"headwater": [ids ...], ...}}.  A headwater
@@ -33,7 +33,9 @@ def _upstream_closure(rconn, source, targets):
     return seen
 
 
-def build_diffusive_network_data(diffusive_domain, connections, dataframe, waterbody_ids=()):
+def build_diffusive_network_data(diffusive_domain, connections, dataframe, waterbody_ids=(), bad_topobathy_links=()):
+    """`bad_topobathy_links`: segments of the domain for which no surveyed cross section can be found (hyfeatures.
+    complete_topobathy); the reference stops the upstream walk at them and leaves them to Muskingum-Cunge (:258-264)."""
     connections = {k: list(v) for k, v in connections.items()}
     rconn0 = {k: [] for k in connections}
     for k, dsts in connections.items():
@@ -41,13 +43,14 @@ def build_diffusive_network_data(diffusive_domain, connections, dataframe, water
             rconn0.setdefault(d, []).append(k)
     wbody_ids = list(waterbody_ids)
     outlet_ids = list(chain.from_iterable(connections.get(w, []) for w in wbody_ids))
-    excluded = set(wbody_ids) | set(outlet_ids)
+    bad = list(bad_topobathy_links)
+    excluded = set(wbody_ids) | set(outlet_ids) | set(bad)
     out = {}
     for tw, spec in diffusive_domain.items():
         heads = list(spec["headwater"] if isinstance(spec, dict) else spec)
         boundary_links = []
         if 999999 in heads:
-            targets = [h for h in heads if h != 999999] + wbody_ids
+            targets = [h for h in heads if h != 999999] + wbody_ids + bad
             links = _upstream_closure(rconn0, tw, targets)
         else:
             # single mainstem between a given head and the tailwater

@@ -305,10 +305,38 @@ def lowercolorado_v4_lakes():
                 lake_reaches=sum(1 for r in reaches if set(r) & lakes))
 
 
+def lowercolorado_v4_topobathy():
+    """Surveyed cross sections of the coastal diffusive domain of the shipped hybrid configuration
+    (test_AnA_V4_HYFeature.yaml:81-88: use_natl_xsections True, topobathy_domain domain/troute_test.parquet, domain file
+    domain/coastal_domain_tw.yaml): read and completed by troute_b200.hyfeatures (read_topobathy, complete_topobathy) from
+    the reference's parquet; the table after completion and the flowpaths without any usable section are stored."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(OUT)), "t-route_b200"))
+    sys.path.insert(0, os.path.dirname(OUT))
+    from troute_b200 import hyfeatures as hy
+    from troute_b200.routing import diffusive_domain
+    import test_lowercolorado_hybrid as TH
+    base = f"{REF}/test/LowerColorado_TX_v4"
+    df = hy.read_flowpaths(f"{base}/domain/LowerColorado_NGEN_v201.gpkg")
+    conn = hy.connections(df)
+    dnd, _, _ = diffusive_domain.build_diffusive_network_data({TH.TW: {"headwater": list(TH.HEADS)}}, conn, df)
+    links = dnd[TH.TW]["mainstem_segs"]
+    raw = hy.read_topobathy(f"{base}/domain/troute_test.parquet", links)
+    full, bad = hy.complete_topobathy(raw, links, df)
+    np.savez_compressed(
+        f"{OUT}/lowercolorado_v4_topobathy.npz", hy_id=full.index.values.astype(np.int64),
+        relative_dist=full["relative_dist"].values.astype(np.float64), Z=full["Z"].values.astype(np.float64),
+        roughness=full["roughness"].values.astype(np.float64), cs_id=full["cs_id"].values.astype(np.float64),
+        bad_links=np.asarray(sorted(bad), dtype=np.int64), mainstem=df["mainstem"].reindex(links).values.astype(np.float64),
+        links=np.asarray(links, dtype=np.int64))
+    return dict(domain_links=len(links), with_data=int(raw.index.nunique()), after_fill=int(full.index.nunique()),
+                bad=len(bad), rows=len(full), max_vertices=int(full.groupby(level=0).size().max()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "lowercolorado":
         print("LowerColorado v4:", lowercolorado_v4())
         print("LowerColorado v4 with lakes:", lowercolorado_v4_lakes())
+        print("LowerColorado v4 topobathy:", lowercolorado_v4_topobathy())
         sys.exit(0)
     k = mc_demo_kat()
     print("mc demo KAT:", k["single"]["expected"])
@@ -321,3 +349,5 @@ if __name__ == "__main__":
     print("graph: reaches", {k: len(v) for k, v in g["fixture"]["reaches_bytw"].items()},
           "forest tw", len(g["forest300"]["reaches_bytw"]))
     print("LowerColorado v4:", lowercolorado_v4())
+    print("LowerColorado v4 with lakes:", lowercolorado_v4_lakes())
+    print("LowerColorado v4 topobathy:", lowercolorado_v4_topobathy())

@@ -85,3 +85,34 @@ def test_read_lakes_and_waterbody_connections(tmp_path):
     assert wc == {2: 901, 3: 900, 4: 900, 5: 901}                                  # 555 is not a lake of the table
     wb2, wc2 = hy.drop_inconsistent_lakes(df, wb, wc)
     assert wb2.index.tolist() == [900] and wc2 == {3: 900, 4: 900}                 # lake 901 would have two outlets
+
+
+def test_topobathy_read_and_completion(tmp_path):
+    """read_topobathy + complete_topobathy on a hand-made cross-section table: 5 -> 3 -> 1 is mainstem 77 (2 and 4 are side
+    arms on other mainstems).  1 has no section and borrows the most downstream one (largest cs_id) of 3; 4 has nothing
+    upstream on its mainstem -> bad link; 5 has two sections, the one with the smaller cs_id is kept; incomplete rows are
+    dropped on reading."""
+    import pandas as pd
+    df = pd.DataFrame({"downstream": [1000000001, 1, 1, 3, 3], "mainstem": [77.0, 12.0, 77.0, 13.0, 77.0]},
+                      index=pd.Index([1, 2, 3, 4, 5], name="key"))
+    rows = []
+    for hy_id, cs, pts in (("wb-3", 1.0, 3), ("wb-3", 2.0, 4), ("wb-5", 4.0, 3), ("wb-5", 2.0, 5), ("wb-2", 1.0, 3), ("wb-9", 1.0, 3)):
+        for k in range(pts):
+            rows.append(dict(hy_id=hy_id, cs_id=cs, pt_id=float(k + 1), X=0.0, Y=0.0, Z=100.0 + cs - 0.5 * min(k, pts - 1 - k),
+                             Z_source="x", roughness=0.05 + 0.01 * cs, relative_dist=10.0 * k, pt_measure=0.0))
+    rows.append(dict(hy_id="wb-3", cs_id=1.0, pt_id=9.0, X=0.0, Y=0.0, Z=None, Z_source="x", roughness=0.06, relative_dist=99.0,
+                     pt_measure=0.0))                                               # incomplete: dropped
+    path = str(tmp_path / "xs.parquet")
+    pd.DataFrame(rows).to_parquet(path)
+    links = [1, 3, 4, 5]
+    tb = hy.read_topobathy(path, links)
+    assert sorted(tb.index.unique().tolist()) == [3, 5] and len(tb) == 3 + 4 + 3 + 5          # wb-2 / wb-9 not asked for
+    assert tb.columns.tolist() == ["relative_dist", "Z", "roughness", "cs_id"]
+    full, bad = hy.complete_topobathy(tb, links, df)
+    assert bad == [4]
+    assert sorted(full.index.unique().tolist()) == [1, 3, 5]
+    assert len(full.loc[3]) == 3 and (full.loc[3, "cs_id"] == 1.0).all()                      # smallest cs_id of 3
+    assert len(full.loc[5]) == 5 and (full.loc[5, "cs_id"] == 2.0).all()                      # smallest cs_id of 5
+    borrowed = full.loc[1]
+    assert len(borrowed) == 4 and (borrowed["cs_id"] == 1.0).all()                            # section 2 of flowpath 3, relabelled
+    assert borrowed["roughness"].iloc[0] == pytest.approx(0.07) and borrowed["relative_dist"].tolist() == [0.0, 10.0, 20.0, 30.0]

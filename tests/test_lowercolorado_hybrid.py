@@ -5,6 +5,7 @@ channel parameters (the `MCwithDiffusive` routing type, hybrid without topobathy
 
 CPU: the domain builder, the packer, the oracle and the host build of the product's solver source on the real domain.
 GPU (test_zz_gpu_diffusive.py imports this module): the same through compute_diffusive_routing on the device."""
+import os
 from datetime import datetime
 
 import numpy as np
@@ -176,3 +177,64 @@ def test_nwm_route_chains_both_halves(oracle, monkeypatch):
     assert seg_ids[keep].tolist() == dw[0].tolist() and np.array_equal(dat[keep][:, 3:], dw[1], equal_nan=True)
     # together the two halves cover every flowpath of the hydrofabric exactly once
     assert sorted(mc[0].tolist() + dw[0].tolist()) == c["ids"].tolist()
+
+
+# ---- the shipped hybrid configuration: surveyed cross sections from the hydrofabric's cross-section table ---------------
+def natural_inputs(oracle):
+    """The coastal domain the way test_AnA_V4_HYFeature.yaml runs it (use_natl_xsections: True, topobathy_domain:
+    domain/troute_test.parquet): the cross-section table after troute_b200.hyfeatures.complete_topobathy (fixture
+    tests/golden/lowercolorado_v4_topobathy.npz), the domain rebuilt below the flowpaths without any usable section
+    (AbstractRouting.py:256-264), Muskingum-Cunge results of the whole network as junction inflows."""
+    from troute_b200.routing import diffusive_domain
+    z = np.load(os.path.join(LC.GOLD, "lowercolorado_v4_topobathy.npz"))
+    topo = pd.DataFrame({"relative_dist": z["relative_dist"], "Z": z["Z"], "roughness": z["roughness"], "cs_id": z["cs_id"]},
+                        index=pd.Index(z["hy_id"], name="hy_id"))
+    bad = z["bad_links"].tolist()
+    c = LC._load()
+    ids = c["ids"]
+    param_df = pd.DataFrame(c["params"].astype(np.float64), index=pd.Index(ids.tolist()), columns=c["cols"])
+    dnd, df_mc, conn_mc = diffusive_domain.build_diffusive_network_data({TW: {"headwater": list(HEADS)}}, c["connections"],
+                                                                        param_df, bad_topobathy_links=bad)
+    mc = LC._oracle_call(oracle, c, True)
+    fvd = mc[1].reshape(ids.shape[0], LC.NTS, 3)[:, :NTS, :].reshape(ids.shape[0], -1)
+    results = [(ids.copy(), fvd.astype(np.float32), 0)]
+    q0 = pd.DataFrame(np.full((ids.shape[0], 3), 0.5), index=pd.Index(ids.tolist()), columns=["qu0", "qd0", "h0"])
+    qlats = pd.DataFrame(c["qlat"].astype(np.float64), index=pd.Index(ids.tolist()))
+    return c, dnd, results, q0, qlats, topo, bad, z
+
+
+def pack_natural(dnd, results, q0, qlats, topo):
+    from troute_b200.routing import diffusive_utils
+    net = dnd[TW]
+    r = results[0]
+    x = np.isin(r[0], net["tributary_segments"])
+    ji = pd.DataFrame(r[1][x, ::3], index=r[0][x])
+    dq = qlats.copy(); dq.columns = range(dq.shape[1])
+    return diffusive_utils.diffusive_input_data_v02(
+        TW, net["connections"], net["rconn"], net["reaches"], net["mainstem_segs"], net["tributary_segments"], None,
+        net["param_df"], dq, q0, ji, 12, datetime(2023, 4, 2), NTS, 300.0, pd.DataFrame(), topo.loc[net["mainstem_segs"]],
+        pd.DataFrame(), None, None, pd.DataFrame(), pd.DataFrame())
+
+
+def test_shipped_hybrid_configuration_with_surveyed_sections(oracle):
+    from oracle import diffusive as od
+    od.build()
+    c, dnd, results, q0, qlats, topo, bad, z = natural_inputs(oracle)
+    net = dnd[TW]
+    main = net["mainstem_segs"]
+    assert len(z["links"]) == 787 and len(bad) == 704                      # the cross-section table covers the lowest 83 flowpaths
+    assert len(main) == 83 and set(main) <= set(topo.index) and not set(main) & set(bad)
+    assert TW in main and set(net["tributary_segments"]) & set(bad)        # the domain now ends where the sections end
+    ins = pack_natural(dnd, results, q0, qlats, topo)
+    assert ins["mxnbathy_g"] == 500 and ins["nrch_g"] == len(net["reaches"])
+    sizes = ins["size_bathy_g"]
+    assert sizes.max() == 500 and (sizes[sizes > 0] >= 25).all()
+    ref = od.compute_diffusive(ins, od.POW_DET)
+    got = HD.replica_compute_diffusive(ins)
+    for name, a, b in zip(("q_ev_g", "elv_ev_g", "depth_ev_g"), ref, got):
+        HD.assert_bits64(b, a, name)
+    from troute_b200.routing import diffusive_utils
+    ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref[0], ref[2])
+    keep = np.isin(ids, main)
+    q, depth = dat[keep][:, 3::3], dat[keep][:, 5::3]
+    assert np.isfinite(q).all() and np.isfinite(depth).all() and (depth > 0).all() and q.max() < 1000.0

@@ -138,6 +138,26 @@ def test_compute_diffusive_routing_on_gpu(gpu, od):
         assert np.array_equal(dat[keep][:, 3:], tup[1], equal_nan=True)
 
 
+def test_lowercolorado_shipped_hybrid_configuration_on_gpu(gpu, od, oracle):
+    """The shipped hybrid configuration (use_natl_xsections: True): the coastal domain with the surveyed cross sections of the
+    hydrofabric's cross-section table (up to 500 vertices per section), truncated where the sections end, through
+    compute_diffusive_routing on the device == the oracle (surveyed-section table kernels + time loop on real data)."""
+    import datetime
+    import pandas as pd
+    import test_lowercolorado_hybrid as LH
+    from troute_b200.routing import compute, diffusive_utils
+    c, dnd, results, q0, qlats, topo, bad, _ = LH.natural_inputs(oracle)
+    out = compute.compute_diffusive_routing(results, dnd, None, datetime.datetime(2023, 4, 2), 300.0, LH.NTS, q0, qlats, 12,
+                                            pd.DataFrame(), pd.DataFrame(), {}, pd.DataFrame(), topo, None, None,
+                                            pd.DataFrame(), pd.DataFrame())
+    ins = LH.pack_natural(dnd, results, q0, qlats, topo)
+    ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
+    ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
+    keep = ~np.isin(ids, dnd[LH.TW]["tributary_segments"])
+    assert ids[keep].tolist() == out[0][0].tolist()
+    assert np.array_equal(dat[keep][:, 3:], out[0][1], equal_nan=True)
+
+
 def test_lowercolorado_hybrid_domain_on_gpu(gpu, od, oracle):
     """BASELINE configs[3] on the real hydrofabric: the coastal diffusive domain of LowerColorado_TX_v4 (787 mainstem
     segments, 640 reaches, 7 Muskingum-Cunge tributaries) through compute_diffusive_routing on the device == the oracle."""
