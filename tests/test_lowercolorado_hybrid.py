@@ -238,3 +238,24 @@ def test_shipped_hybrid_configuration_with_surveyed_sections(oracle):
     keep = np.isin(ids, main)
     q, depth = dat[keep][:, 3::3], dat[keep][:, 5::3]
     assert np.isfinite(q).all() and np.isfinite(depth).all() and (depth > 0).all() and q.max() < 1000.0
+
+
+def test_compute_diffusive_routing_slices_the_cross_section_table(oracle, monkeypatch):
+    """compute_diffusive_routing (compute.py:1740-1884 mirrored) with the topobathy table of the whole domain: it hands the
+    packer the rows of the mainstem segments of each tailwater (:1786-1796); device call replaced by the host build of the
+    solver source, result == the oracle on the separately packed inputs."""
+    from oracle import diffusive as od
+    from troute_b200.routing import compute, diffusive_utils
+    from troute_b200.routing.fast_reach import diffusive
+    od.build()
+    monkeypatch.setattr(diffusive, "compute_diffusive_batch", lambda L: [HD.replica_compute_diffusive(d) for d in L])
+    c, dnd, results, q0, qlats, topo, bad, _ = natural_inputs(oracle)
+    out = compute.compute_diffusive_routing(results, dnd, None, datetime(2023, 4, 2), 300.0, NTS, q0, qlats, 12,
+                                            pd.DataFrame(), pd.DataFrame(), {}, pd.DataFrame(), topo, None, None,
+                                            pd.DataFrame(), pd.DataFrame())
+    ins = pack_natural(dnd, results, q0, qlats, topo)
+    ref_q, _, ref_depth = od.compute_diffusive(ins, od.POW_DET)
+    ids, dat = diffusive_utils.unpack_output(ins["pynw"], ins["ordered_reaches"], ref_q, ref_depth)
+    keep = ~np.isin(ids, dnd[TW]["tributary_segments"])
+    assert len(out) == 1 and ids[keep].tolist() == out[0][0].tolist()
+    assert np.array_equal(dat[keep][:, 3:], out[0][1], equal_nan=True)
