@@ -160,3 +160,41 @@ def test_gpu_routes_lowercolorado_with_its_reservoirs(oracle, short_ts):
     H.assert_bit_equal(fvd, ref_fvd, "LowerColorado with reservoirs: flowveldepth")
     lake_rows = np.searchsorted(ids, c["lake_ids"])
     H.assert_bit_equal(inflow[lake_rows], ref_inflow[lake_rows], "reservoir inflow")
+
+
+def test_windows_with_reservoirs_equal_one_call(oracle, monkeypatch):
+    """The driver loop on the real network with its reservoirs: four 24-step windows through nwm_routing.route_windows
+    (nwm_route per window, then new_q0 and update_waterbody_water_elevation: a reservoir starts the next window from its last
+    outflow and water elevation) == one 96-step call.  Oracle as the stand-in for the device call."""
+    from troute_b200 import nwm_routing
+    from troute_b200.routing import compute
+
+    def stand_in(*a, **k):
+        k.pop("device", None)
+        return oracle.compute_network_structured(*a, **k)
+    monkeypatch.setitem(compute._compute_func_map, "V02-structured", stand_in)
+    c = _load()
+    _, full, _ = _route(c, True)
+    param_df, qlats, q0 = _frames(c)
+    wb = c["waterbodies_df"][WB_COLS + ["id"]].copy()
+    e = pd.DataFrame()
+    indep = {tw: c["rconn"] for tw in c["reaches_bytw"]}
+    W, n_w = 4, NTS // 4                                            # 24 steps = 2 forcing hours per window (qlat is hourly)
+
+    def route_window(w, q0_df, wb_df, lo_df):
+        ql = qlats.iloc[:, w * (n_w // QTS):(w + 1) * (n_w // QTS)]
+        return nwm_routing.nwm_route(
+            c["connections"], c["rconn"], c["wbody_conn"], c["reaches_bytw"], "by-subnetwork-jit-clustered", "V02-structured",
+            10000, 36, datetime(2023, 4, 2), DT, n_w, QTS, indep, param_df, q0_df, ql, e, e, e, e, e, e, e, e, e, e, e, {},
+            True, False, wb_df, {}, e, False, None, e, None, None, [None, None], e, e)
+
+    per_window, q0_end, wb_end, _ = nwm_routing.route_windows(route_window, range(W), q0, wb, e, DT, n_w)
+    pieces = []
+    for results in per_window:
+        (r,) = results
+        pieces.append(r[1][np.argsort(r[0])])
+    H.assert_bit_equal(np.concatenate(pieces, axis=1), full, "4 windows with reservoirs vs one call")
+    ids = np.sort(per_window[-1][0][0])
+    lake_rows = np.searchsorted(ids, c["lake_ids"])
+    assert np.array_equal(wb_end.loc[c["lake_ids"], "h0"].to_numpy(np.float32), full[lake_rows, -1])      # last water elevation
+    assert np.array_equal(wb_end.loc[c["lake_ids"], "qd0"].to_numpy(np.float32), full[lake_rows, -3])     # last outflow
