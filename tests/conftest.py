@@ -9,7 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "t-route_b200")):
         sys.path.insert(0, p)
 
 FIRST_LIGHT_REASON = ("device code that has not executed on a B200 yet (written after round 1's GPU minutes were spent; "
-                      "verified on the CPU only, DESIGN.md section 9): a failure is reported as xfailed, a pass as XPASS; "
+                      "verified on the CPU only, DESIGN.md sections 5, 6 and 9): a failure is reported as xfailed, a pass as XPASS; "
                       "TRT_TEST_STRICT=1 (tools/gpu_round.sh) turns the mark off")
 
 
