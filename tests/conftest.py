@@ -20,6 +20,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     strict = bool(os.environ.get("TRT_TEST_STRICT"))
+    # first-light tests run after everything else (stable): device code that has never executed must not be able to
+    # disturb the CUDA context of the tests that have a GPU history
+    items.sort(key=lambda item: item.get_closest_marker("first_light") is not None)
     for item in items:
         if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
             # a hung kernel must end the run, not the GPU box's lease (thread method: the process is killed even when the
