@@ -78,9 +78,10 @@ def new_lastobs(run_results, time_increment):
     the start of the window to the last assimilated observation, its value) -- with the times re-based to the start of
     the next window (DataAssimilation.new_lastobs, DataAssimilation.py:1506-1551)."""
     ids = np.concatenate([np.asarray(rr[3][0]) for rr in run_results]) if run_results else np.zeros(0, dtype=np.int64)
-    when = np.concatenate([np.asarray(rr[3][1], dtype=np.float64) for rr in run_results]) if run_results else np.zeros(0)
-    value = np.concatenate([np.asarray(rr[3][2], dtype=np.float64) for rr in run_results]) if run_results else np.zeros(0)
-    return pd.DataFrame({"time_since_lastobs": when - time_increment, "lastobs_discharge": value}, index=ids)
+    # the arithmetic stays in the precision of the kernel's arrays (float32), as in the reference
+    when = np.concatenate([np.asarray(rr[3][1]) for rr in run_results]) if run_results else np.zeros(0, dtype=np.float32)
+    value = np.concatenate([np.asarray(rr[3][2]) for rr in run_results]) if run_results else np.zeros(0, dtype=np.float32)
+    return pd.DataFrame({"time_since_lastobs": when - when.dtype.type(time_increment), "lastobs_discharge": value}, index=ids)
 
 
 def route_windows(route_window, windows, q0, waterbodies_df, lastobs_df, dt, nts):

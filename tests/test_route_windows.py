@@ -110,3 +110,55 @@ def test_windows_equal_one_call_on_the_device(oracle, W):
         assert len(mc_reach._NET_CACHE) == 1
     finally:
         mc_reach.clear_network_cache()
+
+
+REF = "/root/reference/src/troute-network/troute"
+
+
+def _reference_function(path, name, cls=None):
+    """compile ONE function out of a reference module (the modules themselves import xarray / netCDF4, absent here)"""
+    import ast
+    tree = ast.parse(open(path).read())
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"pd": pd, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF), reason="pins the helpers against the reference tree, present only in the build container")
+def test_state_handoff_helpers_equal_the_reference_functions():
+    """new_q0 / new_lastobs / update_waterbody_water_elevation against the reference's own source (AbstractNetwork.new_q0,
+    update_waterbody_water_elevation :177-198; DataAssimilation.new_lastobs :1506-1551), compiled function by function."""
+    import warnings
+    from troute_b200 import nwm_routing
+    rng = np.random.default_rng(5)
+    results = []
+    for k, n in enumerate((7, 4)):
+        ids = np.arange(100 * k + 1, 100 * k + 1 + n)
+        fvd = rng.uniform(0, 5, (n, 9)).astype(np.float32)
+        gi = ids[::2]
+        results.append((ids, fvd, 0, (gi, rng.uniform(0, 900, gi.size).astype(np.float32), rng.uniform(0, 9, gi.size).astype(np.float32))))
+    ref_new_q0 = _reference_function(f"{REF}/AbstractNetwork.py", "new_q0", cls="AbstractNetwork")
+    ref_update = _reference_function(f"{REF}/AbstractNetwork.py", "update_waterbody_water_elevation", cls="AbstractNetwork")
+    ref_lastobs = _reference_function(f"{REF}/DataAssimilation.py", "new_lastobs")
+
+    class Net:
+        pass
+    net = Net()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                               # pandas deprecates the reference's copy=False
+        q0_ref = ref_new_q0(net, results)
+        lo_ref = ref_lastobs(results, 900.0)
+    q0 = nwm_routing.new_q0(results)
+    pd.testing.assert_frame_equal(q0, q0_ref, check_dtype=False)
+    lo = nwm_routing.new_lastobs(results, 900.0)
+    pd.testing.assert_frame_equal(lo, lo_ref, check_dtype=False, check_exact=True)
+    wb = pd.DataFrame({"LkArea": [1.0, 2.0, 3.0], "qd0": [0.0, 0.0, 0.0], "h0": [-1.0, -1.0, -1.0]}, index=[3, 102, 999])
+    net._waterbody_df = wb.copy()
+    net._q0 = q0_ref
+    ref_update(net)
+    got = nwm_routing.update_waterbody_water_elevation(wb.copy(), q0)
+    pd.testing.assert_frame_equal(got, net._waterbody_df, check_dtype=False)
