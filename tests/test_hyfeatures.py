@@ -116,3 +116,57 @@ def test_topobathy_read_and_completion(tmp_path):
     borrowed = full.loc[1]
     assert len(borrowed) == 4 and (borrowed["cs_id"] == 1.0).all()                            # section 2 of flowpath 3, relabelled
     assert borrowed["roughness"].iloc[0] == pytest.approx(0.07) and borrowed["relative_dist"].tolist() == [0.0, 10.0, 20.0, 30.0]
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="pins complete_topobathy against the reference tree, present only in the build container")
+def test_complete_topobathy_equals_the_reference_fill_in_on_the_real_domain():
+    """complete_topobathy against the reference's own _fill_in_missing_topo_data (AbstractRouting.py:503-526, compiled out
+    of its module, which imports xarray) and the selection rules around it (:404-426), on the real LowerColorado hydrofabric
+    and cross-section table: same borrowed sections for the same flowpaths, same list of flowpaths without any."""
+    import ast
+    import pandas as pd
+    path = f"{REF}/src/troute-network/troute/AbstractRouting.py"
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "_fill_in_missing_topo_data")
+    ns = {"pd": pd, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    fill = ns["_fill_in_missing_topo_data"]
+
+    base = f"{REF}/test/LowerColorado_TX_v4/domain"
+    df = hy.read_flowpaths(f"{base}/LowerColorado_NGEN_v201.gpkg")
+    have = pd.read_parquet(f"{base}/troute_test.parquet", columns=["hy_id"]).dropna()["hy_id"].unique()
+    have = sorted(int(str(x).split("-")[-1]) for x in have)
+    have = [k for k in have if k in df.index]
+    # the coastal diffusive domain of the shipped configuration (787 flowpaths, recorded in the fixture) plus every flowpath
+    # with data and what lies within 3 flowpaths downstream of one
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lowercolorado_v4_topobathy.npz")
+    links = set(np.load(gold)["links"].tolist()) | set(have)
+    for k in have:
+        cur = k
+        for _ in range(3):
+            cur = int(df.loc[cur, "downstream"])
+            if cur not in df.index:
+                break
+            links.add(cur)
+    links = sorted(links)
+    raw = hy.read_topobathy(f"{base}/troute_test.parquet", links)
+    full, bad = hy.complete_topobathy(raw, links, df)
+    # the reference, step by step (:404-426)
+    frame = df.reset_index().rename(columns={"index": "key"}).set_index("key")
+    missing = sorted(set(links) - set(raw.index))
+    pieces = [fill(k, frame, raw) for k in missing]
+    new_topo = pd.concat([p for p in pieces if not p.empty]) if any(not p.empty for p in pieces) else pd.DataFrame()
+    ref_bad = sorted(set(missing) - set(new_topo.index))
+    assert len(missing) > 100 and len(new_topo.index.unique()) >= 3 and len(ref_bad) > 100      # all three cases occur
+    assert bad == ref_bad
+    both = pd.concat([raw, new_topo])
+    r = both.reset_index()
+    r = r[r["cs_id"] == r.groupby("hy_id")["cs_id"].transform("min")].set_index("hy_id")
+    cols = ["relative_dist", "Z", "roughness", "cs_id"]
+    a = full[cols].sort_index(kind="stable")
+    b = r[cols].sort_index(kind="stable")
+    assert a.index.tolist() == b.index.tolist()
+    assert np.array_equal(a.to_numpy(), b.to_numpy())

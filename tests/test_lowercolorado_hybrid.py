@@ -259,3 +259,93 @@ def test_compute_diffusive_routing_slices_the_cross_section_table(oracle, monkey
     keep = ~np.isin(ids, dnd[TW]["tributary_segments"])
     assert len(out) == 1 and ids[keep].tolist() == out[0][0].tolist()
     assert np.array_equal(dat[keep][:, 3:], out[0][1], equal_nan=True)
+
+
+REF = "/root/reference/src/troute-network/troute"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="pins the domain builder against the reference tree, present only in the build container")
+@pytest.mark.parametrize("variant", ["walk upstream (999999)", "with flowpaths without sections", "between two ids"])
+def test_domain_builder_equals_the_reference_method(variant):
+    """build_diffusive_network_data against MCwithDiffusive.update_routing_domain itself (AbstractRouting.py:209-328) and
+    the functions it calls (diffusive_domain_by_both_ends_streamid :361-380, organize_independent_networks
+    nhd_network_utilities_v02.py:133-200), compiled one by one out of their modules (which import xarray / netCDF4) and run
+    on a stand-in object, with the reference's own nhd_network for the graph calls: same mainstem, tributaries, connections,
+    reaches, parameter rows and the same Muskingum-Cunge network left over, on the real LowerColorado hydrofabric."""
+    import ast
+    import sys
+    import types
+    import importlib.util
+    from functools import partial
+    from itertools import chain
+    from troute_b200.routing import diffusive_domain
+    if "toolz" not in sys.modules:
+        tz = types.ModuleType("toolz")
+        tz.pluck = lambda ind, seqs: (s_[ind] for s_ in seqs)
+        sys.modules["toolz"] = tz
+    spec = importlib.util.spec_from_file_location("ref_nhd_network_dd", f"{REF}/nhd_network.py")
+    nn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nn)
+
+    def grab(path, name, cls=None):
+        tree = ast.parse(open(path).read())
+        body = tree.body
+        if cls is not None:
+            body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
+        return next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
+
+    class Log:
+        def debug(self, *a, **k):
+            pass
+
+    ns = {"pd": pd, "np": np, "nhd_network": nn, "partial": partial, "chain": chain, "reverse_network": nn.reverse_network,
+          "reachable": nn.reachable, "LOG": Log()}
+    mod = ast.Module(body=[grab(f"{REF}/nhd_network_utilities_v02.py", "organize_independent_networks"),
+                           grab(f"{REF}/AbstractRouting.py", "update_routing_domain", "MCwithDiffusive"),
+                           grab(f"{REF}/AbstractRouting.py", "diffusive_domain_by_both_ends_streamid", "MCwithDiffusive")],
+                     type_ignores=[])
+    exec(compile(mod, "reference", "exec"), ns)
+
+    c = LC._load()
+    ids = c["ids"]
+    param_df = pd.DataFrame(c["params"].astype(np.float64), index=pd.Index(ids.tolist()), columns=c["cols"])
+    bad = []
+    if variant == "walk upstream (999999)":
+        heads = list(HEADS)
+    elif variant == "with flowpaths without sections":
+        heads = list(HEADS)
+        bad = np.load(os.path.join(LC.GOLD, "lowercolorado_v4_topobathy.npz"))["bad_links"].tolist()
+    else:
+        # a single mainstem: from a flowpath 40 links upstream of the tailwater down to it
+        rconn = {}
+        for k, v in c["connections"].items():
+            for d in v:
+                rconn.setdefault(d, []).append(k)
+        cur = TW
+        for _ in range(40):
+            cur = rconn[cur][0]
+        heads = [cur]
+
+    class Stand:
+        pass
+    me = Stand()
+    me.hybrid_params = {"diffusive_domain": "unused"}
+    me._bad_topobathy_links = list(bad)
+    me.topobathy_df = pd.DataFrame()
+    me.diffusive_domain_by_both_ends_streamid = types.MethodType(ns["diffusive_domain_by_both_ends_streamid"], me)
+    ns["read_diffusive_domain"] = lambda f: {TW: {"links": list(heads), "rfc": None, "rpu": None}}
+    conn_ref = {k: list(v) for k, v in c["connections"].items()}
+    df_ref, conn_ref = ns["update_routing_domain"](me, param_df.copy(), conn_ref, pd.DataFrame())
+    ref = me._diffusive_network_data[TW]
+
+    dnd, df_mc, conn_mc = diffusive_domain.build_diffusive_network_data({TW: {"headwater": list(heads)}}, c["connections"],
+                                                                        param_df, bad_topobathy_links=bad)
+    got = dnd[TW]
+    assert sorted(got["mainstem_segs"]) == sorted(ref["mainstem_segs"]) and len(got["mainstem_segs"]) > 30
+    assert sorted(got["tributary_segments"]) == sorted(ref["tributary_segments"])
+    assert got["connections"] == ref["connections"]
+    assert {k: sorted(v) for k, v in got["rconn"].items()} == {k: sorted(v) for k, v in ref["rconn"].items()}
+    assert sorted(map(tuple, got["reaches"])) == sorted(map(tuple, ref["reaches"]))
+    assert sorted(got["param_df"].index.tolist()) == sorted(ref["param_df"].index.tolist())
+    assert got["upstream_boundary_link"] == ref["upstream_boundary_link"]
+    assert conn_mc == conn_ref and sorted(df_mc.index.tolist()) == sorted(df_ref.index.tolist())
