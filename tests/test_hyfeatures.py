@@ -170,3 +170,66 @@ def test_complete_topobathy_equals_the_reference_fill_in_on_the_real_domain():
     b = r[cols].sort_index(kind="stable")
     assert a.index.tolist() == b.index.tolist()
     assert np.array_equal(a.to_numpy(), b.to_numpy())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="pins the lake readers against the reference tree, present only in the build container")
+def test_lake_readers_equal_the_reference_preprocessing_on_the_real_hydrofabric():
+    """read_lakes / waterbody_connections / drop_inconsistent_lakes against HYFeaturesNetwork.preprocess_waterbodies and
+    bandaid themselves (HYFeaturesNetwork.py:456-560, :819-856), compiled out of their module (which imports geopandas /
+    xarray) and run on a stand-in object with the `lakes` and `nexus` layers read through sqlite3: same waterbody table, same
+    flowpath -> lake map; and the collapsed graph / outlet crosswalk the reference derives from them equal the committed
+    fixture tests/golden/lowercolorado_v4_lakes.npz."""
+    import ast
+    import importlib.util
+    import sys
+    import types
+    import pandas as pd
+    src = f"{REF}/src/troute-network/troute"
+    if "toolz" not in sys.modules:
+        tz = types.ModuleType("toolz")
+        tz.pluck = lambda ind, seqs: (s_[ind] for s_ in seqs)
+        sys.modules["toolz"] = tz
+    spec = importlib.util.spec_from_file_location("ref_nhd_network_wb", f"{src}/nhd_network.py")
+    nn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nn)
+    tree = ast.parse(open(f"{src}/HYFeaturesNetwork.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "HYFeaturesNetwork")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("preprocess_waterbodies", "bandaid")]
+    ns = {"pd": pd, "np": np, "replace_waterbodies_connections": nn.replace_waterbodies_connections}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "reference", "exec"), ns)
+
+    gpkg = f"{REF}/test/LowerColorado_TX_v4/domain/LowerColorado_NGEN_v201.gpkg"
+    con = sqlite3.connect(f"file:{gpkg}?mode=ro", uri=True)
+    try:
+        lakes = pd.read_sql_query("SELECT * FROM lakes", con).drop(columns=["geom"])
+        nexus = pd.read_sql_query("SELECT id, toid, hl_uri FROM nexus", con)
+    finally:
+        con.close()
+    df = hy.read_flowpaths(gpkg)
+
+    class Stand:
+        waterbody_dataframe = property(lambda self: self._waterbody_df)
+        dataframe = property(lambda self: self._dataframe)
+        connections = property(lambda self: self._connections)
+        waterbody_connections = property(lambda self: self._waterbody_connections)
+    me = Stand()
+    me._dataframe = df.copy()
+    me._dataframe.index.name = "key"
+    me._connections = {k: list(v) for k, v in hy.connections(df).items()}
+    me.waterbody_parameters = {"break_network_at_waterbodies": True}
+    me.output_parameters = {}
+    me.bandaid = types.MethodType(ns["bandaid"], me)
+    ns["preprocess_waterbodies"](me, lakes, nexus)
+
+    wb = hy.read_lakes(gpkg)
+    wc = hy.waterbody_connections(df, wb)
+    wb, wc = hy.drop_inconsistent_lakes(df, wb, wc)
+    assert me._waterbody_df.index.tolist() == wb.index.tolist() and len(wb) == 19
+    assert np.array_equal(me._waterbody_df[wb.columns.tolist()].to_numpy(dtype=float), wb.to_numpy(dtype=float))
+    assert me._waterbody_connections == wc and len(wc) == 248
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lowercolorado_v4_lakes.npz"))
+    assert dict(zip(z["link_lake_lake"].tolist(), z["link_lake_seg"].tolist())) == {int(k): int(v) for k, v in me._link_lake_crosswalk.items()}
+    fixture = {int(k): ([int(d)] if d >= 0 else []) for k, d in zip(z["nodes"], z["downstream"])}
+    ref_conn = {int(k): [int(x) for x in v] for k, v in me._connections.items()}
+    assert {k: v for k, v in fixture.items() if k in ref_conn} == ref_conn
+    assert all(v == [] for k, v in fixture.items() if k not in ref_conn)                      # the three phantom outlets
