@@ -349,3 +349,60 @@ def test_domain_builder_equals_the_reference_method(variant):
     assert sorted(got["param_df"].index.tolist()) == sorted(ref["param_df"].index.tolist())
     assert got["upstream_boundary_link"] == ref["upstream_boundary_link"]
     assert conn_mc == conn_ref and sorted(df_mc.index.tolist()) == sorted(df_ref.index.tolist())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="pins compute_diffusive_routing against the reference tree, present only in the build container")
+@pytest.mark.parametrize("sections", ["synthetic", "surveyed"])
+def test_compute_diffusive_routing_equals_the_reference_function(oracle, monkeypatch, sections):
+    """troute_b200.routing.compute.compute_diffusive_routing against the reference's own function (compute.py:1740-1884,
+    compiled out of its module, which imports the Cython kernels) running the reference's own packer / unpacker
+    (diffusive_utils_v02.py, importable): with the SAME solver stand-in behind both (the host build of the product's solver
+    source in place of the Fortran call and of the device call) the two return the same tuples on the real coastal domain --
+    junction inflows out of the MC results, cross-section slicing, packing, unpacking, tuple layout."""
+    import ast
+    import importlib.util
+    import sys
+    import types
+    from troute_b200.routing import compute
+    from troute_b200.routing.fast_reach import diffusive
+    root = "/root/reference/src"
+    if "toolz" not in sys.modules:
+        tz = types.ModuleType("toolz")
+        tz.pluck = lambda ind, seqs: (s_[ind] for s_ in seqs)
+        sys.modules["toolz"] = tz
+    saved = {k: sys.modules.get(k) for k in ("troute", "troute.nhd_network")}
+    try:
+        pkg = types.ModuleType("troute"); pkg.__path__ = [root + "/troute-network/troute"]; sys.modules["troute"] = pkg
+        spec = importlib.util.spec_from_file_location("troute.nhd_network", root + "/troute-network/troute/nhd_network.py")
+        nn = importlib.util.module_from_spec(spec); sys.modules["troute.nhd_network"] = nn; spec.loader.exec_module(nn)
+        spec = importlib.util.spec_from_file_location("ref_diffusive_utils_v02_pin", root + "/troute-routing/troute/routing/diffusive_utils_v02.py")
+        du = importlib.util.module_from_spec(spec); spec.loader.exec_module(du)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    tree = ast.parse(open(root + "/troute-routing/troute/routing/compute.py").read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "compute_diffusive_routing")
+    stand_in = types.SimpleNamespace(compute_diffusive=HD.replica_compute_diffusive)
+    ns = {"pd": pd, "np": np, "diff_utils": du, "diffusive": stand_in}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "reference compute.py", "exec"), ns)
+
+    if sections == "synthetic":
+        c, dnd, results, q0, qlats, _, _ = hybrid_inputs(oracle)
+        topo = pd.DataFrame()
+    else:
+        c, dnd, results, q0, qlats, topo, bad, _ = natural_inputs(oracle)
+    e = pd.DataFrame()
+    args = (results, dnd, None, datetime(2023, 4, 2), 300.0, NTS, q0, qlats, 12, e, e, {}, e, topo, None, None, e, e)
+    ref = ns["compute_diffusive_routing"](*args)
+    monkeypatch.setattr(diffusive, "compute_diffusive_batch", lambda L: [HD.replica_compute_diffusive(d) for d in L])
+    got = compute.compute_diffusive_routing(*args)
+    assert len(got) == len(ref) == 1
+    for a, b in zip(got, ref):
+        assert len(a) == len(b) == 10
+        assert np.array_equal(a[0], b[0]) and a[1].shape == b[1].shape and np.array_equal(a[1], b[1], equal_nan=True)
+        assert a[2] == b[2] == 0 and np.array_equal(a[6], b[6]) and a[8].shape == b[8].shape
+        for k in (3, 4, 5, 7, 9):
+            assert len(a[k]) == len(b[k]) and all(np.asarray(x).size == 0 for x in a[k])
