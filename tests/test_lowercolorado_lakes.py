@@ -198,3 +198,58 @@ def test_windows_with_reservoirs_equal_one_call(oracle, monkeypatch):
     lake_rows = np.searchsorted(ids, c["lake_ids"])
     assert np.array_equal(wb_end.loc[c["lake_ids"], "h0"].to_numpy(np.float32), full[lake_rows, -1])      # last water elevation
     assert np.array_equal(wb_end.loc[c["lake_ids"], "qd0"].to_numpy(np.float32), full[lake_rows, -3])     # last outflow
+
+
+REF_COMPUTE = "/root/reference/src/troute-routing/troute/routing/compute.py"
+
+
+def _reference_compute_nhd_routing_v02(kernel):
+    """the reference's compute_nhd_routing_v02 and its module-level helpers, compiled out of compute.py (whose imports need
+    the Cython kernels) with `kernel` registered as the compute function"""
+    import ast
+    import copy
+    import logging
+    import time
+    from collections import defaultdict
+    from datetime import timedelta
+    from functools import partial
+    from itertools import chain
+    tree = ast.parse(open(REF_COMPUTE).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name != "compute_diffusive_routing"]
+    ns = {"pd": pd, "np": np, "time": time, "LOG": logging.getLogger("reference"), "chain": chain, "defaultdict": defaultdict,
+          "partial": partial, "datetime": datetime, "timedelta": timedelta, "copy": copy, "os": os,
+          "_compute_func_map": defaultdict(lambda: kernel, {"V02-structured": kernel})}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "reference compute.py", "exec"), ns)
+    return ns["compute_nhd_routing_v02"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_COMPUTE), reason="pins compute_nhd_routing_v02 against the reference tree, present only in the build container")
+@pytest.mark.parametrize("short_ts", [True, False])
+def test_compute_nhd_routing_v02_equals_the_reference_function(oracle, monkeypatch, short_ts):
+    """The drop-in boundary B1 against the function it replaces: the reference's own compute_nhd_routing_v02
+    (compute.py:507-1738, `serial` branch: one kernel call per tail-water, frames sliced per network) and the mirror (one
+    call for all tail-waters), BOTH with the oracle as the compute kernel, on the real hydrofabric with its 19 reservoirs and
+    4 tail-waters: same segment ids, bit-identical flow / velocity / depth, same reservoir inflow series."""
+    from troute_b200.routing import compute
+
+    def kernel(*a, **k):
+        k.pop("device", None)
+        return oracle.compute_network_structured(*a, **k)
+    monkeypatch.setitem(compute._compute_func_map, "V02-structured", kernel)
+    c = _load()
+    param_df, qlats, q0 = _frames(c)
+    e = pd.DataFrame()
+    indep = {tw: c["rconn"] for tw in c["reaches_bytw"]}
+    wb = c["waterbodies_df"][WB_COLS + ["id"]]
+    ref_fn = _reference_compute_nhd_routing_v02(kernel)
+    ref, _ = ref_fn(c["connections"], c["rconn"], c["wbody_conn"], c["reaches_bytw"], "V02-structured", "serial", 10000, 1,
+                    datetime(2023, 4, 2), DT, NTS, QTS, indep, param_df, q0, qlats, e, e, e, e, e, e, e, e, e, e, e, {},
+                    short_ts, False, wb, {}, e, False, [None, None])
+    assert len(ref) == len(c["reaches_bytw"]) == 4                                   # one tuple per tail-water
+    ids = np.concatenate([r[0] for r in ref])
+    order = np.argsort(ids)
+    got_ids, got_fvd, got_inflow = _route(c, short_ts)
+    assert np.array_equal(ids[order], got_ids)
+    H.assert_bit_equal(got_fvd, np.concatenate([r[1] for r in ref])[order], "mirror vs the reference function: flowveldepth")
+    lake_rows = np.searchsorted(got_ids, c["lake_ids"])
+    H.assert_bit_equal(got_inflow[lake_rows], np.concatenate([r[6] for r in ref])[order][lake_rows], "reservoir inflow")
