@@ -224,8 +224,26 @@ def _reference_compute_nhd_routing_v02(kernel):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_COMPUTE), reason="pins compute_nhd_routing_v02 against the reference tree, present only in the build container")
+def _gage_frames(c, n_gages=25, obs_steps=30, seed=3):
+    """usgs_df (one row per gage segment, one column per routing step, gaps) and lastobs_df as the DA object hands them to
+    nwm_route; gages sit on the last segment of channel reaches (T-Route breaks reaches at gages)"""
+    rng = np.random.default_rng(seed)
+    lakes = set(c["lake_ids"].tolist())
+    cand = [r[-1] for r in c["reaches"] if not (set(r) & lakes)]
+    segs = np.sort(rng.choice(np.asarray(cand, dtype=np.int64), size=n_gages, replace=False))
+    obs = rng.uniform(0.5, 30.0, size=(n_gages, obs_steps))
+    obs[rng.random(obs.shape) < 0.25] = np.nan
+    t0 = datetime(2023, 4, 2)
+    usgs_df = pd.DataFrame(obs, index=segs, columns=pd.date_range(t0, periods=obs_steps, freq="300s"))
+    since = -300.0 * rng.integers(0, 12, n_gages).astype(np.float64)
+    lastobs_df = pd.DataFrame({"time_since_lastobs": since, "lastobs_discharge": rng.uniform(0.5, 30.0, n_gages)}, index=segs)
+    lastobs_df.iloc[::6] = np.nan                                            # gages without a previous observation
+    return usgs_df, lastobs_df
+
+
+@pytest.mark.parametrize("gages", [False, True])
 @pytest.mark.parametrize("short_ts", [True, False])
-def test_compute_nhd_routing_v02_equals_the_reference_function(oracle, monkeypatch, short_ts):
+def test_compute_nhd_routing_v02_equals_the_reference_function(oracle, monkeypatch, short_ts, gages):
     """The drop-in boundary B1 against the function it replaces: the reference's own compute_nhd_routing_v02
     (compute.py:507-1738, `serial` branch: one kernel call per tail-water, frames sliced per network) and the mirror (one
     call for all tail-waters), BOTH with the oracle as the compute kernel, on the real hydrofabric with its 19 reservoirs and
@@ -242,13 +260,30 @@ def test_compute_nhd_routing_v02_equals_the_reference_function(oracle, monkeypat
     indep = {tw: c["rconn"] for tw in c["reaches_bytw"]}
     wb = c["waterbodies_df"][WB_COLS + ["id"]]
     ref_fn = _reference_compute_nhd_routing_v02(kernel)
-    ref, _ = ref_fn(c["connections"], c["rconn"], c["wbody_conn"], c["reaches_bytw"], "V02-structured", "serial", 10000, 1,
-                    datetime(2023, 4, 2), DT, NTS, QTS, indep, param_df, q0, qlats, e, e, e, e, e, e, e, e, e, e, e, {},
-                    short_ts, False, wb, {}, e, False, [None, None])
+    usgs_df, lastobs_df = _gage_frames(c) if gages else (e, e)
+    da = {"da_decay_coefficient": 120.0} if gages else {}
+    args = (c["connections"], c["rconn"], c["wbody_conn"], c["reaches_bytw"], "V02-structured", "serial", 10000, 1,
+            datetime(2023, 4, 2), DT, NTS, QTS, indep, param_df, q0, qlats, usgs_df, lastobs_df, e, e, e, e, e, e, e, e, e, da,
+            short_ts, False, wb, {}, e, False, [None, None])
+    ref, _ = ref_fn(*args)
     assert len(ref) == len(c["reaches_bytw"]) == 4                                   # one tuple per tail-water
     ids = np.concatenate([r[0] for r in ref])
     order = np.argsort(ids)
-    got_ids, got_fvd, got_inflow = _route(c, short_ts)
+    if gages:
+        # streamflow nudging: the mirror prepares the gage arrays for ONE network, the reference per tail-water
+        (r,) = compute.compute_nhd_routing_v02(*(args[:5] + ("by-subnetwork-jit-clustered",) + args[6:]))[0]
+        o2 = np.argsort(r[0])
+        got_ids, got_fvd, got_inflow = r[0][o2], r[1][o2], r[6][o2]
+        plain = _route(c, short_ts)[1]
+        assert not np.array_equal(got_fvd, plain)                                    # the gages change the answer
+        # last-observation state per gage, whatever the grouping into tuples
+        ref_lo = {int(g): (t, v) for rr in ref for g, t, v in zip(rr[3][0], rr[3][1], rr[3][2])}
+        got_lo = {int(g): (t, v) for g, t, v in zip(r[3][0], r[3][1], r[3][2])}
+        assert set(ref_lo) == set(got_lo) == set(usgs_df.index.tolist())
+        for g in ref_lo:
+            assert np.array_equal(np.float32(ref_lo[g]), np.float32(got_lo[g]), equal_nan=True), g
+    else:
+        got_ids, got_fvd, got_inflow = _route(c, short_ts)
     assert np.array_equal(ids[order], got_ids)
     H.assert_bit_equal(got_fvd, np.concatenate([r[1] for r in ref])[order], "mirror vs the reference function: flowveldepth")
     lake_rows = np.searchsorted(got_ids, c["lake_ids"])
