@@ -934,11 +934,31 @@ int trt_sync(trt_network* net)
             }
         }
         if (net->mode >= 2 && net->d_ctrl.p && net->launches > 0) {
-            int ctrl[4] = {0, 0, 0, 0};
+            int ctrl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             CU(cudaMemcpy(ctrl, net->d_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost));
-            if (ctrl[2] != 0)
+            if (ctrl[2] != 0) {
+                // which input never arrived: ctrl[2] = 1 dataflow lane, 2 run-ahead gate (stage in ctrl[5]), 3 marching lane;
+                // ctrl[6..7] = address of the flow-state slot the lane was polling
+                char where[256] = "";
+                unsigned long long addr = 0;
+                memcpy(&addr, ctrl + 6, sizeof(addr));
+                const unsigned long long base = (unsigned long long)(uintptr_t)net->d_S.p;
+                if (ctrl[2] == 2) snprintf(where, sizeof(where), "; the run-ahead gate waited for stage %d", ctrl[5]);
+                else if (addr >= base && net->T >= 0) {
+                    const unsigned long long off = (addr - base) / sizeof(float);
+                    const long long pos = (long long)(off / (3ull * (unsigned long long)(net->T + 1)));
+                    const int t = (int)((off / 3ull) % (unsigned long long)(net->T + 1)), c = (int)(off % 3ull);
+                    if (pos >= 0 && pos < net->n) {
+                        const int64_t r = net->row_of_pos[(size_t)pos];
+                        snprintf(where, sizeof(where), "; a %s lane polled %s of row %lld (kind %d, level %d, %s) at step %d",
+                                 ctrl[2] == 3 ? "marching" : "dataflow", c == 0 ? "q" : (c == 2 ? "depth" : "v"), (long long)r,
+                                 (int)net->kind_of_row[(size_t)r], net->level_of_row[(size_t)r],
+                                 net->imported[(size_t)r] ? "written by a peer shard" : "not imported", t);
+                    }
+                }
                 return fail(TRT_ERR_STATE, "dataflow run aborted: a lane waited > 8 s for an input that never arrived "
-                                           "(peer shard missing, or an unprescribed boundary row)");
+                                           "(peer shard missing, or an unprescribed boundary row)%s", where);
+            }
         }
     }
     return TRT_OK;

@@ -79,7 +79,12 @@ __device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
             if ((++spins & 0x3FFF) == 0) {
                 // ~6 ms of waiting per check; bail out if somebody flagged an error, or after ~8 s on our own
                 if (*reinterpret_cast<volatile int*>(abort_flag) != 0) return __uint_as_float(0x7FC00000u);
-                if (spins > (1u << 24)) { atomicExch(abort_flag, 1); return __uint_as_float(0x7FC00000u); }
+                if (spins > (1u << 24)) {
+                    // the first lane to give up records WHICH slot never arrived (abort_flag = ctrl + 2, address in ctrl[6..7])
+                    if (atomicCAS(abort_flag, 0, 1) == 0)
+                        *reinterpret_cast<volatile unsigned long long*>(abort_flag + 4) = (unsigned long long)p;
+                    return __uint_as_float(0x7FC00000u);
+                }
             }
         } while (v == TRT_SENTINEL);
     }
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
                     __nanosleep(200);
                     if ((++spins & 0x3FFF) == 0) {
                         if (*reinterpret_cast<volatile int*>(sc.abort_flag) != 0) break;
-                        if (spins > (1u << 25)) { atomicExch(sc.abort_flag, 1); break; }
+                        if (spins > (1u << 25)) { if (atomicCAS(sc.abort_flag, 0, 2) == 0) sc.abort_flag[3] = need; break; }
                     }
                 }
             }
@@ -526,7 +531,14 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                 } else if ((++waited & 0xFFF) == 0) {
                     // every 4096 failed polls: somebody flagged an error, or this lane has been starving for seconds
                     if (*reinterpret_cast<volatile int*>(mk.abort_flag) != 0) state = MARCH_DONE;
-                    else if (waited >= (1u << 26)) { atomicExch(mk.abort_flag, 1); state = MARCH_DONE; }
+                    else if (waited >= (1u << 26)) {
+                        if (atomicCAS(mk.abort_flag, 0, 3) == 0) {
+                            const int ti2 = run.short_ts ? t - 1 : t;
+                            *reinterpret_cast<volatile unsigned long long*>(mk.abort_flag + 4) =
+                                (unsigned long long)(run.S + ((size_t)__ldg(net.up_idx + e_cur) * T1 + (size_t)ti2) * 3);
+                        }
+                        state = MARCH_DONE;
+                    }
                 }
             }
             if (state == MARCH_ITER) {

@@ -108,7 +108,7 @@ def compute_nhd_routing_v02(
 
     waterbody_types_df_sub = pd.DataFrame()
     if _nonempty(waterbodies_df):
-        lake_segs = list(waterbodies_df.index.intersection(segs))
+        lake_segs = list(waterbodies_df.index.intersection(segs_all))       # bmi: off-network tail-waters included (:1585-1600)
         waterbodies_df_sub = waterbodies_df.loc[lake_segs, _WB_COLS]
         if _nonempty(waterbody_types_df):
             waterbody_types_df_sub = waterbody_types_df.loc[lake_segs, ["reservoir_type"]]
@@ -118,6 +118,13 @@ def compute_nhd_routing_v02(
 
     param_df_sub = param_df.loc[common_segs, _PARAM_COLS].sort_index()         # :1443-1446
     reaches_list_with_type = _build_reach_type_list(reach_list, wbodies_segs)
+    # The reference slices the forcing with .loc (:1451-1452, :1640-1641): a routed segment without a qlat / q0 row is a
+    # KeyError there, not a segment routed with zeros.  Off-network tail-waters carry no lateral inflow.
+    routed = param_df_sub.index.difference(list(offnetwork_upstreams))
+    for name, df in (("qlats", qlats), ("q0", q0)):
+        missing = routed.difference(df.index) if name == "qlats" else param_df_sub.index.difference(df.index)
+        if len(missing):
+            raise KeyError(f"{list(missing[:10])} not in index of {name} ({len(missing)} routed segments without a row)")
     param_df_sub = param_df_sub.reindex(param_df_sub.index.tolist() + lake_segs).sort_index()   # :1455-1457
     # forcing / state rows follow the parameter index; lake and off-network rows carry no lateral inflow
     qlat_sub = qlats.reindex(param_df_sub.index)

@@ -15,8 +15,10 @@ and its bed elevation from the head of the downstream reach (:10-52).  Reaches a
 order down to the tailwater reach (:887-893), which is the order the solver sweeps them in.
 
 Not mirrored (raise NotImplementedError): the refactored hydrofabric (`refactored_diffusive_domain`), whose crosswalk the
-reference itself no longer fills (:1036-1041), and gage data for diffusive data assimilation (`usgs_df`), which the Fortran
-solver ignores (the DA branch is commented out, diffusive.f90:1283-1306).
+reference itself no longer fills (:1036-1041).  Gage data (`usgs_df`) is packed into `usgs_da_g` / `usgs_da_reach_g` the way
+the reference does (:512-574) although the Fortran solver ignores both (its DA branch is commented out,
+diffusive.f90:1283-1306): compute_diffusive_routing always forwards `usgs_df` (compute.py:1800), so every hybrid run with
+streamflow nudging switched on reaches this function with a non-empty frame.
 """
 import math
 from datetime import timedelta
@@ -91,6 +93,27 @@ def _coastal_boundary(tw, coastal_boundary_depth_df, t0, t0_g, tfin_g):
     return dt_db, 1, n, np.asarray(filled.loc[tw].values, dtype=np.float64)
 
 
+def _gage_arrays(flat, usgs_df, nrch_g, t0, nsteps, dt_da_g, t0_g, tfin_g):
+    """Observed flows per reach at the DA spacing (fp_da_map :512-574): column j of `usgs_da_g` holds the series of the
+    gage on reach j (Fortran reach order), -4444 where there is no observation; `usgs_da_reach_g[j]` = j + 1 marks the reach.
+    When a reach carries several gaged segments the one furthest downstream wins (the reference overwrites in segment order)."""
+    nts_da_g = int((tfin_g - t0_g) * 3600.0 / dt_da_g) + 1
+    usgs_da_g = np.full((nts_da_g, nrch_g), -4444.0)
+    usgs_da_reach_g = np.zeros(nrch_g, dtype="i4")
+    if usgs_df is None or usgs_df.empty:
+        return nts_da_g, usgs_da_g, usgs_da_reach_g
+    step = timedelta(minutes=dt_da_g / 60.0)
+    stamps = pd.date_range(t0, t0 + step * nsteps, freq=step)
+    table = usgs_df.reindex(columns=stamps).fillna(-4444.0)
+    gaged = set(table.index)
+    for j, (_, r) in enumerate(flat):
+        hit = [s for s in r["segments_list"] if s in gaged]
+        if hit:
+            usgs_da_g[:, j] = np.asarray(table.loc[hit[-1]].values, dtype=np.float64)[:nts_da_g]
+            usgs_da_reach_g[j] = j + 1
+    return nts_da_g, usgs_da_g, usgs_da_reach_g
+
+
 def diffusive_input_data_v02(
     tw, connections, rconn, reach_list, mainstem_seg_list, trib_seg_list, diffusive_parameters, param_df, qlat,
     initial_conditions, junction_inflows, qts_subdivisions, t0, nsteps, dt, waterbodies_df, topobathy_bytw, usgs_df,
@@ -99,8 +122,6 @@ def diffusive_input_data_v02(
     if refactored_diffusive_domain:
         raise NotImplementedError("refactored hydrofabric: the reference no longer fills its crosswalk "
                                   "(diffusive_utils_v02.py:1036-1041)")
-    if usgs_df is not None and not usgs_df.empty:
-        raise NotImplementedError("diffusive streamflow DA: the Fortran solver ignores the gage arrays (diffusive.f90:1283-1306)")
     # ---- clocks (:709-738) and solver parameters (:741-753)
     dt_ql_g, dt_ub_g, dt_qtrib_g, dt_da_g, saveinterval = 3600.0, dt, dt, dt, dt
     t0_g = 0.0
@@ -235,8 +256,8 @@ def diffusive_input_data_v02(
         x_bathy_g = np.array([]).reshape(0, 0, 0); z_bathy_g = np.array([]).reshape(0, 0, 0)
         mann_bathy_g = np.array([]).reshape(0, 0, 0); size_bathy_g = np.array([], dtype="i4").reshape(0, 0)
 
-    # ---- gage arrays the solver ignores (:512-574, empty usgs_df), crosswalk placeholders (:1036-1041)
-    nts_da_g = int((tfin_g - t0_g) * 3600.0 / dt_da_g) + 1
+    # ---- gage arrays (:512-574; the solver ignores them), crosswalk placeholders (:1036-1041)
+    nts_da_g, usgs_da_g, usgs_da_reach_g = _gage_arrays(flat, usgs_df, nrch_g, t0, nsteps, dt_da_g, t0_g, tfin_g)
     empty2 = np.array([]).reshape(0, 0)
     return {
         "timestep_ar_g": timestep_ar_g, "nts_ql_g": nts_ql_g, "nts_ub_g": nts_ub_g, "nts_db_g": nts_db_g,
@@ -246,8 +267,8 @@ def diffusive_input_data_v02(
         "dx_ar_g": dx_ar_g, "frnw_col": FRNW_COL, "frnw_g": frnw_g, "qlat_g": qlat_g, "ubcd_g": ubcd_g, "dbcd_g": dbcd_g,
         "qtrib_g": qtrib_g, "paradim": paradim, "para_ar_g": para_ar_g, "mxnbathy_g": mxnbathy_g, "x_bathy_g": x_bathy_g,
         "z_bathy_g": z_bathy_g, "mann_bathy_g": mann_bathy_g, "size_bathy_g": size_bathy_g, "iniq": iniq, "pynw": pynw,
-        "ordered_reaches": ordered_reaches, "usgs_da_g": -4444.0 * np.ones((nts_da_g, nrch_g)),
-        "usgs_da_reach_g": np.zeros(nrch_g, dtype="i4"), "rdx_ar_g": empty2, "cwnrow_g": 0, "cwncol_g": 0,
+        "ordered_reaches": ordered_reaches, "usgs_da_g": usgs_da_g,
+        "usgs_da_reach_g": usgs_da_reach_g, "rdx_ar_g": empty2, "cwnrow_g": 0, "cwncol_g": 0,
         "crosswalk_g": empty2, "z_thalweg_g": empty2,
     }
 

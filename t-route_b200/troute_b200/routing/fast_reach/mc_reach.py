@@ -113,7 +113,10 @@ DEFAULT_OPTIONS = {}          # engine options (trt_set_option) applied to every
 REORDER_MIN_ROWS = 200_000
 
 
-def _fingerprint(reaches_wTypes, data_idx, data_cols, data_values, device):
+def _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
+    """Cache key of a device network: everything flatten_network reads -- the parameter table, the segment ids of every
+    reach in order, the reach types and the upstream list of every reach head (the confluence wiring) -- so that two calls
+    with the same parameters but different connectivity never share a device topology."""
     h = hashlib.blake2b(digest_size=16)
     h.update(np.ascontiguousarray(data_idx).view(np.uint8))
     h.update(np.ascontiguousarray(data_values).view(np.uint8))
@@ -121,10 +124,14 @@ def _fingerprint(reaches_wTypes, data_idx, data_cols, data_values, device):
     nreach = len(reaches_wTypes)
     h.update(repr((nreach, device)).encode())
     if nreach:
-        # reach structure: lengths, types, first/last ids of every reach
-        sig = np.fromiter(chain.from_iterable((len(r), t, r[0], r[-1]) for r, t in reaches_wTypes), dtype=np.int64,
-                          count=4 * nreach)
-        h.update(sig.view(np.uint8))
+        lens = np.fromiter((len(r) for r, _ in reaches_wTypes), dtype=np.int64, count=nreach)
+        types = np.fromiter((t for _, t in reaches_wTypes), dtype=np.int64, count=nreach)
+        segs = np.fromiter(chain.from_iterable(r for r, _ in reaches_wTypes), dtype=np.int64, count=int(lens.sum()))
+        ups = [upstream_connections.get(r[0], ()) for r, _ in reaches_wTypes]
+        up_cnt = np.fromiter((len(u) for u in ups), dtype=np.int64, count=nreach)
+        up_ids = np.fromiter(chain.from_iterable(ups), dtype=np.int64, count=int(up_cnt.sum()))
+        for a in (lens, types, segs, up_cnt, up_ids):
+            h.update(a.view(np.uint8))
     return h.hexdigest()
 
 
@@ -135,7 +142,7 @@ def clear_network_cache():
 
 
 def _get_network(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
-    key = _fingerprint(reaches_wTypes, data_idx, data_cols, data_values, device)
+    key = _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
     entry = _NET_CACHE.get(key)
     if entry is not None:
         _NET_CACHE.move_to_end(key)

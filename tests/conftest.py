@@ -8,28 +8,16 @@ for p in (ROOT, os.path.join(ROOT, "t-route_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-FIRST_LIGHT_REASON = ("device code that has not executed on a B200 yet (written after round 1's GPU minutes were spent; "
-                      "verified on the CPU only, DESIGN.md sections 5, 6 and 9): a failure is reported as xfailed, a pass as XPASS; "
-                      "TRT_TEST_STRICT=1 (tools/gpu_round.sh) turns the mark off")
-
-
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "first_light: GPU test of device code that has never run on a device (see conftest.py)")
 
 
 def pytest_collection_modifyitems(config, items):
-    strict = bool(os.environ.get("TRT_TEST_STRICT"))
-    # first-light tests run after everything else (stable): device code that has never executed must not be able to
-    # disturb the CUDA context of the tests that have a GPU history
-    items.sort(key=lambda item: item.get_closest_marker("first_light") is not None)
     for item in items:
         if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
             # a hung kernel must end the run, not the GPU box's lease (thread method: the process is killed even when the
             # main thread sits inside cudaDeviceSynchronize)
             item.add_marker(pytest.mark.timeout(1200, method="thread"))
-        if item.get_closest_marker("first_light") is not None and not strict:
-            item.add_marker(pytest.mark.xfail(reason=FIRST_LIGHT_REASON, strict=False))
 
 
 @pytest.fixture(scope="session")

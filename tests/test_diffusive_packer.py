@@ -1,6 +1,8 @@
 """troute_b200.routing.diffusive_utils against the reference's own packer: tests/golden/diffusive_inputs.npz holds, for five
 random diffusive domains, the inputs and every array that /root/reference/.../diffusive_utils_v02.py returned for them
-(tests/golden/make_golden_diffusive.py, run in the build container).  Exact equality, including the reach numbering."""
+(tests/golden/make_golden_diffusive.py, run in the build container).  Exact equality, including the reach numbering.
+Case 5 carries a non-empty `usgs_df` (gage observations with gaps): the gage arrays of diffusive DA are packed like the
+reference packs them, although its Fortran ignores them."""
 import datetime
 import os
 
@@ -42,8 +44,12 @@ def rebuild(g, c):
     if p + "coastal" in g:
         v = g[p + "coastal"]
         coastal = pd.DataFrame(v, index=pd.Index([main[0]]), columns=[t0 + datetime.timedelta(hours=h) for h in range(v.shape[1])])
+    usgs = pd.DataFrame()
+    if p + "usgs" in g:
+        v, dt = g[p + "usgs"], float(g[p + "dt"])
+        usgs = pd.DataFrame(v, index=pd.Index(g[p + "usgs_id"]), columns=[t0 + datetime.timedelta(seconds=dt * k) for k in range(v.shape[1])])
     return dict(tw=main[0], connections=connections, rconn=rconn, main=main, tribs=tribs, param_df=param_df, qlat=qlat, ic=ic,
-                ji=ji, topo=topo, coastal=coastal, t0=t0, nsteps=int(g[p + "nsteps"]), dt=float(g[p + "dt"]))
+                ji=ji, topo=topo, coastal=coastal, usgs=usgs, t0=t0, nsteps=int(g[p + "nsteps"]), dt=float(g[p + "dt"]))
 
 
 @pytest.fixture(scope="module")
@@ -57,10 +63,10 @@ def pack(d):
     reaches = [r for _, r in du._decompose(d["tw"], d["rconn"], set(d["tribs"]))]
     return du.diffusive_input_data_v02(
         d["tw"], d["connections"], d["rconn"], reaches, d["main"], d["tribs"], None, d["param_df"], d["qlat"], d["ic"], d["ji"],
-        12, d["t0"], d["nsteps"], d["dt"], pd.DataFrame(), d["topo"], pd.DataFrame(), None, None, d["coastal"], pd.DataFrame())
+        12, d["t0"], d["nsteps"], d["dt"], pd.DataFrame(), d["topo"], d["usgs"], None, None, d["coastal"], pd.DataFrame())
 
 
-@pytest.mark.parametrize("c", range(5))
+@pytest.mark.parametrize("c", range(6))
 def test_packer_reproduces_the_reference_arrays(gold, c):
     d = rebuild(gold, c)
     ins = pack(d)
@@ -74,7 +80,7 @@ def test_packer_reproduces_the_reference_arrays(gold, c):
         assert np.array_equal(got, want, equal_nan=True), k
 
 
-@pytest.mark.parametrize("c", range(5))
+@pytest.mark.parametrize("c", range(6))
 def test_unpack_output_reproduces_the_reference(gold, c):
     from troute_b200.routing import diffusive_utils as du
     d = rebuild(gold, c)

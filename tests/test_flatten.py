@@ -54,3 +54,20 @@ def test_flatten_kinds_and_errors():
         mc_reach.flatten_network([([10], 0), ([10], 0)], {}, data_idx)
     with pytest.raises(ValueError):
         mc_reach.flatten_network([([10, 20], 1)], {}, data_idx)
+
+
+def test_network_cache_key_sees_the_connectivity():
+    """Same ids, same parameters, same reach lengths / types / end points -- but a different confluence wiring or a
+    different interior membership of the reaches -- must not share a cached device network (mc_reach._fingerprint)."""
+    data_idx = np.arange(10, 90, 10, dtype=np.int64)                      # 10 .. 80
+    cols = ["dt", "bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"]
+    vals = np.ones((data_idx.size, len(cols)), dtype=np.float32)
+    reaches = [([10, 20, 30], 0), ([40, 50, 60], 0), ([70], 0), ([80], 0)]
+    ups = {10: [], 40: [], 70: [30], 80: [60]}
+    key = mc_reach._fingerprint(reaches, ups, data_idx, cols, vals, 0)
+    assert key == mc_reach._fingerprint([(list(r), t) for r, t in reaches], dict(ups), data_idx.copy(), list(cols), vals.copy(), 0)
+    rewired = {10: [], 40: [], 70: [60], 80: [30]}                        # the two confluences swapped
+    assert mc_reach._fingerprint(reaches, rewired, data_idx, cols, vals, 0) != key
+    swapped = [([10, 50, 30], 0), ([40, 20, 60], 0), ([70], 0), ([80], 0)]   # interior segments exchanged between reaches
+    assert mc_reach._fingerprint(swapped, ups, data_idx, cols, vals, 0) != key
+    assert mc_reach._fingerprint(reaches, ups, data_idx, cols, vals, 1) != key

@@ -373,7 +373,6 @@ def test_gate_and_grid_options_do_not_change_results(eng, oracle):
         H.assert_bit_equal(out, ref, f"gate={gate} grid={grid}")
 
 
-@pytest.mark.first_light
 @pytest.mark.parametrize("short_ts", [False, True])
 @pytest.mark.parametrize("mode,chunks,grid", [(2, 1, 0), (2, 1, 2), (4, 1, 0), (4, 3, 0)])
 def test_warp_resync_option_does_not_change_results(eng, oracle, short_ts, mode, chunks, grid):

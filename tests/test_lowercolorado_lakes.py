@@ -146,7 +146,6 @@ def test_dataframe_glue_with_lakes_equals_the_oracle(oracle, monkeypatch, short_
 
 
 @pytest.mark.gpu
-@pytest.mark.first_light
 @pytest.mark.parametrize("short_ts", [True, False])
 def test_gpu_routes_lowercolorado_with_its_reservoirs(oracle, short_ts):
     from troute_b200.routing.fast_reach.mc_reach import clear_network_cache

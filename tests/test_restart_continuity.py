@@ -51,7 +51,6 @@ def test_split_run_equals_full_run_on_the_oracle(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_light
 @pytest.mark.parametrize("halves", [2, 4])
 def test_split_run_equals_full_run_on_the_device(oracle, halves):
     from troute_b200.routing.fast_reach import mc_reach

@@ -97,7 +97,6 @@ def test_windows_equal_one_call_on_the_oracle(oracle, W):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_light
 @pytest.mark.parametrize("W", [2, 4])
 def test_windows_equal_one_call_on_the_device(oracle, W):
     from troute_b200.routing.fast_reach import mc_reach

@@ -103,7 +103,6 @@ def test_time_resolved_key_fills_the_warps_better_than_the_total(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_light
 @pytest.mark.parametrize("mode,chunks", [(2, 1), (4, 3)])
 def test_device_trip_counters_equal_the_oracle_per_time_slice(oracle, mode, chunks):
     """trt_trip_counts_bucketed == the oracle's trip count of every (segment, step) summed per slice, exactly (same

@@ -14,7 +14,7 @@ import pytest
 
 import helpers_diffusive as HD
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_light, pytest.mark.timeout(600, method="thread")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 REL_TOL = 1e-5
 
 
