@@ -141,6 +141,28 @@ int trt_download_gages(trt_network* net, float* nudge, float* lastobs_times, flo
 int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, const float* qlat,
                        int32_t nqcols, const float* q0, int64_t n_bnd, const int64_t* bnd_rows,
                        const float* bnd_fvd);
+/*
+ * The next routing window of the same network WITHOUT a host round trip of the model state: the last column of the
+ * finished call (flow and depth of every segment, outflow and water elevation of every reservoir) becomes the initial state
+ * on the device, and the gages' last observations are re-based to the new window start (time -= nsteps_prev * dt).
+ * Replaces, for a device-resident model, what the reference does on the host between two nwm_route calls:
+ * AbstractNetwork.new_q0 + update_waterbody_water_elevation (src/troute-network/troute/AbstractNetwork.py:177-198) and
+ * DataAssimilation.new_lastobs (src/troute-network/troute/DataAssimilation.py:1506-1551); loops
+ * src/troute-nwm/src/nwm_routing/__main__.py:258-266, src/troute_model.py:250-262 (BMI update_until).
+ * Arguments as trt_upload_forcing minus q0; the new window may have a different number of steps.  Follow with trt_run /
+ * trt_run_download.  trt_network_update_gage_observations replaces the observation table (usgs_values of the new window)
+ * and keeps the last-observation state.  Sharded runs: every shard calls trt_continue, then trt_prepare, barrier, run.
+ */
+int trt_continue(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, const float* qlat, int32_t nqcols,
+                 int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd);
+int trt_network_update_gage_observations(trt_network* net, const float* usgs_values, int32_t gage_maxtimestep);
+/*
+ * 64-bit checksum of the device-resident result of the last run: the SUM over the selected rows of
+ * hash(ids[i], bits of result row rows[i]) -- independent of schedule, within-level order and sharding, so the checksums of
+ * the shards of one network add up to the checksum of the unsharded run (bench.py `verify`).  rows = NULL: every row;
+ * ids = NULL: the row numbers.  tests/helpers.py::result_hash is the same function in numpy.
+ */
+int trt_result_hash(trt_network* net, int64_t n_sel, const int64_t* rows, const int64_t* ids, uint64_t* out);
 /* kernels only; everything is already resident in HBM.  Blocks until the device is done. */
 int trt_run(trt_network* net, int32_t assume_short_ts);
 /* trt_run without the final wait: enqueue on the handle's stream and return; trt_sync waits and
@@ -162,6 +184,8 @@ int trt_route(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, int32_
  *   trt_export_flow_series   gathers q[rows, 0..nsteps] into dst (DEVICE pointer, [n, nsteps+1] float32)
  *   trt_import_boundary_flow writes prescribed q[rows, 1..nsteps] from src (DEVICE pointer,
  *                            [n, nsteps+1] float32, column 0 ignored); v and d of those rows stay 0
+ *                            (bulk-synchronous schedules, "mode" 0 / 1, only: the polling schedules rebuild the flow
+ *                            state at the start of every run)
  *   trt_device_results       device pointer of the [n_rows, nsteps*3] result after trt_run
  *                            (valid until the next upload)
  */
@@ -175,8 +199,8 @@ int trt_device_results(trt_network* net, void** fvd_device);
  * by the kernel of the upstream shard straight into the downstream GPU's flow array over NVLink peer memory ("export").
  * This replaces the pickled tail-water series the reference hands from one order of sub-networks to the next
  * (compute.py:882-900 -> mc_reach.pyx:458-469).  No collective is involved: a consumer lane polls the slot it reads.
- *   trt_network_state_ptr   device pointer of this handle's flow state ([n_rows, nsteps+1, 3] float32), valid after
- *                           trt_upload_forcing and until a later upload needs a larger array
+ *   trt_network_state_ptr   device pointer of this handle's flow state ([tiles of 32 positions][nsteps+1][q|d][32] float32,
+ *                           csrc/kernels.cuh), valid after trt_upload_forcing and until a later upload needs a larger array
  *   trt_ipc_get/open/close  CUDA IPC plumbing to map that array into the peer process
  *   trt_network_set_peer    flow array of peer shard `peer` (mapped pointer) and its row count
  *   trt_network_set_exports rows of this shard whose outflow enters peer shard peer[i] at engine position
@@ -206,14 +230,11 @@ int trt_prepare(trt_network* net);
  *                 "deep_lanes" segments (default 8192).  Shards of one network must use the SAME
  *                 deep_level (set it explicitly): a dataflow kernel must never wait for a value that another shard
  *                 produces only in its marching kernel
- *   "march_group" segments per marching warp, 1..32; 0 (default) = the smallest power of two for which all marching
- *                 units are resident at once: fewer = shorter dependency-chain latency, more =
- *                 more segments resident at once
+ *   "march_group" segments per marching warp, 1..32; 0 (default) = 1 up to 16,384 marching segments (shortest
+ *                 dependency-chain latency; measured 19.6 instead of 27.9 ms on the bench network), beyond that the
+ *                 smallest power of two for which all marching units are resident at once
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
- *   "warp_resync" mode 2 / 4: 1 = the lanes of a dataflow unit meet at a __syncwarp between their input polls and the
- *                 solve (the spin loops of the polls leave a quarter of the warps split in two for the whole solve);
- *                 0 (default until measured) = no explicit barrier.  Results do not depend on it
  *   "collect_trips", "trip_buckets"  see trt_trip_counts / trt_trip_counts_bucketed
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
  *   "route_chunks" time chunks of trt_route / trt_run_download (default 4; 1 = compute everything, then copy)

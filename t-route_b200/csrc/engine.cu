@@ -70,21 +70,29 @@ struct trt_network {
     std::vector<int32_t> level_of_row, pos_of_row, row_of_pos, lvl_ptr;
     std::vector<uint8_t> kind_of_row;
 
-    // device topology / parameters
-    DevBuf<int> d_lvl_ptr, d_level, d_up_ptr, d_up_idx, d_row_of_pos;
-    DevBuf<unsigned char> d_kind;
-    DevBuf<float> d_par;
+    // device topology / parameters: tile records (kernels.cuh), CSR of upstream positions, level offsets
+    int64_t n_tiles = 0;
+    std::vector<uint32_t> h_rec;                              // host mirror of d_rec (flags / slots change after creation)
+    DevBuf<unsigned> d_rec;
+    DevBuf<int> d_lvl_ptr, d_up_idx, d_row_of_pos, d_lp_slot;
 
     // level pools
     int64_t n_lp = 0;
     DevBuf<int> d_lp_pos;
+    std::vector<int32_t> host_lp_pos;
     DevBuf<float> d_lp_qd0, d_lp_h0;
 
     // per-call state
     int T = 0, qts = 1, nq = 0;
     bool uploaded = false, ran = false;
-    DevBuf<float> d_qlat_in, d_q0_in, d_qlat_t, d_S, d_fvd, d_up_out, d_bnd_fvd;
+    DevBuf<float> d_qlat_in, d_q0_in, d_qlat_t, d_S, d_fvd, d_up_out, d_bnd_fvd, d_lp_in, d_carry;
+    DevBuf<unsigned> d_fmask;
     DevBuf<int> d_bnd_pos, d_tmp_pos;
+    DevBuf<unsigned long long> d_hash;
+    bool sync_ready = false;                                  // modes 0 / 1: the flow state of the uploaded call is initialised
+    bool carry_valid = false;                                 // d_carry holds the last column of the previous window
+    int carry_T = 0;
+    float carry_dt = 0.f;
 
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -100,7 +108,6 @@ struct trt_network {
     DevBuf<unsigned char> d_unit_shift;
     DevBuf<unsigned long long> d_stage_time;                  // mode 2 + profile_stages: completion time of every stage
     int sched_T = -1, sched_short = -1, sched_gate = -1, sched_nstages = 0, sched_lw = -1;
-    int warp_resync = 0;                                      // dataflow kernel: __syncwarp between input polls and solve
     int gate = 0;                                             // 0 = adaptive run-ahead window, else fixed stages
     int gate_min = 12;
     int64_t gate_lanes = 16384;
@@ -116,11 +123,8 @@ struct trt_network {
     int deep_level = -1;                                      // mode 4: first marching level (-1 = from deep_lanes)
     int64_t deep_lanes = 8192;                                // mode 4 auto: march as many of the deepest levels as fit
     int march_sched_first = -1, march_sched_group = -1, march_units = 0;
-    int time_block = 8;                                       // mode 5: timesteps per wide unit
-    DevBuf<int> d_wide_unit_ptr;
-    int wide_sched_T = -1, wide_sched_lw = -1, wide_sched_tb = -1, wide_units = 0, wide_stages = 0, wide_blocks = 0;
     bool march_profile = false;
-    int poll_mode = 0, poll_sleep = -1, march_prepare = 1;
+    int poll_sleep = -1, march_prepare = 1;
     DevBuf<unsigned long long> d_march_prof;                  // [n][4] + 1
     cudaEvent_t ev_mid = nullptr;                             // between the dataflow and the marching kernel
     double wide_ms = 0.0, march_ms = 0.0;
@@ -133,7 +137,7 @@ struct trt_network {
 
     // cut edges to / from other shards
     std::vector<uint8_t> imported;                            // [n] row is written by a peer
-    DevBuf<int> d_exp_slot, d_exp_peer;
+    DevBuf<int> d_exp_peer;
     DevBuf<long long> d_exp_pos;
     int64_t n_exp = 0;
     float* peer_q[TRT_MAX_PEERS] = {nullptr};
@@ -145,7 +149,8 @@ struct trt_network {
     float gage_dt = 0.f, gage_decay = 0.f;
     std::vector<uint8_t> gage_flag;                           // [n] position carries an active gage
     std::vector<uint8_t> export_flag;                         // [n] position exports to a peer
-    DevBuf<int> d_gage_slot, d_gage_pos;
+    std::vector<int32_t> gage_slot, export_slot;              // [n] gage index / export slot of a flagged position
+    DevBuf<int> d_gage_pos;
     DevBuf<unsigned char> d_gage_active;
     DevBuf<float> d_usgs, d_lastobs, d_lastobs_init, d_nudge;
 
@@ -164,8 +169,8 @@ struct trt_network {
     NetDev netdev() const
     {
         NetDev d;
-        d.n = (int)n; d.nlevels = nlevels; d.lvl_ptr = d_lvl_ptr.p; d.level = d_level.p; d.up_ptr = d_up_ptr.p;
-        d.up_idx = d_up_idx.p; d.kind = d_kind.p; d.par = d_par.p; d.row_of_pos = d_row_of_pos.p;
+        d.n = (int)n; d.nlevels = nlevels; d.lvl_ptr = d_lvl_ptr.p; d.up_idx = d_up_idx.p; d.rec = d_rec.p;
+        d.row_of_pos = d_row_of_pos.p; d.lp_slot = d_lp_slot.p;
         return d;
     }
     RunDev rundev(int short_ts) const
@@ -175,7 +180,8 @@ struct trt_network {
         r.trip_sum = collect_trips ? d_trip_sum.p : nullptr;
         r.trip_buckets = trip_buckets;
         r.gage.n_gages = (int)n_gages; r.gage.gmax = gage_max; r.gage.dt = gage_dt; r.gage.decay = gage_decay;
-        r.gage.slot = d_gage_slot.p; r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
+        r.gage.usgs = d_usgs.p; r.gage.lastobs = d_lastobs.p; r.gage.nudge = d_nudge.p;
+        r.fmask = d_fmask.p; r.lp_in = d_lp_in.p;
         return r;
     }
 };
@@ -185,7 +191,7 @@ int trt_internal_fail(int code, const char* msg) { return fail(code, "%s", msg);
 extern "C" {
 
 const char* trt_last_error(void) { return g_err.c_str(); }
-int trt_version(void) { return 110; }   /* 1.1: diffusive-wave entry points */
+int trt_version(void) { return 200; }   /* 2.0: tiled flow state + TMA-staged tile records, trt_continue, trt_result_hash */
 
 int trt_device_count(void)
 {
@@ -315,42 +321,54 @@ int trt_network_create_ordered(int device, int64_t n_rows, const int64_t* up_ptr
     net->kind_of_row.assign(kind, kind + n);
     net->imported.assign((size_t)n, 0);
 
-    // ---- position-space arrays ----
-    std::vector<int32_t> h_level((size_t)n), h_up_ptr((size_t)n + 1, 0), h_up_idx((size_t)E);
-    std::vector<unsigned char> h_kind((size_t)n);
-    std::vector<float> h_par((size_t)9 * (size_t)std::max<int64_t>(n, 1));
-    for (int64_t p = 0; p < n; ++p) {
-        const int64_t r = net->row_of_pos[(size_t)p];
-        h_level[(size_t)p] = level[(size_t)r];
-        h_kind[(size_t)p] = kind[r];
-        h_up_ptr[(size_t)p + 1] = h_up_ptr[(size_t)p] + (int32_t)(up_ptr[r + 1] - up_ptr[r]);
-        int32_t o = h_up_ptr[(size_t)p];
-        for (int64_t e = up_ptr[r]; e < up_ptr[r + 1]; ++e) h_up_idx[(size_t)o++] = net->pos_of_row[(size_t)up_rows[e]];
-        const float* dv = data_values + (size_t)r * ncols;
-        for (int c = 0; c < 9; ++c) h_par[(size_t)c * n + p] = dv[scols[c]];
+    // ---- position-space arrays: one 2 KB record per tile of 32 positions (kernels.cuh), CSR of upstream positions ----
+    const int64_t n_tiles = (n + 31) / 32;
+    net->n_tiles = n_tiles;
+    std::vector<int32_t> h_up_idx((size_t)E);
+    std::vector<uint32_t>& rec = net->h_rec;
+    rec.assign((size_t)n_tiles * R_TILE_WORDS, 0u);
+    auto f2u = [](float x) { uint32_t u; memcpy(&u, &x, 4); return u; };
+    for (int64_t p = n; p < n_tiles * 32; ++p) {                      // padding lanes of the last tile: never routed
+        rec[rec_idx(p, R_FLAGS)] = TRT_KIND_BOUNDARY;
+        rec[rec_idx(p, R_UP0)] = rec[rec_idx(p, R_UP1)] = (uint32_t)-1;
+    }
+    {
+        int64_t o = 0;
+        for (int64_t p = 0; p < n; ++p) {
+            const int64_t r = net->row_of_pos[(size_t)p];
+            const int64_t cnt = up_ptr[r + 1] - up_ptr[r];
+            if (cnt >= (1 << 24)) { delete net; return fail(TRT_ERR_INVALID, "row %lld has too many upstream rows", (long long)r); }
+            const float* dv = data_values + (size_t)r * ncols;
+            for (int c = 0; c < 9; ++c) rec[rec_idx(p, R_PAR + c)] = f2u(dv[scols[c]]);
+            rec[rec_idx(p, R_LEVEL)] = (uint32_t)level[(size_t)r];
+            rec[rec_idx(p, R_FLAGS)] = (uint32_t)kind[r] | ((uint32_t)cnt << 8);
+            rec[rec_idx(p, R_ESTART)] = (uint32_t)o;
+            rec[rec_idx(p, R_UP0)] = rec[rec_idx(p, R_UP1)] = (uint32_t)-1;
+            for (int64_t e = up_ptr[r]; e < up_ptr[r + 1]; ++e) {
+                const int32_t up = net->pos_of_row[(size_t)up_rows[e]];
+                if (e - up_ptr[r] == 0) rec[rec_idx(p, R_UP0)] = (uint32_t)up;
+                if (e - up_ptr[r] == 1) rec[rec_idx(p, R_UP1)] = (uint32_t)up;
+                h_up_idx[(size_t)o++] = up;
+            }
+        }
     }
 
     // ---- upload ----
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = preload_routing_kernels();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&net->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&net->ev1);
     if (e == cudaSuccess) e = net->d_lvl_ptr.reserve((size_t)nlev + 1);
-    if (e == cudaSuccess) e = net->d_level.reserve((size_t)n);
-    if (e == cudaSuccess) e = net->d_up_ptr.reserve((size_t)n + 1);
     if (e == cudaSuccess) e = net->d_up_idx.reserve((size_t)E);
     if (e == cudaSuccess) e = net->d_row_of_pos.reserve((size_t)n);
-    if (e == cudaSuccess) e = net->d_kind.reserve((size_t)n);
-    if (e == cudaSuccess) e = net->d_par.reserve((size_t)9 * n);
+    if (e == cudaSuccess) e = net->d_rec.reserve(rec.size());
 #define UP(dst, src, count) \
     if (e == cudaSuccess && (count) > 0) e = cudaMemcpy(dst, src, (size_t)(count) * sizeof(*(src)), cudaMemcpyHostToDevice)
     UP(net->d_lvl_ptr.p, net->lvl_ptr.data(), nlev + 1);
-    UP(net->d_level.p, h_level.data(), n);
-    UP(net->d_up_ptr.p, h_up_ptr.data(), n + 1);
     UP(net->d_up_idx.p, h_up_idx.data(), E);
     UP(net->d_row_of_pos.p, net->row_of_pos.data(), n);
-    UP(net->d_kind.p, h_kind.data(), n);
-    UP(net->d_par.p, h_par.data(), 9 * n);
+    UP(net->d_rec.p, rec.data(), (int64_t)rec.size());
 #undef UP
     if (e != cudaSuccess) {
         const int rc = fail(TRT_ERR_CUDA, "network upload failed: %s", cudaGetErrorString(e));
@@ -424,6 +442,7 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
         // mc_reach.pyx:272,553), not a table column -- lake rows carry NaN channel parameters (compute.py:1455-1457)
         p[0] = routing_period;
         p[1] = area; p[2] = max_depth; p[3] = oa; p[4] = oc; p[5] = oe; p[6] = wc; p[7] = we; p[8] = wl;
+        for (int c = 0; c < 9; ++c) memcpy(&net->h_rec[rec_idx(pos[(size_t)i], R_PAR + c)], &p[c], 4);   // host mirror
     }
     CU(net->d_lp_pos.reserve((size_t)n_lp));
     CU(net->d_lp_qd0.reserve((size_t)n_lp));
@@ -435,26 +454,40 @@ int trt_network_set_levelpools(trt_network* net, int64_t n_lp, const int64_t* lp
         DevBuf<float> d_par9;
         CU(d_par9.reserve((size_t)n_lp * 9));
         CU(cudaMemcpy(d_par9.p, par.data(), (size_t)n_lp * 9 * sizeof(float), cudaMemcpyHostToDevice));
-        CU(launch_scatter_lp_params(net->d_lp_pos.p, d_par9.p, net->d_par.p, (int)n, (int)n_lp, net->stream));
+        CU(launch_scatter_lp_params(net->d_lp_pos.p, d_par9.p, net->d_rec.p, (int)n_lp, net->stream));
+        if (pos != net->host_lp_pos || !net->d_lp_slot.p) {
+            // level-pool index of every level-pool position (the reservoir-inflow series is kept per reservoir)
+            std::vector<int32_t> slot((size_t)std::max<int64_t>(n, 1), -1);
+            for (int64_t i = 0; i < n_lp; ++i) slot[(size_t)pos[(size_t)i]] = (int32_t)i;
+            CU(net->d_lp_slot.reserve((size_t)std::max<int64_t>(n, 1)));
+            CU(cudaMemcpyAsync(net->d_lp_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, net->stream));
+            CU(cudaStreamSynchronize(net->stream));
+            net->host_lp_pos = pos;
+        }
         CU(cudaStreamSynchronize(net->stream));
     }
     net->n_lp = n_lp;
     return TRT_OK;
 }
 
-// device kind = reach kind | export flag | gage flag
+// flag bits and the gage / export slot words of the tile records follow the host mirror
 static int upload_kind(trt_network* net)
 {
     const int64_t n = net->n;
     if (n == 0) return TRT_OK;
-    std::vector<unsigned char> h((size_t)n);
     for (int64_t p = 0; p < n; ++p) {
-        unsigned char k = net->kind_of_row[(size_t)net->row_of_pos[(size_t)p]];
-        if (!net->export_flag.empty() && net->export_flag[(size_t)p]) k |= TRT_KIND_EXPORT_FLAG;
-        if (!net->gage_flag.empty() && net->gage_flag[(size_t)p]) k |= TRT_KIND_GAGE_FLAG;
-        h[(size_t)p] = k;
+        uint32_t& w = net->h_rec[rec_idx(p, R_FLAGS)];
+        w &= ~(uint32_t)(TRT_KIND_EXPORT_FLAG | TRT_KIND_GAGE_FLAG);
+        if (!net->export_flag.empty() && net->export_flag[(size_t)p]) {
+            w |= TRT_KIND_EXPORT_FLAG;
+            net->h_rec[rec_idx(p, R_EXP)] = (uint32_t)net->export_slot[(size_t)p];
+        }
+        if (!net->gage_flag.empty() && net->gage_flag[(size_t)p]) {
+            w |= TRT_KIND_GAGE_FLAG;
+            net->h_rec[rec_idx(p, R_GAGE)] = (uint32_t)net->gage_slot[(size_t)p];
+        }
     }
-    CU(cudaMemcpy(net->d_kind.p, h.data(), (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(net->d_rec.p, net->h_rec.data(), net->h_rec.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return TRT_OK;
 }
 
@@ -489,14 +522,13 @@ int trt_network_set_gages(trt_network* net, int64_t n_gages, const int64_t* gage
     }
     net->n_gages = n_gages; net->gage_max = gage_maxtimestep;
     net->gage_decay = da_decay_coefficient; net->gage_dt = routing_period;
+    net->gage_slot = slot;
     if (n_gages > 0) {
-        CU(net->d_gage_slot.reserve((size_t)n));
         CU(net->d_gage_pos.reserve((size_t)n_gages));
         CU(net->d_gage_active.reserve((size_t)n_gages));
         CU(net->d_usgs.reserve((size_t)n_gages * (size_t)std::max(1, gage_maxtimestep)));
         CU(net->d_lastobs.reserve((size_t)n_gages * 2));
         CU(net->d_lastobs_init.reserve((size_t)n_gages * 2));
-        CU(cudaMemcpy(net->d_gage_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(net->d_gage_pos.p, pos.data(), (size_t)n_gages * sizeof(int32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(net->d_gage_active.p, active, (size_t)n_gages, cudaMemcpyHostToDevice));
         if (gage_maxtimestep > 0)
@@ -527,8 +559,24 @@ int trt_download_gages(trt_network* net, float* nudge, float* lastobs_times, flo
     return TRT_OK;
 }
 
-int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, const float* q0,
-                       int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd)
+static cudaError_t prepare_state(trt_network* net, bool sentinel);
+
+// initial state of the flow array: column 0 from the caller's q0 / the reservoir table, or -- after trt_continue -- from
+// the last column of the previous window, kept on the device
+static cudaError_t init_columns(trt_network* net)
+{
+    cudaStream_t st = net->stream;
+    if (net->n == 0) return cudaSuccess;
+    if (net->carry_valid)
+        return launch_column_copy(net->d_S.p, net->T + 1, 0, net->d_carry.p, (int)net->n_tiles, 1, st);
+    cudaError_t e = launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_S.p, (int)net->n, net->T, st);
+    if (e == cudaSuccess)
+        e = launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_S.p, net->T, (int)net->n_lp, st);
+    return e;
+}
+
+static int upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, const float* q0,
+                          int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd, bool carry)
 {
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (nsteps < 0) return fail(TRT_ERR_INVALID, "nsteps < 0");
@@ -539,21 +587,37 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
                     "Number of columns (timesteps) in Qlat is incorrect: expected at least (%g), got (%d)",
                     (double)nsteps / (double)qts, nqcols);
     const int64_t n = net->n;
-    if (n > 0 && (!qlat || !q0)) return fail(TRT_ERR_INVALID, "NULL qlat / q0");
+    if (n > 0 && (!qlat || (!q0 && !carry))) return fail(TRT_ERR_INVALID, "NULL qlat / q0");
     if (n_bnd < 0 || (n_bnd > 0 && (!bnd_rows || !bnd_fvd))) return fail(TRT_ERR_INVALID, "bad boundary arguments");
     CU(cudaSetDevice(net->device));
     cudaStream_t st = net->stream;
+    if (carry) {
+        // the last column of the finished window and the gages' last observations become the initial state, on the device
+        // (what AbstractNetwork.new_q0 / update_waterbody_water_elevation / DataAssimilation.new_lastobs do on the host
+        // between two nwm_route calls, AbstractNetwork.py:177-198, DataAssimilation.py:1506-1551)
+        if (!net->ran) return fail(TRT_ERR_STATE, "trt_continue needs a finished routing call on this handle");
+        CU(net->d_carry.reserve((size_t)net->n_tiles * 64));
+        CU(launch_column_copy(net->d_S.p, net->T + 1, net->T, net->d_carry.p, (int)net->n_tiles, 0, st));
+        if (net->n_gages > 0)
+            CU(launch_carry_gages(net->d_lastobs.p, net->d_lastobs_init.p, (int)net->n_gages,
+                                  (float)net->T * net->gage_dt, st));
+        net->carry_valid = true;
+    } else {
+        net->carry_valid = false;
+    }
     net->T = nsteps; net->qts = qts; net->nq = nqcols;
     net->uploaded = false; net->ran = false;
 
-    const size_t rows_t = (size_t)(nsteps + 1) * (size_t)n;
+    const size_t T1 = (size_t)nsteps + 1;
     CU(net->d_qlat_in.reserve((size_t)n * nqcols));
-    CU(net->d_q0_in.reserve((size_t)n * 3));
+    if (!carry) CU(net->d_q0_in.reserve((size_t)n * 3));
     CU(net->d_qlat_t.reserve((size_t)n * nqcols));
-    CU(net->d_S.reserve(rows_t * 3));
+    CU(net->d_S.reserve((size_t)net->n_tiles * T1 * 64));
+    CU(net->d_fmask.reserve((size_t)net->n_tiles * T1));
+    CU(net->d_lp_in.reserve((size_t)net->n_lp * T1));
     // allocate here, not in trt_run: an allocation may synchronise the device, and a peer handle on the same device may
     // already be running a kernel that waits for this handle's kernels
-    if (net->n_gages > 0) CU(net->d_nudge.reserve((size_t)net->n_gages * (size_t)(nsteps + 1)));
+    if (net->n_gages > 0) CU(net->d_nudge.reserve((size_t)net->n_gages * T1));
     {
         // rows of marching segments are copied home from a compact buffer in the chunked route; the strided chunk copies
         // still sweep over their (then unwritten) rows of d_fvd, so give a fresh allocation defined contents once
@@ -565,10 +629,8 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
 
     if (n > 0) {
         CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (!carry) CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(launch_gather_qlat(net->d_qlat_in.p, net->d_row_of_pos.p, net->d_qlat_t.p, (int)n, nqcols, st));
-        CU(launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_S.p, (int)n, nsteps, st));
-        CU(launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_S.p, nsteps, (int)net->n_lp, st));
     }
     if (n_bnd > 0) {
         std::vector<int32_t> pos((size_t)n_bnd);
@@ -584,7 +646,6 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
         CU(cudaMemcpyAsync(net->d_bnd_pos.p, pos.data(), (size_t)n_bnd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(net->d_bnd_fvd.p, bnd_fvd, (size_t)n_bnd * 3 * (size_t)nsteps * sizeof(float),
                            cudaMemcpyHostToDevice, st));
-        CU(launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_S.p, (int)n_bnd, nsteps, st));
         CU(cudaStreamSynchronize(st));   // `pos` is a stack-owned staging vector
         net->host_bnd_pos = pos;
     } else {
@@ -603,24 +664,54 @@ int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const floa
         if (net->n_zero > 0) {
             CU(net->d_zero_pos.reserve(zero_pos.size()));
             CU(cudaMemcpy(net->d_zero_pos.p, zero_pos.data(), zero_pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            CU(launch_fill_zero_rows(net->d_zero_pos.p, net->d_S.p, (int)net->n_zero, nsteps, st));
         }
     }
     net->uploaded = true;
+    net->prepared = false;
+    // The flow state itself is (re)built at the start of every run: prepare_state.  The bulk-synchronous schedules get it
+    // here already, so that trt_import_boundary_flow can write prescribed series between the upload and the run.
+    net->sync_ready = false;
+    if (net->mode < 2) { CU(prepare_state(net, false)); net->sync_ready = true; }
     return TRT_OK;
 }
 
-// Dataflow runs start from q / d rows 1..T holding TRT_SENTINEL (0xFFFFFFFF) everywhere except on prescribed rows.
-static cudaError_t prepare_dataflow(trt_network* net)
+int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, const float* q0,
+                       int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd)
+{
+    if (net && net->n > 0 && !q0) return fail(TRT_ERR_INVALID, "NULL qlat / q0");
+    return upload_forcing(net, nsteps, qts, qlat, nqcols, q0, n_bnd, bnd_rows, bnd_fvd, false);
+}
+
+int trt_continue(trt_network* net, int32_t nsteps, int32_t qts, const float* qlat, int32_t nqcols, int64_t n_bnd,
+                 const int64_t* bnd_rows, const float* bnd_fvd)
+{
+    return upload_forcing(net, nsteps, qts, qlat, nqcols, nullptr, n_bnd, bnd_rows, bnd_fvd, true);
+}
+
+int trt_network_update_gage_observations(trt_network* net, const float* usgs_values, int32_t gage_maxtimestep)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (gage_maxtimestep < 0 || (net->n_gages > 0 && gage_maxtimestep > 0 && !usgs_values))
+        return fail(TRT_ERR_INVALID, "bad gage observation table");
+    CU(cudaSetDevice(net->device));
+    net->gage_max = gage_maxtimestep;
+    if (net->n_gages > 0 && gage_maxtimestep > 0) {
+        CU(net->d_usgs.reserve((size_t)net->n_gages * (size_t)gage_maxtimestep));
+        CU(cudaMemcpy(net->d_usgs.p, usgs_values, (size_t)net->n_gages * gage_maxtimestep * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return TRT_OK;
+}
+
+static cudaError_t prepare_state(trt_network* net, bool sentinel)
 {
     cudaStream_t st = net->stream;
-    const size_t n = (size_t)net->n, T = (size_t)net->T;
-    if (n == 0 || T == 0) return cudaSuccess;
-    // everything "not yet written" (0xFFFFFFFF == TRT_SENTINEL), then the initial state and the prescribed series again
-    cudaError_t e = cudaMemsetAsync(net->d_S.p, 0xFF, n * (T + 1) * 3 * sizeof(float), st);
-    if (e == cudaSuccess) e = launch_init_state(net->d_q0_in.p, net->d_row_of_pos.p, net->d_S.p, (int)n, (int)T, st);
-    if (e == cudaSuccess)
-        e = launch_init_levelpool(net->d_lp_pos.p, net->d_lp_qd0.p, net->d_lp_h0.p, net->d_S.p, (int)T, (int)net->n_lp, st);
+    const size_t T = (size_t)net->T;
+    if (net->n == 0 || T == 0) return cudaSuccess;
+    // polling schedules: everything "not yet written" (0xFFFFFFFF == TRT_SENTINEL); then no flow bits, the initial state
+    // and the prescribed series
+    cudaError_t e = cudaMemsetAsync(net->d_S.p, sentinel ? 0xFF : 0, (size_t)net->n_tiles * (T + 1) * 64 * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(net->d_fmask.p, 0, (size_t)net->n_tiles * (T + 1) * sizeof(unsigned), st);
+    if (e == cudaSuccess) e = init_columns(net);
     if (e == cudaSuccess && net->n_bnd > 0)
         e = launch_fill_boundary(net->d_bnd_pos.p, net->d_bnd_fvd.p, net->d_S.p, (int)net->n_bnd, (int)T, st);
     if (e == cudaSuccess && net->n_zero > 0)
@@ -638,14 +729,25 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run called before trt_upload_forcing");
     CU(cudaSetDevice(net->device));
     cudaStream_t st = net->stream;
-    if (net->n_gages > 0 && first) {
-        // nudging state back to its initial values; the flow-state reset must come first (it rewrites t = 0)
-        CU(net->d_nudge.reserve((size_t)net->n_gages * (size_t)(net->T + 1)));
-        if (net->mode >= 2 && !net->prepared) { CU(prepare_dataflow(net)); net->prepared = true; }
-        RunDev rg = net->rundev(0);
-        CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
+    if (first) {
+        // the flow state of this run: polling schedules start from "not yet written" everywhere (unless trt_prepare has done
+        // it already: shards must all be reset before any of them runs), the bulk-synchronous ones from zeros
+        if (net->mode >= 2) { if (!net->prepared) CU(prepare_state(net, true)); }
+        else {
+            if (!net->sync_ready) CU(prepare_state(net, false));
+            else if (net->n > 0 && net->T > 0)
+                CU(cudaMemsetAsync(net->d_fmask.p, 0, (size_t)net->n_tiles * (size_t)(net->T + 1) * sizeof(unsigned), st));
+            net->sync_ready = true;
+        }
+        net->prepared = false;
+        if (net->n_gages > 0) {
+            // nudging state back to its initial values (after the flow-state reset: it rewrites t = 0)
+            RunDev rg = net->rundev(0);
+            CU(launch_reset_gages(rg.gage, net->d_gage_pos.p, net->d_gage_active.p, net->d_lastobs_init.p, net->d_S.p, net->T, st));
+        }
     }
     if (net->collect_trips) CU(net->d_trip_sum.reserve((size_t)std::max<int64_t>(net->n, 1) * (size_t)(net->trip_buckets + 1)));
+    CU(net->d_lp_in.reserve((size_t)net->n_lp * (size_t)(net->T + 1)));      // reservoirs declared after the upload
     const NetDev nd = net->netdev();
     RunDev rd = net->rundev(assume_short_ts ? 1 : 0);
     rd.t_off = t_off; rd.Tc = Tc;
@@ -657,7 +759,10 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         net->trip_buckets_ran = net->trip_buckets;
     }
 
-    if (first) CU(cudaEventRecord(net->ev0, st));
+    if (first) {
+        CU(cudaEventRecord(net->ev0, st));
+        net->launches += 3 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0) + (net->n_gages > 0);   // state reset
+    }
     if (net->n > 0 && T > 0 && L > 0) {
         const int k_begin = 1, k_end = L + T;   // stages k = level + t, level in [0, L), t in [1, T]
         net->stages = k_end - k_begin;
@@ -677,35 +782,15 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             }
             net->deep_level_used = Lw;
             const int pos_deep = net->lvl_ptr[(size_t)Lw];
-            const bool unified = net->mode == 5;                      // wide units go through the marching kernel too
-            const int Lk = unified ? 0 : (assume_short_ts ? (Lw > 0 ? 1 : 0) : Lw);   // levels the stage index runs over
+            const int Lk = assume_short_ts ? (Lw > 0 ? 1 : 0) : Lw;   // levels the stage index runs over
             // (re)build the unit table of this (T, schedule) pair
             const int nstages = Lk > 0 ? Lk + T - 1 : 0;
-            if (unified && Lw > 0 &&
-                (net->wide_sched_T != T || net->wide_sched_lw != Lw || net->wide_sched_tb != net->time_block)) {
-                // wide units: stage K = level + block, 32 positions x time_block steps each
-                const int Tb = net->time_block, B = (T + Tb - 1) / Tb, ns = Lw + B - 1;
-                std::vector<int32_t> ptr((size_t)ns + 1, 0);
-                int64_t units = 0;
-                for (int K = 0; K < ns; ++K) {
-                    const int64_t lo = net->lvl_ptr[(size_t)std::max(0, K - B + 1)];
-                    const int64_t hi = net->lvl_ptr[(size_t)std::min(Lw, K + 1)];
-                    units += (hi - lo + 31) >> 5;
-                    if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
-                    ptr[(size_t)K + 1] = (int32_t)units;
-                }
-                CU(net->d_wide_unit_ptr.reserve((size_t)ns + 1));
-                CU(cudaMemcpy(net->d_wide_unit_ptr.p, ptr.data(), ((size_t)ns + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-                net->wide_units = (int)units; net->wide_stages = ns; net->wide_blocks = B;
-                net->wide_sched_T = T; net->wide_sched_lw = Lw; net->wide_sched_tb = Tb;
-            }
-            net->stages = (unified && Lw > 0 ? Lw + (T + net->time_block - 1) / net->time_block - 1 : nstages) +
-                          (pos_deep < net->n ? T : 0);
+            net->stages = nstages + (pos_deep < net->n ? T : 0);
             if (nstages > 0 && (net->sched_T != T || net->sched_short != (assume_short_ts ? 1 : 0) ||
                                 net->sched_gate != net->gate || net->sched_nstages != nstages ||
                                 net->sched_lw != Lw)) {
                 std::vector<int32_t> unit_ptr((size_t)nstages + 1, 0), gate_stage((size_t)nstages, 0);
-                std::vector<unsigned char> shift((size_t)nstages, 5);
+                std::vector<unsigned char> shift((size_t)nstages, 0);
                 std::vector<int32_t> last_nonempty((size_t)nstages + 1, 0);   // last non-empty stage <= k
                 std::vector<int64_t> cum((size_t)nstages + 1, 0);             // lanes in stages 1..k
                 int64_t units = 0;
@@ -718,12 +803,13 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                         hi = net->lvl_ptr[(size_t)std::min(Lw, k)];
                     }
                     const int64_t width = hi - lo;
-                    // 128-position units amortise the claim when a stage is many waves wide; narrower stages (a shard
-                    // of a multi-GPU run, the medium-depth levels) use 32-position units so that a stage is not four
-                    // sequential chunks long
-                    const int sh = width >= (int64_t)1 << 20 ? 7 : (width >= 400000 ? 6 : 5);
+                    // A unit = 1, 2 or 4 whole tiles (32 aligned positions each).  4-tile units amortise the claim when a
+                    // stage is many waves wide; narrower stages (a shard of a multi-GPU run, the medium-depth levels) use
+                    // single tiles so that a stage is not four sequential tiles long.
+                    const int sh = width >= (int64_t)1 << 20 ? 2 : (width >= 400000 ? 1 : 0);
+                    const int64_t tiles = width > 0 ? ((hi - 1) >> 5) - (lo >> 5) + 1 : 0;
                     shift[(size_t)k - 1] = (unsigned char)sh;
-                    units += (width + (1 << sh) - 1) >> sh;
+                    units += (tiles + (1 << sh) - 1) >> sh;
                     if (units > 2000000000LL) return fail(TRT_ERR_INVALID, "too many work units");
                     unit_ptr[(size_t)k] = (int32_t)units;
                     last_nonempty[(size_t)k] = width > 0 ? k : last_nonempty[(size_t)k - 1];
@@ -757,13 +843,18 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             // marching units over positions [pos_deep, n)
             int G = net->march_group;
             if (G == 0) {
-                // auto: the fewest segments per warp that still lets every marching unit be resident at once
+                // Auto: one segment per warp up to 16,384 marching segments.  Residency of every unit is NOT needed: units
+                // are claimed in position order and a segment at level l is finished by (l + T) link times, so only
+                // ~T levels x a few segments are live at any moment; one lane per warp took the marching phase of the
+                // bench network from 27.9 to 19.6 ms (profiles/r02_lease1).  Beyond that: the fewest segments per warp
+                // that lets every unit be resident at once.
                 int mg = 0;
                 CU(march_max_grid(&mg));
                 if (net->grid_blocks > 0) mg = std::min(mg, net->grid_blocks);
                 const int64_t warps = std::max<int64_t>(1, (int64_t)mg * 8);
                 G = 1;
-                while (G < 32 && (net->n - pos_deep + G - 1) / G > warps) G *= 2;
+                if (net->n - pos_deep > 16384 || net->grid_blocks > 0)
+                    while (G < 32 && (net->n - pos_deep + G - 1) / G > warps) G *= 2;
             }
             if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != G)) {
                 std::vector<int32_t> start;
@@ -786,7 +877,6 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             sd.claim = (unsigned int*)net->d_ctrl.p; sd.frontier = net->d_ctrl.p + 1; sd.abort_flag = net->d_ctrl.p + 2;
             sd.done = net->d_done.p; sd.gate_stage = net->d_gate_stage.p;
             sd.stage_time = nullptr;
-            sd.resync = net->warp_resync;
             if (net->profile_stages && nstages > 0) {
                 CU(net->d_stage_time.reserve((size_t)nstages + 1));
                 CU(cudaMemsetAsync(net->d_stage_time.p, 0, ((size_t)nstages + 1) * sizeof(unsigned long long), st));
@@ -797,7 +887,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                         : net->lvl_ptr[(size_t)std::min(Lw, k)] - net->lvl_ptr[(size_t)std::max(0, k - T)];
             }
             PeerDev pd;
-            pd.exp_slot = net->d_exp_slot.p; pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
+            pd.exp_peer = net->d_exp_peer.p; pd.exp_pos = net->d_exp_pos.p;
             for (int i = 0; i < TRT_MAX_PEERS; ++i) pd.S[i] = net->peer_q[i];
             int grid = net->grid_blocks, max_grid = 0;
             CU(dataflow_max_grid(&max_grid));
@@ -805,27 +895,17 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             if (grid <= 0) grid = max_grid;
             CU(cudaMemsetAsync(net->d_ctrl.p, 0, 8 * sizeof(int), st));
             if (nstages > 0) CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
-            if (first) {
-                if (!net->prepared) CU(prepare_dataflow(net));
-                net->prepared = false;
-                CU(cudaEventRecord(net->ev0, st));
-                net->launches += 1 + (net->n_lp > 0) + (net->n_bnd > 0) + (net->n_zero > 0);  // state reset kernels
-            }
+            if (first) CU(cudaEventRecord(net->ev0, st));
             if (nstages > 0 && phase != PHASE_DEEP) {
                 CU(launch_dataflow(nd, rd, sd, pd, grid, st));
                 net->launches++;
             }
-            if ((pos_deep < net->n || (unified && Lw > 0)) && phase != PHASE_WIDE) {
+            if (pos_deep < net->n && phase != PHASE_WIDE) {
                 MarchDev md;
-                md.n_wide_units = 0; md.wide_levels = 0; md.nblocks = 1; md.Tb = T; md.nstages = 0; md.wide_unit_ptr = nullptr;
-                if (unified && Lw > 0) {
-                    md.n_wide_units = net->wide_units; md.wide_levels = Lw; md.nblocks = net->wide_blocks;
-                    md.Tb = net->time_block; md.nstages = net->wide_stages; md.wide_unit_ptr = net->d_wide_unit_ptr.p;
-                }
-                md.n_units = pos_deep < net->n ? net->march_units : 0;
+                md.n_units = net->march_units;
                 md.unit_start = net->d_march_start.p; md.unit_cnt = net->d_march_cnt.p;
                 md.claim = (unsigned int*)net->d_ctrl.p + 4; md.abort_flag = net->d_ctrl.p + 2;
-                md.prof = nullptr; md.t_start = nullptr; md.poll_mode = net->poll_mode; md.poll_sleep = net->poll_sleep; md.prepare = net->march_prepare;
+                md.prof = nullptr; md.t_start = nullptr; md.poll_sleep = net->poll_sleep; md.prepare = net->march_prepare;
                 if (net->march_profile) {
                     CU(net->d_march_prof.reserve((size_t)net->n * 4 + 1));
                     CU(cudaMemsetAsync(net->d_march_prof.p, 0, (size_t)net->n * 4 * sizeof(unsigned long long), st));
@@ -838,7 +918,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                 CU(march_max_grid(&mgrid));
                 if (mgrid <= 0) return fail(TRT_ERR_CUDA, "marching kernel cannot be made resident");
                 if (net->grid_blocks > 0) mgrid = std::min(mgrid, net->grid_blocks);
-                mgrid = (int)std::min<int64_t>(mgrid, ((int64_t)md.n_units + md.n_wide_units + 7) / 8);
+                mgrid = (int)std::min<int64_t>(mgrid, ((int64_t)md.n_units + 7) / 8);
                 CU(launch_march(nd, rd, md, pd, mgrid, st));
                 net->launches++;
             }
@@ -877,17 +957,20 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
         }
     }
     CU(cudaEventRecord(net->ev1, st));
-    if (phase == PHASE_ALL) CU(launch_finalize(nd, rd, net->d_fvd.p, st));
+    const int* bp = net->d_bnd_pos.p;
+    const float* bf = net->d_bnd_fvd.p;
+    const int nb = (int)net->n_bnd;
+    if (phase == PHASE_ALL) CU(launch_finalize(nd, rd, net->d_fvd.p, bp, bf, nb, st));
     else {
         // split result pass: the dataflow rows in place; the marching rows into a compact buffer that goes home on its own
         const int pos_deep = net->mode >= 2 ? net->lvl_ptr[(size_t)net->deep_level_used] : (int)net->n;
-        if (phase == PHASE_WIDE) CU(launch_finalize(nd, rd, net->d_fvd.p, st, 0, pos_deep, -1));
+        if (phase == PHASE_WIDE) CU(launch_finalize(nd, rd, net->d_fvd.p, bp, bf, nb, st, 0, pos_deep, -1));
         else {
             CU(net->d_deep_fvd.reserve((size_t)(net->n - pos_deep) * 3 * (size_t)net->T));
-            CU(launch_finalize(nd, rd, net->d_deep_fvd.p, st, pos_deep, (int)net->n, pos_deep));
+            CU(launch_finalize(nd, rd, net->d_deep_fvd.p, bp, bf, nb, st, pos_deep, (int)net->n, pos_deep));
         }
     }
-    net->launches += (net->n > 0 && T > 0) ? 1 : 0;
+    net->launches += (net->n > 0 && T > 0) ? 1 + (nb > 0) : 0;
     net->ran = true;
     return TRT_OK;
 }
@@ -945,9 +1028,10 @@ int trt_sync(trt_network* net)
                 const unsigned long long base = (unsigned long long)(uintptr_t)net->d_S.p;
                 if (ctrl[2] == 2) snprintf(where, sizeof(where), "; the run-ahead gate waited for stage %d", ctrl[5]);
                 else if (addr >= base && net->T >= 0) {
-                    const unsigned long long off = (addr - base) / sizeof(float);
-                    const long long pos = (long long)(off / (3ull * (unsigned long long)(net->T + 1)));
-                    const int t = (int)((off / 3ull) % (unsigned long long)(net->T + 1)), c = (int)(off % 3ull);
+                    // S[tile][t][plane][lane]: 64 floats per (tile, t)
+                    const unsigned long long off = (addr - base) / sizeof(float), T1 = (unsigned long long)(net->T + 1);
+                    const long long pos = (long long)((off / (64ull * T1)) * 32ull + (off & 31ull));
+                    const int t = (int)((off >> 6) % T1), c = (off & 32ull) ? 2 : 0;
                     if (pos >= 0 && pos < net->n) {
                         const int64_t r = net->row_of_pos[(size_t)pos];
                         snprintf(where, sizeof(where), "; a %s lane polled %s of row %lld (kind %d, level %d, %s) at step %d",
@@ -983,7 +1067,7 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
     if (upstream_out && n * T > 0) {
         CU(net->d_up_out.reserve(n * T));
         CU(cudaMemsetAsync(net->d_up_out.p, 0, n * T * sizeof(float), st));
-        CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_S.p, net->d_up_out.p, (int)net->n_lp, (int)T, st));
+        CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_lp_in.p, net->d_up_out.p, (int)net->n_lp, (int)T, st));
         CU(cudaMemcpyAsync(upstream_out, net->d_up_out.p, n * T * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
@@ -1116,13 +1200,43 @@ int trt_device_results(trt_network* net, void** fvd_device)
     return TRT_OK;
 }
 
+int trt_result_hash(trt_network* net, int64_t n_sel, const int64_t* rows, const int64_t* ids, uint64_t* out)
+{
+    if (!net || !out) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_result_hash called before trt_run");
+    if (n_sel < 0) return fail(TRT_ERR_INVALID, "n_sel < 0");
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = net->stream;
+    const int64_t count = rows ? n_sel : net->n;
+    for (int64_t i = 0; rows && i < n_sel; ++i)
+        if (rows[i] < 0 || rows[i] >= net->n) return fail(TRT_ERR_INVALID, "row %lld out of range", (long long)rows[i]);
+    DevBuf<long long> d_rows, d_ids;
+    CU(net->d_hash.reserve(1));
+    CU(cudaMemsetAsync(net->d_hash.p, 0, sizeof(unsigned long long), st));
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long");
+    if (rows && count > 0) {
+        CU(d_rows.reserve((size_t)count));
+        CU(cudaMemcpyAsync(d_rows.p, rows, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    if (ids && count > 0) {
+        CU(d_ids.reserve((size_t)count));
+        CU(cudaMemcpyAsync(d_ids.p, ids, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    CU(launch_hash_rows(net->d_fvd.p, rows ? d_rows.p : nullptr, ids ? d_ids.p : nullptr, count, 3LL * net->T, net->d_hash.p, st));
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, net->d_hash.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out = (uint64_t)h;
+    return TRT_OK;
+}
+
 int trt_prepare(trt_network* net)
 {
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_prepare called before trt_upload_forcing");
     CU(cudaSetDevice(net->device));
     if (net->mode >= 2) {
-        CU(prepare_dataflow(net));
+        CU(prepare_state(net, true));
         CU(cudaStreamSynchronize(net->stream));
         net->prepared = true;
     }
@@ -1163,11 +1277,10 @@ int trt_network_set_exports(trt_network* net, int64_t count, const int64_t* rows
         h_pos[(size_t)i] = peer_pos[i];
         net->export_flag[(size_t)pos] = 1;
     }
-    CU(net->d_exp_slot.reserve((size_t)n));
     CU(net->d_exp_peer.reserve((size_t)count));
     CU(net->d_exp_pos.reserve((size_t)count));
+    net->export_slot = slot;
     if (n > 0) {
-        CU(cudaMemcpy(net->d_exp_slot.p, slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
         const int rc = upload_kind(net);
         if (rc != TRT_OK) return rc;
     }
@@ -1226,9 +1339,9 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
 {
     if (!net || !key) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "mode")) {
-        if (value < 0 || value > 5)
+        if (value < 0 || value > 4)
             return fail(TRT_ERR_INVALID, "mode must be 0 (stage launches), 1 (persistent, grid.sync), 2 (dataflow), "
-                                         "3 (marching), 4 (dataflow + marching) or 5 (time-blocked + marching)");
+                                         "3 (marching) or 4 (dataflow + marching)");
         net->mode = (int)value;
     } else if (!strcmp(key, "grid_blocks")) {
         if (value < 0) return fail(TRT_ERR_INVALID, "grid_blocks must be >= 0");
@@ -1247,8 +1360,6 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1) return fail(TRT_ERR_INVALID, "gate_lanes must be >= 1");
         net->gate_lanes = value;
         net->sched_T = -1;
-    } else if (!strcmp(key, "warp_resync")) {
-        net->warp_resync = value != 0;
     } else if (!strcmp(key, "collect_trips")) {
         net->collect_trips = value != 0;
     } else if (!strcmp(key, "trip_buckets")) {
@@ -1257,16 +1368,11 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
     } else if (!strcmp(key, "route_chunks")) {
         if (value < 1 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 1..1024");
         net->route_chunks = (int)value;
-    } else if (!strcmp(key, "time_block")) {
-        if (value < 1 || value > 100000) return fail(TRT_ERR_INVALID, "time_block must be >= 1");
-        net->time_block = (int)value;
     } else if (!strcmp(key, "march_group")) {
         if (value < 0 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 0..32");
         net->march_group = (int)value;
     } else if (!strcmp(key, "march_prepare")) {
         net->march_prepare = value != 0;
-    } else if (!strcmp(key, "poll_mode")) {
-        net->poll_mode = (int)value;
     } else if (!strcmp(key, "poll_sleep")) {
         net->poll_sleep = (int)value;
     } else if (!strcmp(key, "march_profile")) {

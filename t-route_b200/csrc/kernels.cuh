@@ -1,22 +1,35 @@
 /*
  * kernels.cuh -- device-side view of a routing network and the launchers of routing_kernels.cu.
  *
- * HBM layout (all float32 unless noted; `pos` = level-sorted engine position, n = segments):
- *   par      [9][n]      structure-of-arrays channel geometry: dt, dx, bw, tw, twcc, n, ncc, cs, s0
- *                        (for level-pool rows the same 9 slots hold dt, LkArea, LkMxE, OrificeA, OrificeC,
- *                         OrificeE, WeirC, WeirE, WeirL -- a reservoir has no channel geometry)
- *   kind     [n] u8      TRT_KIND_*
- *   level    [n] i32     wavefront level; positions are sorted by it, lvl_ptr[L+1] delimits the levels
- *   up_ptr   [n+1] i32, up_idx [E] i32   CSR of upstream positions, reference summation order
+ * HBM layout (`pos` = level-sorted engine position, n = segments, a TILE = 32 consecutive positions, n_tiles = ceil(n/32)):
+ *
+ *   rec      [n_tiles][16][32] 32-bit words   the STATIC record of a tile, 2 KB, lane-interleaved (word w of position p sits
+ *                        at rec[(p >> 5) * 512 + w * 32 + (p & 31)]).  One `cp.async.bulk` (TMA bulk copy, completion on an
+ *                        mbarrier) brings everything a warp needs to know about its 32 segments into shared memory, one
+ *                        work item ahead of the solve:
+ *                          0..8   dt, dx, bw, tw, twcc, n, ncc, cs, s0   (level-pool rows: dt, LkArea, LkMxE, OrificeA,
+ *                                 OrificeC, OrificeE, WeirC, WeirE, WeirL -- a reservoir has no channel geometry)
+ *                          9      wavefront level
+ *                          10     kind | TRT_KIND_EXPORT_FLAG | TRT_KIND_GAGE_FLAG | (number of upstream positions << 8)
+ *                          11,12  the first two upstream positions (reference summation order; 97 % of NHD segments have
+ *                                 at most two), -1 = none
+ *                          13     offset of this position's upstream list in up_idx (used when there are more than two)
+ *                          14     gage index (TRT_KIND_GAGE_FLAG)      15  export slot (TRT_KIND_EXPORT_FLAG)
+ *   up_idx   [E] i32     CSR of upstream positions, reference summation order (mc_reach.pyx:499-502)
+ *   lvl_ptr  [L+1] i32   positions are sorted by level
  *   qlat_t   [nq][n]     lateral inflow, time-major
- *   S        [n][T+1][3] flow / velocity / depth of every position for t = 0..T (t = 0 = initial state), each
- *                        segment's series contiguous.  This is the only state of the model: (s, t) reads (s, t-1) and
- *                        (u, t), (u, t-1) of its upstream neighbours.  A time-major [T+1][n] layout coalesces better in
- *                        the wide headwater levels but makes the ~600 lanes of a deep-mainstem stage (one segment per
- *                        level, each at a different t) touch ~1200 distinct 2 MB pages per stage: measured 95 us per
- *                        stage of TLB misses instead of 12 us (profiles/r01_*).  Position-major keeps such a stage inside
- *                        one or two pages, and it IS the reference's result layout, so the final transpose
- *                        degenerates into a row permutation.
+ *   S        [n_tiles][T+1][2][32] f32   flow q (plane 0) and depth d (plane 1) of every position for t = 0..T (t = 0 =
+ *                        initial state): THE model state -- (s, t) reads (s, t-1) and (u, t), (u, t-1) of its upstream
+ *                        neighbours.  A warp routes the 32 positions of a tile at one timestep, so its own-state read and
+ *                        its result write are two full 128-byte lines each (no partial sectors, nothing to merge), and a
+ *                        segment's series stays inside one 2 MB page (the T+1 lines of a tile are contiguous: 74 KB for a
+ *                        day at 300 s), which is what the marching lanes of the deep main stem need (a time-major [T+1][n]
+ *                        array costs them a TLB miss per step: measured 95 us instead of 12 us per stage in round 1).
+ *                        A not-yet-written slot holds TRT_SENTINEL; publishing a value is ONE 4-byte (lane) / 128-byte
+ *                        (warp) store.  Velocity is NOT state: nobody downstream reads it, the result pass evaluates it.
+ *   fmask    [n_tiles][T+1] u32   bit (p & 31) set when the Muskingum-Cunge solve of (p, t) took the flow branch, i.e.
+ *                        velocity = f(depth) (MCsingleSegStime_f2py_NOLOOP.f90:163-169); clear = the no-flow branch (:171-178), v = 0
+ *   lp_in    [n_lp][T+1] reservoir inflow of every level pool (upstream_array, mc_reach.pyx:710)
  *   fvd      [n_rows][3T] the reference's result layout (mc_reach.pyx:807-813), caller row order
  */
 #pragma once
@@ -25,16 +38,27 @@
 
 namespace trt {
 
+enum { R_PAR = 0, R_LEVEL = 9, R_FLAGS = 10, R_UP0 = 11, R_UP1 = 12, R_ESTART = 13, R_GAGE = 14, R_EXP = 15,
+       R_WORDS = 16, R_TILE_WORDS = 16 * 32 };
+
+// index of q[pos, t] in S; depth is 32 floats further on, the previous timestep 64 floats back
+__host__ __device__ __forceinline__ size_t s_idx(long long pos, int t, int T1)
+{
+    return (((size_t)(pos >> 5) * (size_t)T1 + (size_t)t) << 6) + (size_t)(pos & 31);
+}
+__host__ __device__ __forceinline__ size_t rec_idx(long long pos, int word)
+{
+    return (size_t)(pos >> 5) * R_TILE_WORDS + (size_t)word * 32 + (size_t)(pos & 31);
+}
+
 struct NetDev {
     int n;                     // segments
     int nlevels;               // wavefront levels of the dependent (assume_short_ts = false) schedule
     const int* lvl_ptr;        // [nlevels + 1]
-    const int* level;          // [n]
-    const int* up_ptr;         // [n + 1]
     const int* up_idx;         // [E]
-    const unsigned char* kind; // [n]
-    const float* par;          // [9][n]
+    const unsigned* rec;       // [n_tiles][16][32]
     const int* row_of_pos;     // [n]
+    const int* lp_slot;        // [n] level-pool index of a level-pool position (NULL without reservoirs)
 };
 
 // Streamflow nudging (simple_da.pyx:21-128, call site mc_reach.pyx:761-796): the flow of a gage segment is replaced, right
@@ -48,7 +72,6 @@ struct GageDev {
     int gmax;                    // observation columns per gage (gage_maxtimestep)
     float dt;                    // routing period of the call
     float decay;                 // da_decay_coefficient
-    const int* slot;             // [n] gage index of a position whose kind carries TRT_KIND_GAGE_FLAG
     const float* usgs;           // [n_gages][gmax] observations (NaN = missing)
     float* lastobs;              // [n_gages][2] (time, value)
     float* nudge;                // [n_gages][T + 1]
@@ -67,14 +90,17 @@ struct RunDev {
     int nq;         // qlat columns
     int short_ts;   // assume_short_ts
     const float* qlat_t;
-    float* S;       // flow state [n][T + 1][3] = (q, v, d) of every position for t = 0 .. T (t = 0: initial state)
+    float* S;       // flow state, see the file header
+    unsigned* fmask;
+    float* lp_in;
 };
 
-// Dataflow schedule (mode 2).  Work = the stages of the wavefront, cut into units of 32 or 128 consecutive positions
-// and claimed IN ORDER from one counter; a unit never waits on a stage barrier, its lanes wait on exactly the values
-// they read (a not-yet-written q / d slot holds TRT_SENTINEL).  Because units are claimed in stage order, everything a
-// claimed unit waits for has been claimed earlier by a warp that is running, so the earliest unfinished unit always
-// progresses: no deadlock, and a lane stuck in the 750-iteration retry ladder delays only its own dependents.
+// Dataflow schedule (mode 2).  Work = the stages of the wavefront, cut into units of 1, 2 or 4 tiles and claimed IN ORDER
+// from one counter; a unit never waits on a stage barrier, its lanes wait on exactly the values they read (a
+// not-yet-written q / d slot holds TRT_SENTINEL).  Because units are claimed in stage order, everything a claimed unit
+// waits for has been claimed earlier by a warp that is running (or that is finishing the one unit it claimed before),
+// so the earliest unfinished unit always progresses: no deadlock, and a lane stuck in the 750-iteration retry ladder
+// delays only its own dependents.
 #define TRT_SENTINEL 0xFFFFFFFFu
 
 struct SchedDev {
@@ -84,7 +110,7 @@ struct SchedDev {
                                       // 1 with assume_short_ts: every segment of a step is independent
     int pos_end;                      // positions [0, pos_end) belong to this schedule
     const int* unit_ptr;              // [nstages + 1] first unit of stage k is unit_ptr[k - 1]
-    const unsigned char* unit_shift;  // [nstages] log2 of the unit width of that stage (5 or 7)
+    const unsigned char* unit_shift;  // [nstages] log2 of the tiles per unit of that stage (0, 1 or 2)
     unsigned int* claim;              // [1] next unit to hand out
     int* done;                        // [nstages] finished units per stage
     int* frontier;                    // [1] highest stage known to be complete (run-ahead gate)
@@ -93,39 +119,21 @@ struct SchedDev {
                                       // the last non-empty stage <= k - gate (0 = no wait)
     unsigned long long* stage_time;   // [nstages + 1] or NULL: %globaltimer (ns) when stage k completed, in slot k;
                                       // slot 0 = kernel start ("profile_stages" option)
-    int resync;                       // 1: the lanes of a unit meet at a __syncwarp between their input polls and the solve
-                                      // ("warp_resync" option, see dataflow_kernel)
 };
 
 // cut edges to other shards: lane s with (kind & TRT_KIND_EXPORT_FLAG) stores q also to peer memory
 #define TRT_KIND_EXPORT_FLAG 0x10
 #define TRT_MAX_PEERS 16
 struct PeerDev {
-    const int* exp_slot;              // [n] index into exp_peer / exp_pos, valid where the flag is set
     const int* exp_peer;              // [n_exp]
     const long long* exp_pos;         // [n_exp] position in the peer's arrays
-    float* S[TRT_MAX_PEERS];          // peer flow-state arrays (mapped peer memory)
+    float* S[TRT_MAX_PEERS];          // peer flow-state arrays (mapped peer memory, same layout and T as ours)
 };
 
 // Marching schedule (mode 3, and the deep levels of mode 4): units of <= 32 consecutive positions, claimed in position
 // order; every lane walks its segment through all T timesteps, waiting on the q slots of its upstream neighbours.
-//
-// Mode 5 puts the wide shallow levels through the same lanes, in pieces: a wide unit is 32 consecutive positions x one
-// BLOCK of Tb consecutive timesteps, and units are handed out in order of stage K = level + block index, the wavefront of
-// mode 2 with blocks in place of steps.  Everything a unit reads was produced by a unit of a lower stage (upstream
-// segments: lower level, same block; its own previous block), i.e. by a unit claimed earlier.  Compared with one step
-// per unit the channel geometry is loaded and pre-processed once per Tb steps, flow and depth of the previous step stay
-// in registers, the previous upstream sum is reused as qup, and the lanes of a warp drift apart in time so that a lane
-// needing 5 secant trips does not hold up 31 lanes that needed 2.  The wide units come first in the queue, the deep
-// marching units (all T steps) after them: the deep lanes start while the last wide stages drain.
 struct MarchDev {
-    int n_wide_units;                 // units [0, n_wide_units) are wide units
-    int wide_levels;                  // levels [0, wide_levels) are routed by wide units
-    int nblocks;                      // time blocks per segment = ceil(T / Tb)
-    int Tb;                           // timesteps per block
-    int nstages;                      // wide stages K = 0 .. nstages - 1 = wide_levels + nblocks - 1
-    const int* wide_unit_ptr;         // [nstages + 1] first unit of stage K
-    int n_units;                      // deep units follow: unit n_wide_units + i is deep unit i
+    int n_units;
     const int* unit_start;            // [n_units] first position of the unit
     const unsigned char* unit_cnt;    // [n_units] lanes in use (1..32)
     unsigned int* claim;              // [1] next unit to hand out
@@ -134,9 +142,12 @@ struct MarchDev {
                                       // done, ns between the inputs of a step arriving and its flow being published (summed over steps), failed polls ("march_profile" option)
     unsigned long long* t_start;      // [1] %globaltimer at kernel start (prof only)
     int prepare;                      // 1: evaluate the first-trip phase A of the next step right after a step is done
-    int poll_mode;                    // experiment: 0 ld.volatile, 1 ld.relaxed.gpu, 2 atomicOr(p, 0)
-    int poll_sleep;                   // experiment: ns of back-off between polls of an idle warp (-1 = adaptive)
+    int poll_sleep;                   // ns of back-off between polls of an idle warp (-1 = adaptive)
 };
+
+// force the module of every kernel of the library onto the current device (see routing_kernels.cu)
+cudaError_t preload_routing_kernels();
+
 cudaError_t march_max_grid(int* blocks);
 cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
                          int grid_blocks, cudaStream_t st);
@@ -158,18 +169,29 @@ cudaError_t launch_gather_qlat(const float* qlat_rows, const int* row_of_pos, fl
 cudaError_t launch_init_state(const float* q0_rows, const int* row_of_pos, float* S, int n, int T, cudaStream_t st);
 cudaError_t launch_init_levelpool(const int* lp_pos, const float* lp_qd0, const float* lp_h0, float* S, int T, int n_lp,
                                   cudaStream_t st);
-cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st);
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, unsigned* rec, int n_lp, cudaStream_t st);
 cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* S, int n_bnd, int T, cudaStream_t st);
+// Device-resident hand-off between consecutive routing windows (trt_continue): column t of the flow state <-> a compact
+// [n_tiles][2][32] buffer.  The last column of one window becomes column 0 of the next (whose T may differ).
+cudaError_t launch_column_copy(float* S, int T1, int t, float* col, int n_tiles, int to_state, cudaStream_t st);
+// last-observation state of the gages after a window -> initial state of the next: times shifted by -(nsteps * dt), as
+// compute_network_structured returns them (mc_reach.pyx:822-836)
+cudaError_t launch_carry_gages(const float* lastobs, float* lastobs_init, int n_gages, float shift, cudaStream_t st);
 // result pass over the steps of run's time chunk
 // positions [p_begin, p_end) (p_end < 0: all); compact_from >= 0: destination row = position - compact_from
-cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, cudaStream_t st, int p_begin = 0,
-                            int p_end = -1, int compact_from = -1);
-cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up_rows, int n_lp, int T,
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd_rows, const int* bnd_pos, const float* bnd_fvd,
+                            int n_bnd, cudaStream_t st, int p_begin = 0, int p_end = -1, int compact_from = -1);
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* lp_in, float* up_rows, int n_lp, int T,
                                 cudaStream_t st);
 cudaError_t launch_reset_gages(const GageDev& g, const int* gage_pos, const unsigned char* gage_active,
                                const float* lastobs_init, float* S, int T, cudaStream_t st);
 cudaError_t launch_export_series(const int* pos, const float* S, float* dst, int count, int T, cudaStream_t st);
 cudaError_t launch_import_series(const int* pos, const float* src, float* S, int count, int T, cudaStream_t st);
+// 64-bit checksum of a result table in row order: sum over rows of hash(row, bits of the row) -- independent of how the
+// rows were sharded or scheduled (bench.py `verify`)
+// rows: result rows to hash (NULL = 0 .. n_rows - 1); row_ids: the id each of them is hashed under (NULL = the row number)
+cudaError_t launch_hash_rows(const float* fvd, const long long* rows, const long long* row_ids, long long n_rows,
+                             long long row_len, unsigned long long* out, cudaStream_t st);
 
 cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long long count, cudaStream_t st);
 cudaError_t launch_levelpool_series(const float* lp9, float h0, const float* inflow, float ql, float dt,

@@ -10,12 +10,17 @@
  * path from a headwater, all pairs (s, t) with level(s) + t == k are mutually independent, so the
  * network is routed as a wavefront over k = 1 .. L + T - 1 instead of T * L dependent level-steps.
  * Positions are sorted by level, hence the active set of stage k is ONE contiguous position range
- * [lvl_ptr[max(0, k-T)], lvl_ptr[min(L, k)]) and every load below is a unit-stride sweep of an SoA
- * array (the upstream gather is the only indexed access).  With assume_short_ts every segment of a
- * step is independent (quc := qup) and the same kernel runs with L = 1.
+ * [lvl_ptr[max(0, k-T)], lvl_ptr[min(L, k)]).  With assume_short_ts every segment of a step is
+ * independent (quc := qup) and the same kernel runs with L = 1.
  *
- * One lane = one segment-step; 32 consecutive positions per warp.  No tensor cores: the work is
- * ~2k dependent scalar FP32/FP64 instructions per lane, not a contraction.
+ * Data movement (kernels.cuh has the layout).  One lane = one segment-step, one warp = one TILE of 32
+ * consecutive positions.  Everything static about a tile (channel geometry, level, kind, the first two
+ * upstream positions) is ONE 2 KB record that the warp brings into shared memory with a TMA bulk copy
+ * (cp.async.bulk + mbarrier) while it is still solving the previous tile; the flow state is tiled the same
+ * way, so the previous state comes in and the new state goes out as full 128-byte lines, and the upstream
+ * gather reads lines that were written one stage ago and are still in L2.  All loads of a lane-step are
+ * issued before the first one is examined: one memory round trip per tile instead of a chain of eight.
+ * No tensor cores: the work is ~2k dependent scalar FP32/FP64 instructions per lane, not a contraction.
  *
  * Compile with -fmad=false (see mc_device.cuh).
  */
@@ -50,7 +55,7 @@ __device__ __forceinline__ PowTabs stage_tables(SmemTabs& s)
 
 // ---- loads / stores of the flow state --------------------------------------------------------------------
 // Bulk-synchronous schedules read finished rows with ld.cg.  The dataflow schedule reads slots that another warp
-// (or another GPU, over NVLink) may not have written yet: they hold TRT_SENTINEL until the one 4-byte store that
+// (or another GPU, over NVLink) may not have written yet: they hold TRT_SENTINEL until the one store that
 // publishes the value lands in L2, so a volatile (L1-bypassing) poll is the whole synchronisation.
 __device__ __forceinline__ unsigned ld_volatile_u32(const float* p)
 {
@@ -66,12 +71,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
+// first read of a slot; settle() below turns it into a value
 template <bool WAIT>
-__device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
+__device__ __forceinline__ unsigned ld_slot(const float* p)
 {
-    if (!WAIT) return __ldcg(p);
-    unsigned v = ld_volatile_u32(p);
-    if (v == TRT_SENTINEL) {
+    return WAIT ? ld_volatile_u32(p) : __float_as_uint(__ldcg(p));
+}
+
+// the value of slot `p` whose first read returned `v`: `v` itself once it has arrived, else poll
+template <bool WAIT>
+__device__ __forceinline__ float settle(const float* p, unsigned v, int* abort_flag)
+{
+    if (WAIT && v == TRT_SENTINEL) {
         unsigned spins = 0;
         do {
             __nanosleep(spins < 16 ? 40 : 400);
@@ -92,6 +103,12 @@ __device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
 }
 
 template <bool WAIT>
+__device__ __forceinline__ float ld_state(const float* p, int* abort_flag)
+{
+    return settle<WAIT>(p, ld_slot<WAIT>(p), abort_flag);
+}
+
+template <bool WAIT>
 __device__ __forceinline__ void st_state(float* p, float x)
 {
     if (WAIT) {
@@ -108,18 +125,71 @@ __device__ __forceinline__ void prefetch_l2(const float* p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier) -----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// the static record of one position (see kernels.cuh); `rb` points at word 0 of the lane, words are 32 apart -- in the
+// shared-memory copy of a tile and in the global array alike
+struct LaneRec {
+    float p0, p1, p2, p3, p4, p5, p6, p7, p8;
+    unsigned flags;
+    int up0, up1, estart, gage, exp;
+};
+__device__ __forceinline__ LaneRec load_rec(const unsigned* rb)
+{
+    LaneRec r;
+    r.p0 = __uint_as_float(rb[0 * 32]); r.p1 = __uint_as_float(rb[1 * 32]); r.p2 = __uint_as_float(rb[2 * 32]);
+    r.p3 = __uint_as_float(rb[3 * 32]); r.p4 = __uint_as_float(rb[4 * 32]); r.p5 = __uint_as_float(rb[5 * 32]);
+    r.p6 = __uint_as_float(rb[6 * 32]); r.p7 = __uint_as_float(rb[7 * 32]); r.p8 = __uint_as_float(rb[8 * 32]);
+    r.flags = rb[R_FLAGS * 32];
+    r.up0 = (int)rb[R_UP0 * 32]; r.up1 = (int)rb[R_UP1 * 32]; r.estart = (int)rb[R_ESTART * 32];
+    r.gage = (int)rb[R_GAGE * 32]; r.exp = (int)rb[R_EXP * 32];
+    return r;
+}
+
 // q[s, t] becomes visible to every consumer (same GPU: the poll of a downstream lane; other GPU: the import row of the
 // downstream shard, written over NVLink peer memory) with ONE 4-byte store each.
-__device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflags, int s, int t, size_t T1,
+__device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflags, int xslot, int t, int T1,
                                              const PeerDev& peers)
 {
     unsigned b = __float_as_uint(q);
     if (b == TRT_SENTINEL) b = 0x7FC00000u;      // a NaN payload that happens to equal the sentinel
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(own), "r"(b) : "memory");
     if (kflags & TRT_KIND_EXPORT_FLAG) {
-        const int x = __ldg(peers.exp_slot + s);
-        const int pr = __ldg(peers.exp_peer + x);
-        float* dst = peers.S[pr] + ((size_t)__ldg(peers.exp_pos + x) * T1 + (size_t)t) * 3;
+        const int pr = __ldg(peers.exp_peer + xslot);
+        float* dst = peers.S[pr] + s_idx(__ldg(peers.exp_pos + xslot), t, T1);
         asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
     }
 }
@@ -128,10 +198,9 @@ __device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflag
 // nudge and updates the last-observation state.  Float expressions keep the operand order of the Cython source; the decay
 // weight is trt_expf_det (include/trt_detmath.h).  Ordering: the lane of step t reads the state the lane of step t - 1
 // wrote; that lane fences before it publishes its flow / depth and this one fences after it has seen them.
-__device__ __forceinline__ float apply_nudging(const RunDev& run, int s, int t, float model_val, const PowTabs& tabs)
+__device__ __forceinline__ float apply_nudging(const RunDev& run, int g, int t, float model_val, const PowTabs& tabs)
 {
     const GageDev& G = run.gage;
-    const int g = __ldg(G.slot + s);
     __threadfence();
     float lastobs_time = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g));
     float lastobs_val = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g + 1));
@@ -164,95 +233,110 @@ __device__ __forceinline__ float apply_nudging(const RunDev& run, int s, int t, 
     return replacement_val;
 }
 
-// route segment `s` (engine position) at step `t`.  sync_mask != 0 (polling schedules only): the lanes named in it -- exactly
-// the lanes of the warp that call this function for a routed (non-boundary) segment -- meet at a __syncwarp after their
-// inputs have arrived and before the solve.
+// Route position `s` at step `t`; `r` is its static record.  Returns true when the Muskingum-Cunge solve took the flow
+// branch (the caller records it in fmask: the result pass derives the velocity from the depth exactly then).
 template <bool WAIT>
-__device__ __forceinline__ void route_lane(const NetDev& net, const RunDev& run, int s, int t, const PowTabs& tabs,
-                                           const PeerDev* peers, int* abort_flag, unsigned sync_mask = 0)
+__device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run, const LaneRec& r, int s, int t,
+                                           const PowTabs& tabs, const PeerDev* peers, int* abort_flag)
 {
-    const unsigned kflags = net.kind[s];
-    const unsigned kind = kflags & 0x0F;
-    if (kind == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
+    const unsigned kflags = r.flags & 0xFFu;
+    const bool is_lp = (kflags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+    const int cnt = (int)(r.flags >> 8);
+    const int T1 = run.T + 1;
+    float* S = run.S;
+    float* own = S + s_idx(s, t, T1);        // q[s, t]; depth at +32; the previous step 64 floats back
 
-    const size_t n = (size_t)net.n;
-    const size_t T1 = (size_t)run.T + 1;
-    float* own = run.S + ((size_t)s * T1 + (size_t)t) * 3;   // (q, v, d) of (s, t); own - 3 is (s, t-1)
-
-    // parameters first: they do not depend on anybody's results, so their latency overlaps the waits below
-    const float* par = net.par + s;
-    const float p0 = __ldg(par + 0 * n), p1 = __ldg(par + 1 * n), p2 = __ldg(par + 2 * n), p3 = __ldg(par + 3 * n),
-                p4 = __ldg(par + 4 * n), p5 = __ldg(par + 5 * n), p6 = __ldg(par + 6 * n), p7 = __ldg(par + 7 * n),
-                p8 = __ldg(par + 8 * n);
-    const int e0 = __ldg(net.up_ptr + s), e1 = __ldg(net.up_ptr + s + 1);
-
+    // Issue EVERY load of this lane-step before the first of them is examined: own state, lateral inflow and the flows of
+    // the first two upstream neighbours are independent, so they cost one memory round trip, not one each.
+    const unsigned v_d = ld_slot<WAIT>(own - 32);                                  // depth / water elevation at t-1
+    unsigned v_q = 0;
+    float ql = 0.0f;
+    if (!is_lp) {
+        v_q = ld_slot<WAIT>(own - 64);                                             // :733
+        ql = __ldcs(run.qlat_t + (size_t)((t - 1) / run.qts) * (size_t)net.n + s); // :723
+    }
+    const float* pu0 = S;
+    const float* pu1 = S;
+    unsigned a0c = 0, a0p = 0, a1c = 0, a1p = 0;
+    if (cnt > 0) {
+        pu0 = S + s_idx(r.up0, t, T1);
+        if (!run.short_ts) a0c = ld_slot<WAIT>(pu0);
+        a0p = ld_slot<WAIT>(pu0 - 64);
+    }
+    if (cnt > 1) {
+        pu1 = S + s_idx(r.up1, t, T1);
+        if (!run.short_ts) a1c = ld_slot<WAIT>(pu1);
+        a1p = ld_slot<WAIT>(pu1 - 64);
+    }
     // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
     float quc = 0.0f, qup = 0.0f;
-    if (run.short_ts) {
-        for (int e = e0; e < e1; ++e) {
-            const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)t) * 3;
-            qup += ld_state<WAIT>(up - 3, abort_flag);
-        }
-        quc = qup;
-    } else {
-        for (int e = e0; e < e1; ++e) {
-            const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)t) * 3;
-            quc += ld_state<WAIT>(up, abort_flag);
-            qup += ld_state<WAIT>(up - 3, abort_flag);
-        }
+    if (cnt > 0) {
+        if (!run.short_ts) quc += settle<WAIT>(pu0, a0c, abort_flag);
+        qup += settle<WAIT>(pu0 - 64, a0p, abort_flag);
     }
-    // depth (MC) / water elevation (level pool) at t-1
-    const float statep = ld_state<WAIT>(own - 1, abort_flag);
-    float ql = 0.0f, qdp = 0.0f;
-    if (kind != TRT_KIND_LEVELPOOL) {
-        ql = __ldg(run.qlat_t + (size_t)((t - 1) / run.qts) * n + s);              // :723
-        qdp = ld_state<WAIT>(own - 3, abort_flag);                                  // :733
+    if (cnt > 1) {
+        if (!run.short_ts) quc += settle<WAIT>(pu1, a1c, abort_flag);
+        qup += settle<WAIT>(pu1 - 64, a1p, abort_flag);
     }
-    // Every input is here.  The polls above are spin loops with a sleep in them; the warp does not reliably come back
-    // together behind them on its own (ncu, profiles/r01_v5_trip_order: 2.46e7 unit iterations but 3.12e7 executions of the
-    // code from here on, at 25 of 32 lanes -- a quarter of the warps run the whole solve in two pieces).
-    if (WAIT && sync_mask) __syncwarp(sync_mask);
+    for (int e = r.estart + 2; e < r.estart + cnt; ++e) {                          // the rare confluence of 3+ rivers
+        const float* up = S + s_idx(__ldg(net.up_idx + e), t, T1);
+        if (!run.short_ts) quc += ld_state<WAIT>(up, abort_flag);
+        qup += ld_state<WAIT>(up - 64, abort_flag);
+    }
+    if (run.short_ts) quc = qup;
+    const float statep = settle<WAIT>(own - 32, v_d, abort_flag);
+    const float qdp = is_lp ? 0.0f : settle<WAIT>(own - 64, v_q, abort_flag);
 
-    float o_q, o_v, o_d;
-    bool write_v = true;
-    if (kind == TRT_KIND_LEVELPOOL) {
+    float o_q, o_d;
+    bool flow = false;
+    if (is_lp) {
         // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
         LpParams lp;
-        lp.area = p1; lp.max_depth = p2; lp.orifice_area = p3; lp.orifice_coefficient = p4; lp.orifice_elevation = p5;
-        lp.weir_coefficient = p6; lp.weir_elevation = p7; lp.weir_length = p8; lp.dam_length = 10.0f;
+        lp.area = r.p1; lp.max_depth = r.p2; lp.orifice_area = r.p3; lp.orifice_coefficient = r.p4;
+        lp.orifice_elevation = r.p5; lp.weir_coefficient = r.p6; lp.weir_elevation = r.p7; lp.weir_length = r.p8;
+        lp.dam_length = 10.0f;
         float H = statep, outflow;
-        trt_levelpool_step(lp, quc, 0.0f, p0, H, outflow, tabs);
+        trt_levelpool_step(lp, quc, 0.0f, r.p0, H, outflow, tabs);
         o_q = outflow;
-        o_v = quc;      // velocity slot carries the reservoir inflow (upstream_array, :710); finalize writes 0 for v
         o_d = H;
+        run.lp_in[(size_t)__ldg(net.lp_slot + s) * T1 + t] = quc;      // reservoir inflow (upstream_array, :710)
     } else {
-        // polling schedules (WAIT): the velocity slot keeps TRT_SENTINEL and the result pass fills it in from the depth
-        const McResult r = trt_mc_segment<false, !WAIT>(p0, qup, quc, qdp, ql, p1, p2, p3, p4, p5, p6, p7, p8, statep, tabs);
-        o_q = r.qdc; o_v = r.velc; o_d = r.depthc;
+        // velocity is not computed here: the result pass evaluates it from the final depth (finalize_kernel)
+        const McResult res = trt_mc_segment<false, false>(r.p0, qup, quc, qdp, ql, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7,
+                                                          r.p8, statep, tabs);
+        o_q = res.qdc; o_d = res.depthc;
         if (run.trip_sum) {
-            atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * n + s, r.iters);
-            if (r.over) atomicAdd(run.trip_sum + (size_t)run.trip_buckets * n + s, 1);       // row trip_buckets: over-bank steps
+            atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * (size_t)net.n + s, res.iters);
+            if (res.over) atomicAdd(run.trip_sum + (size_t)run.trip_buckets * (size_t)net.n + s, 1);   // over-bank steps
         }
-        write_v = !WAIT || !(ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);   // no-flow branch: v = 0 (:171-178)
+        flow = (ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);             // else the no-flow branch: v = 0 (:171-178)
     }
-    if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, s, t, o_q, tabs);    // mc_reach.pyx:761-796
-    if (write_v) own[1] = o_v;
-    st_state<WAIT>(own + 2, o_d);
+    if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, r.gage, t, o_q, tabs);   // mc_reach.pyx:761-796
+    st_state<WAIT>(own + 32, o_d);
     st_state<WAIT>(own, o_q);
     if (WAIT && (kflags & TRT_KIND_EXPORT_FLAG)) {
         // this segment drains into another shard: scatter its outflow into that GPU's inflow slot (peer memory)
-        const int x = __ldg(peers->exp_slot + s);
-        const int pr = __ldg(peers->exp_peer + x);
-        float* dst = peers->S[pr] + ((size_t)__ldg(peers->exp_pos + x) * T1 + (size_t)t) * 3;
+        const int pr = __ldg(peers->exp_peer + r.exp);
+        float* dst = peers->S[pr] + s_idx(__ldg(peers->exp_pos + r.exp), t, T1);
         unsigned b = __float_as_uint(o_q);
         if (b == TRT_SENTINEL) b = 0x7FC00000u;
         asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
     }
+    return flow;
 }
 
-__device__ __forceinline__ int lane_step(const NetDev& net, const RunDev& run, int k, int s)
+// bulk-synchronous schedules (modes 0, 1): record from global memory, flow bit straight into fmask
+__device__ __forceinline__ void route_lane_sync(const NetDev& net, const RunDev& run, int k, int s, const PowTabs& tabs)
 {
-    return run.short_ts ? k : k - __ldg(net.level + s);
+    const unsigned* rb = net.rec + rec_idx(s, 0);
+    const unsigned flags = __ldg(rb + R_FLAGS * 32);
+    if ((flags & 0x0Fu) == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
+    const int t = run.short_ts ? k : k - (int)__ldg(rb + R_LEVEL * 32);
+    if (t < 1 || t > run.Tc) return;
+    const LaneRec r = load_rec(rb);
+    const int tt = t + run.t_off;
+    if (route_lane<false>(net, run, r, s, tt, tabs, nullptr, nullptr))
+        atomicOr(run.fmask + (size_t)(s >> 5) * (run.T + 1) + tt, 1u << (s & 31));
 }
 
 __global__ void __launch_bounds__(kBlock) stage_kernel(NetDev net, RunDev run, int k, int lo, int hi)
@@ -261,9 +345,7 @@ __global__ void __launch_bounds__(kBlock) stage_kernel(NetDev net, RunDev run, i
     const PowTabs tabs = stage_tables(smem);
     const int s = lo + blockIdx.x * kBlock + threadIdx.x;
     if (s >= hi) return;
-    const int t = lane_step(net, run, k, s);
-    if (t < 1 || t > run.Tc) return;
-    route_lane<false>(net, run, s, t + run.t_off, tabs, nullptr, nullptr);
+    route_lane_sync(net, run, k, s, tabs);
 }
 
 __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev run, int k_begin, int k_end)
@@ -281,10 +363,7 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
             lo = __ldg(net.lvl_ptr + max(0, k - run.Tc));
             hi = __ldg(net.lvl_ptr + min(L, k));
         }
-        for (int s = lo + gtid; s < hi; s += gstride) {
-            const int t = lane_step(net, run, k, s);
-            if (t >= 1 && t <= run.Tc) route_lane<false>(net, run, s, t + run.t_off, tabs, nullptr, nullptr);
-        }
+        for (int s = lo + gtid; s < hi; s += gstride) route_lane_sync(net, run, k, s, tabs);
         grid.sync();
     }
 }
@@ -292,85 +371,164 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
 // ---------------------------------------------------------------------------------------------------------
 // dataflow schedule (see kernels.cuh): persistent warps claim units in stage order, lanes wait on their own inputs
 // ---------------------------------------------------------------------------------------------------------
-// 4 CTAs per SM = 64 registers per thread (60 bytes of spill stores, 32 warps per SM); 3 would give 80 registers, no spills
-// and 24 warps -- an A/B for a GPU session: make EXTRA=-DTRT_DATAFLOW_MIN_BLOCKS=3
+// 4 CTAs per SM = 64 registers per thread, 32 warps per SM.  Measured (profiles/r02_*): 3 CTAs (80 registers, no spills,
+// 24 warps) is 15 % SLOWER -- the kernel hides latency with warps, not with registers.
 #ifndef TRT_DATAFLOW_MIN_BLOCKS
 #define TRT_DATAFLOW_MIN_BLOCKS 4
 #endif
+
+// A claimed unit, decoded (warp-uniform), lives in the warp's shared-memory control block -- NOT in registers: the secant
+// solve needs every one of the 64 registers, and the unit is looked at only before and after it.
+enum { DU_LO = 0, DU_HI = 1, DU_STAGE = 2, DU_TILE0 = 3, DU_NTILES = 4, DU_WORDS = 5 };
+
+// unit u -> cw[0 .. DU_WORDS); returns false when the queue is exhausted
+__device__ __forceinline__ bool df_decode(const NetDev& net, const RunDev& run, const SchedDev& sc, unsigned u, int& cursor,
+                                          int* cw, int lane)
+{
+    if (u >= (unsigned)__ldg(sc.unit_ptr + sc.nstages)) return false;
+    // stage of unit u: last index i >= cursor with unit_ptr[i] <= u (units are handed out in order, so it is almost
+    // always the stage of this warp's previous unit or the next one)
+    int lo_i = cursor;
+    if (u >= (unsigned)__ldg(sc.unit_ptr + lo_i + 1)) {
+        ++lo_i;
+        if (u >= (unsigned)__ldg(sc.unit_ptr + lo_i + 1)) {
+            int hi_i = sc.nstages;                    // invariant: unit_ptr[lo_i] <= u < unit_ptr[hi_i]
+            while (hi_i - lo_i > 1) {
+                const int mid = (lo_i + hi_i) >> 1;
+                if ((unsigned)__ldg(sc.unit_ptr + mid) <= u) lo_i = mid; else hi_i = mid;
+            }
+        }
+    }
+    cursor = lo_i;
+    const int k = lo_i + 1;
+    int lo = 0, hi = sc.pos_end;
+    if (!run.short_ts) {
+        lo = __ldg(net.lvl_ptr + max(0, k - run.Tc));
+        hi = __ldg(net.lvl_ptr + min(sc.wide_levels, k));
+    }
+    const int shift = __ldg(sc.unit_shift + lo_i);
+    const int tile_end = (hi - 1) >> 5;               // last tile of the stage (hi > lo: empty stages have no units)
+    const int tile0 = (lo >> 5) + (int)((u - (unsigned)__ldg(sc.unit_ptr + lo_i)) << shift);
+    if (lane == 0) {
+        cw[DU_LO] = lo; cw[DU_HI] = hi; cw[DU_STAGE] = lo_i; cw[DU_TILE0] = tile0;
+        cw[DU_NTILES] = min(1 << shift, tile_end + 1 - tile0);
+    }
+    __syncwarp();
+    return true;
+}
+
 __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
 {
     __shared__ SmemTabs smem;
+    __shared__ __align__(128) unsigned recbuf[kBlock / 32][2][R_TILE_WORDS];     // per warp: two 2 KB tile records
+    __shared__ __align__(8) unsigned long long bars[kBlock / 32][2];
+    __shared__ int ctl[kBlock / 32][2][8];                                        // per warp: this unit, the next unit
     const PowTabs tabs = stage_tables(smem);
-    const int lane = threadIdx.x & 31;
-    const unsigned total = (unsigned)__ldg(sc.unit_ptr + sc.nstages);
-    const int L = sc.wide_levels;
-    const int pos_end = sc.pos_end;
-    int cursor = 0;                                   // stage index (k - 1) of this warp's previous unit
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(smem_u32(&bars[warp][0]), 1); mbar_init(smem_u32(&bars[warp][1]), 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
     if (sc.stage_time && blockIdx.x == 0 && threadIdx.x == 0) sc.stage_time[0] = globaltimer_ns();
-    for (;;) {
-        unsigned u = 0;
-        if (lane == 0) u = atomicAdd(sc.claim, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= total) break;
-        // stage of unit u: last index i >= cursor with unit_ptr[i] <= u
-        int lo_i = cursor, hi_i = sc.nstages;         // invariant: unit_ptr[lo_i] <= u < unit_ptr[hi_i]
-        while (hi_i - lo_i > 1) {
-            const int mid = (lo_i + hi_i) >> 1;
-            if ((unsigned)__ldg(sc.unit_ptr + mid) <= u) lo_i = mid; else hi_i = mid;
-        }
-        cursor = lo_i;
-        const int k = lo_i + 1;
-        int lo, hi;
-        if (run.short_ts) { lo = 0; hi = pos_end; }
-        else {
-            lo = __ldg(net.lvl_ptr + max(0, k - run.Tc));
-            hi = __ldg(net.lvl_ptr + min(L, k));
-        }
-        const int shift = __ldg(sc.unit_shift + lo_i);
-        const int p0 = lo + (int)((u - (unsigned)__ldg(sc.unit_ptr + lo_i)) << shift);
-        const int p1 = min(hi, p0 + (1 << shift));
 
-        // run-ahead gate: do not start polling individual slots before stage k - gate is complete
-        const int need = __ldg(sc.gate_stage + lo_i);   // last non-empty stage <= k - gate (0 = none)
-        if (need >= 1) {
-            if (lane == 0) {
-                unsigned spins = 0;
-                while (*reinterpret_cast<volatile int*>(sc.frontier) < need) {
-                    __nanosleep(200);
-                    if ((++spins & 0x3FFF) == 0) {
-                        if (*reinterpret_cast<volatile int*>(sc.abort_flag) != 0) break;
-                        if (spins > (1u << 25)) { if (atomicCAS(sc.abort_flag, 0, 2) == 0) sc.abort_flag[3] = need; break; }
+    // lane 0 owns the copy-engine side: arm the barrier with the byte count, start the 2 KB copy.  The records stream
+    // through L2 once per stage (evict-first); the flow state, which is re-read one stage later, stays.
+    auto fetch_tile = [&](int tile, int b) {
+        if (lane == 0) {
+            const unsigned bar = smem_u32(&bars[warp][b]);
+            mbar_expect_tx(bar, R_TILE_WORDS * 4);
+            bulk_g2s(smem_u32(&recbuf[warp][b][0]), net.rec + (size_t)tile * R_TILE_WORDS, R_TILE_WORDS * 4, bar,
+                     l2_evict_first_policy());
+        }
+    };
+    // claim: lane 0 only; the result is consumed (broadcast) when the unit is needed, one work item later
+    auto claim = [&]() -> unsigned { return lane == 0 ? atomicAdd(sc.claim, 1u) : 0u; };
+
+    int cursor = 0;
+    unsigned pend = claim();
+    if (!df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, ctl[warp][0], lane)) return;
+    pend = claim();                                  // the unit after this one: in flight while this one is routed
+    fetch_tile(ctl[warp][0][DU_TILE0], 0);
+    // st: bit 0 = record buffer in use, bit 1 / 2 = phase parity of barrier 0 / 1, bit 3 = control block of the current
+    // unit, bit 4 = a next unit exists, bits 8.. = tile index inside the current unit
+    unsigned st = 0;
+    for (;;) {
+        const int b = st & 1;
+        int* cu = ctl[warp][(st >> 3) & 1];
+        const int j = (int)(st >> 8);
+        const bool last_of_unit = j + 1 >= cu[DU_NTILES];
+        // ---- the work item after this one: its record travels while this tile is solved ----
+        if (!last_of_unit) fetch_tile(cu[DU_TILE0] + j + 1, b ^ 1);
+        else {
+            int* nx = ctl[warp][((st >> 3) & 1) ^ 1];
+            if (df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, nx, lane)) {
+                st |= 16u;
+                pend = claim();
+                fetch_tile(nx[DU_TILE0], b ^ 1);
+            } else st &= ~16u;
+        }
+        if (j == 0) {
+            // run-ahead gate: do not start polling individual slots before stage k - gate is complete
+            const int need = __ldg(sc.gate_stage + cu[DU_STAGE]);   // last non-empty stage <= k - gate (0 = none)
+            if (need >= 1) {
+                if (lane == 0) {
+                    unsigned spins = 0;
+                    while (*reinterpret_cast<volatile int*>(sc.frontier) < need) {
+                        __nanosleep(200);
+                        if ((++spins & 0x3FFF) == 0) {
+                            if (*reinterpret_cast<volatile int*>(sc.abort_flag) != 0) break;
+                            if (spins > (1u << 25)) { if (atomicCAS(sc.abort_flag, 0, 2) == 0) sc.abort_flag[3] = need; break; }
+                        }
                     }
                 }
-            }
-            __syncwarp();
-        }
-
-        for (int base = p0; base < p1; base += 32) {
-            const int s = base + lane;
-            bool live = s < p1;
-            unsigned mask = 0;
-            if (sc.resync) {
-                // all 32 lanes are here together: name the ones that will route a segment for the __syncwarp in route_lane
-                live = live && (net.kind[s] & 0x0F) != TRT_KIND_BOUNDARY;
-                mask = __ballot_sync(0xffffffffu, live);
-            }
-            if (live) {
-                const int t = (run.short_ts ? k : k - __ldg(net.level + s)) + run.t_off;
-                route_lane<true>(net, run, s, t, tabs, &peers, sc.abort_flag, mask);
-            }
-            if (sc.resync) __syncwarp();
-        }
-        __syncwarp();
-        if (lane == 0) {
-            // stage bookkeeping for the gate: the warp that finishes the last unit of stage k advances the frontier
-            const int units_k = __ldg(sc.unit_ptr + lo_i + 1) - __ldg(sc.unit_ptr + lo_i);
-            __threadfence();
-            if (atomicAdd(sc.done + lo_i, 1) + 1 == units_k) {
-                atomicMax(sc.frontier, k);
-                if (sc.stage_time) sc.stage_time[k] = globaltimer_ns();
+                __syncwarp();
             }
         }
+        // ---- this tile ----
+        mbar_wait(smem_u32(&bars[warp][b]), (st >> (1 + b)) & 1u);
+        st ^= 2u << b;
+        const int tile = cu[DU_TILE0] + j;
+        const int s = (tile << 5) + lane;
+        const unsigned* rb = &recbuf[warp][b][lane];
+        const bool live = s >= cu[DU_LO] && s < cu[DU_HI] && (rb[R_FLAGS * 32] & 0x0Fu) != TRT_KIND_BOUNDARY;
+        int t = 0;
+        bool flow = false;
+        if (live) {
+            const int k = cu[DU_STAGE] + 1;
+            t = (run.short_ts ? k : k - (int)rb[R_LEVEL * 32]) + run.t_off;
+            const LaneRec r = load_rec(rb);
+            flow = route_lane<true>(net, run, r, s, t, tabs, &peers, sc.abort_flag);
+        }
+        __syncwarp();                                // every lane is done with this buffer: it may be refilled
+        // flow bits of the tile: one word per (tile, t).  Lanes of a tile share t except where two levels meet in a tile.
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (live_mask) {
+            const unsigned flow_mask = __ballot_sync(0xffffffffu, flow);
+            const int t_lead = __shfl_sync(0xffffffffu, t, __ffs(live_mask) - 1);
+            unsigned* fm = run.fmask + (size_t)tile * (run.T + 1);
+            if (__all_sync(0xffffffffu, !live || t == t_lead)) {
+                if (lane == 0 && flow_mask) atomicOr(fm + t_lead, flow_mask);
+            } else if (flow) {
+                atomicOr(fm + t, 1u << lane);
+            }
+        }
+        if (!last_of_unit) st += 256u;
+        else {
+            if (lane == 0) {
+                // stage bookkeeping for the gate: the warp that finishes the last unit of stage k advances the frontier
+                const int si = cu[DU_STAGE];
+                const int units_k = __ldg(sc.unit_ptr + si + 1) - __ldg(sc.unit_ptr + si);
+                __threadfence();
+                if (atomicAdd(sc.done + si, 1) + 1 == units_k) {
+                    atomicMax(sc.frontier, si + 1);
+                    if (sc.stage_time) sc.stage_time[si + 1] = globaltimer_ns();
+                }
+            }
+            if (!(st & 16u)) break;
+            st = (st & 0xFFu) ^ 8u;                  // the next unit becomes the current one, tile 0
+        }
+        st ^= 1u;
     }
 }
 
@@ -397,59 +555,34 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
     const int lane = threadIdx.x & 31;
     const size_t n = (size_t)net.n;
     const int T = run.T;
-    const size_t T1 = (size_t)T + 1;
+    const int T1 = T + 1;
     if (mk.prof && blockIdx.x == 0 && threadIdx.x == 0) atomicMin(mk.t_start, globaltimer_ns());
-    int cursor = 0;                               // stage of this warp's previous wide unit
     for (;;) {
         unsigned u = 0;
         if (lane == 0) u = atomicAdd(mk.claim, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= (unsigned)(mk.n_wide_units + mk.n_units)) break;
-        int p, t_first = run.t_off + 1, t_last = run.t_off + run.Tc;
-        bool mine;
-        if (u < (unsigned)mk.n_wide_units) {
-            // stage of wide unit u: last K >= cursor with wide_unit_ptr[K] <= u
-            int lo_i = cursor, hi_i = mk.nstages;
-            while (hi_i - lo_i > 1) {
-                const int mid = (lo_i + hi_i) >> 1;
-                if ((unsigned)__ldg(mk.wide_unit_ptr + mid) <= u) lo_i = mid; else hi_i = mid;
-            }
-            cursor = lo_i;
-            const int K = lo_i;
-            const int lo = __ldg(net.lvl_ptr + max(0, K - mk.nblocks + 1));
-            const int hi = __ldg(net.lvl_ptr + min(mk.wide_levels, K + 1));
-            p = lo + (int)((u - (unsigned)__ldg(mk.wide_unit_ptr + K)) << 5) + lane;
-            mine = p < hi;
-            if (mine) {
-                const int b = K - __ldg(net.level + p);           // 0 <= b < nblocks by construction of [lo, hi)
-                t_first = run.t_off + b * mk.Tb + 1;
-                t_last = min(run.t_off + run.Tc, t_first + mk.Tb - 1);
-            }
-        } else {
-            const unsigned v = u - (unsigned)mk.n_wide_units;
-            p = __ldg(mk.unit_start + v) + lane;
-            mine = lane < (int)__ldg(mk.unit_cnt + v);
-        }
+        if (u >= (unsigned)mk.n_units) break;
+        const int t_first = run.t_off + 1, t_last = run.t_off + run.Tc;
+        const int p = __ldg(mk.unit_start + u) + lane;
+        const bool mine = lane < (int)__ldg(mk.unit_cnt + u);
         unsigned long long prof_first = 0, prof_wait = 0, prof_fail = 0;
         long long wait_since = 0;
 
         int state = MARCH_DONE;
-        unsigned kflags = 0, kind = TRT_KIND_BOUNDARY;
-        if (mine) { kflags = net.kind[p]; kind = kflags & 0x0F; }
-        float* row = run.S;                       // (q, v, d) series of this lane's segment
-        float p0 = 0.f, p1 = 1.f, p2 = 1.f, p3 = 1.f, p4 = 0.f, p5 = 1.f, p6 = 0.f, p7 = 1.f, p8 = 1.f;
-        int e0 = 0, e1 = 0;
+        LaneRec r;
+        r.p0 = 0.f; r.p1 = 1.f; r.p2 = 1.f; r.p3 = 1.f; r.p4 = 0.f; r.p5 = 1.f; r.p6 = 0.f; r.p7 = 1.f; r.p8 = 1.f;
+        r.flags = TRT_KIND_BOUNDARY; r.up0 = r.up1 = -1; r.estart = 0; r.gage = 0; r.exp = 0;
+        if (mine) r = load_rec(net.rec + rec_idx(p, 0));
+        const unsigned kflags = r.flags & 0xFFu, kind = kflags & 0x0Fu;
+        const int e0 = r.estart, e1 = r.estart + (int)(r.flags >> 8);
+        float* row = run.S;                       // q[p, 0]: step t of this lane's segment is 64 * t floats further on
         if (kind != TRT_KIND_BOUNDARY) {          // prescribed rows are never computed
             state = MARCH_WAIT;
-            row = run.S + (size_t)p * T1 * 3;
-            const float* par = net.par + p;
-            p0 = __ldg(par + 0 * n); p1 = __ldg(par + 1 * n); p2 = __ldg(par + 2 * n); p3 = __ldg(par + 3 * n);
-            p4 = __ldg(par + 4 * n); p5 = __ldg(par + 5 * n); p6 = __ldg(par + 6 * n); p7 = __ldg(par + 7 * n);
-            p8 = __ldg(par + 8 * n);
-            e0 = __ldg(net.up_ptr + p); e1 = __ldg(net.up_ptr + p + 1);
+            row = run.S + s_idx(p, 0, T1);
         }
         const bool is_lp = kind == TRT_KIND_LEVELPOOL;
-        const McChannel c = mc_channel(p0, p1, p2, p3, p4, p5, p6, p7, p8);
+        const int lp_slot = is_lp ? __ldg(net.lp_slot + p) : 0;
+        const McChannel c = mc_channel(r.p0, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7, r.p8);
         McSolve s;
         s.have0 = false; s.have1 = false;
         int t = t_first;
@@ -459,15 +592,13 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
         int e_cur = e0;                           // next upstream slot to read for the current step
         float psum = 0.0f;                        // flows of the slots before e_cur, summed in order
         if (state == MARCH_WAIT) {
-            // State at t_first - 1: the initial condition (t_first == 1; init_state_kernel / init_levelpool_kernel) or
-            // the last step of this segment's previous block, written by a unit of the previous stage.  That unit and
-            // the units of the upstream segments were claimed before this one, so waiting here cannot deadlock.
-            const float* prev = row + (size_t)(t_first - 1) * 3;
+            // State at t_first - 1: the initial condition (init_state_kernel / init_levelpool_kernel), or the last step of
+            // the previous time chunk.
+            const float* prev = row + (size_t)(t_first - 1) * 64;
             qdp = ld_state<true>(prev, mk.abort_flag);
-            statep = ld_state<true>(prev + 2, mk.abort_flag);
+            statep = ld_state<true>(prev + 32, mk.abort_flag);
             for (int e = e0; e < e1; ++e)         // previous_upstream_flows of step t_first  (mc_reach.pyx:499-502)
-                upsum_prev += ld_state<true>(run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)(t_first - 1)) * 3,
-                                             mk.abort_flag);
+                upsum_prev += ld_state<true>(run.S + s_idx(__ldg(net.up_idx + e), t_first - 1, T1), mk.abort_flag);
             if (t_last < t_first) state = MARCH_DONE;
         }
 
@@ -484,9 +615,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int e = min(e_cur + j, e1 - 1);
-                        const float* up = run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)ti) * 3;
-                        if (mk.poll_mode == 1) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[j]) : "l"(up) : "memory");
-                        else v[j] = ld_volatile_u32(up);
+                        v[j] = ld_volatile_u32(run.S + s_idx(__ldg(net.up_idx + e), ti, T1));
                     }
                     const int m = min(8, e1 - e_cur);
 #pragma unroll
@@ -516,13 +645,12 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     upsum_prev = sum;
                     mc_begin<true>(s, qup, quc, qdp, ql, statep);
                     state = MARCH_ITER;
-                    if (!is_lp && !s.flow) {                                         // :171-178
-                        float* own = row + (size_t)t * 3;
-                        own[1] = 0.0f;
+                    if (!is_lp && !s.flow) {                                         // :171-178 (fmask bit stays clear: v = 0)
+                        float* own = row + (size_t)t * 64;
                         float q = 0.0f;
-                        if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, p, t, q, tabs);
-                        st_state<true>(own + 2, 0.0f);
-                        publish_flow(own, q, kflags, p, t, T1, peers);
+                        if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs);
+                        st_state<true>(own + 32, 0.0f);
+                        publish_flow(own, q, kflags, r.exp, t, T1, peers);
                         qdp = q; statep = 0.0f;
                         s.have0 = false; s.have1 = false;
                         ++t;
@@ -532,44 +660,42 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     // every 4096 failed polls: somebody flagged an error, or this lane has been starving for seconds
                     if (*reinterpret_cast<volatile int*>(mk.abort_flag) != 0) state = MARCH_DONE;
                     else if (waited >= (1u << 26)) {
-                        if (atomicCAS(mk.abort_flag, 0, 3) == 0) {
-                            const int ti2 = run.short_ts ? t - 1 : t;
+                        if (atomicCAS(mk.abort_flag, 0, 3) == 0)
                             *reinterpret_cast<volatile unsigned long long*>(mk.abort_flag + 4) =
-                                (unsigned long long)(run.S + ((size_t)__ldg(net.up_idx + e_cur) * T1 + (size_t)ti2) * 3);
-                        }
+                                (unsigned long long)(run.S + s_idx(__ldg(net.up_idx + e_cur), ti, T1));
                         state = MARCH_DONE;
                     }
                 }
             }
             if (state == MARCH_ITER) {
-                float* own = row + (size_t)t * 3;
+                float* own = row + (size_t)t * 64;
                 if (is_lp) {
                     // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
                     LpParams lp;
-                    lp.area = p1; lp.max_depth = p2; lp.orifice_area = p3; lp.orifice_coefficient = p4;
-                    lp.orifice_elevation = p5; lp.weir_coefficient = p6; lp.weir_elevation = p7; lp.weir_length = p8;
+                    lp.area = r.p1; lp.max_depth = r.p2; lp.orifice_area = r.p3; lp.orifice_coefficient = r.p4;
+                    lp.orifice_elevation = r.p5; lp.weir_coefficient = r.p6; lp.weir_elevation = r.p7; lp.weir_length = r.p8;
                     lp.dam_length = 10.0f;
                     float H = statep, outflow;
-                    trt_levelpool_step(lp, s.quc, 0.0f, p0, H, outflow, tabs);
-                    if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, p, t, outflow, tabs);
-                    publish_flow(own, outflow, kflags, p, t, T1, peers);
-                    own[1] = s.quc;             // reservoir inflow rides in the velocity slot (upstream_array, :710)
-                    st_state<true>(own + 2, H);
+                    trt_levelpool_step(lp, s.quc, 0.0f, r.p0, H, outflow, tabs);
+                    if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, r.gage, t, outflow, tabs);
+                    publish_flow(own, outflow, kflags, r.exp, t, T1, peers);
+                    run.lp_in[(size_t)lp_slot * T1 + t] = s.quc;      // reservoir inflow (upstream_array, :710)
+                    st_state<true>(own + 32, H);
                     qdp = outflow; statep = H;
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                 } else if (mc_iterate(c, s, tabs)) {
                     float q = mc_outflow(s);
-                    if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, p, t, q, tabs);
-                    publish_flow(own, q, kflags, p, t, T1, peers);   // downstream lanes are waiting for this
+                    if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs);
+                    publish_flow(own, q, kflags, r.exp, t, T1, peers);   // downstream lanes are waiting for this
                     if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
-                    st_state<true>(own + 2, s.h);                    // own[1] (velocity): result pass, from this depth
-                    if ((t & 1) == 0) {
-                        // cold tributary rows (finished long ago, evicted from L2): pull the sectors of the coming steps
-                        // in, off the critical path.  One 32-byte sector holds 2.67 steps of (q, v, d).
+                    st_state<true>(own + 32, s.h);                       // velocity: result pass, from this depth
+                    atomicOr(run.fmask + (size_t)(p >> 5) * T1 + t, 1u << (p & 31));
+                    {
+                        // cold tributary lines (finished long ago, evicted from L2): pull the sector of a coming step in,
+                        // off the critical path
                         const int tp = min(t + 8, T);      // T: last column of the flow state
-                        for (int e = e0; e < e1; ++e)
-                            prefetch_l2(run.S + ((size_t)__ldg(net.up_idx + e) * T1 + (size_t)tp) * 3);
+                        for (int e = e0; e < e1; ++e) prefetch_l2(run.S + s_idx(__ldg(net.up_idx + e), tp, T1));
                     }
                     qdp = q; statep = s.h;
                     if (mk.prof && t == 1) prof_first = globaltimer_ns();
@@ -581,7 +707,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
             const unsigned iterating = __ballot_sync(0xffffffffu, state == MARCH_ITER);
             if (iterating == 0) {
                 if (__all_sync(0xffffffffu, state == MARCH_DONE)) {
-                    if (mk.prof && mine && u >= (unsigned)mk.n_wide_units) {
+                    if (mk.prof && mine) {
                         const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(mk.t_start);
                         unsigned long long* o = mk.prof + (size_t)p * 4;
                         o[0] = prof_first ? prof_first - t0 : 0; o[1] = globaltimer_ns() - t0; o[2] = prof_wait; o[3] = prof_fail;
@@ -598,37 +724,28 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
     }
 }
 
-cudaError_t march_max_grid(int* blocks)
+template <class K>
+static cudaError_t max_grid_of(K kernel, int* blocks)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, march_kernel, kBlock, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
     if (e != cudaSuccess) return e;
     *blocks = sms * per_sm;
     return cudaSuccess;
 }
+cudaError_t march_max_grid(int* blocks) { return max_grid_of(march_kernel, blocks); }
+cudaError_t dataflow_max_grid(int* blocks) { return max_grid_of(dataflow_kernel, blocks); }
+cudaError_t persistent_max_grid(int* blocks) { return max_grid_of(persistent_kernel, blocks); }
 
 cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
                          int grid_blocks, cudaStream_t st)
 {
     march_kernel<<<grid_blocks, kBlock, 0, st>>>(net, run, march, peers);
     return cudaGetLastError();
-}
-
-cudaError_t dataflow_max_grid(int* blocks)
-{
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dataflow_kernel, kBlock, 0);
-    if (e != cudaSuccess) return e;
-    *blocks = sms * per_sm;
-    return cudaSuccess;
 }
 
 cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
@@ -646,19 +763,6 @@ cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, in
     return cudaGetLastError();
 }
 
-cudaError_t persistent_max_grid(int* blocks)
-{
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel, kBlock, 0);
-    if (e != cudaSuccess) return e;
-    *blocks = sms * per_sm;
-    return cudaSuccess;
-}
-
 cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin, int k_end, int grid_blocks,
                               cudaStream_t st)
 {
@@ -668,7 +772,7 @@ cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin,
 }
 
 // ------------------------------------------------------------------------------------------------
-// boundary conversions between the caller's row-major tables and the time-major engine arrays
+// boundary conversions between the caller's row-major tables and the engine arrays
 // ------------------------------------------------------------------------------------------------
 
 // qlat_t[c][pos] = qlat_rows[row_of_pos[pos]][c]
@@ -681,107 +785,159 @@ __global__ void gather_qlat_kernel(const float* __restrict__ in, const int* __re
     for (int c = 0; c < nq; ++c) out[(size_t)c * n + pos] = __ldg(src + c);
 }
 
-// state[pos][0][:] = initial_conditions[row][:]  (flowveldepth_nd[ids, 0] = init_array[ids], mc_reach.pyx:361)
+// state[pos][0] = (qu0, h0) of initial_conditions[row]  (flowveldepth_nd[ids, 0] = init_array[ids], mc_reach.pyx:361)
 __global__ void init_state_kernel(const float* __restrict__ q0, const int* __restrict__ row_of_pos, float* __restrict__ S,
                                   int n, int T1)
 {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n) return;
     const float* src = q0 + (size_t)row_of_pos[pos] * 3;
-    float* dst = S + (size_t)pos * T1 * 3;
+    float* dst = S + s_idx(pos, 0, T1);
     // a NaN whose bits happen to equal TRT_SENTINEL would read as "not yet written": canonicalise it
-    for (int c = 0; c < 3; ++c) {
-        unsigned b = __float_as_uint(src[c]);
-        if (b == TRT_SENTINEL) b = 0x7FC00000u;
-        dst[c] = __uint_as_float(b);
-    }
+    unsigned bq = __float_as_uint(src[0]), bd = __float_as_uint(src[2]);
+    if (bq == TRT_SENTINEL) bq = 0x7FC00000u;
+    if (bd == TRT_SENTINEL) bd = 0x7FC00000u;
+    dst[0] = __uint_as_float(bq);
+    dst[32] = __uint_as_float(bd);
 }
 
-// reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth slot
+// reservoirs: flowveldepth[row, 0, 0] = qd0 (mc_reach.pyx:298); the elevation state lives in the depth plane
 __global__ void init_levelpool_kernel(const int* __restrict__ lp_pos, const float* __restrict__ qd0,
                                       const float* __restrict__ h0, float* S, int T1, int n_lp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lp) return;
-    float* dst = S + (size_t)lp_pos[i] * T1 * 3;
-    dst[0] = qd0[i]; dst[1] = 0.0f; dst[2] = h0[i];
+    float* dst = S + s_idx(lp_pos[i], 0, T1);
+    dst[0] = qd0[i]; dst[32] = h0[i];
 }
 
-// overlay the routing period and the 8 reservoir parameters on the 9 parameter slots of the level-pool positions
-__global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const float* __restrict__ par9, float* par, int n,
+// overlay the routing period and the 8 reservoir parameters on the 9 parameter words of the level-pool positions
+__global__ void scatter_lp_params_kernel(const int* __restrict__ lp_pos, const float* __restrict__ par9, unsigned* rec,
                                          int n_lp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lp * 9) return;
     const int l = i / 9, c = i % 9;
-    par[(size_t)c * n + lp_pos[l]] = par9[i];
+    rec[rec_idx(lp_pos[l], c)] = __float_as_uint(par9[i]);
 }
 
-// prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463) -- one contiguous series
+// prescribed rows: flowveldepth[row, t, :] = results[(t-1)*3 + :]  (mc_reach.pyx:462-463); the state keeps q and d, the
+// result pass copies the prescribed triplets (velocity included) straight into the result
 __global__ void fill_boundary_kernel(const int* __restrict__ bnd_pos, const float* __restrict__ bnd_fvd, float* S,
                                      int n_bnd, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long w = 3LL * T;
-    if (i >= (long long)n_bnd * w) return;
-    const int b = (int)(i / w);
-    const long long c = i % w;
-    S[((size_t)bnd_pos[b] * (T + 1) + 1) * 3 + c] = bnd_fvd[(size_t)b * w + c];
+    if (i >= (long long)n_bnd * T) return;
+    const int b = (int)(i / T), t = (int)(i % T) + 1;
+    float* dst = S + s_idx(bnd_pos[b], t, T + 1);
+    const float* src = bnd_fvd + ((size_t)b * T + (t - 1)) * 3;
+    unsigned bq = __float_as_uint(src[0]), bd = __float_as_uint(src[2]);
+    if (bq == TRT_SENTINEL) bq = 0x7FC00000u;
+    if (bd == TRT_SENTINEL) bd = 0x7FC00000u;
+    dst[0] = __uint_as_float(bq); dst[32] = __uint_as_float(bd);
 }
 
 // boundary rows nobody prescribes stay zero for every step (flowveldepth is zero-initialised, mc_reach.pyx:253)
 __global__ void fill_zero_rows_kernel(const int* __restrict__ pos, float* S, int count, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long w = 3LL * T;
-    if (i >= (long long)count * w) return;
-    S[((size_t)pos[i / w] * (T + 1) + 1) * 3 + (i % w)] = 0.0f;
+    if (i >= (long long)count * T) return;
+    float* dst = S + s_idx(pos[i / T], (int)(i % T) + 1, T + 1);
+    dst[0] = 0.0f; dst[32] = 0.0f;
 }
 
-// Result in the reference's layout (mc_reach.pyx:807-813): fvd[row][3*(t-1) + c] = state[pos][t][c], t = 1..T.
-// The engine already keeps every segment's series contiguous, so this is one 12*T-byte copy per segment -- a
-// permutation from level-sorted positions to the caller's rows, one warp per segment.  The polling schedules leave the
-// velocity slot of a Muskingum-Cunge step at TRT_SENTINEL: velocity is a function of the final depth and the channel
-// alone (:163-169), nobody downstream reads it, and here one warp = one segment evaluates it with uniform parameters and
-// no divergence instead of inside the branchy solve.
+// column t of the state <-> a compact [n_tiles][2][32] buffer (trt_continue: last column of a window -> column 0 of the next)
+__global__ void column_copy_kernel(float* __restrict__ S, int T1, int t, float* __restrict__ col, long long words, int to_state)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    float* s = S + (((size_t)(i >> 6) * T1 + t) << 6) + (i & 63);
+    if (to_state) {
+        unsigned b = __float_as_uint(col[i]);
+        if (b == TRT_SENTINEL) b = 0x7FC00000u;
+        *s = __uint_as_float(b);
+    } else col[i] = *s;
+}
+
+__global__ void carry_gages_kernel(const float* __restrict__ lastobs, float* __restrict__ lastobs_init, int n_gages, float shift)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_gages) return;
+    lastobs_init[2 * g] = lastobs[2 * g] - shift;          // lastobs_times - ((timestep - 1) * dt)   (mc_reach.pyx:822-836)
+    lastobs_init[2 * g + 1] = lastobs[2 * g + 1];
+}
+
+// Result in the reference's layout (mc_reach.pyx:807-813): fvd[row][3*(t-1) + c] = (q, v, d)[pos][t], t = 1..T -- a
+// transposition from tiles of 32 positions (lanes across positions) to rows (lanes across time), through shared memory,
+// 128-byte lines on both sides.  One block = one tile x up to 96 timesteps.  Velocity (:163-169) is a function of the final
+// depth and the channel alone and nobody downstream reads it, so it is evaluated HERE, where a lane keeps one segment's
+// channel for all its steps and the only divergence is the flow / no-flow bit, instead of inside the branchy solve.
 // Positions [p_begin, p_end); compact_from >= 0: row (p - compact_from) of a compact buffer instead of the caller's row
 // (the marching rows of a time-chunked trt_route go home separately, see engine.cu).
-__global__ void __launch_bounds__(256) permute_rows_kernel(NetDev net, RunDev run, float* __restrict__ fvd, int p_begin,
-                                                           int p_end, int compact_from)
+constexpr int kFinSteps = 96;
+__global__ void __launch_bounds__(256) finalize_kernel(NetDev net, RunDev run, float* __restrict__ fvd, int p_begin, int p_end,
+                                                       int compact_from, int tile_begin, int t_blocks)
 {
     __shared__ SmemTabs smem;
+    __shared__ float sm[32][kFinSteps * 3 + 1];       // +1: lanes of a warp write one column, 289 = 1 mod 32 banks
     const PowTabs tabs = stage_tables(smem);
-    const int warps_per_block = 256 / 32;
-    const int lane = threadIdx.x & 31;
-    const size_t n = (size_t)net.n;
-    for (long long p = p_begin + (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < p_end;
-         p += (long long)gridDim.x * warps_per_block) {
-        const float* src = run.S + ((size_t)p * (run.T + 1) + 1) * 3;
-        float* dst = fvd + (size_t)(compact_from >= 0 ? (int)p - compact_from : net.row_of_pos[p]) * 3 * run.T;
-        const unsigned kind = net.kind[p] & 0x0F;
-        const float* par = net.par + p;
-        const McChannel c = mc_channel(__ldg(par + 0 * n), __ldg(par + 1 * n), __ldg(par + 2 * n), __ldg(par + 3 * n),
-                                       __ldg(par + 4 * n), __ldg(par + 5 * n), __ldg(par + 6 * n), __ldg(par + 7 * n),
-                                       __ldg(par + 8 * n));
-        for (int t = run.t_off + lane; t < run.t_off + run.Tc; t += 32) {
-            const float q = __ldcs(src + 3 * t), d = __ldcs(src + 3 * t + 2);
-            float v = __ldcs(src + 3 * t + 1);
-            if (kind == TRT_KIND_LEVELPOOL) v = 0.0f;      // flowveldepth[r.id, t, 1] = 0.0  (:708)
-            else if (kind == TRT_KIND_MC && __float_as_uint(v) == TRT_SENTINEL) v = mc_velocity(c, d, tabs);
-            __stcs(dst + 3 * t, q); __stcs(dst + 3 * t + 1, v); __stcs(dst + 3 * t + 2, d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = tile_begin + (int)(blockIdx.x / t_blocks);
+    const int t0 = run.t_off + 1 + (int)(blockIdx.x % t_blocks) * kFinSteps;
+    const int t1 = min(run.t_off + run.Tc, t0 + kFinSteps - 1);
+    const int T1 = run.T + 1;
+    const int p = (tile << 5) + lane;
+    const bool valid = p >= p_begin && p < p_end;
+    unsigned kind = TRT_KIND_BOUNDARY;
+    LaneRec r;
+    r.p0 = 0.f; r.p1 = 1.f; r.p2 = 1.f; r.p3 = 1.f; r.p4 = 0.f; r.p5 = 1.f; r.p6 = 0.f; r.p7 = 1.f; r.p8 = 1.f;
+    if (valid) { r = load_rec(net.rec + rec_idx(p, 0)); kind = r.flags & 0x0Fu; }
+    const McChannel c = mc_channel(r.p0, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7, r.p8);
+    for (int t = t0 + warp; t <= t1; t += 8) {
+        float q = 0.0f, d = 0.0f, v = 0.0f;
+        if (valid) {
+            const float* src = run.S + s_idx(p, t, T1);
+            q = __ldcs(src); d = __ldcs(src + 32);
+            // level pools: flowveldepth[r.id, t, 1] = 0.0 (:708); prescribed rows: overwritten by boundary_rows_kernel
+            if (kind == TRT_KIND_MC && ((__ldg(run.fmask + (size_t)tile * T1 + t) >> lane) & 1u)) v = mc_velocity(c, d, tabs);
         }
+        float* o = &sm[lane][(t - t0) * 3];
+        o[0] = q; o[1] = v; o[2] = d;
+    }
+    __syncthreads();
+    const int len = (t1 - t0 + 1) * 3;
+    for (int pl = warp; pl < 32; pl += 8) {
+        const int pp = (tile << 5) + pl;
+        if (pp < p_begin || pp >= p_end) continue;
+        const size_t row = (size_t)(compact_from >= 0 ? pp - compact_from : __ldg(net.row_of_pos + pp));
+        float* dst = fvd + row * 3 * (size_t)run.T + (size_t)(t0 - 1) * 3;
+        for (int j = lane; j < len; j += 32) __stcs(dst + j, sm[pl][j]);
     }
 }
 
-// upstream_array[row, t] = reservoir inflow (mc_reach.pyx:710), carried in the velocity slot of level-pool rows
+// prescribed rows keep their prescribed (q, v, d) in the result
+__global__ void boundary_rows_kernel(NetDev net, RunDev run, const int* __restrict__ bnd_pos, const float* __restrict__ bnd_fvd,
+                                     int n_bnd, float* __restrict__ fvd, int p_begin, int p_end, int compact_from)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = 3LL * run.Tc;
+    if (i >= (long long)n_bnd * w) return;
+    const int b = (int)(i / w);
+    const long long j = (long long)run.t_off * 3 + i % w;
+    const int pos = bnd_pos[b];
+    if (pos < p_begin || pos >= p_end) return;
+    const size_t row = (size_t)(compact_from >= 0 ? pos - compact_from : net.row_of_pos[pos]);
+    fvd[row * 3 * (size_t)run.T + j] = bnd_fvd[(size_t)b * 3 * run.T + j];
+}
+
+// upstream_array[row, t] = reservoir inflow (mc_reach.pyx:710)
 __global__ void upstream_out_kernel(const int* __restrict__ lp_pos, const int* __restrict__ row_of_pos,
-                                    const float* __restrict__ S, float* __restrict__ up, int n_lp, int T)
+                                    const float* __restrict__ lp_in, float* __restrict__ up, int n_lp, int T)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_lp * T) return;
     const int l = (int)(i / T), t = (int)(i % T) + 1;
-    const int pos = lp_pos[l];
-    up[(size_t)row_of_pos[pos] * T + (t - 1)] = S[((size_t)pos * (T + 1) + t) * 3 + 1];
+    up[(size_t)row_of_pos[lp_pos[l]] * T + (t - 1)] = lp_in[(size_t)l * (T + 1) + t];
 }
 
 // start of a run: last-observation state back to its initial values, nudge cleared, and the initial flow of every gage
@@ -797,7 +953,7 @@ __global__ void reset_gages_kernel(GageDev g, const int* __restrict__ gage_pos, 
         g.lastobs[2 * i + 1] = lastobs_init[2 * i + 1];
         if (g.gmax > 0) {
             const float v = g.usgs[(size_t)i * g.gmax];
-            if (!(v != v)) S[(size_t)gage_pos[i] * w * 3] = v;
+            if (!(v != v)) S[s_idx(gage_pos[i], 0, T + 1)] = v;
         }
     }
 }
@@ -808,7 +964,7 @@ __global__ void export_series_kernel(const int* __restrict__ pos, const float* _
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)count * (T + 1)) return;
     const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
-    dst[i] = S[((size_t)pos[c] * (T + 1) + t) * 3];
+    dst[i] = S[s_idx(pos[c], t, T + 1)];
 }
 
 __global__ void import_series_kernel(const int* __restrict__ pos, const float* __restrict__ src, float* __restrict__ S,
@@ -818,7 +974,53 @@ __global__ void import_series_kernel(const int* __restrict__ pos, const float* _
     if (i >= (long long)count * (T + 1)) return;
     const int c = (int)(i / (T + 1)), t = (int)(i % (T + 1));
     if (t == 0) return;
-    S[((size_t)pos[c] * (T + 1) + t) * 3] = src[i];
+    S[s_idx(pos[c], t, T + 1)] = src[i];
+}
+
+// Checksum of a result table that does not depend on how its rows were computed, sharded or ordered: the SUM over rows of
+// a 64-bit hash of (row id, the row's bits).  splitmix64 finaliser; one warp per row.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) hash_rows_kernel(const float* __restrict__ fvd, const long long* __restrict__ rows,
+                                                        const long long* __restrict__ row_ids, long long n_rows,
+                                                        long long row_len, unsigned long long* out)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long acc = 0;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (long long)gridDim.x * 8) {
+        const unsigned* row = reinterpret_cast<const unsigned*>(fvd) + (size_t)(rows ? rows[r] : r) * row_len;
+        unsigned long long h = 0;
+        for (long long j = lane; j < row_len; j += 32) h += mix64(((unsigned long long)j << 32) | row[j]);
+        for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        const unsigned long long id = (unsigned long long)(row_ids ? row_ids[r] : r);
+        if (lane == 0) acc += mix64(h ^ mix64(id));
+    }
+    if (lane == 0 && acc) atomicAdd(out, acc);
+}
+
+// Lazy module loading (the CUDA 12 default) loads a kernel at its FIRST launch, and that load can wait for the device to
+// drain.  Two shard handles in one process launch kernels that wait for each other's values: if the second handle's first
+// launch has to load a kernel while the first handle's kernel is spinning on that second handle's output, neither returns
+// (the round-1 "sharded nudging" failure: whichever sharded test ran first in a process timed out).  Touching every kernel
+// once, before any launch, makes the loads happen while the device is idle.
+cudaError_t preload_routing_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define TRT_TOUCH(k) if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k)
+    TRT_TOUCH(stage_kernel); TRT_TOUCH(persistent_kernel); TRT_TOUCH(dataflow_kernel); TRT_TOUCH(march_kernel);
+    TRT_TOUCH(gather_qlat_kernel); TRT_TOUCH(init_state_kernel); TRT_TOUCH(init_levelpool_kernel);
+    TRT_TOUCH(scatter_lp_params_kernel); TRT_TOUCH(fill_boundary_kernel); TRT_TOUCH(fill_zero_rows_kernel);
+    TRT_TOUCH(column_copy_kernel); TRT_TOUCH(carry_gages_kernel); TRT_TOUCH(finalize_kernel); TRT_TOUCH(boundary_rows_kernel);
+    TRT_TOUCH(upstream_out_kernel); TRT_TOUCH(reset_gages_kernel); TRT_TOUCH(export_series_kernel);
+    TRT_TOUCH(import_series_kernel); TRT_TOUCH(hash_rows_kernel);
+#undef TRT_TOUCH
+    return e;
 }
 
 #define TRT_GRID1D(total, block) (unsigned)(((total) + (block)-1) / (block))
@@ -842,42 +1044,63 @@ cudaError_t launch_init_levelpool(const int* lp_pos, const float* qd0, const flo
     init_levelpool_kernel<<<TRT_GRID1D(n_lp, 128), 128, 0, st>>>(lp_pos, qd0, h0, S, T + 1, n_lp);
     return cudaGetLastError();
 }
-cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, float* par, int n, int n_lp, cudaStream_t st)
+cudaError_t launch_scatter_lp_params(const int* lp_pos, const float* par9, unsigned* rec, int n_lp, cudaStream_t st)
 {
     if (n_lp == 0) return cudaSuccess;
-    scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 9, 128), 128, 0, st>>>(lp_pos, par9, par, n, n_lp);
+    scatter_lp_params_kernel<<<TRT_GRID1D(n_lp * 9, 128), 128, 0, st>>>(lp_pos, par9, rec, n_lp);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_boundary(const int* bnd_pos, const float* bnd_fvd, float* S, int n_bnd, int T, cudaStream_t st)
 {
-    const long long total = 3LL * n_bnd * T;
+    const long long total = (long long)n_bnd * T;
     if (total == 0) return cudaSuccess;
     fill_boundary_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(bnd_pos, bnd_fvd, S, n_bnd, T);
     return cudaGetLastError();
 }
 cudaError_t launch_fill_zero_rows(const int* pos, float* S, int count, int T, cudaStream_t st)
 {
-    const long long total = 3LL * count * T;
+    const long long total = (long long)count * T;
     if (total == 0) return cudaSuccess;
     fill_zero_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, S, count, T);
     return cudaGetLastError();
 }
-cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, cudaStream_t st, int p_begin, int p_end,
-                            int compact_from)
+cudaError_t launch_column_copy(float* S, int T1, int t, float* col, int n_tiles, int to_state, cudaStream_t st)
+{
+    const long long words = (long long)n_tiles * 64;
+    if (words == 0) return cudaSuccess;
+    column_copy_kernel<<<TRT_GRID1D(words, 256), 256, 0, st>>>(S, T1, t, col, words, to_state);
+    return cudaGetLastError();
+}
+cudaError_t launch_carry_gages(const float* lastobs, float* lastobs_init, int n_gages, float shift, cudaStream_t st)
+{
+    if (n_gages == 0) return cudaSuccess;
+    carry_gages_kernel<<<TRT_GRID1D(n_gages, 128), 128, 0, st>>>(lastobs, lastobs_init, n_gages, shift);
+    return cudaGetLastError();
+}
+cudaError_t launch_finalize(const NetDev& net, const RunDev& run, float* fvd, const int* bnd_pos, const float* bnd_fvd,
+                            int n_bnd, cudaStream_t st, int p_begin, int p_end, int compact_from)
 {
     if (p_end < 0) p_end = net.n;
     if (p_end <= p_begin || run.Tc == 0) return cudaSuccess;
-    const long long rows_per_block = 8;
-    const unsigned blocks = (unsigned)std::min<long long>((p_end - p_begin + rows_per_block - 1) / rows_per_block, 148LL * 32);
-    permute_rows_kernel<<<blocks, 256, 0, st>>>(net, run, fvd, p_begin, p_end, compact_from);
-    return cudaGetLastError();
+    const int tile_begin = p_begin >> 5, tiles = ((p_end - 1) >> 5) - tile_begin + 1;
+    const int t_blocks = (run.Tc + kFinSteps - 1) / kFinSteps;
+    finalize_kernel<<<(unsigned)tiles * (unsigned)t_blocks, 256, 0, st>>>(net, run, fvd, p_begin, p_end, compact_from,
+                                                                         tile_begin, t_blocks);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && n_bnd > 0) {
+        const long long total = 3LL * n_bnd * run.Tc;
+        boundary_rows_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(net, run, bnd_pos, bnd_fvd, n_bnd, fvd, p_begin, p_end,
+                                                                    compact_from);
+        e = cudaGetLastError();
+    }
+    return e;
 }
-cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* S, float* up, int n_lp, int T,
+cudaError_t launch_upstream_out(const int* lp_pos, const int* row_of_pos, const float* lp_in, float* up, int n_lp, int T,
                                 cudaStream_t st)
 {
     const long long total = (long long)n_lp * T;
     if (total == 0) return cudaSuccess;
-    upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, S, up, n_lp, T);
+    upstream_out_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(lp_pos, row_of_pos, lp_in, up, n_lp, T);
     return cudaGetLastError();
 }
 cudaError_t launch_reset_gages(const GageDev& g, const int* gage_pos, const unsigned char* gage_active,
@@ -900,6 +1123,14 @@ cudaError_t launch_import_series(const int* pos, const float* src, float* S, int
     const long long total = (long long)count * (T + 1);
     if (total == 0) return cudaSuccess;
     import_series_kernel<<<TRT_GRID1D(total, 256), 256, 0, st>>>(pos, src, S, count, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_hash_rows(const float* fvd, const long long* rows, const long long* row_ids, long long n_rows,
+                             long long row_len, unsigned long long* out, cudaStream_t st)
+{
+    if (n_rows == 0 || row_len == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<long long>((n_rows + 7) / 8, 148LL * 16);
+    hash_rows_kernel<<<blocks, 256, 0, st>>>(fvd, rows, row_ids, n_rows, row_len, out);
     return cudaGetLastError();
 }
 

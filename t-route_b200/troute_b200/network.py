@@ -122,7 +122,7 @@ class RoutingNetwork:
         self.nsteps = 0
         self._lp_rows = np.zeros(0, dtype=np.int64)
         # TRT_OPTIONS="key=value,...": engine options applied to every network of the process -- lets a whole test or
-        # bench run go through an alternative schedule knob (e.g. TRT_OPTIONS=warp_resync=1 pytest -m gpu)
+        # bench run go through an alternative schedule knob (e.g. TRT_OPTIONS=march_group=4 pytest -m gpu)
         for kv in filter(None, os.environ.get("TRT_OPTIONS", "").split(",")):
             k, _, v = kv.partition("=")
             self.set_option(k.strip(), int(v))
@@ -262,6 +262,39 @@ class RoutingNetwork:
         check(self._L.trt_upload_forcing(self._h, int(nsteps), int(qts_subdivisions), qlat_ptr, int(nqcols), q0_ptr,
                                          0, None, None))
         self.nsteps = int(nsteps)
+
+    def continue_window(self, nsteps, qts_subdivisions, qlat, usgs_values=None, bnd_rows=None, bnd_fvd=None):
+        """The next routing window, started from the device-resident state of the finished one (trt_continue): no q0, no
+        reservoir table, no last-observation table cross PCIe.  `usgs_values` [n_gages, columns]: the observation table of
+        the new window (None keeps the current one)."""
+        qlat = as_c(qlat, np.float32)
+        if qlat.ndim != 2 or qlat.shape[0] != self.n_rows:
+            raise ValueError(f"Number of rows in Qlat is incorrect: expected ({self.n_rows}), got ({qlat.shape[0]})")
+        if usgs_values is not None and getattr(self, "_n_gages", 0):
+            usgs = as_c(usgs_values, np.float32).reshape(self._n_gages, -1)
+            check(self._L.trt_network_update_gage_observations(self._h, usgs.ctypes.data, int(usgs.shape[1])))
+        n_bnd, rows_p, fvd_p = 0, None, None
+        if bnd_rows is not None and len(bnd_rows):
+            bnd_rows = as_c(bnd_rows, np.int64); bnd_fvd = as_c(bnd_fvd, np.float32)
+            n_bnd, rows_p, fvd_p = int(bnd_rows.shape[0]), ptr(bnd_rows, C.c_int64), bnd_fvd.ctypes.data
+        check(self._L.trt_continue(self._h, int(nsteps), int(qts_subdivisions), qlat.ctypes.data, int(qlat.shape[1]),
+                                   n_bnd, rows_p, fvd_p))
+        self.nsteps = int(nsteps)
+
+    def continue_ptr(self, nsteps, qts_subdivisions, qlat_ptr, nqcols):
+        """continue_window for a raw host address (pinned buffers)."""
+        check(self._L.trt_continue(self._h, int(nsteps), int(qts_subdivisions), qlat_ptr, int(nqcols), 0, None, None))
+        self.nsteps = int(nsteps)
+
+    def result_hash(self, rows=None, ids=None):
+        """64-bit checksum of the device-resident result (trt_result_hash): sum over rows of hash(id, row bits)."""
+        out = C.c_uint64()
+        r = as_c(rows, np.int64) if rows is not None else None
+        i = as_c(ids, np.int64) if ids is not None else None
+        nsel = int(r.shape[0]) if r is not None else (int(i.shape[0]) if i is not None else 0)
+        check(self._L.trt_result_hash(self._h, nsel, ptr(r, C.c_int64) if r is not None else None,
+                                      ptr(i, C.c_int64) if i is not None else None, C.byref(out)))
+        return int(out.value)
 
     def run(self, assume_short_ts=False):
         check(self._L.trt_run(self._h, 1 if assume_short_ts else 0))

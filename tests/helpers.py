@@ -102,3 +102,21 @@ def engine_route(case, assume_short_ts, mode=None, device=0, want_upstream=True,
     finally:
         net.close()
     return fvd, up, stats
+
+
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic), the hash of csrc/routing_kernels.cu::mix64"""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return x ^ (x >> np.uint64(31))
+
+
+def result_hash(fvd, ids=None):
+    """trt_result_hash in numpy: sum over rows of mix(sum_j mix(j << 32 | bits[row, j]) ^ mix(id)), modulo 2^64."""
+    with np.errstate(over="ignore"):
+        b = np.ascontiguousarray(fvd, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        j = (np.arange(b.shape[1], dtype=np.uint64) << np.uint64(32))[None, :]
+        h = _mix64(j | b).sum(axis=1, dtype=np.uint64)
+        ids = np.arange(b.shape[0], dtype=np.uint64) if ids is None else np.asarray(ids).astype(np.uint64)
+        return int(_mix64(h ^ _mix64(ids)).sum(dtype=np.uint64))

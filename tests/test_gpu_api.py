@@ -116,7 +116,7 @@ def _gage_inputs(c, n_gages, seed, obs_steps):
 
 
 @pytest.mark.parametrize("short_ts", [False, True])
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_streamflow_nudging_matches_oracle(oracle, short_ts, mode):
     """simple_da on the device (mc_reach.pyx:380-411, :761-796; simple_da.pyx:21-128): replaced flows, nudge series and
     final last-observation state equal the oracle's, bit for bit, in every schedule; observation window shorter than

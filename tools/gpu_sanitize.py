@@ -11,7 +11,7 @@ from troute_b200.network import RoutingNetwork
 
 case = H.make_case(synth.conus_like(n_total=3000, n_basins=6, seed=2, style="nhd"), nsteps=16, n_lp=6, warm=True)
 ref, upref, _ = H.oracle_route(o, case, False)
-for mode, opts in ((2, {}), (3, {"march_group": 4}), (4, {"deep_lanes": 600}), (5, {"deep_lanes": 600, "time_block": 4})):
+for mode, opts in ((2, {}), (3, {"march_group": 4}), (4, {"deep_lanes": 600})):
     net = RoutingNetwork(case["up_ptr"], case["up_rows"], case["kind"], case["params"], case["cols"])
     net.set_levelpools(case["lp_rows"], case["wbody"])
     net.set_option("mode", mode)
