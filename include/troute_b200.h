@@ -136,7 +136,8 @@ int trt_download_gages(trt_network* net, float* nudge, float* lastobs_times, flo
  *   fvd_out    [n_rows, nsteps*3] float32 (q, v, d interleaved per step)      (:807-813)
  *   upstream_out [n_rows, nsteps] float32 or NULL: reservoir inflow on level-pool rows, 0 elsewhere
  *              (the reference leaves np.empty garbage on non-reservoir rows, mc_reach.pyx:487)
- * Host pointers may be pageable or pinned; pinned buffers make the copies asynchronous-capable.
+ * Host pointers may be pageable or pinned; pinned buffers make the copies asynchronous-capable.  qlat and q0 may also be
+ * DEVICE pointers (forcing kept resident by the caller): the copies use cudaMemcpyDefault.
  */
 int trt_upload_forcing(trt_network* net, int32_t nsteps, int32_t qts_subdivisions, const float* qlat,
                        int32_t nqcols, const float* q0, int64_t n_bnd, const int64_t* bnd_rows,
@@ -163,6 +164,8 @@ int trt_network_update_gage_observations(trt_network* net, const float* usgs_val
  * ids = NULL: the row numbers.  tests/helpers.py::result_hash is the same function in numpy.
  */
 int trt_result_hash(trt_network* net, int64_t n_sel, const int64_t* rows, const int64_t* ids, uint64_t* out);
+/* result rows rows[0 .. n_sel) of the last run -> fvd_out [n_sel, nsteps*3] (host), without moving the whole table */
+int trt_download_rows(trt_network* net, int64_t n_sel, const int64_t* rows, float* fvd_out);
 /* kernels only; everything is already resident in HBM.  Blocks until the device is done. */
 int trt_run(trt_network* net, int32_t assume_short_ts);
 /* trt_run without the final wait: enqueue on the handle's stream and return; trt_sync waits and

@@ -69,6 +69,8 @@ struct trt_network {
     int nlevels = 0;
     std::vector<int32_t> level_of_row, pos_of_row, row_of_pos, lvl_ptr;
     std::vector<uint8_t> kind_of_row;
+    std::vector<int64_t> boundary_rows;                       // rows of kind TRT_KIND_BOUNDARY
+    int64_t n_routed = 0;                                     // all other rows
 
     // device topology / parameters: tile records (kernels.cuh), CSR of upstream positions, level offsets
     int64_t n_tiles = 0;
@@ -320,6 +322,8 @@ int trt_network_create_ordered(int device, int64_t n_rows, const int64_t* up_ptr
     }
     net->kind_of_row.assign(kind, kind + n);
     net->imported.assign((size_t)n, 0);
+    for (int64_t r = 0; r < n; ++r)
+        if (kind[r] == TRT_KIND_BOUNDARY) net->boundary_rows.push_back(r); else net->n_routed++;
 
     // ---- position-space arrays: one 2 KB record per tile of 32 positions (kernels.cuh), CSR of upstream positions ----
     const int64_t n_tiles = (n + 31) / 32;
@@ -628,8 +632,10 @@ static int upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const f
     }
 
     if (n > 0) {
-        CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (!carry) CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        // cudaMemcpyDefault: the forcing may already live on the device (a caller that keeps several windows of lateral
+        // inflow resident passes device pointers)
+        CU(cudaMemcpyAsync(net->d_qlat_in.p, qlat, (size_t)n * nqcols * sizeof(float), cudaMemcpyDefault, st));
+        if (!carry) CU(cudaMemcpyAsync(net->d_q0_in.p, q0, (size_t)n * 3 * sizeof(float), cudaMemcpyDefault, st));
         CU(launch_gather_qlat(net->d_qlat_in.p, net->d_row_of_pos.p, net->d_qlat_t.p, (int)n, nqcols, st));
     }
     if (n_bnd > 0) {
@@ -654,11 +660,11 @@ static int upload_forcing(trt_network* net, int32_t nsteps, int32_t qts, const f
     net->n_bnd = n_bnd;
     {
         // boundary rows that are neither prescribed here nor written by a peer shard hold zero for every step
-        std::vector<uint8_t> covered((size_t)n, 0);
-        for (int64_t i = 0; i < n_bnd; ++i) covered[(size_t)bnd_rows[i]] = 1;
+        std::vector<int64_t> covered(bnd_rows, bnd_rows + n_bnd);
+        std::sort(covered.begin(), covered.end());
         std::vector<int32_t> zero_pos;
-        for (int64_t r = 0; r < n; ++r)
-            if (net->kind_of_row[(size_t)r] == TRT_KIND_BOUNDARY && !covered[(size_t)r] && !net->imported[(size_t)r])
+        for (int64_t r : net->boundary_rows)
+            if (!std::binary_search(covered.begin(), covered.end(), r) && !net->imported[(size_t)r])
                 zero_pos.push_back(net->pos_of_row[(size_t)r]);
         net->n_zero = (int64_t)zero_pos.size();
         if (net->n_zero > 0) {
@@ -766,9 +772,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
     if (net->n > 0 && T > 0 && L > 0) {
         const int k_begin = 1, k_end = L + T;   // stages k = level + t, level in [0, L), t in [1, T]
         net->stages = k_end - k_begin;
-        int64_t routed = 0;
-        for (int64_t r = 0; r < net->n; ++r) routed += net->kind_of_row[(size_t)r] != TRT_KIND_BOUNDARY;
-        net->lane_steps += routed * T;
+        net->lane_steps += net->n_routed * T;
         if (net->mode >= 2) {
             // levels [0, Lw) go through the dataflow wavefront, levels [Lw, nlevels) march
             int Lw = net->nlevels;
@@ -1197,6 +1201,28 @@ int trt_device_results(trt_network* net, void** fvd_device)
     if (!net || !fvd_device) return fail(TRT_ERR_INVALID, "NULL argument");
     if (!net->ran) return fail(TRT_ERR_STATE, "trt_device_results called before trt_run");
     *fvd_device = net->d_fvd.p;
+    return TRT_OK;
+}
+
+int trt_download_rows(trt_network* net, int64_t n_sel, const int64_t* rows, float* fvd_out)
+{
+    if (!net || (n_sel > 0 && (!rows || !fvd_out))) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_download_rows called before trt_run");
+    if (n_sel <= 0 || net->T == 0) return TRT_OK;
+    CU(cudaSetDevice(net->device));
+    CU(cudaStreamSynchronize(net->stream));
+    const size_t w = 3 * (size_t)net->T * sizeof(float);
+    // runs of consecutive rows go home as one strided copy each (a basin listed in row order is a handful of runs)
+    int64_t i = 0;
+    while (i < n_sel) {
+        if (rows[i] < 0 || rows[i] >= net->n) return fail(TRT_ERR_INVALID, "row %lld out of range", (long long)rows[i]);
+        int64_t j = i + 1;
+        while (j < n_sel && rows[j] == rows[j - 1] + 1) ++j;
+        CU(cudaMemcpyAsync((char*)fvd_out + (size_t)i * w, (const char*)net->d_fvd.p + (size_t)rows[i] * w, (size_t)(j - i) * w,
+                           cudaMemcpyDeviceToHost, net->stream));
+        i = j;
+    }
+    CU(cudaStreamSynchronize(net->stream));
     return TRT_OK;
 }
 

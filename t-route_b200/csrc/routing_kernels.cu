@@ -46,7 +46,9 @@ struct SmemTabs {
 
 __device__ __forceinline__ PowTabs stage_tables(SmemTabs& s)
 {
+#pragma unroll 1
     for (int i = threadIdx.x; i < 2 * TRT_LOG2_TAB_N; i += blockDim.x) s.tl[i] = g_log2_tab[i];
+#pragma unroll 1
     for (int i = threadIdx.x; i < TRT_EXP2_TAB_N; i += blockDim.x) s.te[i] = g_exp2_tab[i];
     __syncthreads();
     PowTabs t; t.tl = s.tl; t.te = s.te;
@@ -78,27 +80,34 @@ __device__ __forceinline__ unsigned ld_slot(const float* p)
     return WAIT ? ld_volatile_u32(p) : __float_as_uint(__ldcg(p));
 }
 
+// Poll slot `p` until its value has been published.  Inline on purpose: an out-of-line call in the prologue makes the
+// compiler park every loaded value on the stack right after its load (caller-saved registers), which serialises the loads
+// the prologue issues together (ncu, profiles/r02_smallcode: 4.5 % of all long-scoreboard stalls on one such STL).
+__device__ __forceinline__ unsigned poll_slot(const float* p, int* abort_flag)
+{
+    unsigned v, spins = 0;
+    do {
+        __nanosleep(spins < 16 ? 40 : 400);
+        v = ld_volatile_u32(p);
+        if ((++spins & 0x3FFF) == 0) {
+            // ~6 ms of waiting per check; bail out if somebody flagged an error, or after ~8 s on our own
+            if (*reinterpret_cast<volatile int*>(abort_flag) != 0) return 0x7FC00000u;
+            if (spins > (1u << 24)) {
+                // the first lane to give up records WHICH slot never arrived (abort_flag = ctrl + 2, address in ctrl[6..7])
+                if (atomicCAS(abort_flag, 0, 1) == 0)
+                    *reinterpret_cast<volatile unsigned long long*>(abort_flag + 4) = (unsigned long long)p;
+                return 0x7FC00000u;
+            }
+        }
+    } while (v == TRT_SENTINEL);
+    return v;
+}
+
 // the value of slot `p` whose first read returned `v`: `v` itself once it has arrived, else poll
 template <bool WAIT>
 __device__ __forceinline__ float settle(const float* p, unsigned v, int* abort_flag)
 {
-    if (WAIT && v == TRT_SENTINEL) {
-        unsigned spins = 0;
-        do {
-            __nanosleep(spins < 16 ? 40 : 400);
-            v = ld_volatile_u32(p);
-            if ((++spins & 0x3FFF) == 0) {
-                // ~6 ms of waiting per check; bail out if somebody flagged an error, or after ~8 s on our own
-                if (*reinterpret_cast<volatile int*>(abort_flag) != 0) return __uint_as_float(0x7FC00000u);
-                if (spins > (1u << 24)) {
-                    // the first lane to give up records WHICH slot never arrived (abort_flag = ctrl + 2, address in ctrl[6..7])
-                    if (atomicCAS(abort_flag, 0, 1) == 0)
-                        *reinterpret_cast<volatile unsigned long long*>(abort_flag + 4) = (unsigned long long)p;
-                    return __uint_as_float(0x7FC00000u);
-                }
-            }
-        } while (v == TRT_SENTINEL);
-    }
+    if (WAIT && v == TRT_SENTINEL) v = poll_slot(p, abort_flag);
     return __uint_as_float(v);
 }
 
@@ -160,24 +169,11 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     } while (!ok);
 }
 
-// the static record of one position (see kernels.cuh); `rb` points at word 0 of the lane, words are 32 apart -- in the
-// shared-memory copy of a tile and in the global array alike
-struct LaneRec {
-    float p0, p1, p2, p3, p4, p5, p6, p7, p8;
-    unsigned flags;
-    int up0, up1, estart, gage, exp;
-};
-__device__ __forceinline__ LaneRec load_rec(const unsigned* rb)
-{
-    LaneRec r;
-    r.p0 = __uint_as_float(rb[0 * 32]); r.p1 = __uint_as_float(rb[1 * 32]); r.p2 = __uint_as_float(rb[2 * 32]);
-    r.p3 = __uint_as_float(rb[3 * 32]); r.p4 = __uint_as_float(rb[4 * 32]); r.p5 = __uint_as_float(rb[5 * 32]);
-    r.p6 = __uint_as_float(rb[6 * 32]); r.p7 = __uint_as_float(rb[7 * 32]); r.p8 = __uint_as_float(rb[8 * 32]);
-    r.flags = rb[R_FLAGS * 32];
-    r.up0 = (int)rb[R_UP0 * 32]; r.up1 = (int)rb[R_UP1 * 32]; r.estart = (int)rb[R_ESTART * 32];
-    r.gage = (int)rb[R_GAGE * 32]; r.exp = (int)rb[R_EXP * 32];
-    return r;
-}
+// The static record of one position (see kernels.cuh): `rb` points at word 0 of the lane, words are 32 apart -- in the
+// shared-memory copy of a tile and in the global array alike.  Words are read where they are needed (the channel
+// parameters only after the inputs of the step have arrived), not gathered up front: the solve has no register to spare.
+__device__ __forceinline__ float rec_f(const unsigned* rb, int w) { return __uint_as_float(rb[w * 32]); }
+__device__ __forceinline__ int rec_i(const unsigned* rb, int w) { return (int)rb[w * 32]; }
 
 // q[s, t] becomes visible to every consumer (same GPU: the poll of a downstream lane; other GPU: the import row of the
 // downstream shard, written over NVLink peer memory) with ONE 4-byte store each.
@@ -198,7 +194,7 @@ __device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflag
 // nudge and updates the last-observation state.  Float expressions keep the operand order of the Cython source; the decay
 // weight is trt_expf_det (include/trt_detmath.h).  Ordering: the lane of step t reads the state the lane of step t - 1
 // wrote; that lane fences before it publishes its flow / depth and this one fences after it has seen them.
-__device__ __forceinline__ float apply_nudging(const RunDev& run, int g, int t, float model_val, const PowTabs& tabs)
+__device__ __noinline__ float apply_nudging(const RunDev& run, int g, int t, float model_val, const trt_u64* tabs_te)
 {
     const GageDev& G = run.gage;
     __threadfence();
@@ -220,7 +216,7 @@ __device__ __forceinline__ float apply_nudging(const RunDev& run, int g, int t, 
     } else {                                                                       // :66-75, obs_persist_shift :109-128
         const float da_decay_minutes = ((timestep) * G.dt - lastobs_time) / 60;
         const double arg = fabs((double)da_decay_minutes) / -(double)G.decay;
-        const float da_weight = trt_expf_det(arg, tabs.te);
+        const float da_weight = trt_expf_det(arg, tabs_te);
         const float da_shift = lastobs_val - model_val;
         const float da_weighted_shift = da_shift * da_weight;
         nudge_val = da_weighted_shift;
@@ -233,77 +229,152 @@ __device__ __forceinline__ float apply_nudging(const RunDev& run, int g, int t, 
     return replacement_val;
 }
 
-// Route position `s` at step `t`; `r` is its static record.  Returns true when the Muskingum-Cunge solve took the flow
-// branch (the caller records it in fmask: the result pass derives the velocity from the depth exactly then).
-template <bool WAIT>
-__device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run, const LaneRec& r, int s, int t,
-                                           const PowTabs& tabs, const PeerDev* peers, int* abort_flag)
+// ---- inputs of a lane-step -----------------------------------------------------------------------------------------
+// (s, t) reads: own depth and flow at t-1, lateral inflow, and q[u, t], q[u, t-1] of every upstream neighbour u.
+// Polling schedules fetch them ASYNCHRONOUSLY into a per-warp staging area in shared memory (cp.async, 4 bytes per lane and
+// value; slots below), all at once and without holding a register per value in flight -- the solve that follows owns the
+// register file, and a value parked in a register was spilled the moment it was loaded, which made the loads queue up
+// behind one another (ncu, profiles/r02_smallcode).  The copies go through L1: a line cached before its producer stored
+// can only show TRT_SENTINEL ("not yet written"; a slot changes once per run and L1 does not survive a kernel boundary), and
+// a sentinel sends the lane to the L1-bypassing poll, so staleness costs time, never correctness.
+enum { IN_D = 0, IN_Q = 1, IN_QL = 2, IN_U0C = 3, IN_U0P = 4, IN_U1C = 5, IN_U1P = 6, IN_U2C = 7, IN_U2P = 8, IN_U3C = 9,
+       IN_U3P = 10, IN_SLOTS = 11 };
+
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src)
 {
-    const unsigned kflags = r.flags & 0xFFu;
-    const bool is_lp = (kflags & 0x0Fu) == TRT_KIND_LEVELPOOL;
-    const int cnt = (int)(r.flags >> 8);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+// start the fetch of every input of (s, t); `stg` = this lane's column of the warp's staging area (slots 32 floats apart)
+__device__ __forceinline__ void issue_inputs(const NetDev& net, const RunDev& run, const unsigned* rb, int s, int t, float* stg)
+{
+    const unsigned flags = rb[R_FLAGS * 32];
+    const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+    const int cnt = (int)(flags >> 8);
+    const int T1 = run.T + 1;
+    const float* S = run.S;
+    const unsigned d0 = smem_u32(stg);
+    int ua = 0, ub = 0;
+    if (cnt > 2) {                                   // 3rd and 4th neighbour: their indices first, the flows below
+        const int e = rec_i(rb, R_ESTART);
+        ua = __ldg(net.up_idx + e + 2);
+        ub = __ldg(net.up_idx + e + min(3, cnt - 1));
+    }
+    const float* own = S + s_idx(s, t, T1);
+    cp_async4(d0 + IN_D * 128, own - 32);                                          // depth / water elevation at t-1
+    if (!is_lp) {
+        cp_async4(d0 + IN_Q * 128, own - 64);                                      // :733
+        cp_async4(d0 + IN_QL * 128, run.qlat_t + (size_t)((t - 1) / run.qts) * (size_t)net.n + s);   // :723
+    }
+    if (cnt > 0) {
+        const float* pu = S + s_idx(rec_i(rb, R_UP0), t, T1);
+        if (!run.short_ts) cp_async4(d0 + IN_U0C * 128, pu);
+        cp_async4(d0 + IN_U0P * 128, pu - 64);
+    }
+    if (cnt > 1) {
+        const float* pu = S + s_idx(rec_i(rb, R_UP1), t, T1);
+        if (!run.short_ts) cp_async4(d0 + IN_U1C * 128, pu);
+        cp_async4(d0 + IN_U1P * 128, pu - 64);
+    }
+    if (cnt > 2) {
+        const float* pa = S + s_idx(ua, t, T1);
+        const float* pb = S + s_idx(ub, t, T1);
+        if (!run.short_ts) { cp_async4(d0 + IN_U2C * 128, pa); cp_async4(d0 + IN_U3C * 128, pb); }
+        cp_async4(d0 + IN_U2P * 128, pa - 64);
+        cp_async4(d0 + IN_U3P * 128, pb - 64);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// staged value `k` of this lane, or -- when the slot had not been written yet -- the value polled from `g`
+__device__ __forceinline__ float staged(const float* stg, int k, const float* g, int* abort_flag)
+{
+    unsigned v = __float_as_uint(stg[k * 32]);
+    if (v == TRT_SENTINEL) v = poll_slot(g, abort_flag);
+    return __uint_as_float(v);
+}
+
+// Route position `s` at step `t`; `rb` is its static record.  Returns true when the Muskingum-Cunge solve took the flow
+// branch (the caller records it in fmask: the result pass derives the velocity from the depth exactly then).
+// WAIT (polling schedules): issue_inputs(...) has been called for (s, t) with the same `stg`.
+template <bool WAIT>
+__device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run, const unsigned* rb, int s, int t,
+                                           const PowTabs& tabs, const PeerDev* peers, int* abort_flag, const float* stg)
+{
+    const unsigned flags = rb[R_FLAGS * 32];
+    const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+    const int cnt = (int)(flags >> 8);
     const int T1 = run.T + 1;
     float* S = run.S;
     float* own = S + s_idx(s, t, T1);        // q[s, t]; depth at +32; the previous step 64 floats back
 
-    // Issue EVERY load of this lane-step before the first of them is examined: own state, lateral inflow and the flows of
-    // the first two upstream neighbours are independent, so they cost one memory round trip, not one each.
-    const unsigned v_d = ld_slot<WAIT>(own - 32);                                  // depth / water elevation at t-1
-    unsigned v_q = 0;
-    float ql = 0.0f;
-    if (!is_lp) {
-        v_q = ld_slot<WAIT>(own - 64);                                             // :733
-        ql = __ldcs(run.qlat_t + (size_t)((t - 1) / run.qts) * (size_t)net.n + s); // :723
-    }
-    const float* pu0 = S;
-    const float* pu1 = S;
-    unsigned a0c = 0, a0p = 0, a1c = 0, a1p = 0;
-    if (cnt > 0) {
-        pu0 = S + s_idx(r.up0, t, T1);
-        if (!run.short_ts) a0c = ld_slot<WAIT>(pu0);
-        a0p = ld_slot<WAIT>(pu0 - 64);
-    }
-    if (cnt > 1) {
-        pu1 = S + s_idx(r.up1, t, T1);
-        if (!run.short_ts) a1c = ld_slot<WAIT>(pu1);
-        a1p = ld_slot<WAIT>(pu1 - 64);
-    }
     // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
-    float quc = 0.0f, qup = 0.0f;
-    if (cnt > 0) {
-        if (!run.short_ts) quc += settle<WAIT>(pu0, a0c, abort_flag);
-        qup += settle<WAIT>(pu0 - 64, a0p, abort_flag);
-    }
-    if (cnt > 1) {
-        if (!run.short_ts) quc += settle<WAIT>(pu1, a1c, abort_flag);
-        qup += settle<WAIT>(pu1 - 64, a1p, abort_flag);
-    }
-    for (int e = r.estart + 2; e < r.estart + cnt; ++e) {                          // the rare confluence of 3+ rivers
-        const float* up = S + s_idx(__ldg(net.up_idx + e), t, T1);
-        if (!run.short_ts) quc += ld_state<WAIT>(up, abort_flag);
-        qup += ld_state<WAIT>(up - 64, abort_flag);
+    float quc = 0.0f, qup = 0.0f, statep, qdp = 0.0f, ql = 0.0f;
+    if (WAIT) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (cnt > 0) {
+            const float* pu = S + s_idx(rec_i(rb, R_UP0), t, T1);
+            if (!run.short_ts) quc += staged(stg, IN_U0C, pu, abort_flag);
+            qup += staged(stg, IN_U0P, pu - 64, abort_flag);
+        }
+        if (cnt > 1) {
+            const float* pu = S + s_idx(rec_i(rb, R_UP1), t, T1);
+            if (!run.short_ts) quc += staged(stg, IN_U1C, pu, abort_flag);
+            qup += staged(stg, IN_U1P, pu - 64, abort_flag);
+        }
+        if (cnt > 2) {
+            // 8 % of the segments have 3+ upstream neighbours -- but 9 of 10 warps hold one: the 3rd and 4th came with
+            // the rest, a 5th .. nth (0.3 %) is fetched here, one memory round trip each
+            const int e0 = rec_i(rb, R_ESTART);
+            for (int e = e0 + 2; e < e0 + cnt; ++e) {
+                const float* pu = S + s_idx(__ldg(net.up_idx + e), t, T1);
+                if (e < e0 + 4) {
+                    if (!run.short_ts) quc += staged(stg, e == e0 + 2 ? IN_U2C : IN_U3C, pu, abort_flag);
+                    qup += staged(stg, e == e0 + 2 ? IN_U2P : IN_U3P, pu - 64, abort_flag);
+                } else {
+                    unsigned vc = 0;
+                    if (!run.short_ts) vc = ld_slot<true>(pu);
+                    const unsigned vp = ld_slot<true>(pu - 64);
+                    if (!run.short_ts) quc += settle<true>(pu, vc, abort_flag);
+                    qup += settle<true>(pu - 64, vp, abort_flag);
+                }
+            }
+        }
+        statep = staged(stg, IN_D, own - 32, abort_flag);
+        if (!is_lp) {
+            qdp = staged(stg, IN_Q, own - 64, abort_flag);
+            ql = stg[IN_QL * 32];
+        }
+    } else {
+        for (int e = rec_i(rb, R_ESTART), e1 = e + cnt; e < e1; ++e) {
+            const float* pu = S + s_idx(__ldg(net.up_idx + e), t, T1);
+            if (!run.short_ts) quc += __ldcg(pu);
+            qup += __ldcg(pu - 64);
+        }
+        statep = __ldcg(own - 32);
+        if (!is_lp) {
+            qdp = __ldcg(own - 64);                                                    // :733
+            ql = __ldcs(run.qlat_t + (size_t)((t - 1) / run.qts) * (size_t)net.n + s);  // :723
+        }
     }
     if (run.short_ts) quc = qup;
-    const float statep = settle<WAIT>(own - 32, v_d, abort_flag);
-    const float qdp = is_lp ? 0.0f : settle<WAIT>(own - 64, v_q, abort_flag);
 
     float o_q, o_d;
     bool flow = false;
     if (is_lp) {
         // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
-        LpParams lp;
-        lp.area = r.p1; lp.max_depth = r.p2; lp.orifice_area = r.p3; lp.orifice_coefficient = r.p4;
-        lp.orifice_elevation = r.p5; lp.weir_coefficient = r.p6; lp.weir_elevation = r.p7; lp.weir_length = r.p8;
-        lp.dam_length = 10.0f;
+        const float p9[9] = {rec_f(rb, 0), rec_f(rb, 1), rec_f(rb, 2), rec_f(rb, 3), rec_f(rb, 4), rec_f(rb, 5), rec_f(rb, 6),
+                             rec_f(rb, 7), rec_f(rb, 8)};
         float H = statep, outflow;
-        trt_levelpool_step(lp, quc, 0.0f, r.p0, H, outflow, tabs);
+        trt_levelpool_step_call(p9, quc, &H, &outflow, tabs.tl, tabs.te);
         o_q = outflow;
         o_d = H;
         run.lp_in[(size_t)__ldg(net.lp_slot + s) * T1 + t] = quc;      // reservoir inflow (upstream_array, :710)
     } else {
         // velocity is not computed here: the result pass evaluates it from the final depth (finalize_kernel)
-        const McResult res = trt_mc_segment<false, false>(r.p0, qup, quc, qdp, ql, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7,
-                                                          r.p8, statep, tabs);
+        const McResult res = trt_mc_segment<false, false>(rec_f(rb, 0), qup, quc, qdp, ql, rec_f(rb, 1), rec_f(rb, 2),
+                                                          rec_f(rb, 3), rec_f(rb, 4), rec_f(rb, 5), rec_f(rb, 6), rec_f(rb, 7),
+                                                          rec_f(rb, 8), statep, tabs);
         o_q = res.qdc; o_d = res.depthc;
         if (run.trip_sum) {
             atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * (size_t)net.n + s, res.iters);
@@ -311,13 +382,15 @@ __device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run,
         }
         flow = (ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);             // else the no-flow branch: v = 0 (:171-178)
     }
-    if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, r.gage, t, o_q, tabs);   // mc_reach.pyx:761-796
+    const unsigned kflags = rb[R_FLAGS * 32];                                      // re-read: not kept across the solve
+    if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, rec_i(rb, R_GAGE), t, o_q, tabs.te);   // mc_reach.pyx:761-796
     st_state<WAIT>(own + 32, o_d);
     st_state<WAIT>(own, o_q);
     if (WAIT && (kflags & TRT_KIND_EXPORT_FLAG)) {
         // this segment drains into another shard: scatter its outflow into that GPU's inflow slot (peer memory)
-        const int pr = __ldg(peers->exp_peer + r.exp);
-        float* dst = peers->S[pr] + s_idx(__ldg(peers->exp_pos + r.exp), t, T1);
+        const int x = rec_i(rb, R_EXP);
+        const int pr = __ldg(peers->exp_peer + x);
+        float* dst = peers->S[pr] + s_idx(__ldg(peers->exp_pos + x), t, T1);
         unsigned b = __float_as_uint(o_q);
         if (b == TRT_SENTINEL) b = 0x7FC00000u;
         asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(dst), "r"(b) : "memory");
@@ -333,9 +406,8 @@ __device__ __forceinline__ void route_lane_sync(const NetDev& net, const RunDev&
     if ((flags & 0x0Fu) == TRT_KIND_BOUNDARY) return;            // prescribed rows are never computed
     const int t = run.short_ts ? k : k - (int)__ldg(rb + R_LEVEL * 32);
     if (t < 1 || t > run.Tc) return;
-    const LaneRec r = load_rec(rb);
     const int tt = t + run.t_off;
-    if (route_lane<false>(net, run, r, s, tt, tabs, nullptr, nullptr))
+    if (route_lane<false>(net, run, rb, s, tt, tabs, nullptr, nullptr, nullptr))
         atomicOr(run.fmask + (size_t)(s >> 5) * (run.T + 1) + tt, 1u << (s & 31));
 }
 
@@ -423,6 +495,7 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
     __shared__ __align__(128) unsigned recbuf[kBlock / 32][2][R_TILE_WORDS];     // per warp: two 2 KB tile records
     __shared__ __align__(8) unsigned long long bars[kBlock / 32][2];
     __shared__ int ctl[kBlock / 32][2][8];                                        // per warp: this unit, the next unit
+    __shared__ float stage[kBlock / 32][IN_SLOTS][32];                            // per warp: staged inputs of the tile
     const PowTabs tabs = stage_tables(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -450,6 +523,7 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
     if (!df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, ctl[warp][0], lane)) return;
     pend = claim();                                  // the unit after this one: in flight while this one is routed
     fetch_tile(ctl[warp][0][DU_TILE0], 0);
+    float* stg = &stage[warp][0][lane];
     // st: bit 0 = record buffer in use, bit 1 / 2 = phase parity of barrier 0 / 1, bit 3 = control block of the current
     // unit, bit 4 = a next unit exists, bits 8.. = tile index inside the current unit
     unsigned st = 0;
@@ -458,16 +532,6 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
         int* cu = ctl[warp][(st >> 3) & 1];
         const int j = (int)(st >> 8);
         const bool last_of_unit = j + 1 >= cu[DU_NTILES];
-        // ---- the work item after this one: its record travels while this tile is solved ----
-        if (!last_of_unit) fetch_tile(cu[DU_TILE0] + j + 1, b ^ 1);
-        else {
-            int* nx = ctl[warp][((st >> 3) & 1) ^ 1];
-            if (df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, nx, lane)) {
-                st |= 16u;
-                pend = claim();
-                fetch_tile(nx[DU_TILE0], b ^ 1);
-            } else st &= ~16u;
-        }
         if (j == 0) {
             // run-ahead gate: do not start polling individual slots before stage k - gate is complete
             const int need = __ldg(sc.gate_stage + cu[DU_STAGE]);   // last non-empty stage <= k - gate (0 = none)
@@ -485,7 +549,7 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
                 __syncwarp();
             }
         }
-        // ---- this tile ----
+        // ---- this tile: its record arrived while the previous tile was solved; start the fetch of its inputs ----
         mbar_wait(smem_u32(&bars[warp][b]), (st >> (1 + b)) & 1u);
         st ^= 2u << b;
         const int tile = cu[DU_TILE0] + j;
@@ -493,13 +557,23 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
         const unsigned* rb = &recbuf[warp][b][lane];
         const bool live = s >= cu[DU_LO] && s < cu[DU_HI] && (rb[R_FLAGS * 32] & 0x0Fu) != TRT_KIND_BOUNDARY;
         int t = 0;
-        bool flow = false;
         if (live) {
             const int k = cu[DU_STAGE] + 1;
             t = (run.short_ts ? k : k - (int)rb[R_LEVEL * 32]) + run.t_off;
-            const LaneRec r = load_rec(rb);
-            flow = route_lane<true>(net, run, r, s, t, tabs, &peers, sc.abort_flag);
+            issue_inputs(net, run, rb, s, t, stg);
         }
+        // ---- the work item after this one: its record travels while this tile is solved ----
+        if (!last_of_unit) fetch_tile(cu[DU_TILE0] + j + 1, b ^ 1);
+        else {
+            int* nx = ctl[warp][((st >> 3) & 1) ^ 1];
+            if (df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, nx, lane)) {
+                st |= 16u;
+                pend = claim();
+                fetch_tile(nx[DU_TILE0], b ^ 1);
+            } else st &= ~16u;
+        }
+        bool flow = false;
+        if (live) flow = route_lane<true>(net, run, rb, s, t, tabs, &peers, sc.abort_flag, stg);
         __syncwarp();                                // every lane is done with this buffer: it may be refilled
         // flow bits of the tile: one word per (tile, t).  Lanes of a tile share t except where two levels meet in a tile.
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
@@ -545,6 +619,21 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
 // upstream position is lower, hence claimed earlier and resident or finished -- no deadlock.
 enum { MARCH_WAIT = 0, MARCH_ITER = 1, MARCH_DONE = 2 };
 
+struct LaneRec {
+    float p0, p1, p2, p3, p4, p5, p6, p7, p8;
+    unsigned flags;
+    int estart, gage, exp;
+};
+__device__ __forceinline__ LaneRec load_rec(const unsigned* rb)
+{
+    LaneRec r;
+    r.p0 = rec_f(rb, 0); r.p1 = rec_f(rb, 1); r.p2 = rec_f(rb, 2); r.p3 = rec_f(rb, 3); r.p4 = rec_f(rb, 4);
+    r.p5 = rec_f(rb, 5); r.p6 = rec_f(rb, 6); r.p7 = rec_f(rb, 7); r.p8 = rec_f(rb, 8);
+    r.flags = rb[R_FLAGS * 32];
+    r.estart = rec_i(rb, R_ESTART); r.gage = rec_i(rb, R_GAGE); r.exp = rec_i(rb, R_EXP);
+    return r;
+}
+
 #ifndef TRT_MARCH_MIN_BLOCKS
 #define TRT_MARCH_MIN_BLOCKS 2
 #endif
@@ -571,7 +660,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
         int state = MARCH_DONE;
         LaneRec r;
         r.p0 = 0.f; r.p1 = 1.f; r.p2 = 1.f; r.p3 = 1.f; r.p4 = 0.f; r.p5 = 1.f; r.p6 = 0.f; r.p7 = 1.f; r.p8 = 1.f;
-        r.flags = TRT_KIND_BOUNDARY; r.up0 = r.up1 = -1; r.estart = 0; r.gage = 0; r.exp = 0;
+        r.flags = TRT_KIND_BOUNDARY; r.estart = 0; r.gage = 0; r.exp = 0;
         if (mine) r = load_rec(net.rec + rec_idx(p, 0));
         const unsigned kflags = r.flags & 0xFFu, kind = kflags & 0x0Fu;
         const int e0 = r.estart, e1 = r.estart + (int)(r.flags >> 8);
@@ -648,7 +737,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     if (!is_lp && !s.flow) {                                         // :171-178 (fmask bit stays clear: v = 0)
                         float* own = row + (size_t)t * 64;
                         float q = 0.0f;
-                        if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs);
+                        if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs.te);
                         st_state<true>(own + 32, 0.0f);
                         publish_flow(own, q, kflags, r.exp, t, T1, peers);
                         qdp = q; statep = 0.0f;
@@ -671,13 +760,10 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                 float* own = row + (size_t)t * 64;
                 if (is_lp) {
                     // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
-                    LpParams lp;
-                    lp.area = r.p1; lp.max_depth = r.p2; lp.orifice_area = r.p3; lp.orifice_coefficient = r.p4;
-                    lp.orifice_elevation = r.p5; lp.weir_coefficient = r.p6; lp.weir_elevation = r.p7; lp.weir_length = r.p8;
-                    lp.dam_length = 10.0f;
+                    const float p9[9] = {r.p0, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7, r.p8};
                     float H = statep, outflow;
-                    trt_levelpool_step(lp, s.quc, 0.0f, r.p0, H, outflow, tabs);
-                    if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, r.gage, t, outflow, tabs);
+                    trt_levelpool_step_call(p9, s.quc, &H, &outflow, tabs.tl, tabs.te);
+                    if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, r.gage, t, outflow, tabs.te);
                     publish_flow(own, outflow, kflags, r.exp, t, T1, peers);
                     run.lp_in[(size_t)lp_slot * T1 + t] = s.quc;      // reservoir inflow (upstream_array, :710)
                     st_state<true>(own + 32, H);
@@ -686,7 +772,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
                 } else if (mc_iterate(c, s, tabs)) {
                     float q = mc_outflow(s);
-                    if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs);
+                    if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs.te);
                     publish_flow(own, q, kflags, r.exp, t, T1, peers);   // downstream lanes are waiting for this
                     if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
                     st_state<true>(own + 32, s.h);                       // velocity: result pass, from this depth
@@ -738,7 +824,13 @@ static cudaError_t max_grid_of(K kernel, int* blocks)
     return cudaSuccess;
 }
 cudaError_t march_max_grid(int* blocks) { return max_grid_of(march_kernel, blocks); }
-cudaError_t dataflow_max_grid(int* blocks) { return max_grid_of(dataflow_kernel, blocks); }
+cudaError_t dataflow_max_grid(int* blocks)
+{
+    // 4 CTAs x 46 KB of static shared memory per SM: ask for the largest shared-memory carve-out
+    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return max_grid_of(dataflow_kernel, blocks);
+}
 cudaError_t persistent_max_grid(int* blocks) { return max_grid_of(persistent_kernel, blocks); }
 
 cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,

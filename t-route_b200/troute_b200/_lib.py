@@ -57,6 +57,7 @@ SYMBOLS = [
     ("trt_continue", C.c_int, [_net, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, _i64p, C.c_void_p]),
     ("trt_network_update_gage_observations", C.c_int, [_net, C.c_void_p, C.c_int32]),
     ("trt_result_hash", C.c_int, [_net, C.c_int64, _i64p, _i64p, C.POINTER(C.c_uint64)]),
+    ("trt_download_rows", C.c_int, [_net, C.c_int64, _i64p, C.c_void_p]),
     ("trt_run", C.c_int, [_net, C.c_int32]),
     ("trt_run_async", C.c_int, [_net, C.c_int32]),
     ("trt_sync", C.c_int, [_net]),

@@ -3,8 +3,12 @@
 SingleRouter   the whole network on one device.
 ShardedRouter  one sub-basin shard per rank (see partition.py); confluence flows cross shards through peer memory.
 
-torch is used for what it is good at here: pinned host memory, a CUDA stream the caller can time with events,
-and torch.distributed for rendezvous.  All arithmetic is in libtroute_b200.so.
+Both route a call as `windows` consecutive windows of `nsteps` steps (BASELINE configs[4]: a 7-day hindcast = 7 windows of
+288 steps): window 0 starts from q0, every later one from the state the previous window left ON THE DEVICE (trt_continue)
+-- the device-resident form of the reference's window loop (nwm_routing/__main__.py:258-266, troute_model.py:250-262).
+
+torch is used for what it is good at here: pinned host memory, device buffers for resident forcing, a CUDA stream the
+caller can time with events, and torch.distributed for rendezvous.  All arithmetic is in libtroute_b200.so.
 """
 import numpy as np
 
@@ -21,12 +25,74 @@ def global_deep_level(level, shard, n_shards, deep_lanes):
     return L
 
 
-class SingleRouter:
-    kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel",
-                    3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel",
-                    5: "trt::march_kernel"}
+def _window_cols(nsteps, qts, w):
+    """qlat columns of window w (every window has nsteps steps; nsteps must be a multiple of qts for w > 0)"""
+    per = -(-nsteps // qts)
+    return slice(w * per, (w + 1) * per)
 
-    def __init__(self, wl, device, nsteps, qts, short_ts, mode=4):
+
+class _RouterBase:
+    kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel",
+                    3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel"}
+
+    # ---- forcing ------------------------------------------------------------------------------------------------
+    def _make_resident(self):
+        """Device copies of the forcing of every window (the `value` leg: inputs resident in HBM before the timed region)."""
+        torch = self.torch
+        self._q0_dev = torch.from_numpy(np.ascontiguousarray(self.q0)).to(f"cuda:{self.device}")
+        self._qlat_dev = [torch.from_numpy(np.ascontiguousarray(self.qlat[:, _window_cols(self.T, self.qts, w)])).to(f"cuda:{self.device}")
+                          for w in range(self.windows)]
+        torch.cuda.synchronize(self.device)
+
+    def upload(self):
+        """window 0 of the call from host arrays (set-up path: calibration, first touch of the flow array)"""
+        self.net.upload(self.T, self.qts, np.ascontiguousarray(self.qlat[:, _window_cols(self.T, self.qts, 0)]), self.q0)
+
+    def _start_window(self, w, resident):
+        if resident:
+            if self._qlat_dev is None:
+                self._make_resident()
+            ql = self._qlat_dev[w]
+            if w == 0:
+                self.net.upload_ptr(self.T, self.qts, ql.data_ptr(), ql.shape[1], self._q0_dev.data_ptr())
+            else:
+                self.net.continue_ptr(self.T, self.qts, ql.data_ptr(), ql.shape[1])
+        else:
+            qlat, q0, _ = self._host
+            ql = qlat[w]
+            if w == 0:
+                self.net.upload_ptr(self.T, self.qts, ql.data_ptr(), ql.shape[1], q0.data_ptr())
+            else:
+                self.net.continue_ptr(self.T, self.qts, ql.data_ptr(), ql.shape[1])
+
+    def alloc_host(self):
+        torch = self.torch
+        qlat = [torch.from_numpy(np.ascontiguousarray(self.qlat[:, _window_cols(self.T, self.qts, w)])).pin_memory()
+                for w in range(self.windows)]
+        q0 = torch.from_numpy(np.ascontiguousarray(self.q0)).pin_memory()
+        out = torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True)
+        self._host = (qlat, q0, out)
+        self.h2d_bytes = sum(int(q.numel()) * 4 for q in qlat) + int(q0.numel()) * 4
+        self.d2h_bytes = self.n * 3 * self.T * 4 * self.windows
+
+    def host_result(self):
+        return self._host[2].numpy()
+
+    # ---- verification -------------------------------------------------------------------------------------------
+    def window_hash(self):
+        """64-bit checksum of the device-resident result of the last window over this router's OWN rows, labelled with
+        their global row numbers: the checksums of all ranks add up (mod 2^64) to the checksum of the unsharded result."""
+        return self.net.result_hash(rows=self.own_local_rows, ids=self.own_global_rows)
+
+    def download_global_rows(self, global_rows):
+        """(global rows among `global_rows` that this router owns, their result rows of the last window)"""
+        loc = self.local_of_global(np.asarray(global_rows, dtype=np.int64))
+        mine = loc >= 0
+        return np.asarray(global_rows, dtype=np.int64)[mine], self.net.download_rows(loc[mine])
+
+
+class SingleRouter(_RouterBase):
+    def __init__(self, wl, device, nsteps, qts, short_ts, mode=4, windows=1):
         import torch
         self.torch = torch
         self.wl = wl
@@ -36,32 +102,55 @@ class SingleRouter:
         self.short_ts = short_ts
         self.mode = mode
         self.device = device
-        self.net = RoutingNetwork(wl["up_ptr"], wl["up_rows"], wl["kind"], wl["params"], wl["cols"], device=device)
-        self.net.set_option("mode", mode)
+        self.windows = int(windows)
+        self.qlat, self.q0 = wl["qlat"], wl["q0"]
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
-        self.net.set_option("stream", self.tstream.cuda_stream)
+        self.options = {}
         self.reordered = False
+        self._build_net(None)
         self.nq = wl["qlat"].shape[1]
         self.h2d_bytes = wl["qlat"].nbytes + wl["q0"].nbytes
-        self.d2h_bytes = self.n * 3 * nsteps * 4
+        self.d2h_bytes = self.n * 3 * nsteps * 4 * self.windows
         self._host = None
-        self._kernel_ms = []
+        self._qlat_dev = None
+        self.own_local_rows = None                     # every row, labelled by its row number
+        self.own_global_rows = None
 
-    def upload(self):
-        self.net.upload(self.T, self.qts, self.wl["qlat"], self.wl["q0"])
+    def _build_net(self, order_key):
+        wl = self.wl
+        self.net = RoutingNetwork(wl["up_ptr"], wl["up_rows"], wl["kind"], wl["params"], wl["cols"], device=self.device,
+                                  order_key=order_key)
+        self.net.set_option("mode", self.mode)
+        self.net.set_option("stream", self.tstream.cuda_stream)
+        for k, v in self.options.items():
+            self.net.set_option(k, v)
+        if len(wl.get("lp_rows", ())):
+            self.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=wl.get("dt", 300.0))
 
-    def reorder_by_trip_history(self, options=None, buckets=None):
+    def set_option(self, key, value):
+        self.options[key] = int(value)
+        self.net.set_option(key, int(value))
+
+    def local_of_global(self, rows):
+        return rows
+
+    def reorder_by_trip_history(self, buckets=None, calibration_qlat=None):
         """One calibration call that records how many secant trips every segment needed, then the network is rebuilt
         with the segments of every wavefront level ordered by that history (network.order_key_from_trips: the trips of
         16 time slices of the call): a segment's trip count repeats from step to step (p = 0.82) and moves with the storm
         pulse, so the 32 lanes of a warp -- which run in lockstep -- now mostly need the same number of trips.
         What an operational deployment would do once per network (the handle is cached across calls); the results do
-        not depend on the order."""
+        not depend on the order.  `calibration_qlat`: forcing of the calibration call ([n, columns]; None = window 0 of
+        the router's own forcing) -- bench.py calibrates on a DIFFERENT storm than the one it times."""
         from ._lib import TrouteB200Error
         from .network import TRIP_BUCKETS
         buckets = TRIP_BUCKETS if buckets is None else int(buckets)
         self.net.collect_trips(buckets)
+        if calibration_qlat is None:
+            self.upload()
+        else:
+            self.net.upload(self.T, self.qts, np.ascontiguousarray(calibration_qlat), self.q0)
         self.net.run(self.short_ts)
         try:
             if buckets <= 1:
@@ -71,46 +160,48 @@ class SingleRouter:
         except TrouteB200Error:                      # the time-resolved table is an optimisation: the totals still order
             key = self.net.trip_counts()
             self.order_source = "secant trip counts of one calibration call"
-        wl = self.wl
         self.net.close()
-        self.net = RoutingNetwork(wl["up_ptr"], wl["up_rows"], wl["kind"], wl["params"], wl["cols"], device=self.device,
-                                  order_key=key)
-        self.net.set_option("mode", self.mode)
-        self.net.set_option("stream", self.tstream.cuda_stream)
-        for k, v in (options or {}).items():
-            self.net.set_option(k, v)
-        if len(wl.get("lp_rows", ())):
-            self.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=wl.get("dt", 300.0))
+        self._build_net(key)
         self.upload()
         self.reordered = True
 
     def run_resident(self):
-        self.net.run_async(self.short_ts)
+        for w in range(self.windows):
+            self._start_window(w, True)
+            self.net.run_async(self.short_ts)
 
-    def alloc_host(self):
-        torch = self.torch
-        qlat = torch.from_numpy(np.ascontiguousarray(self.wl["qlat"])).pin_memory()
-        q0 = torch.from_numpy(np.ascontiguousarray(self.wl["q0"])).pin_memory()
-        out = torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True)
-        self._host = (qlat, q0, out)
+    def run_resident_incl_h2d(self):
+        """the resident step with the forcing coming from pinned HOST memory (SURVEY.md 8d counts the qlat / q0 upload)"""
+        for w in range(self.windows):
+            self._start_window(w, False)
+            self.net.run_async(self.short_ts)
 
     def run_e2e(self):
-        qlat, q0, out = self._host
-        self.net.route_ptr(self.T, self.qts, self.short_ts, qlat.data_ptr(), self.nq, q0.data_ptr(), out.data_ptr())
+        _, _, out = self._host
+        for w in range(self.windows):
+            self._start_window(w, False)
+            self.net.run_download_ptr(self.short_ts, out.data_ptr())
 
-    def host_result(self):
-        return self._host[2].numpy()
+    def run_checked(self, on_window):
+        """run_resident with a stop after every window: on_window(w) sees the complete device-resident result of window w"""
+        for w in range(self.windows):
+            self._start_window(w, True)
+            self.net.run_async(self.short_ts)
+            self.net.sync()
+            on_window(w)
 
     def collect_stats(self):
         self.net.sync()
         st = self.net.last_run_stats()
         launches = st["launches"]
         lev = self.net.levels()
-        wide_rows = int((lev < st["first_marching_level"]).sum()) if self.mode == 4 else (self.n if self.mode < 3 else 0)
-        return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": launches,
+        wide_rows = int(((lev < st["first_marching_level"]) & (self.wl["kind"] != 2)).sum()) if self.mode == 4 else (
+            self.n if self.mode < 3 else 0)
+        return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"] * self.windows,
+                "launches_per_call": launches * self.windows,
                 "wide_ms": st["wide_ms"], "march_ms": st["march_ms"], "wide_lane_steps": wide_rows * self.T,
                 "first_marching_level": st["first_marching_level"],
-                "launches_per_call_e2e": launches + 2, "stages": st["stages"],
+                "launches_per_call_e2e": launches * self.windows, "stages": st["stages"],
                 "levels": self.net.num_levels, "kernel_name": self.kernel_names[self.mode],
                 "sharding": "single GPU"}
 
@@ -118,21 +209,21 @@ class SingleRouter:
         self.net.close()
 
 
-class ShardedRouter:
+class ShardedRouter(_RouterBase):
     """One sub-basin shard per rank.  Cut-edge flows travel through CUDA-IPC-mapped peer memory inside the routing
     kernel (no collective on the data path); torch.distributed is used for rendezvous (IPC handles, import positions)
     and for the barrier between resetting the flow state and launching."""
-    kernel_names = SingleRouter.kernel_names
 
-    def __init__(self, wl, world, rank, device, nsteps, qts, short_ts, mode=4, pieces_per_shard=16, deep_lanes=8192):
+    def __init__(self, wl, world, rank, device, nsteps, qts, short_ts, mode=4, pieces_per_shard=16, deep_lanes=8192, windows=1):
         import torch
         import torch.distributed as dist
         from . import hostgraph, partition
-        if mode not in (2, 3, 4, 5):
+        if mode not in (2, 3, 4):
             raise ValueError("sharded routing needs a polling schedule (mode 2, 3 or 4)")
         self.torch, self.dist = torch, dist
         self.wl, self.world, self.rank, self.device = wl, world, rank, device
         self.T, self.qts, self.short_ts, self.mode = nsteps, qts, short_ts, mode
+        self.windows = int(windows)
         level = hostgraph.levels(wl["down"], wl["up_ptr"])
         self.shard, plans, self.plan_stats = partition.plan_shards(wl["down"], wl["up_ptr"], wl["up_rows"], wl["kind"],
                                                                    world, pieces_per_shard=pieces_per_shard, level=level)
@@ -151,9 +242,12 @@ class ShardedRouter:
         self.q0 = np.ascontiguousarray(wl["q0"][plan.rows])
         self.nq = self.qlat.shape[1]
         self.h2d_bytes = self.qlat.nbytes + self.q0.nbytes
-        self.d2h_bytes = self.n * 3 * nsteps * 4
+        self.d2h_bytes = self.n * 3 * nsteps * 4 * self.windows
         self._host = None
+        self._qlat_dev = None
         self._wired = False
+        self.own_local_rows = np.nonzero(plan.own)[0].astype(np.int64)
+        self.own_global_rows = plan.rows[plan.own].astype(np.int64)
 
     def _build_net(self, order_key):
         """The shard's device network (again, in a new within-level order, for reorder_by_trip_history)."""
@@ -180,14 +274,30 @@ class ShardedRouter:
         self.options[key] = int(value)
         self.net.set_option(key, int(value))
 
-    def reorder_by_trip_history(self, buckets=None):
+    def local_of_global(self, rows):
+        """local row of every global row this shard OWNS, -1 elsewhere"""
+        plan = self.plan
+        i = np.searchsorted(plan.rows, rows)
+        i = np.minimum(i, plan.rows.size - 1)
+        hit = (plan.rows[i] == rows) & plan.own[i]
+        return np.where(hit, i, -1).astype(np.int64)
+
+    def reorder_by_trip_history(self, buckets=None, calibration_qlat=None):
         """SingleRouter.reorder_by_trip_history for a sharded run: every rank records the trips of its own segments in one
         calibration call, rebuilds its network in that order and the shards are wired again (positions and flow arrays are
-        new).  Opt-in (bench.py --sharded-trip-order) until it has been measured."""
+        new)."""
         from .network import TRIP_BUCKETS
         buckets = TRIP_BUCKETS if buckets is None else int(buckets)
         self.net.collect_trips(buckets)
-        self.run_resident()
+        if calibration_qlat is None:
+            self.upload()
+        else:
+            self.net.upload(self.T, self.qts, np.ascontiguousarray(calibration_qlat[self.plan.rows]), self.q0)
+            if not self._wired:
+                self._wire()
+        self.net.prepare()
+        self.dist.barrier()
+        self.net.run_async(self.short_ts)
         self.net.sync()
         self.dist.barrier()
         key = self.net.trip_order_key(buckets) if buckets > 1 else self.net.trip_counts()
@@ -221,26 +331,39 @@ class ShardedRouter:
         dist.barrier()
 
     def upload(self):
-        self.net.upload(self.T, self.qts, self.qlat, self.q0)
+        self.net.upload(self.T, self.qts, np.ascontiguousarray(self.qlat[:, _window_cols(self.T, self.qts, 0)]), self.q0)
         if not self._wired:
             self._wire()
 
-    def run_resident(self):
-        self.net.prepare()             # flow state back to "not yet written"; complete before any peer may write
-        self.dist.barrier()
-        self.net.run_async(self.short_ts)
+    def _run_windows(self, resident, download, on_window=None):
+        for w in range(self.windows):
+            self._start_window(w, resident)
+            self.net.prepare()             # flow state back to "not yet written"; complete before any peer may write
+            self.dist.barrier()
+            if download:
+                self.net.run_download_ptr(self.short_ts, self._host[2].data_ptr())
+            else:
+                self.net.run_async(self.short_ts)
+            if on_window is not None:
+                self.net.sync()
+                on_window(w)
+            if w + 1 < self.windows:
+                # a peer may still be writing its last values into this shard's flow array: the next window's reset must
+                # not start before every shard has finished this one
+                self.net.sync()
+                self.dist.barrier()
 
-    def alloc_host(self):
-        torch = self.torch
-        self._host = (torch.from_numpy(self.qlat).pin_memory(), torch.from_numpy(self.q0).pin_memory(),
-                      torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True))
+    def run_resident(self):
+        self._run_windows(True, False)
+
+    def run_resident_incl_h2d(self):
+        self._run_windows(False, False)
 
     def run_e2e(self):
-        qlat, q0, out = self._host
-        self.net.upload_ptr(self.T, self.qts, qlat.data_ptr(), self.nq, q0.data_ptr())
-        self.net.prepare()
-        self.dist.barrier()
-        self.net.run_download_ptr(self.short_ts, out.data_ptr())
+        self._run_windows(False, True)
+
+    def run_checked(self, on_window):
+        self._run_windows(True, False, on_window)
 
     def host_result(self):
         """(global rows of this shard's own segments, their [n_own, 3T] results)"""
@@ -253,10 +376,11 @@ class ShardedRouter:
         kinds = self.plan.kind
         wide_rows = int(((lev < st["first_marching_level"]) & (kinds != 2)).sum()) if self.mode == 4 else (
             self.n_own if self.mode < 3 else 0)
-        return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"], "launches_per_call": st["launches"],
+        return {"kernel_ms_per_call": st["kernel_ms"], "lane_steps": st["lane_steps"] * self.windows,
+                "launches_per_call": st["launches"] * self.windows,
                 "wide_ms": st["wide_ms"], "march_ms": st["march_ms"], "wide_lane_steps": wide_rows * self.T,
                 "first_marching_level": st["first_marching_level"],
-                "launches_per_call_e2e": st["launches"] + 2, "stages": st["stages"], "levels": self.net.num_levels,
+                "launches_per_call_e2e": st["launches"] * self.windows, "stages": st["stages"], "levels": self.net.num_levels,
                 "kernel_name": self.kernel_names[self.mode],
                 "sharding": f"{self.world} sub-basin shards, {self.plan_stats['n_cut_edges']} cut edges, "
                             f"imbalance {self.plan_stats['imbalance']:.3f}, peer-memory stores (no collective)"}

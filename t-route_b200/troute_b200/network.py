@@ -286,6 +286,13 @@ class RoutingNetwork:
         check(self._L.trt_continue(self._h, int(nsteps), int(qts_subdivisions), qlat_ptr, int(nqcols), 0, None, None))
         self.nsteps = int(nsteps)
 
+    def download_rows(self, rows):
+        """Result rows `rows` of the last run -> [len(rows), 3 * nsteps] (trt_download_rows)."""
+        rows = as_c(rows, np.int64)
+        out = np.empty((rows.shape[0], 3 * self.nsteps), dtype=np.float32)
+        check(self._L.trt_download_rows(self._h, int(rows.shape[0]), ptr(rows, C.c_int64), out.ctypes.data))
+        return out
+
     def result_hash(self, rows=None, ids=None):
         """64-bit checksum of the device-resident result (trt_result_hash): sum over rows of hash(id, row bits)."""
         out = C.c_uint64()

@@ -150,6 +150,17 @@ def conus_like(n_total=2_729_077, n_basins=14_713, largest_frac=0.5, seed=16, ha
     return np.concatenate(parts)
 
 
+def basin_of(down):
+    """Outlet segment of the basin every segment belongs to (pointer jumping: log2(depth) vectorised rounds)."""
+    n = down.shape[0]
+    nxt = np.where(down >= 0, down, np.arange(n, dtype=down.dtype))
+    while True:
+        nn = nxt[nxt]
+        if np.array_equal(nn, nxt):
+            return nxt
+        nxt = nn
+
+
 def upstream_csr(down):
     """CSR of upstream ids per segment, upstream ids ascending (the order nhd_network.reverse_network
     yields for sorted keys)."""
@@ -256,14 +267,16 @@ def channel_params(down, dt=300.0, seed=16):
     return table.astype(np.float32)
 
 
-def lateral_inflow(n, nsteps, qts_subdivisions=12, seed=16):
-    """[n, ceil(nsteps/qts)] float32: per-segment base U(0.01, 0.1) m3/s times a storm pulse
-    1 + 2 exp(-(hour-8)^2/8)."""
+def lateral_inflow(n, nsteps, qts_subdivisions=12, seed=16, storms=((8.0, 2.0, 8.0),)):
+    """[n, ceil(nsteps/qts)] float32: per-segment base U(0.01, 0.1) m3/s times storm pulses
+    1 + sum_i a_i exp(-(hour - c_i)^2 / w_i); `storms` = ((c, a, w), ...), default one pulse 1 + 2 exp(-(hour-8)^2/8)."""
     rng = np.random.default_rng(seed + 1000)
     ncol = int(np.ceil(nsteps / qts_subdivisions))
     base = rng.uniform(0.01, 0.1, n)
     hour = np.arange(ncol, dtype=np.float64)
-    pulse = 1.0 + 2.0 * np.exp(-((hour - 8.0) ** 2) / 8.0)
+    pulse = np.ones(ncol)
+    for c, a, w in storms:
+        pulse = pulse + a * np.exp(-((hour - c) ** 2) / w)
     return (base[:, None] * pulse[None, :]).astype(np.float32)
 
 
