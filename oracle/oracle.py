@@ -27,7 +27,9 @@ _f64p = C.POINTER(C.c_double)
 
 def build(force=False):
     """Compile liboracle.so with oracle/Makefile (gcc -O2 -ffp-contract=off)."""
-    if force or not os.path.exists(LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("troute_oracle.c", "mc_wrfhydro.c", "mc_kernel.inc")]
+    stale = os.path.exists(LIB_PATH) and any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
+    if force or stale or not os.path.exists(LIB_PATH):
         flags = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
         args = ["make", "-C", _HERE] + (["-B"] if force else [])
         if " fma" not in flags:
@@ -52,6 +54,8 @@ def lib():
         L.oracle_simple_da_with_decay.restype = C.c_float
         L.oracle_simple_da_with_decay.argtypes = [C.c_float] * 4
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_wrfhydro_mc_batch.restype = None
+        L.oracle_wrfhydro_mc_batch.argtypes = [C.c_int, C.c_longlong, _f32p, _f32p, _i32p, _i32p]
         L.oracle_route_network.restype = C.c_int
         L.oracle_route_network.argtypes = [
             C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,            # pow_mode nsteps dt qts short_ts
@@ -94,6 +98,22 @@ def mc_segment_batch(in15, pow_mode=POW_DET):
     iters = np.empty(in15.shape[0], dtype=np.int32)
     lib().oracle_mc_segment_batch(pow_mode, in15.shape[0], _p(in15, C.c_float), _p(out, C.c_float), _p(iters, C.c_int32))
     return out, iters
+
+
+WRF_RETRY, WRF_NO_FLOODPLAIN, WRF_ZERO_CELERITY, WRF_ZERO_PERIMETER, WRF_ONLY_QUC = 1, 2, 4, 8, 16
+
+
+def wrfhydro_mc_batch(in15, pow_mode=POW_DET):
+    """The WRF-Hydro original (MUSKINGCUNGE.f90, oracle/mc_wrfhydro.c) on [count, 15] rows in the argument order of
+    mc_segment_batch -> ([count, 3] (qdc, velc, depthc), flags [count] (WRF_* bits: where the two Fortran sources differ by
+    design), secant trips [count])."""
+    in15 = np.ascontiguousarray(in15, dtype=np.float32).reshape(-1, 15)
+    out = np.zeros((in15.shape[0], 3), dtype=np.float32)
+    flags = np.zeros(in15.shape[0], dtype=np.int32)
+    iters = np.zeros(in15.shape[0], dtype=np.int32)
+    lib().oracle_wrfhydro_mc_batch(pow_mode, in15.shape[0], _p(in15, C.c_float), _p(out, C.c_float), _p(flags, C.c_int32),
+                                   _p(iters, C.c_int32))
+    return out, flags, iters
 
 
 def powf(x, y, pow_mode=POW_DET):
