@@ -194,19 +194,22 @@ __device__ __forceinline__ void publish_flow(float* own, float q, unsigned kflag
 // nudge and updates the last-observation state.  Float expressions keep the operand order of the Cython source; the decay
 // weight is trt_expf_det (include/trt_detmath.h).  Ordering: the lane of step t reads the state the lane of step t - 1
 // wrote; that lane fences before it publishes its flow / depth and this one fences after it has seen them.
-__device__ __noinline__ float apply_nudging(const RunDev& run, int g, int t, float model_val, const trt_u64* tabs_te)
+// Out of line (a few hundred gages among millions of segments) and with SCALAR arguments: a kernel-parameter struct passed
+// by reference to a real call has to be addressable, and the compiler then keeps a copy of every parameter struct in local
+// memory and reads the hot path's run.S, run.T ... from there instead of the constant bank.
+__device__ __noinline__ float apply_nudging_call(const float* usgs, float* lastobs, float* nudge, int gmax, float dt, float decay,
+                                                 int T1, int g, int t, float model_val, const trt_u64* tabs_te)
 {
-    const GageDev& G = run.gage;
     __threadfence();
-    float lastobs_time = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g));
-    float lastobs_val = __uint_as_float(ld_volatile_u32(G.lastobs + 2 * g + 1));
-    const float timestep = (float)t, gage_maxtimestep = (float)G.gmax;
-    const float target_val = (t >= G.gmax) ? __uint_as_float(0x7FC00000u) : __ldg(G.usgs + (size_t)g * G.gmax + t);
+    float lastobs_time = __uint_as_float(ld_volatile_u32(lastobs + 2 * g));
+    float lastobs_val = __uint_as_float(ld_volatile_u32(lastobs + 2 * g + 1));
+    const float timestep = (float)t, gage_maxtimestep = (float)gmax;
+    const float target_val = (t >= gmax) ? __uint_as_float(0x7FC00000u) : __ldg(usgs + (size_t)g * gmax + t);
     float replacement_val, nudge_val;
     if ((timestep <= gage_maxtimestep) && !(target_val != target_val)) {           // :47-55
         replacement_val = target_val;
         nudge_val = target_val - model_val;
-        lastobs_time = (timestep) * G.dt;
+        lastobs_time = (timestep) * dt;
         lastobs_val = target_val;
     } else if ((target_val != target_val) && (lastobs_val != lastobs_val)) {       // :58-62
         replacement_val = model_val;
@@ -214,31 +217,36 @@ __device__ __noinline__ float apply_nudging(const RunDev& run, int g, int t, flo
         lastobs_val = __uint_as_float(0x7FC00000u);
         lastobs_time = __uint_as_float(0x7FC00000u);
     } else {                                                                       // :66-75, obs_persist_shift :109-128
-        const float da_decay_minutes = ((timestep) * G.dt - lastobs_time) / 60;
-        const double arg = fabs((double)da_decay_minutes) / -(double)G.decay;
+        const float da_decay_minutes = ((timestep) * dt - lastobs_time) / 60;
+        const double arg = fabs((double)da_decay_minutes) / -(double)decay;
         const float da_weight = trt_expf_det(arg, tabs_te);
         const float da_shift = lastobs_val - model_val;
         const float da_weighted_shift = da_shift * da_weight;
         nudge_val = da_weighted_shift;
         replacement_val = model_val + da_weighted_shift;
     }
-    G.nudge[(size_t)g * (run.T + 1) + t] = nudge_val;
-    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(G.lastobs + 2 * g), "f"(lastobs_time) : "memory");
-    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(G.lastobs + 2 * g + 1), "f"(lastobs_val) : "memory");
+    nudge[(size_t)g * T1 + t] = nudge_val;
+    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(lastobs + 2 * g), "f"(lastobs_time) : "memory");
+    asm volatile("st.volatile.global.f32 [%0], %1;" ::"l"(lastobs + 2 * g + 1), "f"(lastobs_val) : "memory");
     __threadfence();
     return replacement_val;
+}
+__device__ __forceinline__ float apply_nudging(const RunDev& run, int g, int t, float model_val, const trt_u64* tabs_te)
+{
+    const GageDev& G = run.gage;
+    return apply_nudging_call(G.usgs, G.lastobs, G.nudge, G.gmax, G.dt, G.decay, run.T + 1, g, t, model_val, tabs_te);
 }
 
 // ---- inputs of a lane-step -----------------------------------------------------------------------------------------
 // (s, t) reads: own depth and flow at t-1, lateral inflow, and q[u, t], q[u, t-1] of every upstream neighbour u.
 // Polling schedules fetch them ASYNCHRONOUSLY into a per-warp staging area in shared memory (cp.async, 4 bytes per lane and
-// value; slots below), all at once and without holding a register per value in flight -- the solve that follows owns the
-// register file, and a value parked in a register was spilled the moment it was loaded, which made the loads queue up
-// behind one another (ncu, profiles/r02_smallcode).  The copies go through L1: a line cached before its producer stored
-// can only show TRT_SENTINEL ("not yet written"; a slot changes once per run and L1 does not survive a kernel boundary), and
-// a sentinel sends the lane to the L1-bypassing poll, so staleness costs time, never correctness.
-enum { IN_D = 0, IN_Q = 1, IN_QL = 2, IN_U0C = 3, IN_U0P = 4, IN_U1C = 5, IN_U1P = 6, IN_U2C = 7, IN_U2P = 8, IN_U3C = 9,
-       IN_U3P = 10, IN_SLOTS = 11 };
+// value; slots below), all at once and without holding a register per value in flight.  The copies go through L1: a line
+// cached before its producer stored can only show TRT_SENTINEL ("not yet written"; a slot changes once per run and L1 does
+// not survive a kernel boundary), and a sentinel sends the lane to the L1-bypassing poll, so staleness costs time, never
+// correctness.  The first four slots are what the solve reads all along (mc_device.cuh: McInSm) and stay in shared memory
+// for its whole duration, next to the derived channel values (McChannelSm): the solve owns the 64 registers.
+enum { IN_QUP = MC_IN_QUP, IN_QUC = MC_IN_QUC, IN_Q = MC_IN_QDP, IN_QL = MC_IN_QL, IN_D = 4, IN_U0C = 5, IN_U0P = 6,
+       IN_U1C = 7, IN_U1P = 8, IN_U2C = 9, IN_U2P = 10, IN_U3C = 11, IN_U3P = 12, IN_DV = 13, IN_SLOTS = IN_DV + MC_DV_WORDS };
 
 __device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src)
 {
@@ -286,20 +294,59 @@ __device__ __forceinline__ void issue_inputs(const NetDev& net, const RunDev& ru
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// staged value `k` of this lane, or -- when the slot had not been written yet -- the value polled from `g`
-__device__ __forceinline__ float staged(const float* stg, int k, const float* g, int* abort_flag)
+// The slow side of the gather, out of line (one copy each, off the hot path's instruction footprint).
+// resolve_inputs: every staged slot of (s, t) that still shows TRT_SENTINEL is polled at its source until the value is
+// published, and patched in place.  Scalar arguments: see apply_nudging_call.
+__device__ __noinline__ void resolve_inputs(const float* S, const int* up_idx, int T1, int short_ts, const unsigned* rb, int s,
+                                            int t, float* stg, int* abort_flag)
 {
-    unsigned v = __float_as_uint(stg[k * 32]);
-    if (v == TRT_SENTINEL) v = poll_slot(g, abort_flag);
-    return __uint_as_float(v);
+    const unsigned flags = rb[R_FLAGS * 32];
+    const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+    const int cnt = (int)(flags >> 8);
+    const float* own = S + s_idx(s, t, T1);
+    const int e0 = rec_i(rb, R_ESTART);
+#pragma unroll 1
+    for (int k = IN_Q; k <= IN_U3P; ++k) {
+        if (k == IN_QL) continue;
+        const float* src;
+        if (k == IN_Q) { if (is_lp) continue; src = own - 64; }
+        else if (k == IN_D) src = own - 32;
+        else {
+            const int j = (k - IN_U0C) >> 1;                       // which neighbour
+            const bool prev = ((k - IN_U0C) & 1) != 0;             // its flow at t-1
+            if (j >= cnt || (!prev && short_ts)) continue;
+            const int u = j == 0 ? rec_i(rb, R_UP0) : j == 1 ? rec_i(rb, R_UP1) : __ldg(up_idx + e0 + j);
+            src = S + s_idx(u, t, T1) - (prev ? 64 : 0);
+        }
+        if (__float_as_uint(stg[k * 32]) == TRT_SENTINEL) stg[k * 32] = __uint_as_float(poll_slot(src, abort_flag));
+    }
+}
+
+// gather_rest: the flows of a 5th .. nth upstream neighbour (0.3 % of the segments), which have no staging slot, added to
+// the running sums (quc, qup) of the first four IN REFERENCE ORDER (mc_reach.pyx:499-502: one accumulator per sum, so
+// the association of the float additions is part of the result); returns the two sums.
+__device__ __noinline__ float2 gather_rest(const float* S, const int* up_idx, int T1, int short_ts, int e_begin, int e_end, int t,
+                                           float quc, float qup, int* abort_flag)
+{
+#pragma unroll 1
+    for (int e = e_begin; e < e_end; ++e) {
+        const float* pu = S + s_idx(__ldg(up_idx + e), t, T1);
+        unsigned vc = 0;
+        if (!short_ts) vc = ld_slot<true>(pu);
+        const unsigned vp = ld_slot<true>(pu - 64);
+        if (!short_ts) quc += settle<true>(pu, vc, abort_flag);
+        qup += settle<true>(pu - 64, vp, abort_flag);
+    }
+    return make_float2(quc, qup);
 }
 
 // Route position `s` at step `t`; `rb` is its static record.  Returns true when the Muskingum-Cunge solve took the flow
 // branch (the caller records it in fmask: the result pass derives the velocity from the depth exactly then).
-// WAIT (polling schedules): issue_inputs(...) has been called for (s, t) with the same `stg`.
+// WAIT (polling schedules): issue_inputs(...) has been called for (s, t) with the same `stg`; `rb` and `stg` are in
+// shared memory.
 template <bool WAIT>
 __device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run, const unsigned* rb, int s, int t,
-                                           const PowTabs& tabs, const PeerDev* peers, int* abort_flag, const float* stg)
+                                           const PowTabs& tabs, const PeerDev* peers, int* abort_flag, float* stg)
 {
     const unsigned flags = rb[R_FLAGS * 32];
     const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
@@ -312,39 +359,25 @@ __device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run,
     float quc = 0.0f, qup = 0.0f, statep, qdp = 0.0f, ql = 0.0f;
     if (WAIT) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (cnt > 0) {
-            const float* pu = S + s_idx(rec_i(rb, R_UP0), t, T1);
-            if (!run.short_ts) quc += staged(stg, IN_U0C, pu, abort_flag);
-            qup += staged(stg, IN_U0P, pu - 64, abort_flag);
-        }
-        if (cnt > 1) {
-            const float* pu = S + s_idx(rec_i(rb, R_UP1), t, T1);
-            if (!run.short_ts) quc += staged(stg, IN_U1C, pu, abort_flag);
-            qup += staged(stg, IN_U1P, pu - 64, abort_flag);
-        }
-        if (cnt > 2) {
-            // 8 % of the segments have 3+ upstream neighbours -- but 9 of 10 warps hold one: the 3rd and 4th came with
-            // the rest, a 5th .. nth (0.3 %) is fetched here, one memory round trip each
+        // anything not yet published among what this lane staged?
+        const bool cur = !run.short_ts;             // the flows of the current step are read
+        bool miss = __float_as_uint(stg[IN_D * 32]) == TRT_SENTINEL;
+        if (!is_lp) miss |= __float_as_uint(stg[IN_Q * 32]) == TRT_SENTINEL;
+        if (cnt > 0) miss |= (cur && __float_as_uint(stg[IN_U0C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U0P * 32]) == TRT_SENTINEL);
+        if (cnt > 1) miss |= (cur && __float_as_uint(stg[IN_U1C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U1P * 32]) == TRT_SENTINEL);
+        if (cnt > 2) miss |= (cur && __float_as_uint(stg[IN_U2C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U2P * 32]) == TRT_SENTINEL);
+        if (cnt > 3) miss |= (cur && __float_as_uint(stg[IN_U3C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U3P * 32]) == TRT_SENTINEL);
+        if (miss) resolve_inputs(run.S, net.up_idx, T1, run.short_ts, rb, s, t, stg, abort_flag);
+        if (cnt > 0) { if (!run.short_ts) quc += stg[IN_U0C * 32]; qup += stg[IN_U0P * 32]; }
+        if (cnt > 1) { if (!run.short_ts) quc += stg[IN_U1C * 32]; qup += stg[IN_U1P * 32]; }
+        if (cnt > 2) { if (!run.short_ts) quc += stg[IN_U2C * 32]; qup += stg[IN_U2P * 32]; }
+        if (cnt > 3) { if (!run.short_ts) quc += stg[IN_U3C * 32]; qup += stg[IN_U3P * 32]; }
+        if (cnt > 4) {
             const int e0 = rec_i(rb, R_ESTART);
-            for (int e = e0 + 2; e < e0 + cnt; ++e) {
-                const float* pu = S + s_idx(__ldg(net.up_idx + e), t, T1);
-                if (e < e0 + 4) {
-                    if (!run.short_ts) quc += staged(stg, e == e0 + 2 ? IN_U2C : IN_U3C, pu, abort_flag);
-                    qup += staged(stg, e == e0 + 2 ? IN_U2P : IN_U3P, pu - 64, abort_flag);
-                } else {
-                    unsigned vc = 0;
-                    if (!run.short_ts) vc = ld_slot<true>(pu);
-                    const unsigned vp = ld_slot<true>(pu - 64);
-                    if (!run.short_ts) quc += settle<true>(pu, vc, abort_flag);
-                    qup += settle<true>(pu - 64, vp, abort_flag);
-                }
-            }
+            const float2 x = gather_rest(run.S, net.up_idx, T1, run.short_ts, e0 + 4, e0 + cnt, t, quc, qup, abort_flag);
+            quc = x.x; qup = x.y;
         }
-        statep = staged(stg, IN_D, own - 32, abort_flag);
-        if (!is_lp) {
-            qdp = staged(stg, IN_Q, own - 64, abort_flag);
-            ql = stg[IN_QL * 32];
-        }
+        statep = stg[IN_D * 32];
     } else {
         for (int e = rec_i(rb, R_ESTART), e1 = e + cnt; e < e1; ++e) {
             const float* pu = S + s_idx(__ldg(net.up_idx + e), t, T1);
@@ -372,15 +405,24 @@ __device__ __forceinline__ bool route_lane(const NetDev& net, const RunDev& run,
         run.lp_in[(size_t)__ldg(net.lp_slot + s) * T1 + t] = quc;      // reservoir inflow (upstream_array, :710)
     } else {
         // velocity is not computed here: the result pass evaluates it from the final depth (finalize_kernel)
-        const McResult res = trt_mc_segment<false, false>(rec_f(rb, 0), qup, quc, qdp, ql, rec_f(rb, 1), rec_f(rb, 2),
-                                                          rec_f(rb, 3), rec_f(rb, 4), rec_f(rb, 5), rec_f(rb, 6), rec_f(rb, 7),
-                                                          rec_f(rb, 8), statep, tabs);
+        McResult res;
+        if (WAIT) {
+            // the solve reads the channel and the four inflows from shared memory (qdp and ql are where cp.async put them)
+            trt_sm_st<IN_QUP>(smem_u32(stg), qup); trt_sm_st<IN_QUC>(smem_u32(stg), quc);
+            const McChannelSm c = mc_channel_to_shared(smem_u32(rb), smem_u32(stg + IN_DV * 32));
+            McInSm in; in.p = smem_u32(stg);
+            res = trt_mc_solve<false, false>(c, in, statep, tabs);
+            flow = (in.ql() > 0.0f || in.qup() > 0.0f || in.quc() > 0.0f || in.qdp() > 0.0f);   // else the no-flow branch: v = 0 (:171-178)
+        } else {
+            res = trt_mc_segment<false, false>(rec_f(rb, 0), qup, quc, qdp, ql, rec_f(rb, 1), rec_f(rb, 2), rec_f(rb, 3),
+                                               rec_f(rb, 4), rec_f(rb, 5), rec_f(rb, 6), rec_f(rb, 7), rec_f(rb, 8), statep, tabs);
+            flow = (ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);
+        }
         o_q = res.qdc; o_d = res.depthc;
         if (run.trip_sum) {
             atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * (size_t)net.n + s, res.iters);
             if (res.over) atomicAdd(run.trip_sum + (size_t)run.trip_buckets * (size_t)net.n + s, 1);   // over-bank steps
         }
-        flow = (ql > 0.0f || qup > 0.0f || quc > 0.0f || qdp > 0.0f);             // else the no-flow branch: v = 0 (:171-178)
     }
     const unsigned kflags = rb[R_FLAGS * 32];                                      // re-read: not kept across the solve
     if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, rec_i(rb, R_GAGE), t, o_q, tabs.te);   // mc_reach.pyx:761-796
@@ -489,13 +531,25 @@ __device__ __forceinline__ bool df_decode(const NetDev& net, const RunDev& run, 
     return true;
 }
 
+struct DataflowSmem {
+    __align__(128) unsigned recbuf[kBlock / 32][2][R_TILE_WORDS];     // per warp: two 2 KB tile records (TMA destinations)
+    float stage[kBlock / 32][IN_SLOTS][32];                           // per warp: staged inputs of the tile, then what the
+                                                                      // solve reads (inflows, derived channel values)
+    SmemTabs tabs;                                                    // tables of the bit-specified pow
+    __align__(8) unsigned long long bars[kBlock / 32][2];             // per warp: one mbarrier per record buffer
+    int ctl[kBlock / 32][2][8];                                       // per warp: this unit, the next unit
+};
+
 __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
 {
-    __shared__ SmemTabs smem;
-    __shared__ __align__(128) unsigned recbuf[kBlock / 32][2][R_TILE_WORDS];     // per warp: two 2 KB tile records
-    __shared__ __align__(8) unsigned long long bars[kBlock / 32][2];
-    __shared__ int ctl[kBlock / 32][2][8];                                        // per warp: this unit, the next unit
-    __shared__ float stage[kBlock / 32][IN_SLOTS][32];                            // per warp: staged inputs of the tile
+    // 53 KB per CTA (above the 48 KB a kernel may declare statically): one dynamic allocation, see DataflowSmem
+    extern __shared__ __align__(128) unsigned char df_smem_raw[];
+    DataflowSmem& sm = *reinterpret_cast<DataflowSmem*>(df_smem_raw);
+    SmemTabs& smem = sm.tabs;
+    auto& recbuf = sm.recbuf;
+    auto& bars = sm.bars;
+    auto& ctl = sm.ctl;
+    auto& stage = sm.stage;
     const PowTabs tabs = stage_tables(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
@@ -673,6 +727,8 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
         const int lp_slot = is_lp ? __ldg(net.lp_slot + p) : 0;
         const McChannel c = mc_channel(r.p0, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7, r.p8);
         McSolve s;
+        McIn in;
+        in.qup_ = in.quc_ = in.qdp_ = in.ql_ = 0.0f;
         s.have0 = false; s.have1 = false;
         int t = t_first;
         float qdp = 0.f, statep = 0.f, upsum_prev = 0.f, ql = 0.f;
@@ -732,7 +788,8 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     const float quc = sum;
                     const float qup = run.short_ts ? sum : upsum_prev;
                     upsum_prev = sum;
-                    mc_begin<true>(s, qup, quc, qdp, ql, statep);
+                    in.qup_ = qup; in.quc_ = quc; in.qdp_ = qdp; in.ql_ = ql;
+                    mc_begin<true>(s, in, statep);
                     state = MARCH_ITER;
                     if (!is_lp && !s.flow) {                                         // :171-178 (fmask bit stays clear: v = 0)
                         float* own = row + (size_t)t * 64;
@@ -762,16 +819,16 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
                     const float p9[9] = {r.p0, r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.p7, r.p8};
                     float H = statep, outflow;
-                    trt_levelpool_step_call(p9, s.quc, &H, &outflow, tabs.tl, tabs.te);
+                    trt_levelpool_step_call(p9, in.quc_, &H, &outflow, tabs.tl, tabs.te);
                     if (kflags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, r.gage, t, outflow, tabs.te);
                     publish_flow(own, outflow, kflags, r.exp, t, T1, peers);
-                    run.lp_in[(size_t)lp_slot * T1 + t] = s.quc;      // reservoir inflow (upstream_array, :710)
+                    run.lp_in[(size_t)lp_slot * T1 + t] = in.quc_;      // reservoir inflow (upstream_array, :710)
                     st_state<true>(own + 32, H);
                     qdp = outflow; statep = H;
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
-                } else if (mc_iterate(c, s, tabs)) {
-                    float q = mc_outflow(s);
+                } else if (mc_iterate(c, in, s, tabs)) {
+                    float q = mc_outflow(s, in);
                     if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs.te);
                     publish_flow(own, q, kflags, r.exp, t, T1, peers);   // downstream lanes are waiting for this
                     if (mk.prof) prof_wait += globaltimer_ns() - (unsigned long long)wait_since;
@@ -811,14 +868,14 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
 }
 
 template <class K>
-static cudaError_t max_grid_of(K kernel, int* blocks)
+static cudaError_t max_grid_of(K kernel, int* blocks, size_t dyn_smem = 0)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn_smem);
     if (e != cudaSuccess) return e;
     *blocks = sms * per_sm;
     return cudaSuccess;
@@ -826,10 +883,12 @@ static cudaError_t max_grid_of(K kernel, int* blocks)
 cudaError_t march_max_grid(int* blocks) { return max_grid_of(march_kernel, blocks); }
 cudaError_t dataflow_max_grid(int* blocks)
 {
-    // 4 CTAs x 46 KB of static shared memory per SM: ask for the largest shared-memory carve-out
-    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // 4 CTAs x 53 KB of dynamic shared memory per SM: opt in above 48 KB, ask for the largest shared-memory carve-out
+    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DataflowSmem));
     if (e != cudaSuccess) return e;
-    return max_grid_of(dataflow_kernel, blocks);
+    e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return max_grid_of(dataflow_kernel, blocks, sizeof(DataflowSmem));
 }
 cudaError_t persistent_max_grid(int* blocks) { return max_grid_of(persistent_kernel, blocks); }
 
@@ -843,7 +902,10 @@ cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& m
 cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
                             int grid_blocks, cudaStream_t st)
 {
-    dataflow_kernel<<<grid_blocks, kBlock, 0, st>>>(net, run, sched, peers);
+    // the opt-in above 48 KB is per device and per context: repeat it here (microseconds) rather than rely on the caller
+    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DataflowSmem));
+    if (e != cudaSuccess) return e;
+    dataflow_kernel<<<grid_blocks, kBlock, sizeof(DataflowSmem), st>>>(net, run, sched, peers);
     return cudaGetLastError();
 }
 

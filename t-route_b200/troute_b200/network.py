@@ -33,7 +33,12 @@ TRIP_BUCKETS = 16
 OVERBANK_BINS = 16
 
 
-def order_key_from_trips(trips, nsteps=None, quantum=0.5, overbank=None):
+def _expensive_first():
+    # A/B switch (TRT_TRIP_ORDER=asc restores the ascending order of round 1); read at call time
+    return os.environ.get("TRT_TRIP_ORDER", "desc") != "asc"
+
+
+def order_key_from_trips(trips, nsteps=None, quantum=0.5, overbank=None, expensive_first=None):
     """Within-level sort key (one int32 per row) from the secant trip counts of a calibration call.
 
     The 32 lanes of a dataflow warp run until the slowest of them has finished its secant solve, so a warp is full when its
@@ -49,9 +54,10 @@ def order_key_from_trips(trips, nsteps=None, quantum=0.5, overbank=None):
     classes: a flooded compound channel takes the other branch of the celerity (one more power) and a warp with both kinds
     of lanes executes both branches.  Same model, 60,000 x 288: 25 % of the warp-steps mixed instead of 55 %, busy lanes
     28.4 (28.0 without)."""
+    expensive_first = _expensive_first() if expensive_first is None else expensive_first
     trips = np.asarray(trips)
     if trips.ndim == 1:
-        return np.ascontiguousarray(trips, dtype=np.int32)
+        return np.ascontiguousarray(-trips if expensive_first else trips, dtype=np.int32)
     B, n = trips.shape
     if nsteps:
         # steps of the call that fall into each slice: step t (1-based) -> (t - 1) * B // nsteps
@@ -68,7 +74,10 @@ def order_key_from_trips(trips, nsteps=None, quantum=0.5, overbank=None):
     order = np.lexsort(tuple(keys))
     key = np.empty(n, dtype=np.int32)
     key[order] = np.arange(n, dtype=np.int32)
-    return key
+    # Units of a stage are claimed in position order: with the EXPENSIVE tiles first (longest processing time first) a
+    # stage ends with its cheap tiles, so its completion -- which the run-ahead gate of later stages waits for -- is not
+    # held up by a tile of 6-trip lanes that was claimed last.
+    return (n - 1 - key).astype(np.int32) if expensive_first else key
 
 
 class RoutingNetwork:

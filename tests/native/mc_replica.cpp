@@ -15,8 +15,20 @@ extern "C" void trt_replica_mc_segment_batch(long n, const float* in15, float* o
     for (long i = 0; i < n; ++i) {
         const float* a = in15 + 15 * i;   /* dt,qup,quc,qdp,ql,dx,bw,tw,twcc,n,ncc,cs,s0,velp,depthp */
         trt::McResult r;
-        if (!resumable) {
+        if (resumable == 0) {
             r = trt::trt_mc_segment<true, true>(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[14], T);
+        } else if (resumable == 2) {
+            /* the dataflow kernel's form: channel and inflows read through the shared-memory views (here: plain arrays with
+             * the words 32 floats apart, lane 5 of a tile) */
+            static float rec[16 * 32], dv[trt::MC_DV_WORDS * 32], inw[trt::MC_IN_WORDS * 32];
+            const int lane = 5;
+            const int map[9] = {0, 5, 6, 7, 8, 9, 10, 11, 12};   /* record words dt dx bw tw twcc n ncc cs s0 <- row columns */
+            for (int w = 0; w < 9; ++w) rec[w * 32 + lane] = a[map[w]];
+            inw[trt::MC_IN_QUP * 32 + lane] = a[1]; inw[trt::MC_IN_QUC * 32 + lane] = a[2];
+            inw[trt::MC_IN_QDP * 32 + lane] = a[3]; inw[trt::MC_IN_QL * 32 + lane] = a[4];
+            const trt::McChannelSm c = trt::mc_channel_to_shared(rec + lane, dv + lane);
+            trt::McInSm in; in.p = inw + lane;
+            r = trt::trt_mc_solve<true, true>(c, in, a[14], T);
         } else {
             /* the marching kernel's decomposition: prepare (phase A of the first trip from the previous depth), begin,
              * one trip per call, outflow, velocity from the final depth */
@@ -24,13 +36,14 @@ extern "C" void trt_replica_mc_segment_batch(long n, const float* in15, float* o
             trt::McSolve s;
             s.have0 = false; s.have1 = false;
             trt::mc_prepare(c, s, a[14], T);
-            trt::mc_begin<true>(s, a[1], a[2], a[3], a[4], a[14]);
+            trt::McIn in; in.qup_ = a[1]; in.quc_ = a[2]; in.qdp_ = a[3]; in.ql_ = a[4];
+            trt::mc_begin<true>(s, in, a[14]);
             r.ck = r.cn = 0.0f;
             if (s.flow) {
-                while (!trt::mc_iterate(c, s, T)) {}
-                r.qdc = trt::mc_outflow(s); r.depthc = s.h; r.velc = trt::mc_velocity(c, s.h, T); r.X = s.k.X;
+                while (!trt::mc_iterate(c, in, s, T)) {}
+                r.qdc = trt::mc_outflow(s, in); r.depthc = s.h; r.velc = trt::mc_velocity(c, s.h, T); r.X = s.k.X;
             } else { r.qdc = r.velc = r.depthc = r.X = 0.0f; }
-            r.iters = s.iters_total;
+            r.iters = trt::mc_total_trips(s);
         }
         float* o = out6 + 6 * i;
         o[0] = r.qdc; o[1] = r.velc; o[2] = r.depthc; o[3] = r.ck; o[4] = r.cn; o[5] = r.X;

@@ -52,17 +52,19 @@ def _mixed_fraction(over, level, key):
 def test_order_key_is_a_ranking_and_total_breaks_ties():
     from troute_b200.network import order_key_from_trips
     total = np.array([5, 1, 3, 3], dtype=np.int32)
-    assert order_key_from_trips(total).tolist() == total.tolist()            # 1-D: the totals are the key
+    assert order_key_from_trips(total, expensive_first=False).tolist() == total.tolist()   # 1-D: the totals are the key
+    assert order_key_from_trips(total, expensive_first=True).tolist() == (-total).tolist() # ... expensive segments first
     # two slices of 4 steps; rows 0 and 1 are slow early, rows 2 and 3 late; the second slice spreads more
     t = np.array([[12, 12, 8, 8], [8, 9, 16, 20]], dtype=np.int32)
-    key = order_key_from_trips(t, nsteps=8)
+    key = order_key_from_trips(t, nsteps=8, expensive_first=False)
     assert sorted(key.tolist()) == [0, 1, 2, 3]
     assert key[0] < key[1] < key[2] < key[3]                                 # slice 2 first (8 < 9 < 16 < 20)
+    assert order_key_from_trips(t, nsteps=8, expensive_first=True).tolist() == (3 - key).tolist()   # the same ranking, reversed
     same = np.array([[4, 4, 4], [4, 4, 4]], dtype=np.int32)
-    assert order_key_from_trips(same, nsteps=2).tolist() == [0, 1, 2]        # stable for equal rows
+    assert order_key_from_trips(same, nsteps=2, expensive_first=False).tolist() == [0, 1, 2]        # stable for equal rows
     # quantisation: means 2.0 and 2.1 trips per step fall into one class, the total then decides
     t = np.array([[20, 21, 20], [30, 20, 20]], dtype=np.int32)
-    key = order_key_from_trips(t, nsteps=20)
+    key = order_key_from_trips(t, nsteps=20, expensive_first=False)
     assert key[1] < key[0] and key[2] < key[0]
 
 
