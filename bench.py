@@ -429,7 +429,27 @@ class Verifier:
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal CPU affinity): the pinned result buffer is then first-touched on
+    that NUMA node and the D2H DMA of 8 ranks does not cross the socket interconnect.  Best effort; returns a note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return f"rank bound to {len(use)} of {len(allowed)} CPUs next to its GPU"
+        return "single NUMA domain (no binding needed)"
+    except Exception as e:                                # noqa: BLE001 -- placement is an optimisation
+        return f"not bound ({type(e).__name__})"
+
+
 def run_ours(args, rank, world, local_rank):
+    numa_note = bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
     from troute_b200 import _lib, synth
@@ -603,6 +623,7 @@ def run_ours(args, rank, world, local_rank):
                                     4: "dataflow wavefront over the wide shallow levels, marching lanes over the deep "
                                        "levels"}[args.mode],
                        "l2": "inputs larger than L2 (16 GB working set per window), no flush", "sharding": stats["sharding"],
+                       "host_placement": numa_note,
                        "value_definition": "forcing resident in HBM; value_incl_h2d: the same region with qlat / q0 copied from "
                                            "pinned host memory inside it (SURVEY.md 8d); value_uncalibrated: caller row order",
                        "within_level_order": (getattr(runner, "order_source", "") + (

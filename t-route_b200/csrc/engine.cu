@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,9 +101,11 @@ struct trt_network {
     bool own_stream = true;
     cudaStream_t copy_stream = nullptr;                       // trt_route: results of chunk c go home while c + 1 runs
     std::vector<cudaEvent_t> chunk_events;
-    int route_chunks = 4;
+    int route_chunks = 6;                                     // measured (profiles/r02_e2e_timeline): 4 -> 232 ms, 6 -> 220, 8 -> 292
     DevBuf<float> d_deep_fvd;                                 // [n_deep][3T] results of the marching rows (chunked trt_route)
-    std::vector<float> h_deep_fvd;
+    float* h_deep_fvd = nullptr;                              // pinned staging of d_deep_fvd
+    size_t h_deep_cap = 0;
+    std::vector<cudaEvent_t> copy_events;                     // chunk c has reached the host (TRT_TIMELINE read-out)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // dataflow schedule (mode 2)
@@ -391,6 +394,8 @@ int trt_network_destroy(trt_network* net)
     if (net->ev1) cudaEventDestroy(net->ev1);
     if (net->ev_mid) cudaEventDestroy(net->ev_mid);
     for (cudaEvent_t ev : net->chunk_events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : net->copy_events) cudaEventDestroy(ev);
+    if (net->h_deep_fvd) cudaFreeHost(net->h_deep_fvd);
     for (cudaEvent_t ev : net->stage_events) cudaEventDestroy(ev);
     if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
     if (net->stream && net->own_stream) cudaStreamDestroy(net->stream);
@@ -1082,7 +1087,8 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
 // into time chunks: while the kernels of chunk c + 1 run, the finished columns of chunk c travel to the host on a second
 // stream (a strided 2-D copy out of the [n_rows, 3T] result) -- the 9.4 GB result of a CONUS day takes longer to cross
 // PCIe than to compute, so hiding one behind the other is worth more than any kernel tuning.  Every chunk pays the
-// latency-bound main-stem tail once, which bounds the useful number of chunks (default 2).
+// narrow tail of the wavefront once and narrower chunks make shorter DMA rows (below ~500 bytes the copy engine
+// slows down), which bounds the useful number of chunks (default 6).
 int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_short_ts, const float* qlat, int32_t nqcols,
               const float* q0, int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd, float* fvd_out,
               float* upstream_out)
@@ -1109,8 +1115,10 @@ int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, 
     CU(cudaSetDevice(net->device));
     if (!net->copy_stream) CU(cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking));
     while ((int)net->chunk_events.size() < C + 1) {
-        cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); net->chunk_events.push_back(ev);
+        cudaEvent_t ev; CU(cudaEventCreate(&ev)); net->chunk_events.push_back(ev);
+        CU(cudaEventCreate(&ev)); net->copy_events.push_back(ev);
     }
+    static const bool timeline = getenv("TRT_TIMELINE") != nullptr;   // debug: where the time of a chunked call goes
     const size_t n = (size_t)net->n, T = (size_t)nsteps;
     // Mode 4: only the dataflow (wide) levels are chunked -- their rows are 99 % of the result; the marching levels run
     // ONCE over all steps after the last wide chunk (a marching lane needs nothing from a later wide chunk), so the
@@ -1131,6 +1139,7 @@ int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, 
         CU(cudaMemcpy2DAsync(fvd_out + (size_t)t_off * 3, 3 * T * sizeof(float), net->d_fvd.p + (size_t)t_off * 3,
                              3 * T * sizeof(float), (size_t)Tc * 3 * sizeof(float), n, cudaMemcpyDeviceToHost,
                              net->copy_stream));
+        if (timeline) CU(cudaEventRecord(net->copy_events[(size_t)c], net->copy_stream));
         t_off += Tc;
     }
     if (split) {
@@ -1138,14 +1147,33 @@ int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, 
         if (rc != TRT_OK) return rc;
         const int pos_deep = net->lvl_ptr[(size_t)Lw];
         const size_t n_deep = n - (size_t)pos_deep;
-        net->h_deep_fvd.resize(n_deep * 3 * T);
-        CU(cudaMemcpyAsync(net->h_deep_fvd.data(), net->d_deep_fvd.p, n_deep * 3 * T * sizeof(float), cudaMemcpyDeviceToHost,
+        if (net->h_deep_cap < n_deep * 3 * T) {
+            if (net->h_deep_fvd) cudaFreeHost(net->h_deep_fvd);
+            net->h_deep_fvd = nullptr; net->h_deep_cap = 0;
+            CU(cudaMallocHost(&net->h_deep_fvd, n_deep * 3 * T * sizeof(float)));
+            net->h_deep_cap = n_deep * 3 * T;
+        }
+        if (timeline) CU(cudaEventRecord(net->chunk_events[(size_t)C], net->stream));
+        CU(cudaMemcpyAsync(net->h_deep_fvd, net->d_deep_fvd.p, n_deep * 3 * T * sizeof(float), cudaMemcpyDeviceToHost,
                            net->stream));
         CU(cudaStreamSynchronize(net->stream));
         CU(cudaStreamSynchronize(net->copy_stream));          // the chunk copies wrote stale values into these rows
         for (size_t i = 0; i < n_deep; ++i)
-            memcpy(fvd_out + (size_t)net->row_of_pos[(size_t)pos_deep + i] * 3 * T, net->h_deep_fvd.data() + i * 3 * T,
+            memcpy(fvd_out + (size_t)net->row_of_pos[(size_t)pos_deep + i] * 3 * T, net->h_deep_fvd + i * 3 * T,
                    3 * T * sizeof(float));
+    }
+    if (timeline) {
+        CU(cudaStreamSynchronize(net->copy_stream));
+        CU(cudaStreamSynchronize(net->stream));
+        fprintf(stderr, "[trt timeline] ms after the state reset:");
+        for (int c = 0; c < C; ++c) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, net->ev0, net->chunk_events[(size_t)c]);
+            cudaEventElapsedTime(&b, net->ev0, net->copy_events[(size_t)c]);
+            fprintf(stderr, " chunk %d computed %.1f home %.1f |", c, a, b);
+        }
+        if (split) { float a = 0.f; cudaEventElapsedTime(&a, net->ev0, net->chunk_events[(size_t)C]); fprintf(stderr, " marching rows computed %.1f", a); }
+        fprintf(stderr, "\n");
     }
     if (upstream_out) {
         rc = trt_download_results(net, nullptr, upstream_out);
