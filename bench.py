@@ -381,26 +381,35 @@ class Verifier:
     def __init__(self, args, wl, runner, rank, world, dist):
         self.args, self.wl, self.runner, self.rank, self.world, self.dist = args, wl, runner, rank, world, dist
         self.rows, self.sub, self.n_basins = verification_basins(wl, args.verify_segments)
-        self.hash = 0
+        self.win_hashes = []                             # per window: checksum of this rank's own rows (they ADD over ranks)
         self.parts = []                                  # per window: (global rows owned, their [*, 3T] results)
 
     def window_done(self, w):
-        h = self.runner.window_hash()
-        self.hash = (self.hash + int(_mix64(np.asarray([h ^ int(_mix64(np.asarray([w], dtype=np.uint64))[0])], dtype=np.uint64))[0])) % (1 << 64)
+        self.win_hashes.append(int(self.runner.window_hash()))
         self.parts.append(self.runner.download_global_rows(self.rows))
+
+    @staticmethod
+    def combine(per_rank):
+        """per_rank[r][w] = checksum of rank r's rows of window w -> one 64-bit value: the rank sums of a window add up to
+        the checksum of the whole window (whatever the sharding); windows are then mixed with their index and summed."""
+        total = 0
+        for w in range(len(per_rank[0])):
+            hw = sum(int(h[w]) for h in per_rank) % (1 << 64)
+            total = (total + int(_mix64(np.asarray([hw ^ int(_mix64(np.asarray([w], dtype=np.uint64))[0])], dtype=np.uint64))[0])) % (1 << 64)
+        return total
 
     def finish(self):
         from oracle import oracle as o
-        total = self.hash
+        every = [self.win_hashes]
         gathered = [self.parts]
         if self.world > 1:
             every = [None] * self.world
-            self.dist.all_gather_object(every, self.hash)
-            total = sum(every) % (1 << 64)
+            self.dist.all_gather_object(every, self.win_hashes)
             gathered = [None] * self.world if self.rank == 0 else None
             self.dist.gather_object(self.parts, gathered, dst=0)
         if self.rank != 0:
             return None
+        total = self.combine(every)
         T, W = self.args.nsteps, self.wl["windows"]
         got = np.full((self.rows.size, 3 * T * W), np.nan, dtype=np.float32)
         for parts in gathered:

@@ -6,7 +6,8 @@ routing path needs can be read with `sqlite3` -- no geometry, no GDAL.  This cov
 (BASELINE config 0: test/LowerColorado_TX_v4) and its level-pool reservoirs (the `lakes` layer: read_lakes,
 waterbody_connections, drop_inconsistent_lakes -- what preprocess_waterbodies :456-526 and bandaid :819-856 derive) and
 the surveyed cross sections of a diffusive domain (read_topobathy, complete_topobathy -- AbstractRouting.py:57-82, :390-428,
-:503-526; parquet through pandas / pyarrow); gages / coastal boundaries are not read here.
+:503-526; parquet through pandas / pyarrow) and the stream gages of streamflow data assimilation (read_gages -- the
+`network` layer, preprocess_data_assimilation :606-637); coastal boundaries are not read here.
 """
 import glob
 import os
@@ -188,3 +189,29 @@ def complete_topobathy(topobathy_df, links, dataframe):
     df = pd.concat(pieces, ignore_index=True)
     df = df[df["cs_id"] == df.groupby("hy_id")["cs_id"].transform("min")]
     return df.set_index("hy_id"), bad
+
+
+def read_gages(gpkg_path):
+    """{flowpath id: USGS gage id} for streamflow nudging -- what HYFeaturesNetwork.preprocess_data_assimilation (:606-637)
+    leaves in `network.gages["gages"]`: the hydrolocations of the `network` layer whose `hl_uri` is `Gages-<id>` or `NID-<id>`
+    (several ids separated by blanks are several gages), numeric ids only (USGS; the alphanumeric ones are USACE / NID
+    reservoir gages), and when a gage is listed on more than one flowpath the one with the largest `hydroseq` -- the
+    reference's "furthest downstream" rule (`sort_values('hydroseq').drop_duplicates(keep='last')`) -- wins.  The gage ids
+    are the strings of the hydrofabric ('08121000'), the keys the numeric flowpath ids."""
+    con = sqlite3.connect(f"file:{gpkg_path}?mode=ro", uri=True)
+    try:
+        net = pd.read_sql_query("SELECT id, hl_uri, hydroseq FROM network", con)
+    finally:
+        con.close()
+    g = net.drop_duplicates()
+    g = g[~g["hl_uri"].isnull() & ~g["hydroseq"].isnull()]
+    if g.empty:
+        return {}
+    kind = g["hl_uri"].str.split("-", n=1).str[0]
+    g = g[kind.isin(["Gages", "NID"])]
+    g = pd.DataFrame({"id": g["id"].map(_numeric_id).to_numpy(), "hydroseq": g["hydroseq"].to_numpy(),
+                      "value": g["hl_uri"].str.split("-", n=1).str[1].str.split(" ").to_numpy()})
+    g = g.explode("value")
+    g = g[g["value"].str.isnumeric()]
+    g = g.sort_values("hydroseq", kind="stable").drop_duplicates(["value"], keep="last")
+    return dict(zip(g["id"].astype(int).tolist(), g["value"].tolist()))

@@ -31,7 +31,54 @@ def _window_cols(nsteps, qts, w):
     return slice(w * per, (w + 1) * per)
 
 
+def _q0_with_step0_observations(wl):
+    """A gage with an observation at step 0 replaces the INITIAL flow of its segment (mc_reach.pyx:403-411).  The owning
+    network does that on the device (reset_gages_kernel); a shard that only IMPORTS the segment reads q[u, 0] from its own
+    import row, which is initialised from the q0 it was given -- so every router starts from the replaced value."""
+    g = wl.get("gages")
+    q0 = wl["q0"]
+    if not g or len(g["usgs_positions"]) == 0:
+        return q0
+    usgs = np.asarray(g["usgs_values"], dtype=np.float32).reshape(len(g["usgs_positions"]), -1)
+    if usgs.shape[1] == 0:
+        return q0
+    q0 = np.array(q0, dtype=np.float32, copy=True)
+    obs0 = ~np.isnan(usgs[:, 0])
+    q0[np.asarray(g["usgs_positions"])[obs0], 0] = usgs[obs0, 0]
+    return q0
+
+
 class _RouterBase:
+    def _set_gages(self, local_rows_of_global):
+        """Streamflow nudging (simple_da, mc_reach.pyx:380-411, :761-796) for the gages of wl["gages"] (the reference's
+        arguments with GLOBAL rows in usgs_positions; every gage ends its reach) that sit on rows this router owns.
+        `local_rows_of_global(rows)` -> local row or -1.  Remembers which gages are here (self.gage_sel)."""
+        g = self.wl.get("gages")
+        self.gage_sel = np.zeros(0, dtype=np.int64)
+        if not g or len(g["usgs_positions"]) == 0:
+            return
+        grow = np.asarray(g["usgs_positions"], dtype=np.int64)
+        loc_all = np.asarray(local_rows_of_global(grow), dtype=np.int64)
+        sel = np.nonzero(loc_all >= 0)[0]
+        self.gage_sel = sel
+        loc = loc_all[sel].astype(np.int32)
+        G = len(grow)
+        usgs = np.asarray(g["usgs_values"], dtype=np.float32).reshape(G, -1)
+        self.net.set_gages(dict(usgs_values=usgs[sel], usgs_positions=loc, usgs_positions_reach=loc,
+                                usgs_positions_gage=np.arange(sel.size, dtype=np.int32),
+                                lastobs_values_init=np.asarray(g["lastobs_values_init"], dtype=np.float32)[sel],
+                                time_since_lastobs_init=np.asarray(g["time_since_lastobs_init"], dtype=np.float32)[sel],
+                                da_decay_coefficient=g["da_decay_coefficient"],
+                                reach_len=np.ones(self.n, dtype=np.int64), seg_rows=np.arange(self.n)),
+                           self.T, routing_period=self.wl.get("dt", 300.0))
+
+    def gage_results(self):
+        """(indices into wl["gages"] of the gages routed here, nudge [*, T + 1], lastobs_times, lastobs_values) of the last window"""
+        if self.gage_sel.size == 0:
+            return self.gage_sel, np.zeros((0, self.T + 1), np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32)
+        nudge, lt, lv = self.net.download_gages()
+        return self.gage_sel, nudge, lt, lv
+
     kernel_names = {0: "trt::stage_kernel", 1: "trt::persistent_kernel", 2: "trt::dataflow_kernel",
                     3: "trt::march_kernel", 4: "trt::dataflow_kernel + trt::march_kernel"}
 
@@ -103,7 +150,7 @@ class SingleRouter(_RouterBase):
         self.mode = mode
         self.device = device
         self.windows = int(windows)
-        self.qlat, self.q0 = wl["qlat"], wl["q0"]
+        self.qlat, self.q0 = wl["qlat"], _q0_with_step0_observations(wl)
         self.tstream = torch.cuda.Stream(device=device)
         self.stream = self.tstream
         self.options = {}
@@ -127,6 +174,7 @@ class SingleRouter(_RouterBase):
             self.net.set_option(k, v)
         if len(wl.get("lp_rows", ())):
             self.net.set_levelpools(wl["lp_rows"], wl["wbody"], routing_period=wl.get("dt", 300.0))
+        self._set_gages(lambda rows: rows)
 
     def set_option(self, key, value):
         self.options[key] = int(value)
@@ -239,7 +287,7 @@ class ShardedRouter(_RouterBase):
         self.reordered = False
         self._build_net(None)
         self.qlat = np.ascontiguousarray(wl["qlat"][plan.rows])
-        self.q0 = np.ascontiguousarray(wl["q0"][plan.rows])
+        self.q0 = np.ascontiguousarray(_q0_with_step0_observations(wl)[plan.rows])
         self.nq = self.qlat.shape[1]
         self.h2d_bytes = self.qlat.nbytes + self.q0.nbytes
         self.d2h_bytes = self.n * 3 * nsteps * 4 * self.windows
@@ -267,6 +315,7 @@ class ShardedRouter(_RouterBase):
         for k, v in self.options.items():
             self.net.set_option(k, v)
         self.net.set_imports(plan.imports)
+        self._set_gages(self.local_of_global)          # every shard assimilates the gages on the segments it owns
         self._wired = False
 
     def set_option(self, key, value):

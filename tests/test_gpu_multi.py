@@ -24,19 +24,46 @@ down = synth.conus_like(n_total=60000, n_basins=40, seed=12)
 case = H.make_case(down, nsteps=36, warm=True, n_lp=40)
 wl = dict(n=case["n"], down=down, params=case["params"], cols=case["cols"], qlat=case["qlat"], q0=case["q0"],
           up_ptr=case["up_ptr"], up_rows=case["up_rows"], kind=case["kind"], lp_rows=case["lp_rows"], wbody=case["wbody"])
-for short in (False, True):
-    r = multigpu.ShardedRouter(wl, world, rank, rank, 36, 12, short, pieces_per_shard=6)
+# streamflow nudging (simple_da): 150 gages, gaps in the observations, carried-in last observations, some unknown
+from troute_b200 import hostgraph
+rng = np.random.default_rng(4)
+G, n = 150, case["n"]
+grow = np.sort(rng.choice(np.nonzero(case["kind"] == 0)[0], size=G, replace=False)).astype(np.int32)
+usgs = rng.uniform(0.2, 20.0, size=(G, 18)).astype(np.float32)
+usgs[rng.random(usgs.shape) < 0.3] = np.nan
+lastobs = rng.uniform(0.2, 20.0, G).astype(np.float32)
+since = -rng.uniform(0.0, 3600.0, G).astype(np.float32)
+lastobs[::7] = np.nan; since[::7] = np.nan
+level = hostgraph.levels(down, case["up_ptr"])
+inv_order = np.empty(n, dtype=np.int64)
+inv_order[np.argsort(level, kind="stable")] = np.arange(n)      # H.oracle_route lists one-segment reaches in this order
+gages = dict(usgs_values=usgs, usgs_positions=grow, usgs_positions_reach=inv_order[grow].astype(np.int32),
+             usgs_positions_gage=np.arange(G, dtype=np.int32), lastobs_values_init=lastobs,
+             time_since_lastobs_init=since, da_decay_coefficient=120.0)
+for short, nudging in ((False, False), (True, False), (False, True)):
+    w = dict(wl, gages=gages) if nudging else wl
+    r = multigpu.ShardedRouter(w, world, rank, rank, 36, 12, short, pieces_per_shard=6)
     r.upload(); r.alloc_host()
     for rep in range(2):
         r.run_e2e()
     rows, out = r.host_result()
-    ref, _, _ = H.oracle_route(o, case, short)
+    ref, _, extras = H.oracle_route(o, case, short, gages=gages if nudging else None)
     ok = bool(np.array_equal(out.view(np.int32), ref[rows].view(np.int32)))
+    n_here = 0
+    if nudging:
+        plain, _, _ = H.oracle_route(o, case, short)
+        assert not np.array_equal(ref, plain)                   # the gages do change the flows
+        sel, nudge, lt, lv = r.gage_results()
+        n_here = int(sel.size)
+        same = lambda a, b: bool(np.array_equal(np.asarray(a, np.float32).view(np.int32), np.asarray(b, np.float32).view(np.int32)))
+        ok = ok and same(nudge, extras["nudge"][sel]) and same(lt, extras["lastobs_times"][sel]) and same(lv, extras["lastobs_values"][sel])
     res = [None] * world
-    dist.all_gather_object(res, ok)
-    assert all(res), (short, res)
+    dist.all_gather_object(res, (ok, n_here))
+    assert all(x[0] for x in res), (short, nudging, res)
+    if nudging:
+        assert sum(x[1] for x in res) == G and min(x[1] for x in res) > 0, res   # every gage assimilated, on both GPUs
     if rank == 0:
-        print("OK short_ts=%s cut_edges=%d" % (short, r.plan_stats["n_cut_edges"]), flush=True)
+        print("OK short_ts=%s nudging=%s cut_edges=%d" % (short, nudging, r.plan_stats["n_cut_edges"]), flush=True)
     r.close()
 dist.destroy_process_group()
 """
@@ -60,4 +87,5 @@ def test_two_gpu_sharded_routing_matches_oracle(tmp_path):
     outs = [p.communicate(timeout=900)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
-    assert "OK short_ts=True" in outs[0]
+    assert "OK short_ts=True" in outs[0] and "OK short_ts=False nudging=True" in outs[0], outs[0]
+    print(outs[0])

@@ -233,3 +233,47 @@ def test_lake_readers_equal_the_reference_preprocessing_on_the_real_hydrofabric(
     ref_conn = {int(k): [int(x) for x in v] for k, v in me._connections.items()}
     assert {k: v for k, v in fixture.items() if k in ref_conn} == ref_conn
     assert all(v == [] for k, v in fixture.items() if k not in ref_conn)                      # the three phantom outlets
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs /root/reference")
+def test_gage_reader_equals_the_reference_method():
+    """hyfeatures.read_gages == the statements of HYFeaturesNetwork.preprocess_data_assimilation that build `self._gages`
+    (:606-637; the lake-gage crosswalks that follow use a pandas < 2 groupby signature and are outside the routing path),
+    compiled out of the reference module (which imports geopandas / xarray and cannot be imported here) and run on a
+    stand-in object with the `network` layer read through sqlite3: the same {flowpath id: USGS gage id} dictionary on the
+    real hydrofabric (86 gages)."""
+    import ast
+    import sqlite3
+    import types
+    import pandas as pd
+    src = f"{REF}/src/troute-network/troute"
+    tree = ast.parse(open(f"{src}/HYFeaturesNetwork.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "HYFeaturesNetwork")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "preprocess_data_assimilation"]
+    branch = fns[0].body[0]                                                   # if not network.empty:
+    assert isinstance(branch, ast.If)
+    last = next(i for i, st in enumerate(branch.body) if isinstance(st, ast.Assign) and ast.unparse(st.targets[0]) == "self._gages")
+    branch.body = branch.body[:last + 1]
+    ns = {"pd": pd, "np": np}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "reference", "exec"), ns)
+    gpkg = f"{REF}/test/LowerColorado_TX_v4/domain/LowerColorado_NGEN_v201.gpkg"
+    con = sqlite3.connect(f"file:{gpkg}?mode=ro", uri=True)
+    try:
+        network = pd.read_sql_query("SELECT * FROM network", con)
+    finally:
+        con.close()
+    df = hy.read_flowpaths(gpkg)
+    wb = hy.read_lakes(gpkg)
+    wc = hy.waterbody_connections(df, wb)
+
+    class Stand:
+        waterbody_connections = property(lambda self: self._wc)
+    me = Stand()
+    me._wc = wc
+    me.data_assimilation_parameters = {}
+    me._waterbody_types_df = pd.DataFrame()
+    ns["preprocess_data_assimilation"](me, network)
+    want = {int(k): str(v) for k, v in me._gages["gages"].items()}
+    got = hy.read_gages(gpkg)
+    assert got == want and len(got) == 86
+    assert all(k in df.index for k in got)                                   # every gage sits on a flowpath of the domain
