@@ -97,8 +97,9 @@ def parse():
                     help="forcing of the calibration call: a different storm than the timed one (default), or the timed one")
     ap.add_argument("--trip-buckets", type=int, default=0,
                     help="time slices of the calibration call's trip counts (0 = network.TRIP_BUCKETS, 1 = totals only)")
-    ap.add_argument("--no-sharded-trip-order", action="store_true",
-                    help="N > 1: keep every shard in caller row order (default: calibrate and re-order every shard)")
+    ap.add_argument("--sharded-trip-order", action="store_true",
+                    help="N > 1: calibrate and re-order every shard too (default: caller row order -- measured, an order "
+                         "calibrated on another storm is worth nothing, profiles/r02_v4_final, r02_multi_gpu)")
     ap.add_argument("--no-verify", action="store_true", help="skip the verify object (result hash + oracle comparison)")
     ap.add_argument("--verify-segments", type=int, default=50000, help="oracle comparison: at least this many segments")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -523,7 +524,7 @@ def run_ours(args, rank, world, local_rank):
     runner.upload()                                          # first touch: allocations, peer wiring
 
     # ---- the same region before the trip-count ordering (caller row order) ----
-    reorder = (not args.no_trip_order and args.mode in (2, 4) and (world == 1 or not args.no_sharded_trip_order))
+    reorder = (not args.no_trip_order and args.mode in (2, 4) and (world == 1 or args.sharded_trip_order))
     uncal = None
     if reorder:
         ms, _ = timed(runner.run_resident, max(1, min(args.steps, 3)), 2)

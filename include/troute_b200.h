@@ -173,6 +173,9 @@ int trt_run(trt_network* net, int32_t assume_short_ts);
 int trt_run_async(trt_network* net, int32_t assume_short_ts);
 int trt_sync(trt_network* net);
 int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out);
+/* (q, v, d) of the LAST timestep of the last run, every row in caller order -> qvd_out [n_rows, 3] (host): what the BMI model
+ * reads back after a window (src/troute_model.py:318-330 `_retrieve_last_output`); 12 bytes per segment cross PCIe. */
+int trt_download_last_step(trt_network* net, float* qvd_out);
 /* trt_run + trt_download_results with the two overlapped: the call is cut into "route_chunks" time chunks and the
  * finished columns of chunk c are copied to the host while chunk c + 1 is computed (see trt_route).  Shards of one
  * network must use the same "route_chunks". */

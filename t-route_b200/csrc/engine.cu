@@ -103,6 +103,7 @@ struct trt_network {
     std::vector<cudaEvent_t> chunk_events;
     int route_chunks = 6;                                     // measured (profiles/r02_e2e_timeline): 4 -> 232 ms, 6 -> 220, 8 -> 292
     DevBuf<float> d_deep_fvd;                                 // [n_deep][3T] results of the marching rows (chunked trt_route)
+    DevBuf<float> d_last;                                     // [n][3] last timestep of every row (trt_download_last_step)
     float* h_deep_fvd = nullptr;                              // pinned staging of d_deep_fvd
     size_t h_deep_cap = 0;
     std::vector<cudaEvent_t> copy_events;                     // chunk c has reached the host (TRT_TIMELINE read-out)
@@ -1079,6 +1080,25 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
         CU(launch_upstream_out(net->d_lp_pos.p, net->d_row_of_pos.p, net->d_lp_in.p, net->d_up_out.p, (int)net->n_lp, (int)T, st));
         CU(cudaMemcpyAsync(upstream_out, net->d_up_out.p, n * T * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    CU(cudaStreamSynchronize(st));
+    return TRT_OK;
+}
+
+// (q, v, d) of the LAST timestep of every row: all a BMI-style caller reads back after a window (troute_model.py:318-330,
+// _retrieve_last_output) -- 12 bytes per segment instead of 12 * nsteps
+int trt_download_last_step(trt_network* net, float* qvd_out)
+{
+    if (!net || !qvd_out) return fail(TRT_ERR_INVALID, "NULL argument");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_download_last_step called before trt_run");
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = net->stream;
+    const size_t n = (size_t)net->n, T = (size_t)net->T;
+    if (n * T == 0) return TRT_OK;
+    CU(net->d_last.reserve(n * 3));
+    // device-side gather of the last three columns into a contiguous [n, 3] buffer, then one contiguous copy
+    CU(cudaMemcpy2DAsync(net->d_last.p, 3 * sizeof(float), net->d_fvd.p + 3 * (T - 1), 3 * T * sizeof(float), 3 * sizeof(float), n,
+                         cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(qvd_out, net->d_last.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return TRT_OK;
 }

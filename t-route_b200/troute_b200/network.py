@@ -328,6 +328,12 @@ class RoutingNetwork:
         check(self._L.trt_download_results(self._h, fvd.ctypes.data, up.ctypes.data if up is not None else None))
         return fvd, up
 
+    def download_last_step(self):
+        """(q, v, d) of the last timestep of the last run, [n_rows, 3] in caller row order (trt_download_last_step)."""
+        out = np.empty((self.n_rows, 3), dtype=np.float32)
+        check(self._L.trt_download_last_step(self._h, out.ctypes.data))
+        return out
+
     def run_download_ptr(self, assume_short_ts, fvd_ptr):
         """Time-chunked run with the result copies overlapped (trt_run_download) into a raw host address."""
         check(self._L.trt_run_download(self._h, 1 if assume_short_ts else 0, fvd_ptr, None))
