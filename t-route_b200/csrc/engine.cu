@@ -133,6 +133,12 @@ struct trt_network {
     int poll_sleep = -1, march_prepare = 1;
     DevBuf<unsigned long long> d_march_prof;                  // [n][4] + 1
     cudaEvent_t ev_mid = nullptr;                             // between the dataflow and the marching kernel
+    // "overlap_march": the marching kernel runs BESIDE the dataflow kernel (second stream, 128-thread CTAs in the register
+    // space a fourth dataflow CTA per SM would take) instead of after it; its lanes poll for the flows of the last wide level
+    int overlap_march = 0;
+    cudaStream_t march_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_wide_end = nullptr;
+    bool overlapped_run = false;
     double wide_ms = 0.0, march_ms = 0.0;
     int deep_level_used = 0;
     bool prepared = false;                                    // sentinel reset done for the next run
@@ -394,6 +400,10 @@ int trt_network_destroy(trt_network* net)
     if (net->ev0) cudaEventDestroy(net->ev0);
     if (net->ev1) cudaEventDestroy(net->ev1);
     if (net->ev_mid) cudaEventDestroy(net->ev_mid);
+    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+    if (net->ev_join) cudaEventDestroy(net->ev_join);
+    if (net->ev_wide_end) cudaEventDestroy(net->ev_wide_end);
+    if (net->march_stream) cudaStreamDestroy(net->march_stream);
     for (cudaEvent_t ev : net->chunk_events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : net->copy_events) cudaEventDestroy(ev);
     if (net->h_deep_fvd) cudaFreeHost(net->h_deep_fvd);
@@ -853,18 +863,29 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             // marching units over positions [pos_deep, n)
             int G = net->march_group;
             if (G == 0) {
-                // Auto: one segment per warp up to 16,384 marching segments.  Residency of every unit is NOT needed: units
-                // are claimed in position order and a segment at level l is finished by (l + T) link times, so only
-                // ~T levels x a few segments are live at any moment; one lane per warp took the marching phase of the
-                // bench network from 27.9 to 19.6 ms (profiles/r02_lease1).  Beyond that: the fewest segments per warp
-                // that lets every unit be resident at once.
+                // Auto: as few segments per warp as possible (one lane per warp = the shortest link latency on the chain:
+                // 27.9 -> 19.6 ms on the bench network, profiles/r02_v1_tiled_tma/lease1_ab_march_group1.json).  Residency of
+                // EVERY unit is not needed -- units are claimed in position order and a segment at level l is busy from
+                // link-time l to l + T -- but the segments that are LIVE at the same time must fit the resident warps,
+                // or the chain stalls behind warps that are still walking an upstream segment through its T steps
+                // (T = 2,016 with one lane per warp: 79 ms instead of ~35, profiles/r02_v6_overlap_onecall).  Live
+                // segments = the largest number of marching segments in any window of T consecutive levels.
                 int mg = 0;
                 CU(march_max_grid(&mg));
                 if (net->grid_blocks > 0) mg = std::min(mg, net->grid_blocks);
-                const int64_t warps = std::max<int64_t>(1, (int64_t)mg * 8);
+                int64_t warps = std::max<int64_t>(1, (int64_t)mg * 8);
+                if (net->overlap_march && net->mode == 4 && phase == PHASE_ALL && net->grid_blocks <= 0) {
+                    int sms_m = 0;                                     // beside the dataflow kernel: one 4-warp CTA per SM
+                    CU(cudaDeviceGetAttribute(&sms_m, cudaDevAttrMultiProcessorCount, net->device));
+                    warps = std::max<int64_t>(1, (int64_t)sms_m * 4);
+                }
+                int64_t live = 0;
+                for (int l = Lw; l < net->nlevels; ++l) {
+                    const int hi_l = (int)std::min<int64_t>(net->nlevels, (int64_t)l + std::max(1, T));
+                    live = std::max<int64_t>(live, (int64_t)net->lvl_ptr[(size_t)hi_l] - net->lvl_ptr[(size_t)l]);
+                }
                 G = 1;
-                if (net->n - pos_deep > 16384 || net->grid_blocks > 0)
-                    while (G < 32 && (net->n - pos_deep + G - 1) / G > warps) G *= 2;
+                while (G < 32 && (live + G - 1) / G > warps) G *= 2;
             }
             if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != G)) {
                 std::vector<int32_t> start;
@@ -906,9 +927,26 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             CU(cudaMemsetAsync(net->d_ctrl.p, 0, 8 * sizeof(int), st));
             if (nstages > 0) CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
             if (first) CU(cudaEventRecord(net->ev0, st));
+            // Overlap: both kernels in flight at once.  Needs both phases in this call, and room: the dataflow kernel gives up
+            // one CTA per SM (16 K registers), which holds one 128-thread marching CTA.
+            int sms = 0;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, net->device));
+            const bool overlap = net->overlap_march && net->mode == 4 && phase == PHASE_ALL && nstages > 0 && pos_deep < net->n &&
+                                 net->grid_blocks <= 0 && !net->march_profile && max_grid >= 2 * sms;
+            net->overlapped_run = overlap;
+            if (overlap) {
+                if (!net->march_stream) CU(cudaStreamCreateWithFlags(&net->march_stream, cudaStreamNonBlocking));
+                if (!net->ev_fork) CU(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+                if (!net->ev_join) CU(cudaEventCreate(&net->ev_join));
+                if (!net->ev_wide_end) CU(cudaEventCreate(&net->ev_wide_end));
+                CU(cudaEventRecord(net->ev_fork, st));                 // state reset and control words are in place
+                CU(cudaStreamWaitEvent(net->march_stream, net->ev_fork, 0));
+                grid = max_grid - sms;
+            }
             if (nstages > 0 && phase != PHASE_DEEP) {
                 CU(launch_dataflow(nd, rd, sd, pd, grid, st));
                 net->launches++;
+                if (overlap) CU(cudaEventRecord(net->ev_wide_end, st));
             }
             if (pos_deep < net->n && phase != PHASE_WIDE) {
                 MarchDev md;
@@ -923,13 +961,21 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                     md.prof = net->d_march_prof.p; md.t_start = net->d_march_prof.p + (size_t)net->n * 4;
                 }
                 if (!net->ev_mid) CU(cudaEventCreate(&net->ev_mid));
-                CU(cudaEventRecord(net->ev_mid, st));
+                if (!overlap) CU(cudaEventRecord(net->ev_mid, st));
                 int mgrid = 0;
                 CU(march_max_grid(&mgrid));
                 if (mgrid <= 0) return fail(TRT_ERR_CUDA, "marching kernel cannot be made resident");
                 if (net->grid_blocks > 0) mgrid = std::min(mgrid, net->grid_blocks);
-                mgrid = (int)std::min<int64_t>(mgrid, ((int64_t)md.n_units + 7) / 8);
-                CU(launch_march(nd, rd, md, pd, mgrid, st));
+                if (overlap) {
+                    // one 4-warp CTA per SM beside three dataflow CTAs
+                    mgrid = (int)std::min<int64_t>(sms, ((int64_t)md.n_units + 3) / 4);
+                    CU(launch_march(nd, rd, md, pd, mgrid, net->march_stream, 128));
+                    CU(cudaEventRecord(net->ev_join, net->march_stream));
+                    CU(cudaStreamWaitEvent(st, net->ev_join, 0));       // the result pass needs both
+                } else {
+                    mgrid = (int)std::min<int64_t>(mgrid, ((int64_t)md.n_units + 7) / 8);
+                    CU(launch_march(nd, rd, md, pd, mgrid, st));
+                }
                 net->launches++;
             }
         } else if (net->mode == 1) {
@@ -1004,7 +1050,12 @@ int trt_sync(trt_network* net)
         net->wide_ms = net->kernel_ms; net->march_ms = 0.0;
         if (net->mode >= 3 && net->ev_mid && net->march_units > 0 && net->deep_level_used < net->nlevels) {
             float a = 0.f, b = 0.f;
-            if (cudaEventElapsedTime(&a, net->ev0, net->ev_mid) == cudaSuccess &&
+            if (net->overlapped_run) {
+                // both kernels started together: wide_ms = until the dataflow kernel ended, march_ms = what the marching
+                // kernel added after that
+                if (cudaEventElapsedTime(&a, net->ev0, net->ev_wide_end) == cudaSuccess &&
+                    cudaEventElapsedTime(&b, net->ev0, net->ev_join) == cudaSuccess) { net->wide_ms = a; net->march_ms = std::max(0.f, b - a); }
+            } else if (cudaEventElapsedTime(&a, net->ev0, net->ev_mid) == cudaSuccess &&
                 cudaEventElapsedTime(&b, net->ev_mid, net->ev1) == cudaSuccess) { net->wide_ms = a; net->march_ms = b; }
         }
         if (net->mode == 0 && net->profile_stages && net->stages > 0) {
@@ -1445,6 +1496,8 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
     } else if (!strcmp(key, "march_group")) {
         if (value < 0 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 0..32");
         net->march_group = (int)value;
+    } else if (!strcmp(key, "overlap_march")) {
+        net->overlap_march = value != 0;
     } else if (!strcmp(key, "march_prepare")) {
         net->march_prepare = value != 0;
     } else if (!strcmp(key, "poll_sleep")) {

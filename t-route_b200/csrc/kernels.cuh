@@ -149,8 +149,9 @@ struct MarchDev {
 cudaError_t preload_routing_kernels();
 
 cudaError_t march_max_grid(int* blocks);
+// block_threads: 0 = the kernel's 256; 128 = the small CTA that fits beside three dataflow CTAs per SM ("overlap_march")
 cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
-                         int grid_blocks, cudaStream_t st);
+                         int grid_blocks, cudaStream_t st, int block_threads = 0);
 
 // wavefront: stage k routes every (segment s, step t) with level(s) + t == k
 cudaError_t launch_stage(const NetDev& net, const RunDev& run, int k, int lo, int hi, cudaStream_t st);

@@ -893,9 +893,9 @@ cudaError_t dataflow_max_grid(int* blocks)
 cudaError_t persistent_max_grid(int* blocks) { return max_grid_of(persistent_kernel, blocks); }
 
 cudaError_t launch_march(const NetDev& net, const RunDev& run, const MarchDev& march, const PeerDev& peers,
-                         int grid_blocks, cudaStream_t st)
+                         int grid_blocks, cudaStream_t st, int block_threads)
 {
-    march_kernel<<<grid_blocks, kBlock, 0, st>>>(net, run, march, peers);
+    march_kernel<<<grid_blocks, block_threads > 0 ? block_threads : kBlock, 0, st>>>(net, run, march, peers);
     return cudaGetLastError();
 }
 

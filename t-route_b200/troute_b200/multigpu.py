@@ -32,19 +32,29 @@ def _window_cols(nsteps, qts, w):
 
 
 def _q0_with_step0_observations(wl):
-    """A gage with an observation at step 0 replaces the INITIAL flow of its segment (mc_reach.pyx:403-411).  The owning
-    network does that on the device (reset_gages_kernel); a shard that only IMPORTS the segment reads q[u, 0] from its own
-    import row, which is initialised from the q0 it was given -- so every router starts from the replaced value."""
+    """Initial state [n, 3] every router starts from.  Two things make q[s, 0] differ from the q0 the caller hands in, and both
+    are applied by the network that OWNS the segment on the device -- but a shard that only IMPORTS the segment (it feeds
+    one of its own across a cut edge) reads q[u, 0] from its import row, which is initialised from the q0 it was given:
+      * a gage with an observation at step 0 replaces the initial flow of its segment (mc_reach.pyx:403-411;
+        reset_gages_kernel);
+      * a level pool starts from the outflow of the waterbody table, `qd0` (mc_reach.pyx:298, :359-361;
+        init_levelpool_kernel), not from q0.
+    So the replaced values go into the q0 of every router (found by tools/gpu_verify_windows.py: 164 rows downstream of the
+    cut edges below reservoirs were off at the first steps of a sharded run)."""
     g = wl.get("gages")
     q0 = wl["q0"]
-    if not g or len(g["usgs_positions"]) == 0:
-        return q0
-    usgs = np.asarray(g["usgs_values"], dtype=np.float32).reshape(len(g["usgs_positions"]), -1)
-    if usgs.shape[1] == 0:
+    lp_rows = np.asarray(wl.get("lp_rows", ()), dtype=np.int64)
+    have_gages = bool(g) and len(g["usgs_positions"]) > 0
+    if not have_gages and lp_rows.size == 0:
         return q0
     q0 = np.array(q0, dtype=np.float32, copy=True)
-    obs0 = ~np.isnan(usgs[:, 0])
-    q0[np.asarray(g["usgs_positions"])[obs0], 0] = usgs[obs0, 0]
+    if lp_rows.size:
+        q0[lp_rows, 0] = np.asarray(wl["wbody"], dtype=np.float64)[:, 9].astype(np.float32)
+    if have_gages:
+        usgs = np.asarray(g["usgs_values"], dtype=np.float32).reshape(len(g["usgs_positions"]), -1)
+        if usgs.shape[1] > 0:
+            obs0 = ~np.isnan(usgs[:, 0])
+            q0[np.asarray(g["usgs_positions"])[obs0], 0] = usgs[obs0, 0]
     return q0
 
 
@@ -112,12 +122,13 @@ class _RouterBase:
             else:
                 self.net.continue_ptr(self.T, self.qts, ql.data_ptr(), ql.shape[1])
 
-    def alloc_host(self):
+    def alloc_host(self, result=True):
+        """Pinned host copies of the forcing and (result=True) the pinned [n, 3T] result buffer of the end-to-end leg."""
         torch = self.torch
         qlat = [torch.from_numpy(np.ascontiguousarray(self.qlat[:, _window_cols(self.T, self.qts, w)])).pin_memory()
                 for w in range(self.windows)]
         q0 = torch.from_numpy(np.ascontiguousarray(self.q0)).pin_memory()
-        out = torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True)
+        out = torch.empty((self.n, 3 * self.T), dtype=torch.float32, pin_memory=True) if result else None
         self._host = (qlat, q0, out)
         self.h2d_bytes = sum(int(q.numel()) * 4 for q in qlat) + int(q0.numel()) * 4
         self.d2h_bytes = self.n * 3 * self.T * 4 * self.windows

@@ -65,6 +65,50 @@ for short, nudging in ((False, False), (True, False), (False, True)):
     if rank == 0:
         print("OK short_ts=%s nudging=%s cut_edges=%d" % (short, nudging, r.plan_stats["n_cut_edges"]), flush=True)
     r.close()
+
+# consecutive windows with the state handed over ON THE DEVICES (trt_continue per shard; BASELINE configs[4] in small): two
+# windows of 24 steps == the oracle's one call over 48 steps, every row of every shard (level pools and cut edges included),
+# and the per-window result checksums of the ranks add up to the checksum of the unsharded table
+case2 = H.make_case(down, nsteps=48, warm=True, n_lp=40)
+# ... with reservoirs sitting right ABOVE cut edges: the importing shard must start from the reservoir's initial outflow
+# (qd0 of the waterbody table), not from q0 (a bug of round 1 found by tools/gpu_verify_windows.py)
+from troute_b200 import partition
+from troute_b200._lib import TRT_KIND_LEVELPOOL
+_, plans0, _ = partition.plan_shards(down, case2["up_ptr"], case2["up_rows"], case2["kind"], world, pieces_per_shard=6,
+                                     level=hostgraph.levels(down, case2["up_ptr"]))
+exp = np.unique(np.concatenate([p.exports[2] for p in plans0]))
+cand = exp[(np.diff(case2["up_ptr"])[exp] > 0) & (case2["kind"][exp] == 0)]
+assert cand.size > 0
+case2["lp_rows"] = np.sort(np.concatenate([case2["lp_rows"], cand])).astype(np.int64)
+case2["kind"][cand] = TRT_KIND_LEVELPOOL
+case2["wbody"] = synth.levelpool_params(case2["lp_rows"].size, seed=16)
+wl2 = dict(n=case2["n"], down=down, params=case2["params"], cols=case2["cols"], qlat=case2["qlat"], q0=case2["q0"],
+           up_ptr=case2["up_ptr"], up_rows=case2["up_rows"], kind=case2["kind"], lp_rows=case2["lp_rows"], wbody=case2["wbody"])
+ref2, _, _ = H.oracle_route(o, case2, False)
+for overlap in (0, 1):
+    r = multigpu.ShardedRouter(wl2, world, rank, rank, 24, 12, False, pieces_per_shard=6, windows=2)
+    r.set_option("overlap_march", overlap)
+    lp_on_cut = [None] * world
+    dist.all_gather_object(lp_on_cut, int((case2["kind"][r.plan.exports[2]] == TRT_KIND_LEVELPOOL).sum()))
+    assert sum(lp_on_cut) > 0, lp_on_cut
+    r.upload()
+    oks, hashes = [], []
+    def on_window(w):
+        out, _ = r.net.download()
+        own = r.plan.own
+        want = ref2[r.plan.rows[own], 3 * 24 * w:3 * 24 * (w + 1)]
+        oks.append(bool(np.array_equal(out[own].view(np.int32), want.view(np.int32))))
+        hashes.append(int(r.window_hash()))
+    r.run_checked(on_window)
+    res = [None] * world
+    dist.all_gather_object(res, (oks, hashes))
+    assert all(all(x[0]) for x in res), (overlap, [x[0] for x in res])
+    for w in range(2):
+        total = sum(x[1][w] for x in res) % (1 << 64)
+        assert total == H.result_hash(ref2[:, 3 * 24 * w:3 * 24 * (w + 1)]), (overlap, w)
+    if rank == 0:
+        print("OK windows=2 overlap_march=%d cut_edges=%d" % (overlap, r.plan_stats["n_cut_edges"]), flush=True)
+    r.close()
 dist.destroy_process_group()
 """
 
@@ -88,4 +132,5 @@ def test_two_gpu_sharded_routing_matches_oracle(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "OK short_ts=True" in outs[0] and "OK short_ts=False nudging=True" in outs[0], outs[0]
+    assert "OK windows=2 overlap_march=0" in outs[0] and "OK windows=2 overlap_march=1" in outs[0], outs[0]
     print(outs[0])

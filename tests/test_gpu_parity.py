@@ -277,7 +277,11 @@ def test_marching_schedule_options_do_not_change_results(eng, oracle, short_ts):
               dict(mode=3, march_group=32, grid_blocks=2), dict(mode=4, deep_level=0), dict(mode=4, deep_level=3),
               dict(mode=4, deep_level=40, march_group=4), dict(mode=4, deep_level=100000),
               dict(mode=4, deep_lanes=500, march_group=2), dict(mode=4, deep_lanes=0),
-              dict(mode=4, deep_lanes=20000), dict(mode=4, deep_lanes=3000, grid_blocks=3), dict(mode=2, grid_blocks=1)]
+              dict(mode=4, deep_lanes=20000), dict(mode=4, deep_lanes=3000, grid_blocks=3), dict(mode=2, grid_blocks=1),
+              # the marching kernel BESIDE the dataflow kernel (one un-chunked call: both phases in one launch sequence)
+              dict(mode=4, deep_lanes=3000, route_chunks=1, overlap_march=1),
+              dict(mode=4, deep_level=3, route_chunks=1, overlap_march=1, march_group=2),
+              dict(mode=4, deep_lanes=20000, route_chunks=1, overlap_march=1)]
     for opts in trials:
         out, up, _ = H.engine_route(case, short_ts, options=opts)
         H.assert_bit_equal(out, ref, f"{opts}")

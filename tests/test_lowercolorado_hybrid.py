@@ -406,3 +406,44 @@ def test_compute_diffusive_routing_equals_the_reference_function(oracle, monkeyp
         assert a[2] == b[2] == 0 and np.array_equal(a[6], b[6]) and a[8].shape == b[8].shape
         for k in (3, 4, 5, 7, 9):
             assert len(a[k]) == len(b[k]) and all(np.asarray(x).size == 0 for x in a[k])
+
+
+def test_reference_invariants_hold_on_the_real_domain(oracle):
+    """The diffusive oracle stays `parity unpinned` (the reference holds no vector for this solver and its Fortran cannot be
+    built here or on the GPU box); what the Fortran source itself guarantees is asserted on the real LowerColorado domain
+    (VERDICT r01 item 7), for every reach the solver routes (the 7 Muskingum-Cunge tributary reaches are boundary
+    conditions only; unpack_output drops their rows):
+      * every save time of every node is written (diffnw :803-832): no row of q / elevation / depth is left at its initial 0;
+      * |q| >= q_llm after every sweep (mesh_diffusive_forward :1319-1324), so also at every save time, which is a copy of
+        a sweep result (the output step is a multiple of the routing step here);
+      * depth > 0 and elevation - depth is one bed elevation per node for the whole run (:861-863), the given one up to the
+        solver's minimum-slope adjustment;
+      * the flood wave is attenuated, not amplified: no mainstem node ever carries more than the sum of everything that
+        enters the domain at its peak."""
+    from oracle import diffusive as od
+    od.build()
+    c, dnd, results, q0, qlats, _, _ = hybrid_inputs(oracle)
+    ins = pack(dnd, results, q0, qlats)
+    q, elv, depth = od.compute_diffusive(ins, od.POW_DET)
+    nrch, frnw = int(ins["nrch_g"]), np.asarray(ins["frnw_g"])
+    q_llm = float(np.asarray(ins["para_ar_g"])[7])
+    z = np.asarray(ins["z_ar_g"])
+    qtrib = np.asarray(ins["qtrib_g"])
+    tribs = [j for j in range(nrch) if np.abs(qtrib[:, j]).max() > 0]
+    assert len(tribs) == 7 and q.shape[0] == int(ins["ntss_ev_g"]) and q.shape[2] == nrch
+    routed = 0
+    for j in range(nrch):
+        n = int(frnw[j, 0])
+        qj, ej, dj = q[:, :n, j], elv[:, :n, j], depth[:, :n, j]
+        assert np.isfinite(qj).all() and np.isfinite(ej).all() and np.isfinite(dj).all()
+        if j in tribs:                               # boundary conditions, not routed: unpack_output drops their rows
+            continue
+        routed += 1
+        assert (np.abs(qj[1:]) >= q_llm * (1 - 1e-12)).all(), j                      # rows after the initial state
+        assert (dj[1:] > 0).all(), j
+        bed = ej[1:] - dj[1:]                        # the solver's bed elevation: constant in time, the given one up to its
+        assert np.allclose(bed, bed[:1], rtol=0, atol=1e-9), j          # slope adjustment (so_llm, :727-731)
+        assert np.abs(bed[0] - z[:n, j]).max() < 0.05, j
+    assert routed == nrch - 7
+    inflow_peak = np.abs(qtrib).sum(axis=1).max() + np.abs(np.asarray(ins["qlat_g"])).sum(axis=(1, 2)).max() * float(np.asarray(ins["dx_ar_g"]).max())
+    assert np.abs(q).max() <= 1.05 * max(inflow_peak, float(np.abs(np.asarray(ins["iniq"])).max()))
