@@ -101,7 +101,7 @@ struct trt_network {
     bool own_stream = true;
     cudaStream_t copy_stream = nullptr;                       // trt_route: results of chunk c go home while c + 1 runs
     std::vector<cudaEvent_t> chunk_events;
-    int route_chunks = 6;                                     // measured (profiles/r02_e2e_timeline): 4 -> 232 ms, 6 -> 220, 8 -> 292
+    int route_chunks = 0;                                     // time chunks of trt_run_download; 0 = chosen per call (auto_route_chunks)
     DevBuf<float> d_deep_fvd;                                 // [n_deep][3T] results of the marching rows (chunked trt_route)
     DevBuf<float> d_last;                                     // [n][3] last timestep of every row (trt_download_last_step)
     float* h_deep_fvd = nullptr;                              // pinned staging of d_deep_fvd
@@ -1159,7 +1159,7 @@ int trt_download_last_step(trt_network* net, float* qvd_out)
 // stream (a strided 2-D copy out of the [n_rows, 3T] result) -- the 9.4 GB result of a CONUS day takes longer to cross
 // PCIe than to compute, so hiding one behind the other is worth more than any kernel tuning.  Every chunk pays the
 // narrow tail of the wavefront once and narrower chunks make shorter DMA rows (below ~500 bytes the copy engine
-// slows down), which bounds the useful number of chunks (default 6).
+// slows down), which bounds the useful number of chunks (auto_route_chunks below picks it per call).
 int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_short_ts, const float* qlat, int32_t nqcols,
               const float* q0, int64_t n_bnd, const int64_t* bnd_rows, const float* bnd_fvd, float* fvd_out,
               float* upstream_out)
@@ -1169,13 +1169,48 @@ int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_shor
     return trt_run_download(net, assume_short_ts, fvd_out, upstream_out);
 }
 
+// How many time chunks trt_run_download cuts a call into when the caller does not say ("route_chunks" = 0).
+// More chunks start the D2H copy earlier and leave a shorter last copy exposed; every chunk pays the narrow tail of the
+// wavefront again (one stage latency per wide level), and rows shorter than ~500 bytes slow the copy engine down.
+// Model, constants measured on B200 (profiles/r02_v3_smem_state: stage profile, e2e_timeline_by_chunks.txt, pcie_probe2.txt):
+//   stage time = max(30 us, 0.11 ns x lanes of the stage);  copy rate 50 GB/s (43 GB/s below 576-byte rows);
+//   call(C) = max(compute + (C - 1) x tail + copy / C,  compute / C + tail + copy).
+// One GPU, 2.7 M segments x 288 steps: 6 chunks (measured 232 / 220 / 292 ms for 4 / 6 / 8).  An eighth of that network per
+// GPU: 1-2 chunks -- there the wavefront is latency-bound and six chunks tripled the compute time (113 ms per call measured).
+static int auto_route_chunks(const trt_network* net, int nsteps, int assume_short_ts)
+{
+    if (net->n <= 0 || nsteps <= 1) return 1;
+    int Lw = net->nlevels;
+    if (net->mode == 4) {
+        if (net->deep_level >= 0) Lw = std::min(net->deep_level, net->nlevels);
+        else { while (Lw > 0 && net->n - net->lvl_ptr[(size_t)Lw - 1] <= net->deep_lanes) --Lw; }
+    } else if (net->mode == 3) return 1;
+    const double levels = assume_short_ts ? 1.0 : (double)Lw;
+    const double n_wide = (double)(Lw > 0 ? net->lvl_ptr[(size_t)Lw] : 0);
+    const double t_lat = 30e-6, c_lane = 0.11e-9;
+    const double compute = nsteps * std::max(t_lat, n_wide * c_lane) + levels * t_lat;
+    const double tail = levels * t_lat;
+    const double bytes = (double)net->n * 3.0 * nsteps * sizeof(float);
+    int best = 1;
+    double best_t = 1e30;
+    for (int C : {1, 2, 3, 4, 6, 8, 12}) {
+        if (C > nsteps) break;
+        const double row_bytes = 3.0 * sizeof(float) * (double)(nsteps / C);
+        const double copy = bytes / (row_bytes >= 576.0 ? 50e9 : 43e9 * std::min(1.0, row_bytes / 432.0));
+        const double t = C == 1 ? compute + copy : std::max(compute + (C - 1) * tail + copy / C, compute / C + tail + copy);
+        if (t < best_t * 0.98) { best_t = t; best = C; }            // prefer fewer chunks unless the gain is real
+    }
+    return best;
+}
+
 int trt_run_download(trt_network* net, int32_t assume_short_ts, float* fvd_out, float* upstream_out)
 {
     if (!net) return fail(TRT_ERR_INVALID, "NULL network");
     if (!net->uploaded) return fail(TRT_ERR_STATE, "trt_run_download called before trt_upload_forcing");
     int rc;
     const int nsteps = net->T;
-    const int C = (net->mode >= 2 && fvd_out && net->n > 0) ? std::max(1, std::min(net->route_chunks, nsteps)) : 1;
+    const int want = net->route_chunks > 0 ? net->route_chunks : auto_route_chunks(net, nsteps, assume_short_ts);
+    const int C = (net->mode >= 2 && fvd_out && net->n > 0) ? std::max(1, std::min(want, nsteps)) : 1;
     if (C <= 1) {
         rc = run_async(net, assume_short_ts);
         if (rc != TRT_OK) return rc;
@@ -1491,7 +1526,7 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
         if (value < 1 || value > 64) return fail(TRT_ERR_INVALID, "trip_buckets must be in 1..64");
         net->trip_buckets = (int)value;
     } else if (!strcmp(key, "route_chunks")) {
-        if (value < 1 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 1..1024");
+        if (value < 0 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 0..1024 (0 = chosen per call)");
         net->route_chunks = (int)value;
     } else if (!strcmp(key, "march_group")) {
         if (value < 0 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 0..32");
