@@ -243,7 +243,12 @@ int trt_prepare(trt_network* net);
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
  *   "collect_trips", "trip_buckets"  see trt_trip_counts / trt_trip_counts_bucketed
  *   "grid_blocks" CTAs of the persistent / dataflow kernel (0 = as many as are co-resident)
- *   "route_chunks" time chunks of trt_route / trt_run_download (default 4; 1 = compute everything, then copy)
+ *   "route_chunks" time chunks of trt_route / trt_run_download: the results of chunk c go home while chunk c + 1 is routed;
+ *                 0 (default) = chosen per call from the width of the network, the number of steps and "host_shards";
+ *                 1 = compute everything, then copy
+ *   "host_shards" GPUs of this host that route shards of the same call (default 1): they share the host's copy bandwidth
+ *   "park_max", "park_min_tiles", "early_max_tiles"  second form of the dataflow kernel (parked stragglers / early
+ *                 publication, csrc/routing_kernels.cu: dataflow_park_kernel); defaults 0 / -1 / 0 = off.  Same bits either way
  *   "stream"      adopt a caller-owned cudaStream_t (passed as an integer; 0 = back to the private stream) */
 int trt_set_option(trt_network* net, const char* key, int64_t value);
 /* "profile_stages" = 1 with "mode" = 0: device time and width (lanes) of every wavefront stage of the last run;

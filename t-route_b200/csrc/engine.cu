@@ -102,6 +102,7 @@ struct trt_network {
     cudaStream_t copy_stream = nullptr;                       // trt_route: results of chunk c go home while c + 1 runs
     std::vector<cudaEvent_t> chunk_events;
     int route_chunks = 0;                                     // time chunks of trt_run_download; 0 = chosen per call (auto_route_chunks)
+    int host_shards = 1;                                      // GPUs of this host that route shards of the same call (they share the host's copy bandwidth)
     DevBuf<float> d_deep_fvd;                                 // [n_deep][3T] results of the marching rows (chunked trt_route)
     DevBuf<float> d_last;                                     // [n][3] last timestep of every row (trt_download_last_step)
     float* h_deep_fvd = nullptr;                              // pinned staging of d_deep_fvd
@@ -136,6 +137,14 @@ struct trt_network {
     // "overlap_march": the marching kernel runs BESIDE the dataflow kernel (second stream, 128-thread CTAs in the register
     // space a fourth dataflow CTA per SM would take) instead of after it; its lanes poll for the flows of the last wide level
     int overlap_march = 0;
+    // dataflow_park_kernel (routing_kernels.cu): "park_max" = unfinished solves of a tile that may be parked (0 = never),
+    // in stages at least "park_min_tiles" wide (-1 = 6 tiles per resident warp); stages at most "early_max_tiles" wide
+    // publish lane by lane (-1 = one tile per resident warp).  park_max = 0 and early_max_tiles = 0 (the defaults): the
+    // plain dataflow_kernel -- the parking form is bit-identical and raises the busy lanes per instruction (20.5 -> 24.3)
+    // but its larger hot code falls off the instruction cache (profiles/r02_v7_park), so it is an option, not the default.
+    int park_max = 0;
+    int64_t park_min_tiles = -1, early_max_tiles = 0;
+    DevBuf<unsigned> d_park_pool;
     cudaStream_t march_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_wide_end = nullptr;
     bool overlapped_run = false;
@@ -924,6 +933,19 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
             CU(dataflow_max_grid(&max_grid));
             if (max_grid <= 0) return fail(TRT_ERR_CUDA, "dataflow kernel cannot be made resident");
             if (grid <= 0) grid = max_grid;
+            {
+                const int64_t warps = (int64_t)grid * 8;
+                const int64_t pmin = net->park_min_tiles >= 0 ? net->park_min_tiles : 6 * warps;
+                const int64_t emax = net->early_max_tiles >= 0 ? net->early_max_tiles : warps;
+                sd.park_max = net->park_max;
+                sd.park_min_tiles = (int)std::min<int64_t>(pmin, 0x7fffffff);
+                sd.early_max_tiles = (int)std::min<int64_t>(emax, 0x7fffffff);
+                sd.park_pool = nullptr;
+                if (sd.park_max > 0 || sd.early_max_tiles > 0) {
+                    CU(net->d_park_pool.reserve((size_t)warps * TRT_PARK_WORDS * TRT_PARK_SLOTS));
+                    sd.park_pool = net->d_park_pool.p;
+                }
+            }
             CU(cudaMemsetAsync(net->d_ctrl.p, 0, 8 * sizeof(int), st));
             if (nstages > 0) CU(cudaMemsetAsync(net->d_done.p, 0, (size_t)nstages * sizeof(int), st));
             if (first) CU(cudaEventRecord(net->ev0, st));
@@ -1173,10 +1195,13 @@ int trt_route(trt_network* net, int32_t nsteps, int32_t qts, int32_t assume_shor
 // More chunks start the D2H copy earlier and leave a shorter last copy exposed; every chunk pays the narrow tail of the
 // wavefront again (one stage latency per wide level), and rows shorter than ~500 bytes slow the copy engine down.
 // Model, constants measured on B200 (profiles/r02_v3_smem_state: stage profile, e2e_timeline_by_chunks.txt, pcie_probe2.txt):
-//   stage time = max(30 us, 0.11 ns x lanes of the stage);  copy rate 50 GB/s (43 GB/s below 576-byte rows);
+//   stage time = max(30 us, 0.11 ns x lanes of the stage);  copy rate 50 GB/s per GPU (43 GB/s below 576-byte rows), and
+//   87 GB/s for all the GPUs of the host together (the e2e lines of 2 / 4 / 8 GPUs: 71 / 59 / 83 GB/s aggregate -- with
+//   shards on several GPUs the call is bound by the host side of the copies, whatever the chunking);
 //   call(C) = max(compute + (C - 1) x tail + copy / C,  compute / C + tail + copy).
-// One GPU, 2.7 M segments x 288 steps: 6 chunks (measured 232 / 220 / 292 ms for 4 / 6 / 8).  An eighth of that network per
-// GPU: 1-2 chunks -- there the wavefront is latency-bound and six chunks tripled the compute time (113 ms per call measured).
+// One GPU, 2.7 M segments x 288 steps: 6 chunks (measured 232 / 220 / 292 ms for 4 / 6 / 8).  An eighth of that network on
+// each of 8 GPUs: the copy (108 ms at the host's rate) dwarfs the compute (~20 ms), so what counts is an early first chunk:
+// again ~6 chunks (113 ms measured; one chunk would be compute + copy = ~130).
 static int auto_route_chunks(const trt_network* net, int nsteps, int assume_short_ts)
 {
     if (net->n <= 0 || nsteps <= 1) return 1;
@@ -1191,12 +1216,13 @@ static int auto_route_chunks(const trt_network* net, int nsteps, int assume_shor
     const double compute = nsteps * std::max(t_lat, n_wide * c_lane) + levels * t_lat;
     const double tail = levels * t_lat;
     const double bytes = (double)net->n * 3.0 * nsteps * sizeof(float);
+    const double host_rate = 87e9 / std::max(1, net->host_shards);  // "host_shards": GPUs of this host copying home at once
     int best = 1;
     double best_t = 1e30;
     for (int C : {1, 2, 3, 4, 6, 8, 12}) {
         if (C > nsteps) break;
         const double row_bytes = 3.0 * sizeof(float) * (double)(nsteps / C);
-        const double copy = bytes / (row_bytes >= 576.0 ? 50e9 : 43e9 * std::min(1.0, row_bytes / 432.0));
+        const double copy = bytes / std::min(host_rate, row_bytes >= 576.0 ? 50e9 : 43e9 * std::min(1.0, row_bytes / 432.0));
         const double t = C == 1 ? compute + copy : std::max(compute + (C - 1) * tail + copy / C, compute / C + tail + copy);
         if (t < best_t * 0.98) { best_t = t; best = C; }            // prefer fewer chunks unless the gain is real
     }
@@ -1528,9 +1554,21 @@ int trt_set_option(trt_network* net, const char* key, int64_t value)
     } else if (!strcmp(key, "route_chunks")) {
         if (value < 0 || value > 1024) return fail(TRT_ERR_INVALID, "route_chunks must be in 0..1024 (0 = chosen per call)");
         net->route_chunks = (int)value;
+    } else if (!strcmp(key, "host_shards")) {
+        if (value < 1 || value > 64) return fail(TRT_ERR_INVALID, "host_shards must be in 1..64");
+        net->host_shards = (int)value;
     } else if (!strcmp(key, "march_group")) {
         if (value < 0 || value > 32) return fail(TRT_ERR_INVALID, "march_group must be in 0..32");
         net->march_group = (int)value;
+    } else if (!strcmp(key, "park_max")) {
+        if (value < 0 || value > 31) return fail(TRT_ERR_INVALID, "park_max must be in 0..31");
+        net->park_max = (int)value;
+    } else if (!strcmp(key, "park_min_tiles")) {
+        if (value < -1) return fail(TRT_ERR_INVALID, "park_min_tiles must be >= -1");
+        net->park_min_tiles = value;
+    } else if (!strcmp(key, "early_max_tiles")) {
+        if (value < -1) return fail(TRT_ERR_INVALID, "early_max_tiles must be >= -1");
+        net->early_max_tiles = value;
     } else if (!strcmp(key, "overlap_march")) {
         net->overlap_march = value != 0;
     } else if (!strcmp(key, "march_prepare")) {

@@ -119,7 +119,14 @@ struct SchedDev {
                                       // the last non-empty stage <= k - gate (0 = no wait)
     unsigned long long* stage_time;   // [nstages + 1] or NULL: %globaltimer (ns) when stage k completed, in slot k;
                                       // slot 0 = kernel start ("profile_stages" option)
+    // dataflow_park_kernel (routing_kernels.cu): parked stragglers and early publication
+    unsigned* park_pool;              // [warps of the grid][TRT_PARK_WORDS][TRT_PARK_SLOTS] contexts of parked solves (L2-resident)
+    int park_max;                     // park the unfinished solves of a tile once at most this many are left (0 = never)
+    int park_min_tiles;               // ... in stages at least this many tiles wide (throughput regime)
+    int early_max_tiles;              // stages at most this many tiles wide: every lane publishes when its own solve ends
 };
+#define TRT_PARK_WORDS 40
+#define TRT_PARK_SLOTS 64
 
 // cut edges to other shards: lane s with (kind & TRT_KIND_EXPORT_FLAG) stores q also to peer memory
 #define TRT_KIND_EXPORT_FLAG 0x10
@@ -161,6 +168,7 @@ cudaError_t launch_persistent(const NetDev& net, const RunDev& run, int k_begin,
 // largest co-resident grid (blocks) of the persistent kernel on the current device
 cudaError_t persistent_max_grid(int* blocks);
 cudaError_t dataflow_max_grid(int* blocks);
+// sched.park_pool != NULL selects dataflow_park_kernel (parked stragglers / early publication)
 cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev& sched, const PeerDev& peers,
                             int grid_blocks, cudaStream_t st);
 cudaError_t launch_fill_zero_rows(const int* pos, float* S, int count, int T, cudaStream_t st);

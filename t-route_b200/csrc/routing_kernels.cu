@@ -493,7 +493,10 @@ __global__ void __launch_bounds__(kBlock) persistent_kernel(NetDev net, RunDev r
 
 // A claimed unit, decoded (warp-uniform), lives in the warp's shared-memory control block -- NOT in registers: the secant
 // solve needs every one of the 64 registers, and the unit is looked at only before and after it.
-enum { DU_LO = 0, DU_HI = 1, DU_STAGE = 2, DU_TILE0 = 3, DU_NTILES = 4, DU_WORDS = 5 };
+enum { DU_LO = 0, DU_HI = 1, DU_STAGE = 2, DU_TILE0 = 3, DU_NTILES = 4, DU_MODE = 5, DU_WORDS = 6 };
+// DU_MODE (dataflow_park_kernel): how the lanes of a unit leave the secant loop, decided per STAGE from its width
+enum { DM_PARK = 1,      // throughput regime (many tiles per warp): the last few unfinished solves of a tile are parked
+       DM_EARLY = 2 };   // latency regime (at most ~one tile per warp): a lane publishes as soon as ITS solve ends
 
 // unit u -> cw[0 .. DU_WORDS); returns false when the queue is exhausted
 __device__ __forceinline__ bool df_decode(const NetDev& net, const RunDev& run, const SchedDev& sc, unsigned u, int& cursor,
@@ -526,6 +529,8 @@ __device__ __forceinline__ bool df_decode(const NetDev& net, const RunDev& run, 
     if (lane == 0) {
         cw[DU_LO] = lo; cw[DU_HI] = hi; cw[DU_STAGE] = lo_i; cw[DU_TILE0] = tile0;
         cw[DU_NTILES] = min(1 << shift, tile_end + 1 - tile0);
+        const int tiles_k = tile_end + 1 - (lo >> 5);
+        cw[DU_MODE] = (sc.park_max > 0 && tiles_k >= sc.park_min_tiles ? DM_PARK : 0) | (tiles_k <= sc.early_max_tiles ? DM_EARLY : 0);
     }
     __syncwarp();
     return true;
@@ -538,6 +543,7 @@ struct DataflowSmem {
     SmemTabs tabs;                                                    // tables of the bit-specified pow
     __align__(8) unsigned long long bars[kBlock / 32][2];             // per warp: one mbarrier per record buffer
     int ctl[kBlock / 32][2][8];                                       // per warp: this unit, the next unit
+    int pw[kBlock / 32][4];                                           // per warp: [0] parked solves waiting in its pool
 };
 
 __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
@@ -655,6 +661,415 @@ __global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_kern
             }
             if (!(st & 16u)) break;
             st = (st & 0xFFu) ^ 8u;                  // the next unit becomes the current one, tile 0
+        }
+        st ^= 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dataflow schedule, second form: parked stragglers (throughput regime) and early publication (latency regime)
+// ---------------------------------------------------------------------------------------------------------
+// Same schedule as dataflow_kernel -- units claimed in stage order, lanes wait on the slots they read, tile records by TMA,
+// inputs by cp.async -- but the lanes of a tile no longer leave the secant loop together.
+//
+// Why.  A warp runs until its slowest lane has converged.  88 % of the lane-steps take 2 or 3 trips, 9 % take 4 or more,
+// and almost every tile of 32 holds one of those: the warp executes ~4.4 trips for lanes that need 2.6 (17.6 busy lanes of 32
+// in caller order; a static within-level order only helps when it was calibrated on the storm being routed,
+// DESIGN.md section 6).  Two ways out, chosen per STAGE from its width (DU_MODE):
+//
+//  * DM_PARK -- wide stages, many tiles per warp, throughput-bound.  After a trip that leaves at most `park_max` lanes
+//    unfinished (and at least two trips done), those lanes PARK: the 13 words a solve carries and the 16 words it reads
+//    (channel, inflows) go to a per-warp pool in global memory (L2-resident: written once, read once, 128 bytes per
+//    entry), the tile is finished, the warp moves on.  When 32 entries have gathered -- or the warp is about to change
+//    stage, or to wait for anything -- the warp runs them as one BATCH through the same loop: 32 lanes that all need
+//    "a few more trips".  CPU model on the oracle's trip counts (profiles/r02_v7_park): 21.8 -> 27.1 busy lanes.
+//  * DM_EARLY -- narrow stages (the ramp-down of the wavefront and every stage of a small shard), latency-bound: the
+//    run time is the number of stages times the latency of a link, and a link used to cost the SLOWEST solve of the
+//    upstream tile.  Here a lane stores its depth and flow in the trip in which its own solve ends.
+//
+// Deadlock freedom with parking.  Rule: a warp never WAITS (run-ahead gate, unpublished input) while its pool holds an
+// entry -- it drains the pool first (draining is pure computation: every input of a parked solve had arrived).  Hence a
+// waiting warp holds nothing anybody could be waiting for; parked values belong to running warps, which drain when
+// their pool fills, when they change stage, before they wait, or when the queue ends.  With that, the argument of
+// kernels.cuh carries over: the earliest unfinished unit always progresses.  The stage counters `done` / `frontier` count
+// a unit when its tiles are finished, parked lanes or not: they only feed the run-ahead gate, which is a throttle -- what
+// makes a read safe is the sentinel of the slot itself.
+//
+// Never parked: lanes with a gage (the assimilation state is ordered by timestep) or a cut edge to another GPU, level pools.
+// Results are the same bits whatever is parked when (tests/test_gpu_parity.py runs every network with both kernels).
+// a pool entry: words 0..8 of the tile record (the channel), the 18 staging words of the lane (inflows, derived channel values,
+// position and timestep), the 13 words the solve carries
+enum { PK_REC = 0, PK_STG = 9, PK_H = PK_STG + IN_SLOTS, PK_H0, PK_QJ, PK_QJ0, PK_C1, PK_C2, PK_C3, PK_C4, PK_X, PK_KM, PK_XDEN, PK_MANN,
+       PK_BITS, PK_END };
+enum { PK_FLUSH = 32 };                              // a batch is run as soon as this many entries wait
+static_assert(PK_END <= TRT_PARK_WORDS, "pool entry");
+// where the lane-step keeps its position and timestep while the solve owns the registers (upstream slots: dead by then)
+enum { IN_SPOS = IN_U0C, IN_STEP = IN_U0P };
+
+// anything not yet published among what this lane staged?  (issue_inputs, then cp.async.wait_group 0)
+__device__ __forceinline__ bool staged_inputs_missing(const RunDev& run, const unsigned* rb, const float* stg)
+{
+    const unsigned flags = rb[R_FLAGS * 32];
+    const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+    const int cnt = (int)(flags >> 8);
+    const bool cur = !run.short_ts;             // the flows of the current step are read
+    bool miss = __float_as_uint(stg[IN_D * 32]) == TRT_SENTINEL;
+    if (!is_lp) miss |= __float_as_uint(stg[IN_Q * 32]) == TRT_SENTINEL;
+    if (cnt > 0) miss |= (cur && __float_as_uint(stg[IN_U0C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U0P * 32]) == TRT_SENTINEL);
+    if (cnt > 1) miss |= (cur && __float_as_uint(stg[IN_U1C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U1P * 32]) == TRT_SENTINEL);
+    if (cnt > 2) miss |= (cur && __float_as_uint(stg[IN_U2C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U2P * 32]) == TRT_SENTINEL);
+    if (cnt > 3) miss |= (cur && __float_as_uint(stg[IN_U3C * 32]) == TRT_SENTINEL) | (__float_as_uint(stg[IN_U3P * 32]) == TRT_SENTINEL);
+    return miss;
+}
+
+// lane 0 of a warp at the run-ahead gate: wait until stage `need` is complete (out of line: off the hot path's footprint)
+__device__ __noinline__ void wait_for_frontier(const int* frontier, int* abort_flag, int need)
+{
+    unsigned spins = 0;
+    while (*reinterpret_cast<const volatile int*>(frontier) < need) {
+        __nanosleep(200);
+        if ((++spins & 0x3FFF) == 0) {
+            if (*reinterpret_cast<volatile int*>(abort_flag) != 0) break;
+            if (spins > (1u << 25)) { if (atomicCAS(abort_flag, 0, 2) == 0) abort_flag[3] = need; break; }
+        }
+    }
+}
+
+// would gather_rest(...) have to wait?  One look at the slots of the 5th .. nth neighbour (no staging slot: 0.3 % of the segments)
+__device__ __noinline__ bool rest_missing(const float* S, const int* up_idx, int T1, int short_ts, int e_begin, int e_end, int t)
+{
+    bool miss = false;
+#pragma unroll 1
+    for (int e = e_begin; e < e_end; ++e) {
+        const float* pu = S + s_idx(__ldg(up_idx + e), t, T1);
+        if (!short_ts) miss |= ld_volatile_u32(pu) == TRT_SENTINEL;
+        miss |= ld_volatile_u32(pu - 64) == TRT_SENTINEL;
+    }
+    return miss;
+}
+
+__device__ __forceinline__ unsigned pk_pack(const McSolve& s)
+{
+    return (unsigned)s.iter | ((unsigned)s.tries << 8) | ((unsigned)s.iters_done << 11) | (s.a0.ck_pos ? 1u << 21 : 0u) |
+           (s.a0.wp_pos ? 1u << 22 : 0u) | (s.err_open ? 1u << 23 : 0u) | (s.have0 ? 1u << 24 : 0u);
+}
+
+__global__ void __launch_bounds__(kBlock, TRT_DATAFLOW_MIN_BLOCKS) dataflow_park_kernel(NetDev net, RunDev run, SchedDev sc, PeerDev peers)
+{
+    extern __shared__ __align__(128) unsigned char df_smem_raw[];
+    DataflowSmem& sm = *reinterpret_cast<DataflowSmem*>(df_smem_raw);
+    SmemTabs& smem = sm.tabs;
+    auto& recbuf = sm.recbuf;
+    auto& bars = sm.bars;
+    auto& ctl = sm.ctl;
+    auto& stage = sm.stage;
+    const PowTabs tabs = stage_tables(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* pw = sm.pw[warp];
+    if (lane == 0) {
+        mbar_init(smem_u32(&bars[warp][0]), 1); mbar_init(smem_u32(&bars[warp][1]), 1);
+        mbar_fence_init();
+        pw[0] = 0;
+    }
+    __syncwarp();
+    if (sc.stage_time && blockIdx.x == 0 && threadIdx.x == 0) sc.stage_time[0] = globaltimer_ns();
+    // this warp's pool: word w of entry e at pool[w * TRT_PARK_SLOTS + e] (computed where it is used: not a register of the solve)
+    auto my_pool = [&]() -> unsigned* {
+        return sc.park_pool + (size_t)(blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * (TRT_PARK_WORDS * TRT_PARK_SLOTS);
+    };
+
+    auto fetch_tile = [&](int tile, int b) {
+        if (lane == 0) {
+            const unsigned bar = smem_u32(&bars[warp][b]);
+            mbar_expect_tx(bar, R_TILE_WORDS * 4);
+            bulk_g2s(smem_u32(&recbuf[warp][b][0]), net.rec + (size_t)tile * R_TILE_WORDS, R_TILE_WORDS * 4, bar,
+                     l2_evict_first_policy());
+        }
+    };
+    auto claim = [&]() -> unsigned { return lane == 0 ? atomicAdd(sc.claim, 1u) : 0u; };
+
+    int cursor = 0;
+    unsigned pend = claim();
+    if (!df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, ctl[warp][0], lane)) return;
+    pend = claim();
+    fetch_tile(ctl[warp][0][DU_TILE0], 0);
+    float* stg = &stage[warp][0][lane];
+    // st: bit 0 = record buffer of the current tile, bit 1 / 2 = phase parity of barrier 0 / 1, bit 3 = control block of the
+    // current unit, bit 4 = a next unit exists, bit 5 = drain the pool before anything else, bit 6 = the record of the current
+    // tile has been waited for (a tile set-up that was abandoned for a drain does not wait twice), bit 7 = the queue is
+    // exhausted, bits 8.. = tile index inside the current unit
+    enum : unsigned { ST_NEXT = 16u, ST_DRAIN = 32u, ST_HAVE_REC = 64u, ST_FINAL = 128u };
+    unsigned st = 0;
+    for (;;) {
+        const int b = st & 1;
+        const int pool_n = pw[0];
+        // One work item per trip of this loop: the next tile of the current unit, or a batch of parked solves.  A batch uses
+        // the record buffer b ^ 1: the tile that was routed from it is finished and the record of the NEXT work item is only
+        // sent there further down, after the last point at which a tile set-up can still turn into a drain.
+        const bool batch = (st & ST_DRAIN) || pool_n >= PK_FLUSH;
+        const unsigned* rb = &recbuf[warp][batch ? b ^ 1 : b][lane];
+        int* cu = ctl[warp][(st >> 3) & 1];
+        const int j = (int)(st >> 8);
+        const bool last_of_unit = j + 1 >= cu[DU_NTILES];
+        bool solving = false, pending = false;
+        McSolve sol;
+        sol.flow = false; sol.iter = 0; sol.iters_done = 0; sol.tries = 0; sol.h = 0.0f;
+        if (!batch) {
+            // ---- a tile: its record arrived while the previous work item was solved ----
+            if (!(st & ST_HAVE_REC)) {
+                mbar_wait(smem_u32(&bars[warp][b]), (st >> (1 + b)) & 1u);
+                st ^= 2u << b;
+                st |= ST_HAVE_REC;
+            }
+            if (j == 0) {
+                // run-ahead gate: do not start polling individual slots before stage k - gate is complete
+                const int need = __ldg(sc.gate_stage + cu[DU_STAGE]);   // last non-empty stage <= k - gate (0 = none)
+                if (need >= 1) {
+                    int fr = 0;
+                    if (lane == 0) fr = *reinterpret_cast<volatile int*>(sc.frontier);
+                    fr = __shfl_sync(0xffffffffu, fr, 0);
+                    if (fr < need) {
+                        if (pool_n > 0) { st |= ST_DRAIN; continue; }          // never wait with parked solves
+                        if (lane == 0) wait_for_frontier(sc.frontier, sc.abort_flag, need);
+                        __syncwarp();
+                    }
+                }
+            }
+            const int tile = cu[DU_TILE0] + j;
+            const int s = (tile << 5) + lane;
+            const bool live = s >= cu[DU_LO] && s < cu[DU_HI] && (rb[R_FLAGS * 32] & 0x0Fu) != TRT_KIND_BOUNDARY;
+            int t = 0;
+            if (live) {
+                const int k = cu[DU_STAGE] + 1;
+                t = (run.short_ts ? k : k - (int)rb[R_LEVEL * 32]) + run.t_off;
+                issue_inputs(net, run, rb, s, t, stg);
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const bool miss = live && staged_inputs_missing(run, rb, stg);
+            if (pool_n > 0) {                                                                // never wait with parked solves
+                bool may_wait = miss;
+                if (live && !miss && (rb[R_FLAGS * 32] >> 8) > 4u) {
+                    const int e0 = rec_i(rb, R_ESTART);
+                    may_wait = rest_missing(run.S, net.up_idx, run.T + 1, run.short_ts, e0 + 4, e0 + (int)(rb[R_FLAGS * 32] >> 8), t);
+                }
+                if (__any_sync(0xffffffffu, may_wait)) { st |= ST_DRAIN; continue; }
+            }
+            // ---- the work item after this one: its record travels while this tile is solved ----
+            if (!last_of_unit) fetch_tile(tile + 1, b ^ 1);
+            else {
+                int* nx = ctl[warp][((st >> 3) & 1) ^ 1];
+                if (df_decode(net, run, sc, __shfl_sync(0xffffffffu, pend, 0), cursor, nx, lane)) {
+                    st |= ST_NEXT;
+                    pend = claim();
+                    fetch_tile(nx[DU_TILE0], b ^ 1);
+                } else st &= ~ST_NEXT;
+            }
+            if (live) {
+                const unsigned flags = rb[R_FLAGS * 32];
+                const bool is_lp = (flags & 0x0Fu) == TRT_KIND_LEVELPOOL;
+                const int cnt = (int)(flags >> 8);
+                const int T1 = run.T + 1;
+                if (miss) resolve_inputs(run.S, net.up_idx, T1, run.short_ts, rb, s, t, stg, sc.abort_flag);
+                // upstream gather in reference order: upstream_flows += ..., previous_upstream_flows += ...  (mc_reach.pyx:496-505)
+                float quc = 0.0f, qup = 0.0f;
+                if (cnt > 0) { if (!run.short_ts) quc += stg[IN_U0C * 32]; qup += stg[IN_U0P * 32]; }
+                if (cnt > 1) { if (!run.short_ts) quc += stg[IN_U1C * 32]; qup += stg[IN_U1P * 32]; }
+                if (cnt > 2) { if (!run.short_ts) quc += stg[IN_U2C * 32]; qup += stg[IN_U2P * 32]; }
+                if (cnt > 3) { if (!run.short_ts) quc += stg[IN_U3C * 32]; qup += stg[IN_U3P * 32]; }
+                if (cnt > 4) {
+                    const int e0 = rec_i(rb, R_ESTART);
+                    const float2 x = gather_rest(run.S, net.up_idx, T1, run.short_ts, e0 + 4, e0 + cnt, t, quc, qup, sc.abort_flag);
+                    quc = x.x; qup = x.y;
+                }
+                if (run.short_ts) quc = qup;
+                const float statep = stg[IN_D * 32];
+                if (is_lp) {
+                    // run_lp_c(r, upstream_flows, 0.0, routing_period, ...)  mc_reach.pyx:553; results :706-710
+                    const float p9[9] = {rec_f(rb, 0), rec_f(rb, 1), rec_f(rb, 2), rec_f(rb, 3), rec_f(rb, 4), rec_f(rb, 5),
+                                         rec_f(rb, 6), rec_f(rb, 7), rec_f(rb, 8)};
+                    float H = statep, outflow;
+                    trt_levelpool_step_call(p9, quc, &H, &outflow, tabs.tl, tabs.te);
+                    run.lp_in[(size_t)__ldg(net.lp_slot + s) * T1 + t] = quc;      // reservoir inflow (upstream_array, :710)
+                    if (flags & TRT_KIND_GAGE_FLAG) outflow = apply_nudging(run, rec_i(rb, R_GAGE), t, outflow, tabs.te);
+                    float* own = run.S + s_idx(s, t, T1);
+                    st_state<true>(own + 32, H);
+                    publish_flow(own, outflow, flags, rec_i(rb, R_EXP), t, T1, peers);
+                } else {
+                    stg[IN_SPOS * 32] = __int_as_float(s);
+                    stg[IN_STEP * 32] = __int_as_float(t);
+                    trt_sm_st<IN_QUP>(smem_u32(stg), qup); trt_sm_st<IN_QUC>(smem_u32(stg), quc);
+                    mc_channel_to_shared(smem_u32(rb), smem_u32(stg + IN_DV * 32));
+                    McInSm in0; in0.p = smem_u32(stg);
+                    mc_begin(sol, in0, statep);
+                    solving = sol.flow;                // else the no-flow branch: q = d = v = 0 (:171-178)
+                    pending = true;
+                }
+            }
+        } else {
+            // ---- a batch: the newest (up to) 32 entries of the pool, one per lane ----
+            const int cnt = min(pool_n, 32), base = pool_n - cnt;
+            if (lane < cnt) {
+                const unsigned* e = my_pool() + base + lane;
+                unsigned* rw = const_cast<unsigned*>(rb);
+                unsigned* sw = reinterpret_cast<unsigned*>(stg);
+#pragma unroll 1
+                for (int w = 0; w < 9; ++w) rw[w * 32] = __ldcg(e + (PK_REC + w) * TRT_PARK_SLOTS);
+#pragma unroll 1
+                for (int w = 0; w < IN_SLOTS; ++w) sw[w * 32] = __ldcg(e + (PK_STG + w) * TRT_PARK_SLOTS);
+                rw[R_FLAGS * 32] = TRT_KIND_MC;                        // a parked lane has neither gage nor cut edge
+                sol.h = __uint_as_float(__ldcg(e + PK_H * TRT_PARK_SLOTS)); sol.h_0 = __uint_as_float(__ldcg(e + PK_H0 * TRT_PARK_SLOTS));
+                sol.Qj = __uint_as_float(__ldcg(e + PK_QJ * TRT_PARK_SLOTS)); sol.Qj_0 = __uint_as_float(__ldcg(e + PK_QJ0 * TRT_PARK_SLOTS));
+                sol.k.C1 = __uint_as_float(__ldcg(e + PK_C1 * TRT_PARK_SLOTS)); sol.k.C2 = __uint_as_float(__ldcg(e + PK_C2 * TRT_PARK_SLOTS));
+                sol.k.C3 = __uint_as_float(__ldcg(e + PK_C3 * TRT_PARK_SLOTS)); sol.k.C4 = __uint_as_float(__ldcg(e + PK_C4 * TRT_PARK_SLOTS));
+                sol.k.X = __uint_as_float(__ldcg(e + PK_X * TRT_PARK_SLOTS));
+                sol.a0.Km = __uint_as_float(__ldcg(e + PK_KM * TRT_PARK_SLOTS)); sol.a0.xden = __uint_as_float(__ldcg(e + PK_XDEN * TRT_PARK_SLOTS));
+                sol.a0.manning = __uint_as_float(__ldcg(e + PK_MANN * TRT_PARK_SLOTS));
+                const unsigned bits = __ldcg(e + PK_BITS * TRT_PARK_SLOTS);
+                sol.iter = (int)(bits & 0xFFu); sol.tries = (int)((bits >> 8) & 7u); sol.iters_done = (int)((bits >> 11) & 0x3FFu);
+                sol.a0.ck_pos = (bits >> 21) & 1u; sol.a0.wp_pos = (bits >> 22) & 1u; sol.err_open = (bits >> 23) & 1u;
+                sol.have0 = (bits >> 24) & 1u; sol.have1 = false;
+                sol.flow = true;
+                solving = true; pending = true;
+            }
+            __syncwarp();
+            if (lane == 0) pw[0] = base;
+        }
+
+        // ---- the secant loop, shared by tiles and batches: one trip per pass for every lane still solving ----
+        // the two shared-memory bases the solve reads through: opaque values, so that they are HELD in registers -- left to
+        // itself the compiler re-derives them from threadIdx at every use (6 % of the kernel's instructions, ncu r02_v7)
+        McChannelSm c;
+        McInSm in;
+        asm volatile("mov.u32 %0, %1;" : "=r"(c.rb) : "r"(smem_u32(rb)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(in.p) : "r"(smem_u32(stg)));
+        c.dv = in.p + IN_DV * 128;
+        {
+            // warp-uniform facts the loop looks at once per trip: kept in the warp's shared words, not in registers
+            const unsigned unparkable = __ballot_sync(0xffffffffu, solving && (rb[R_FLAGS * 32] & (TRT_KIND_GAGE_FLAG | TRT_KIND_EXPORT_FLAG)) != 0);
+            if (lane == 0) {
+                pw[1] = batch ? DM_EARLY : cu[DU_MODE];      // a batch publishes lane by lane: somebody may be waiting
+                pw[2] = (int)unparkable;
+            }
+            __syncwarp();
+        }
+        bool parked = false;
+        int trips = 0;
+        unsigned active;
+        for (;;) {
+            // the hot loop: nothing but trips.  It is left when every solve has ended, when what is left has been parked, or --
+            // early publication -- as soon as a lane has something to publish.
+            unsigned ready;
+            do {
+                if (solving && mc_iterate(c, in, sol, tabs)) solving = false;
+                ++trips;
+                active = __ballot_sync(0xffffffffu, solving);
+                const unsigned mode = (unsigned)pw[1];
+                if ((mode & DM_PARK) && trips >= 2 && active != 0u && __popc(active) <= sc.park_max && (active & (unsigned)pw[2]) == 0u) {
+                    parked = solving; solving = false; active = 0u;
+                }
+                ready = (mode & DM_EARLY) ? __ballot_sync(0xffffffffu, pending && !solving) : 0u;
+            } while (active != 0u && ready == 0u);
+            if (pending && !solving && !parked) {
+                // results of the lane-step (velocity: result pass, from this depth)
+                pending = false;
+                const int s = __float_as_int(stg[IN_SPOS * 32]), t = __float_as_int(stg[IN_STEP * 32]);
+                const int T1 = run.T + 1;
+                float o_q = 0.0f, o_d = 0.0f;
+                int over = 0;
+                if (sol.flow) {
+                    o_q = mc_outflow(sol, in);
+                    o_d = sol.h;                                                   // :170
+                    over = (sol.h > c.bfd()) && c.compound();
+                }
+                if (run.trip_sum) {
+                    atomicAdd(run.trip_sum + (size_t)(((t - 1) * run.trip_buckets) / run.T) * (size_t)net.n + s, mc_total_trips(sol));
+                    if (over) atomicAdd(run.trip_sum + (size_t)run.trip_buckets * (size_t)net.n + s, 1);   // over-bank steps
+                }
+                const unsigned kflags = rb[R_FLAGS * 32];
+                if (kflags & TRT_KIND_GAGE_FLAG) o_q = apply_nudging(run, rec_i(rb, R_GAGE), t, o_q, tabs.te);   // mc_reach.pyx:761-796
+                float* own = run.S + s_idx(s, t, T1);
+                st_state<true>(own + 32, o_d);
+                publish_flow(own, o_q, kflags, rec_i(rb, R_EXP), t, T1, peers);
+            }
+            if (active == 0u) break;
+        }
+
+        // ---- park what is left of a tile ----
+        const unsigned pmask = __ballot_sync(0xffffffffu, parked);
+        if (pmask != 0u) {
+            if (parked) {
+                unsigned* e = my_pool() + pw[0] + __popc(pmask & ((1u << lane) - 1u));
+                const unsigned* sw = reinterpret_cast<const unsigned*>(stg);
+#pragma unroll 1
+                for (int w = 0; w < 9; ++w) __stcg(e + (PK_REC + w) * TRT_PARK_SLOTS, rb[w * 32]);
+#pragma unroll 1
+                for (int w = 0; w < IN_SLOTS; ++w) __stcg(e + (PK_STG + w) * TRT_PARK_SLOTS, sw[w * 32]);
+                __stcg(e + PK_H * TRT_PARK_SLOTS, __float_as_uint(sol.h)); __stcg(e + PK_H0 * TRT_PARK_SLOTS, __float_as_uint(sol.h_0));
+                __stcg(e + PK_QJ * TRT_PARK_SLOTS, __float_as_uint(sol.Qj)); __stcg(e + PK_QJ0 * TRT_PARK_SLOTS, __float_as_uint(sol.Qj_0));
+                __stcg(e + PK_C1 * TRT_PARK_SLOTS, __float_as_uint(sol.k.C1)); __stcg(e + PK_C2 * TRT_PARK_SLOTS, __float_as_uint(sol.k.C2));
+                __stcg(e + PK_C3 * TRT_PARK_SLOTS, __float_as_uint(sol.k.C3)); __stcg(e + PK_C4 * TRT_PARK_SLOTS, __float_as_uint(sol.k.C4));
+                __stcg(e + PK_X * TRT_PARK_SLOTS, __float_as_uint(sol.k.X));
+                __stcg(e + PK_KM * TRT_PARK_SLOTS, __float_as_uint(sol.a0.Km)); __stcg(e + PK_XDEN * TRT_PARK_SLOTS, __float_as_uint(sol.a0.xden));
+                __stcg(e + PK_MANN * TRT_PARK_SLOTS, __float_as_uint(sol.a0.manning));
+                __stcg(e + PK_BITS * TRT_PARK_SLOTS, pk_pack(sol));
+            }
+            __syncwarp();
+            if (lane == 0) pw[0] += __popc(pmask);
+        }
+        __syncwarp();                                // every lane is done with the buffers of this work item; pw[0] is visible
+
+        if (batch) {
+            if (pw[0] == 0) {
+                if (st & ST_FINAL) break;
+                st &= ~ST_DRAIN;
+            }
+            continue;
+        }
+        // ---- tile epilogue ----
+        // flow bits of the tile: one word per (tile, t).  Lanes of a tile share t except where two levels meet in a tile.
+        // (live, t, flow) are read back from shared memory rather than carried across the solve in registers.
+        {
+            const int tile = cu[DU_TILE0] + j;
+            const int s = (tile << 5) + lane;
+            const unsigned flags = rb[R_FLAGS * 32];
+            const bool was_live = s >= cu[DU_LO] && s < cu[DU_HI] && (flags & 0x0Fu) != TRT_KIND_BOUNDARY;
+            const unsigned live_mask = __ballot_sync(0xffffffffu, was_live);
+            if (live_mask) {
+                const int k = cu[DU_STAGE] + 1;
+                const int t = (run.short_ts ? k : k - (int)rb[R_LEVEL * 32]) + run.t_off;
+                const bool had_flow = was_live && (flags & 0x0Fu) == TRT_KIND_MC &&
+                                      (in.ql() > 0.0f || in.qup() > 0.0f || in.quc() > 0.0f || in.qdp() > 0.0f);
+                const unsigned flow_mask = __ballot_sync(0xffffffffu, had_flow);
+                const int t_lead = __shfl_sync(0xffffffffu, t, __ffs(live_mask) - 1);
+                unsigned* fm = run.fmask + (size_t)tile * (run.T + 1);
+                if (__all_sync(0xffffffffu, !was_live || t == t_lead)) {
+                    if (lane == 0 && flow_mask) atomicOr(fm + t_lead, flow_mask);
+                } else if (had_flow) {
+                    atomicOr(fm + t, 1u << lane);
+                }
+            }
+        }
+        st &= ~ST_HAVE_REC;
+        if (!last_of_unit) st += 256u;
+        else {
+            if (lane == 0) {
+                // stage bookkeeping for the gate: the warp that finishes the last unit of stage k advances the frontier
+                const int si = cu[DU_STAGE];
+                const int units_k = __ldg(sc.unit_ptr + si + 1) - __ldg(sc.unit_ptr + si);
+                __threadfence();
+                if (atomicAdd(sc.done + si, 1) + 1 == units_k) {
+                    atomicMax(sc.frontier, si + 1);
+                    if (sc.stage_time) sc.stage_time[si + 1] = globaltimer_ns();
+                }
+            }
+            if (!(st & ST_NEXT)) {
+                if (pw[0] == 0) break;
+                st |= ST_DRAIN | ST_FINAL;           // the queue is exhausted: finish what is parked, then leave
+            } else {
+                // a parked solve never lags more than a stage behind: whoever reads it one stage later is about to ask for it
+                if (pw[0] > 0 && ctl[warp][((st >> 3) & 1) ^ 1][DU_STAGE] != cu[DU_STAGE]) st |= ST_DRAIN;
+                st = (st & 0xFFu) ^ 8u;              // the next unit becomes the current one, tile 0
+            }
         }
         st ^= 1u;
     }
@@ -881,14 +1296,24 @@ static cudaError_t max_grid_of(K kernel, int* blocks, size_t dyn_smem = 0)
     return cudaSuccess;
 }
 cudaError_t march_max_grid(int* blocks) { return max_grid_of(march_kernel, blocks); }
-cudaError_t dataflow_max_grid(int* blocks)
+template <class K>
+static cudaError_t dataflow_opt_in(K kernel)
 {
     // 4 CTAs x 53 KB of dynamic shared memory per SM: opt in above 48 KB, ask for the largest shared-memory carve-out
-    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DataflowSmem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DataflowSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+cudaError_t dataflow_max_grid(int* blocks)
+{
+    cudaError_t e = dataflow_opt_in(dataflow_kernel);
+    if (e == cudaSuccess) e = dataflow_opt_in(dataflow_park_kernel);
     if (e != cudaSuccess) return e;
-    return max_grid_of(dataflow_kernel, blocks, sizeof(DataflowSmem));
+    int a = 0, b = 0;                                // both forms of the kernel: the same grid whichever is launched
+    e = max_grid_of(dataflow_kernel, &a, sizeof(DataflowSmem));
+    if (e == cudaSuccess) e = max_grid_of(dataflow_park_kernel, &b, sizeof(DataflowSmem));
+    *blocks = a < b ? a : b;
+    return e;
 }
 cudaError_t persistent_max_grid(int* blocks) { return max_grid_of(persistent_kernel, blocks); }
 
@@ -903,9 +1328,10 @@ cudaError_t launch_dataflow(const NetDev& net, const RunDev& run, const SchedDev
                             int grid_blocks, cudaStream_t st)
 {
     // the opt-in above 48 KB is per device and per context: repeat it here (microseconds) rather than rely on the caller
-    cudaError_t e = cudaFuncSetAttribute(dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DataflowSmem));
+    cudaError_t e = sched.park_pool ? dataflow_opt_in(dataflow_park_kernel) : dataflow_opt_in(dataflow_kernel);
     if (e != cudaSuccess) return e;
-    dataflow_kernel<<<grid_blocks, kBlock, sizeof(DataflowSmem), st>>>(net, run, sched, peers);
+    if (sched.park_pool) dataflow_park_kernel<<<grid_blocks, kBlock, sizeof(DataflowSmem), st>>>(net, run, sched, peers);
+    else dataflow_kernel<<<grid_blocks, kBlock, sizeof(DataflowSmem), st>>>(net, run, sched, peers);
     return cudaGetLastError();
 }
 
@@ -1167,7 +1593,7 @@ cudaError_t preload_routing_kernels()
     cudaFuncAttributes a;
     cudaError_t e = cudaSuccess;
 #define TRT_TOUCH(k) if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k)
-    TRT_TOUCH(stage_kernel); TRT_TOUCH(persistent_kernel); TRT_TOUCH(dataflow_kernel); TRT_TOUCH(march_kernel);
+    TRT_TOUCH(stage_kernel); TRT_TOUCH(persistent_kernel); TRT_TOUCH(dataflow_kernel); TRT_TOUCH(dataflow_park_kernel); TRT_TOUCH(march_kernel);
     TRT_TOUCH(gather_qlat_kernel); TRT_TOUCH(init_state_kernel); TRT_TOUCH(init_levelpool_kernel);
     TRT_TOUCH(scatter_lp_params_kernel); TRT_TOUCH(fill_boundary_kernel); TRT_TOUCH(fill_zero_rows_kernel);
     TRT_TOUCH(column_copy_kernel); TRT_TOUCH(carry_gages_kernel); TRT_TOUCH(finalize_kernel); TRT_TOUCH(boundary_rows_kernel);

@@ -323,6 +323,7 @@ class ShardedRouter(_RouterBase):
         if self.deep_level is not None:
             self.net.set_option("deep_level", self.deep_level)
         self.net.set_option("stream", self.tstream.cuda_stream)
+        self.net.set_option("host_shards", max(1, min(64, self.world)))   # the GPUs of one host share its copy bandwidth
         for k, v in self.options.items():
             self.net.set_option(k, v)
         self.net.set_imports(plan.imports)
