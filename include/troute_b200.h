@@ -280,6 +280,10 @@ int trt_levelpool_series(int device, const double* wbody_row, int64_t nsteps, co
                          float* elevation_series);
 /* elementwise trt_powf_det on the device (numerics-contract test) */
 int trt_powf_batch(int device, int64_t count, const float* x, const float* y, float* out);
+/* elementwise fast-path division of the marching lanes (csrc/mc_device.cuh: McDivFast) on the device: out = the quotient the
+ * inline sequence returns, inside = 1 where both operands lie in the window in which it must equal the IEEE quotient
+ * (numerics-contract test; a / d itself is what every other division of the library compiles to) */
+int trt_fdiv_batch(int device, int64_t count, const float* a, const float* d, float* out, uint8_t* inside);
 
 /* pinned host memory helpers for callers that want asynchronous-capable buffers */
 int trt_host_alloc(void** ptr, uint64_t bytes);

@@ -1758,6 +1758,23 @@ int trt_powf_batch(int device, int64_t count, const float* x, const float* y, fl
     return TRT_OK;
 }
 
+int trt_fdiv_batch(int device, int64_t count, const float* a, const float* d, float* out, uint8_t* inside)
+{
+    if (count < 0 || (count > 0 && (!a || !d || !out || !inside))) return fail(TRT_ERR_INVALID, "bad arguments");
+    if (count == 0) return TRT_OK;
+    CU(cudaSetDevice(device));
+    DevBuf<float> d_a, d_d, d_o;
+    DevBuf<unsigned char> d_i;
+    CU(d_a.reserve((size_t)count)); CU(d_d.reserve((size_t)count)); CU(d_o.reserve((size_t)count)); CU(d_i.reserve((size_t)count));
+    CU(cudaMemcpy(d_a.p, a, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_d.p, d, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_fdiv_batch(d_a.p, d_d.p, d_o.p, d_i.p, count, 0));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, d_o.p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(inside, d_i.p, (size_t)count, cudaMemcpyDeviceToHost));
+    return TRT_OK;
+}
+
 int trt_host_alloc(void** ptr, uint64_t bytes)
 {
     if (!ptr) return fail(TRT_ERR_INVALID, "NULL argument");

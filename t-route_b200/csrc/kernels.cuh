@@ -206,5 +206,6 @@ cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long lon
 cudaError_t launch_levelpool_series(const float* lp9, float h0, const float* inflow, float ql, float dt,
                                     float* outflow, float* elev, long long nsteps, cudaStream_t st);
 cudaError_t launch_powf_batch(const float* x, const float* y, float* out, long long count, cudaStream_t st);
+cudaError_t launch_fdiv_batch(const float* a, const float* d, float* out, unsigned char* inside, long long count, cudaStream_t st);
 
 }  // namespace trt

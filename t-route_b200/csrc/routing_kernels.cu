@@ -1103,6 +1103,25 @@ __device__ __forceinline__ LaneRec load_rec(const unsigned* rb)
     return r;
 }
 
+// One secant trip of a marching lane.  A lane on the dependency chain of the main stem is bound by the LATENCY of its own
+// instruction stream, and ~18 IEEE divisions per trip -- each its own basic block (fast path, FCHK, branch to the slow-path
+// subroutine), four of them re-deriving the reciprocal of one divisor -- are most of what keeps the scheduler from overlapping
+// anything.  The trip therefore runs with McDivFast (mc_device.cuh): the same fast path inline and unconditional, straight-line
+// code, one validity flag.  A trip that met an operand outside the window is discarded and the step starts again with IEEE
+// divisions (`slow`, until the step is published): same bits either way.
+__device__ __forceinline__ bool march_trip(const McChannel& c, const McIn& in, McSolve& s, const PowTabs& tabs, float depthp, bool& slow)
+{
+    if (!slow) {
+        McDivFast fd;
+        const bool done = mc_iterate(c, in, s, tabs, fd);
+        if (fd.good()) return done;
+        slow = true;
+        mc_begin<false>(s, in, depthp);              // the step again, from its beginning
+        return false;
+    }
+    return mc_iterate(c, in, s, tabs);
+}
+
 #ifndef TRT_MARCH_MIN_BLOCKS
 #define TRT_MARCH_MIN_BLOCKS 2
 #endif
@@ -1145,6 +1164,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
         McIn in;
         in.qup_ = in.quc_ = in.qdp_ = in.ql_ = 0.0f;
         s.have0 = false; s.have1 = false;
+        bool slow = false;                        // this step left the window of the fast-path division: IEEE divisions until it is done
         int t = t_first;
         float qdp = 0.f, statep = 0.f, upsum_prev = 0.f, ql = 0.f;
         int ql_left = 0;
@@ -1242,7 +1262,7 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     qdp = outflow; statep = H;
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
-                } else if (mc_iterate(c, in, s, tabs)) {
+                } else if (march_trip(c, in, s, tabs, statep, slow)) {
                     float q = mc_outflow(s, in);
                     if (kflags & TRT_KIND_GAGE_FLAG) q = apply_nudging(run, r.gage, t, q, tabs.te);
                     publish_flow(own, q, kflags, r.exp, t, T1, peers);   // downstream lanes are waiting for this
@@ -1259,7 +1279,12 @@ __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(Net
                     if (mk.prof && t == 1) prof_first = globaltimer_ns();
                     ++t;
                     state = t > t_last ? MARCH_DONE : MARCH_WAIT;
-                    if (state == MARCH_WAIT && mk.prepare) mc_prepare(c, s, statep, tabs);   // while the lane would only poll
+                    slow = false;
+                    if (state == MARCH_WAIT && mk.prepare) {                                 // while the lane would only poll
+                        McDivFast fd;
+                        mc_prepare(c, s, statep, tabs, fd);
+                        if (!fd.good()) { s.have0 = false; s.have1 = false; }               // outside the window: mc_iterate evaluates them
+                    }
                 }
             }
             const unsigned iterating = __ballot_sync(0xffffffffu, state == MARCH_ITER);
@@ -1588,6 +1613,8 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const float* __restrict_
 // launch has to load a kernel while the first handle's kernel is spinning on that second handle's output, neither returns
 // (the round-1 "sharded nudging" failure: whichever sharded test ran first in a process timed out).  Touching every kernel
 // once, before any launch, makes the loads happen while the device is idle.
+__global__ void fdiv_batch_kernel(const float* __restrict__ a, const float* __restrict__ d, float* __restrict__ out,
+                                  unsigned char* __restrict__ inside, long long count);
 cudaError_t preload_routing_kernels()
 {
     cudaFuncAttributes a;
@@ -1598,7 +1625,7 @@ cudaError_t preload_routing_kernels()
     TRT_TOUCH(scatter_lp_params_kernel); TRT_TOUCH(fill_boundary_kernel); TRT_TOUCH(fill_zero_rows_kernel);
     TRT_TOUCH(column_copy_kernel); TRT_TOUCH(carry_gages_kernel); TRT_TOUCH(finalize_kernel); TRT_TOUCH(boundary_rows_kernel);
     TRT_TOUCH(upstream_out_kernel); TRT_TOUCH(reset_gages_kernel); TRT_TOUCH(export_series_kernel);
-    TRT_TOUCH(import_series_kernel); TRT_TOUCH(hash_rows_kernel);
+    TRT_TOUCH(import_series_kernel); TRT_TOUCH(hash_rows_kernel); TRT_TOUCH(fdiv_batch_kernel);
 #undef TRT_TOUCH
     return e;
 }
@@ -1759,6 +1786,24 @@ __global__ void __launch_bounds__(kBlock) powf_batch_kernel(const float* __restr
     const PowTabs tabs = stage_tables(smem);
     const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (i < count) out[i] = dpow(x[i], y[i], tabs);
+}
+
+// McDivFast (mc_device.cuh) element by element: the quotient of the inline fast path and whether the pair was inside its window
+__global__ void __launch_bounds__(kBlock) fdiv_batch_kernel(const float* __restrict__ a, const float* __restrict__ d,
+                                                            float* __restrict__ out, unsigned char* __restrict__ inside, long long count)
+{
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= count) return;
+    McDivFast f;
+    out[i] = f(a[i], d[i]);
+    inside[i] = f.good() ? 1 : 0;
+}
+
+cudaError_t launch_fdiv_batch(const float* a, const float* d, float* out, unsigned char* inside, long long count, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    fdiv_batch_kernel<<<TRT_GRID1D(count, kBlock), kBlock, 0, st>>>(a, d, out, inside, count);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mc_batch(const float* in15, float* out6, int* iters, long long count, cudaStream_t st)

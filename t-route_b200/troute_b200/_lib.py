@@ -84,6 +84,7 @@ SYMBOLS = [
     ("trt_mc_segment_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _i32p]),
     ("trt_levelpool_series", C.c_int, [C.c_int, _f64p, C.c_int64, _f32p, C.c_float, C.c_float, _f32p, _f32p]),
     ("trt_powf_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _f32p]),
+    ("trt_fdiv_batch", C.c_int, [C.c_int, C.c_int64, _f32p, _f32p, _f32p, C.POINTER(C.c_uint8)]),
     ("trt_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("trt_host_free", C.c_int, [C.c_void_p]),
     ("trt_c_diffnw", C.c_int, [C.c_void_p] * 42),

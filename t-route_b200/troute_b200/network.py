@@ -515,5 +515,17 @@ def powf_batch(x, y, device=0):
     return out
 
 
-__all__ = ["RoutingNetwork", "PARAM_COLUMNS", "column_mapper", "mc_segment_batch", "levelpool_series", "powf_batch",
+def fdiv_batch(a, d, device=0):
+    """McDivFast element by element on the device: (quotients, inside-the-window flags)"""
+    L = _lib.lib()
+    a = as_c(a, np.float32)
+    d = as_c(d, np.float32)
+    out = np.empty_like(a)
+    inside = np.zeros(a.shape[0], dtype=np.uint8)
+    check(L.trt_fdiv_batch(int(device), int(a.shape[0]), ptr(a, C.c_float), ptr(d, C.c_float), ptr(out, C.c_float),
+                           ptr(inside, C.c_uint8)))
+    return out, inside.astype(bool)
+
+
+__all__ = ["RoutingNetwork", "PARAM_COLUMNS", "column_mapper", "mc_segment_batch", "levelpool_series", "powf_batch", "fdiv_batch",
            "TRT_KIND_MC", "TRT_KIND_LEVELPOOL", "TRT_KIND_BOUNDARY"]

@@ -29,6 +29,34 @@ extern "C" void trt_replica_mc_segment_batch(long n, const float* in15, float* o
             const trt::McChannelSm c = trt::mc_channel_to_shared(rec + lane, dv + lane);
             trt::McInSm in; in.p = inw + lane;
             r = trt::trt_mc_solve<true, true>(c, in, a[14], T);
+        } else if (resumable == 3) {
+            /* the marching kernel's decomposition with the fast-path division (McDivFast): prepare, begin, one trip per call;
+             * a trip (or the prepare) that met a division outside the window restarts the step with IEEE divisions, exactly
+             * as march_kernel does.  out6[3] reports whether the step stayed on the fast path. */
+            const trt::McChannel c = trt::mc_channel(a[0], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+            trt::McSolve s;
+            s.have0 = false; s.have1 = false;
+            trt::McDivFast fd;
+            trt::mc_prepare(c, s, a[14], T, fd);
+            trt::McIn in; in.qup_ = a[1]; in.quc_ = a[2]; in.qdp_ = a[3]; in.ql_ = a[4];
+            bool slow = !fd.good();
+            if (slow) trt::mc_begin<false>(s, in, a[14]); else trt::mc_begin<true>(s, in, a[14]);
+            r.ck = r.cn = 0.0f;
+            if (s.flow) {
+                for (;;) {
+                    bool done;
+                    if (slow) done = trt::mc_iterate(c, in, s, T);
+                    else {
+                        trt::McDivFast f2;
+                        done = trt::mc_iterate(c, in, s, T, f2);
+                        if (!f2.good()) { slow = true; trt::mc_begin<false>(s, in, a[14]); continue; }
+                    }
+                    if (done) break;
+                }
+                r.qdc = trt::mc_outflow(s, in); r.depthc = s.h; r.velc = trt::mc_velocity(c, s.h, T); r.X = s.k.X;
+            } else { r.qdc = r.velc = r.depthc = r.X = 0.0f; }
+            r.ck = slow ? 0.0f : 1.0f;
+            r.iters = trt::mc_total_trips(s);
         } else {
             /* the marching kernel's decomposition: prepare (phase A of the first trip from the previous depth), begin,
              * one trip per call, outflow, velocity from the final depth */
@@ -49,6 +77,24 @@ extern "C" void trt_replica_mc_segment_batch(long n, const float* in15, float* o
         o[0] = r.qdc; o[1] = r.velc; o[2] = r.depthc; o[3] = r.ck; o[4] = r.cn; o[5] = r.X;
         if (iters) iters[i] = r.iters;
     }
+}
+
+/* trt_div_fastpath against the IEEE quotient on n (a, d) pairs; returns the number of pairs inside the window whose bits differ
+ * and stores how many pairs were inside the window */
+extern "C" long trt_replica_fdiv_check(long n, const float* a, const float* d, long* inside)
+{
+    long bad = 0, in = 0;
+    for (long i = 0; i < n; ++i) {
+        trt::McDivFast f;
+        const float q = f(a[i], d[i]);
+        if (!f.good()) continue;
+        ++in;
+        const float w = a[i] / d[i];
+        unsigned x, y; memcpy(&x, &q, 4); memcpy(&y, &w, 4);
+        bad += x != y;
+    }
+    *inside = in;
+    return bad;
 }
 
 /* wbody_row: the 11 doubles of compute.py:1416-1430 (LkArea, LkMxE, OrificeA, OrificeC, OrificeE, WeirC, WeirE, WeirL, ifd,

@@ -27,6 +27,34 @@ def eng():
     return network
 
 
+def test_fastpath_division_is_the_ieee_quotient_on_the_device(eng):
+    """McDivFast (csrc/mc_device.cuh), what the marching lanes divide with: seeded by the device's MUFU.RCP, the inline fast
+    path returns the IEEE quotient for every pair inside its window of exponents (numpy float32 division is IEEE)."""
+    rng = np.random.default_rng(7)
+    n = 1 << 24
+    for kind in range(3):
+        if kind == 0:
+            a = (rng.standard_normal(n) * np.exp2(rng.uniform(-64, 64, n))).astype(np.float32)
+            d = (rng.standard_normal(n) * np.exp2(rng.uniform(-64, 64, n))).astype(np.float32)
+        elif kind == 1:      # quotients next to rounding boundaries
+            a = rng.integers(1, 1 << 24, n).astype(np.float32) * np.exp2(rng.integers(-30, 30, n)).astype(np.float32)
+            d = rng.integers(1, 1 << 12, n).astype(np.float32) * np.exp2(rng.integers(-30, 30, n)).astype(np.float32)
+        else:                # the magnitudes of the solve, zero dividends of either sign, operands outside the window
+            a = np.exp(rng.uniform(np.log(1e-8), np.log(1e8), n)).astype(np.float32) * rng.choice([-1.0, 1.0], n).astype(np.float32)
+            d = np.exp(rng.uniform(np.log(1e-8), np.log(1e8), n)).astype(np.float32)
+            a[:1000] = 0.0
+            a[1000:2000] = -0.0
+            d[2000:2010] = [0.0, -0.0, np.inf, np.nan, 1e-40, 3e38, 1e-30, 1e30, -np.inf, 1e-45]
+            a[2010:2016] = [np.inf, np.nan, 1e-40, 3e38, -np.inf, 1e-45]
+        q, inside = eng.fdiv_batch(a, d)
+        with np.errstate(all="ignore"):
+            want = a / d
+        assert inside.mean() > 0.8
+        assert np.array_equal(q[inside].view(np.int32), want[inside].view(np.int32)), kind
+        if kind == 2:
+            assert not inside[2000:2016].any()             # zero / non-finite / denormal / huge operands leave the window
+
+
 def test_powf_det_bits(eng, oracle):
     rng = np.random.default_rng(0)
     n = 1 << 20

@@ -20,16 +20,28 @@ DEPS = [SRC, os.path.join(HERE, "native", "shim", "cuda_runtime.h"), os.path.joi
 GOLD = os.path.join(HERE, "golden")
 
 
-@pytest.fixture(scope="module")
-def rep():
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+def _build(lib, extra=()):
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in DEPS):
         flags = open("/proc/cpuinfo").read() if os.path.exists("/proc/cpuinfo") else ""
         cmd = ["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-I", os.path.join(HERE, "native", "shim"),
-               "-shared", "-fPIC", "-o", LIB, SRC]
+               "-shared", "-fPIC", "-o", lib, SRC, *extra]
         if " fma" in flags:
             cmd.insert(1, "-mfma")
         subprocess.run(cmd, check=True)
-    return C.CDLL(LIB)
+    return C.CDLL(lib)
+
+
+@pytest.fixture(scope="module")
+def rep():
+    return _build(LIB)
+
+
+@pytest.fixture(scope="module", params=[-1, 0, 1])
+def rep_seed(request):
+    """the same source with the reciprocal seed of the fast-path division moved by -1 / 0 / +1 ulp: the device's MUFU.RCP is
+    within one ulp of 1/d, and the sequence must not care which way"""
+    u = request.param
+    return _build(os.path.join(HERE, "native", f"libmc_replica_seed{u + 1}.so"), (f"-DTRT_RCP_SEED_ULPS=({u})",))
 
 
 def run_rows(rep, rows, resumable):
@@ -101,3 +113,40 @@ def test_levelpool_kats(rep, oracle):
         wq, wh = oracle.levelpool_series(c["wbody_row"], c["inflow"], 0.0, c["routing_period"], pow_mode=oracle.POW_DET)
         assert np.array_equal(q.view(np.int32), wq.view(np.int32)) and np.array_equal(h.view(np.int32), wh.view(np.int32))
         assert q[-1] == np.float32(c["expected_final_outflow"]) and h[-1] == np.float32(c["expected_final_water_elevation"])
+
+
+def test_fastpath_division_is_the_ieee_quotient(rep_seed):
+    """McDivFast (mc_device.cuh): inside its window of exponents the inline fast path -- reciprocal seed, one Newton step,
+    quotient, exact remainder, correction -- returns the correctly rounded quotient, whatever the last bit of the seed."""
+    rng = np.random.default_rng(5)
+    n = 20_000_000
+    total_in = 0
+    for kind in range(3):
+        if kind == 0:        # anything inside (and a little outside) the window
+            a = (rng.standard_normal(n) * np.exp2(rng.uniform(-64, 64, n))).astype(np.float32)
+            d = (rng.standard_normal(n) * np.exp2(rng.uniform(-64, 64, n))).astype(np.float32)
+        elif kind == 1:      # quotients next to rounding boundaries: small integers over small integers, scaled
+            a = (rng.integers(1, 1 << 24, n).astype(np.float32)) * np.exp2(rng.integers(-30, 30, n)).astype(np.float32)
+            d = (rng.integers(1, 1 << 12, n).astype(np.float32)) * np.exp2(rng.integers(-30, 30, n)).astype(np.float32)
+        else:                # the magnitudes of the solve: flows, areas, depths, dt / dx
+            a = np.exp(rng.uniform(np.log(1e-8), np.log(1e8), n)).astype(np.float32) * rng.choice([-1.0, 1.0], n).astype(np.float32)
+            d = np.exp(rng.uniform(np.log(1e-8), np.log(1e8), n)).astype(np.float32)
+            a[: n // 50] = 0.0
+            a[n // 50: n // 25] = -0.0
+        inside = C.c_long(0)
+        rep_seed.trt_replica_fdiv_check.restype = C.c_long
+        bad = rep_seed.trt_replica_fdiv_check(C.c_long(n), a.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.byref(inside))
+        assert bad == 0, (kind, bad)
+        total_in += inside.value
+    assert total_in > 0.8 * 3 * n
+
+
+def test_marching_pieces_with_fastpath_division(rep_seed, oracle):
+    """the marching kernel's form of the solve with McDivFast (restart with IEEE divisions when a trip leaves the window) ==
+    oracle, bit for bit, and nearly every row stays on the fast path"""
+    rows = np.concatenate([np.load(os.path.join(GOLD, "mc_suite_seed16.npy")), random_rows(100_000, seed=21)])
+    want, wi = oracle.mc_segment_batch(rows, oracle.POW_DET)
+    got, gi = run_rows(rep_seed, rows, 3)
+    assert np.array_equal(got[:, [0, 1, 2, 5]].view(np.int32), want[:, [0, 1, 2, 5]].view(np.int32))
+    assert np.array_equal(gi, wi)
+    assert got[:, 3].mean() > 0.9, float(got[:, 3].mean())
