@@ -173,6 +173,9 @@ int trt_run(trt_network* net, int32_t assume_short_ts);
 int trt_run_async(trt_network* net, int32_t assume_short_ts);
 int trt_sync(trt_network* net);
 int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out);
+/* the reservoir inflow series of the level pools alone: inflow_out [n_lp, nsteps], level pools in the order of
+ * trt_network_set_levelpools -- the non-zero rows of upstream_array (mc_reach.pyx:710, :807-813) without the table of zeros */
+int trt_download_levelpool_inflow(trt_network* net, float* inflow_out);
 /* (q, v, d) of the LAST timestep of the last run, every row in caller order -> qvd_out [n_rows, 3] (host): what the BMI model
  * reads back after a window (src/troute_model.py:318-330 `_retrieve_last_output`); 12 bytes per segment cross PCIe. */
 int trt_download_last_step(trt_network* net, float* qvd_out);

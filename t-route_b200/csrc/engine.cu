@@ -1157,6 +1157,24 @@ int trt_download_results(trt_network* net, float* fvd_out, float* upstream_out)
     return TRT_OK;
 }
 
+// Reservoir inflow series of the level pools alone, [n_lp, nsteps] in the order of trt_network_set_levelpools: what the
+// upstream_array of compute_network_structured holds (mc_reach.pyx:710) without the n_rows x nsteps table of zeros around it
+// (3.1 GB over PCIe for a CONUS day; the mirror fills its zero table on the host).
+int trt_download_levelpool_inflow(trt_network* net, float* inflow_out)
+{
+    if (!net) return fail(TRT_ERR_INVALID, "NULL network");
+    if (!net->ran) return fail(TRT_ERR_STATE, "trt_download_levelpool_inflow called before trt_run");
+    const size_t n_lp = (size_t)net->n_lp, T = (size_t)net->T;
+    if (n_lp * T == 0) return TRT_OK;
+    if (!inflow_out) return fail(TRT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(net->device));
+    // lp_in is [n_lp][T + 1] with column 0 unused: a strided copy of columns 1 .. T
+    CU(cudaMemcpy2DAsync(inflow_out, T * sizeof(float), net->d_lp_in.p + 1, (T + 1) * sizeof(float), T * sizeof(float), n_lp,
+                         cudaMemcpyDeviceToHost, net->stream));
+    CU(cudaStreamSynchronize(net->stream));
+    return TRT_OK;
+}
+
 // (q, v, d) of the LAST timestep of every row: all a BMI-style caller reads back after a window (troute_model.py:318-330,
 // _retrieve_last_output) -- 12 bytes per segment instead of 12 * nsteps
 int trt_download_last_step(trt_network* net, float* qvd_out)

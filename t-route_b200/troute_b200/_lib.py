@@ -62,6 +62,7 @@ SYMBOLS = [
     ("trt_run_async", C.c_int, [_net, C.c_int32]),
     ("trt_sync", C.c_int, [_net]),
     ("trt_download_results", C.c_int, [_net, C.c_void_p, C.c_void_p]),
+    ("trt_download_levelpool_inflow", C.c_int, [_net, C.c_void_p]),
     ("trt_download_last_step", C.c_int, [_net, C.c_void_p]),
     ("trt_run_download", C.c_int, [_net, C.c_int32, C.c_void_p, C.c_void_p]),
     ("trt_route", C.c_int, [_net, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, _i64p, C.c_void_p, C.c_void_p, C.c_void_p]),

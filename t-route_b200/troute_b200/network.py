@@ -11,6 +11,9 @@ Only numpy and ctypes are used here; all arithmetic happens in libtroute_b200.so
 import ctypes as C
 import os
 
+import threading
+import weakref
+
 import numpy as np
 
 from . import _lib
@@ -328,6 +331,13 @@ class RoutingNetwork:
         check(self._L.trt_download_results(self._h, fvd.ctypes.data, up.ctypes.data if up is not None else None))
         return fvd, up
 
+    def download_levelpool_inflow(self, n_lp):
+        """Reservoir inflow of the level pools alone, [n_lp, nsteps] in the order of set_levelpools (trt_download_levelpool_inflow)."""
+        out = np.zeros((int(n_lp), self.nsteps), dtype=np.float32)
+        if out.size:
+            check(self._L.trt_download_levelpool_inflow(self._h, out.ctypes.data))
+        return out
+
     def download_last_step(self):
         """(q, v, d) of the last timestep of the last run, [n_rows, 3] in caller row order (trt_download_last_step)."""
         out = np.empty((self.n_rows, 3), dtype=np.float32)
@@ -348,15 +358,26 @@ class RoutingNetwork:
         self.run(assume_short_ts)
         return self.download(want_upstream)
 
-    def route_call(self, nsteps, qts_subdivisions, qlat, q0, assume_short_ts=False, want_upstream=False):
-        """The single-call C entry point trt_route on numpy arrays (time-chunked, copies overlapped with compute)."""
+    def route_call(self, nsteps, qts_subdivisions, qlat, q0, assume_short_ts=False, want_upstream=False, bnd_rows=None,
+                   bnd_fvd=None, out=None):
+        """The single-call C entry point trt_route on numpy arrays (time-chunked, copies overlapped with compute).
+        `out`: a caller-owned [n_rows, 3*nsteps] float32 buffer for the result (e.g. pinned memory kept across calls)."""
         qlat = as_c(qlat, np.float32)
         q0 = as_c(q0, np.float32)
         self._check_forcing(nsteps, qts_subdivisions, qlat, q0)
-        fvd = np.empty((self.n_rows, 3 * int(nsteps)), dtype=np.float32)
+        fvd = out if out is not None else np.empty((self.n_rows, 3 * int(nsteps)), dtype=np.float32)
+        if fvd.shape != (self.n_rows, 3 * int(nsteps)) or fvd.dtype != np.float32 or not fvd.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape (n_rows, 3 * nsteps)")
         up = np.empty((self.n_rows, int(nsteps)), dtype=np.float32) if want_upstream else None
+        n_bnd, rows_p, fvd_p = 0, None, None
+        if bnd_rows is not None and len(bnd_rows):
+            bnd_rows = as_c(bnd_rows, np.int64)
+            bnd_fvd = as_c(bnd_fvd, np.float32)
+            if bnd_fvd.shape != (bnd_rows.shape[0], 3 * int(nsteps)):
+                raise ValueError("bnd_fvd must have shape (len(bnd_rows), 3 * nsteps)")
+            n_bnd, rows_p, fvd_p = int(bnd_rows.shape[0]), ptr(bnd_rows, C.c_int64), bnd_fvd.ctypes.data
         check(self._L.trt_route(self._h, int(nsteps), int(qts_subdivisions), 1 if assume_short_ts else 0,
-                                qlat.ctypes.data, int(qlat.shape[1]), q0.ctypes.data, 0, None, None, fvd.ctypes.data,
+                                qlat.ctypes.data, int(qlat.shape[1]), q0.ctypes.data, n_bnd, rows_p, fvd_p, fvd.ctypes.data,
                                 up.ctypes.data if up is not None else None))
         self.nsteps = int(nsteps)
         return fvd, up
@@ -515,6 +536,85 @@ def powf_batch(x, y, device=0):
     return out
 
 
+class _PinnedBlock:
+    """owner of one trt_host_alloc block"""
+    def __init__(self, nbytes):
+        self._L = _lib.lib()
+        self.ptr = C.c_void_p()
+        check(self._L.trt_host_alloc(C.byref(self.ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+
+    def free(self):
+        if self.ptr:
+            self._L.trt_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:          # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+class PinnedPool:
+    """numpy arrays in page-locked host memory (trt_host_alloc) that go BACK to the pool when the last reference to them --
+    the array, any view or slice of it -- is dropped.  Pinning gigabytes takes seconds; a routing loop that consumes the result
+    of one window before it routes the next (T-Route's does) keeps re-using one block, and a caller that holds on to old
+    results simply makes the pool allocate another block (up to `limit_bytes`; beyond that `take` returns None and the caller
+    falls back to pageable memory).  No array handed out is ever overwritten behind its owner's back."""
+    def __init__(self):
+        self._free = {}          # nbytes -> [blocks]
+        self._total = 0
+        self._lock = threading.Lock()
+
+    def take(self, shape, dtype, limit_bytes):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = max(count * dtype.itemsize, 1)
+        with self._lock:
+            blocks = self._free.get(nbytes)
+            block = blocks.pop() if blocks else None
+            if block is None:
+                if self._total + nbytes > limit_bytes:
+                    return None
+                self._total += nbytes
+        if block is None:
+            try:
+                block = _PinnedBlock(nbytes)
+            except Exception:      # noqa: BLE001 -- no pinned memory to be had: the caller uses pageable memory
+                with self._lock:
+                    self._total -= nbytes
+                return None
+        buf = (C.c_uint8 * nbytes).from_address(block.ptr.value)
+        weakref.finalize(buf, self._give_back, block)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _give_back(self, block):
+        with self._lock:
+            self._free.setdefault(block.nbytes, []).append(block)
+
+    def clear(self):
+        """free the blocks nobody holds"""
+        with self._lock:
+            blocks = [b for bs in self._free.values() for b in bs]
+            self._free = {}
+            self._total -= sum(b.nbytes for b in blocks)
+        for b in blocks:
+            b.free()
+
+    @property
+    def pinned_bytes(self):
+        return self._total
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array in page-locked host memory of its own (freed when the array is collected)"""
+    arr = PinnedPool().take(shape, dtype, 1 << 62)
+    if arr is None:
+        raise MemoryError("trt_host_alloc failed")
+    return arr
+
+
 def fdiv_batch(a, d, device=0):
     """McDivFast element by element on the device: (quotients, inside-the-window flags)"""
     L = _lib.lib()
@@ -527,5 +627,5 @@ def fdiv_batch(a, d, device=0):
     return out, inside.astype(bool)
 
 
-__all__ = ["RoutingNetwork", "PARAM_COLUMNS", "column_mapper", "mc_segment_batch", "levelpool_series", "powf_batch", "fdiv_batch",
+__all__ = ["RoutingNetwork", "PARAM_COLUMNS", "column_mapper", "mc_segment_batch", "levelpool_series", "powf_batch", "fdiv_batch", "pinned_empty", "PinnedPool",
            "TRT_KIND_MC", "TRT_KIND_LEVELPOOL", "TRT_KIND_BOUNDARY"]

@@ -13,8 +13,9 @@ caller only concatenates result tuples (nwm_routing/output.py:213-216, AbstractN
 returning a single tuple is within the contract ("row order inside a tuple is free").
 """
 import time
-from collections import defaultdict
-from itertools import chain
+import zlib
+from collections import OrderedDict, defaultdict
+from itertools import chain, repeat
 import logging
 
 import numpy as np
@@ -38,9 +39,24 @@ _PARAM_COLS = ["dt", "bw", "tw", "twcc", "dx", "n", "ncc", "cs", "s0", "alt"]
 
 
 def _build_reach_type_list(reach_list, wbodies_segs):
-    """compute.py:41-47."""
-    reach_type_list = [1 if (set(reaches) & wbodies_segs) else 0 for reaches in reach_list]
-    return list(zip(reach_list, reach_type_list))
+    """compute.py:41-47: a reach that holds a waterbody segment is of type 1.  `isdisjoint` looks the few segments of a reach
+    up in the set; the reference's `set(reach) & wbodies_segs` ITERATES the smaller operand, and a set that was built large and
+    emptied (symmetric_difference) keeps its table: 29 s per 100,000 segments."""
+    if not wbodies_segs:
+        return list(zip(reach_list, repeat(0, len(reach_list))))
+    wb = set(wbodies_segs)
+    return [(reaches, 0 if wb.isdisjoint(reaches) else 1) for reaches in reach_list]
+
+
+_TOPO_CACHE = OrderedDict()          # see compute_nhd_routing_v02
+
+
+def _frame_crc(df):
+    """CRC of a frame's index and values (a few ms per million rows): cached sub-frames are reused only for identical tables"""
+    v = df.values
+    if v.dtype == object:
+        return hash((df.shape, tuple(df.columns)))
+    return zlib.crc32(np.ascontiguousarray(v).view(np.uint8), zlib.crc32(np.ascontiguousarray(df.index.values).view(np.uint8)))
 
 
 def _nonempty(df):
@@ -99,36 +115,64 @@ def compute_nhd_routing_v02(
             raise NotImplementedError(f"{name}: hybrid / RFC / Great-Lakes reservoir DA is outside the GPU path")
 
     # union of all tail-waters: one device call routes every independent network
-    reach_list = list(chain.from_iterable(reaches_bytw.values()))
-    segs = list(chain.from_iterable(reach_list))
     offnetwork_upstreams = set(flowveldepth_interorder.keys()) if parallel_compute_method == "bmi" else set()
-    segs_all = segs + list(offnetwork_upstreams)
-    common_segs = param_df.index.intersection(segs_all)
-    wbodies_segs = set(segs_all).symmetric_difference(common_segs)             # :1406-1408
-
-    waterbody_types_df_sub = pd.DataFrame()
-    if _nonempty(waterbodies_df):
-        lake_segs = list(waterbodies_df.index.intersection(segs_all))       # bmi: off-network tail-waters included (:1585-1600)
-        waterbodies_df_sub = waterbodies_df.loc[lake_segs, _WB_COLS]
-        if _nonempty(waterbody_types_df):
-            waterbody_types_df_sub = waterbody_types_df.loc[lake_segs, ["reservoir_type"]]
+    # Everything below that depends on the topology and the parameter tables alone -- reach lists, reach types, the sorted
+    # parameter sub-frame, the lake rows -- is built on the first call and kept in a small module-level cache, the analogue of
+    # the per-network structures the reference's by-subnetwork methods keep in `subnetwork_list` between the calls of a run
+    # (compute.py:556, :652-656, :823-827; `subnetwork_list` itself is returned untouched, as the reference's serial branch
+    # does).  An entry is reused only for the same topology objects and bit-identical parameter / waterbody tables (CRC); a
+    # CONUS call otherwise spends seconds here.
+    topo_key = (id(reaches_bytw), len(reaches_bytw), id(rconn) if rconn is not None else id(independent_networks),
+                tuple(sorted(offnetwork_upstreams)), param_df.shape, _frame_crc(param_df),
+                _frame_crc(waterbodies_df) if _nonempty(waterbodies_df) else 0,
+                _frame_crc(waterbody_types_df) if _nonempty(waterbody_types_df) else 0)
+    cached = _TOPO_CACHE.get(topo_key)
+    if cached is not None:
+        _TOPO_CACHE.move_to_end(topo_key)
+        reach_list, reaches_list_with_type = cached["reach_list"], cached["reaches_list_with_type"]
+        lake_segs, waterbodies_df_sub, waterbody_types_df_sub = cached["lake_segs"], cached["wb_sub"], cached["wbt_sub"]
+        param_df_sub, routed_index, upstream_connections = cached["param_df_sub"], cached["routed_index"], cached["rconn"]
     else:
-        lake_segs = []
-        waterbodies_df_sub = pd.DataFrame()
+        reach_list = list(chain.from_iterable(reaches_bytw.values()))
+        segs = list(chain.from_iterable(reach_list))
+        segs_all = segs + list(offnetwork_upstreams)
+        common_segs = param_df.index.intersection(segs_all)
+        wbodies_segs = set(segs_all).symmetric_difference(common_segs)             # :1406-1408
 
-    param_df_sub = param_df.loc[common_segs, _PARAM_COLS].sort_index()         # :1443-1446
-    reaches_list_with_type = _build_reach_type_list(reach_list, wbodies_segs)
+        waterbody_types_df_sub = pd.DataFrame()
+        if _nonempty(waterbodies_df):
+            lake_segs = list(waterbodies_df.index.intersection(segs_all))       # bmi: off-network tail-waters included (:1585-1600)
+            waterbodies_df_sub = waterbodies_df.loc[lake_segs, _WB_COLS]
+            if _nonempty(waterbody_types_df):
+                waterbody_types_df_sub = waterbody_types_df.loc[lake_segs, ["reservoir_type"]]
+        else:
+            lake_segs = []
+            waterbodies_df_sub = pd.DataFrame()
+
+        param_df_sub = param_df.loc[common_segs, _PARAM_COLS].sort_index()         # :1443-1446
+        reaches_list_with_type = _build_reach_type_list(reach_list, wbodies_segs)
+        routed_index = param_df_sub.index.difference(list(offnetwork_upstreams))
+        param_df_sub = param_df_sub.reindex(param_df_sub.index.tolist() + lake_segs).sort_index()   # :1455-1457
+        # the connections of every tail-water, merged (independent_networks[tw] is rconn restricted to that basin)
+        upstream_connections = rconn if rconn is not None else {
+            k: v for net in independent_networks.values() for k, v in net.items()}
+        _TOPO_CACHE[topo_key] = dict(reach_list=reach_list, reaches_list_with_type=reaches_list_with_type, lake_segs=lake_segs,
+                                     wb_sub=waterbodies_df_sub, wbt_sub=waterbody_types_df_sub, param_df_sub=param_df_sub,
+                                     routed_index=routed_index, rconn=upstream_connections)
+        while len(_TOPO_CACHE) > 4:
+            _TOPO_CACHE.popitem(last=False)
     # The reference slices the forcing with .loc (:1451-1452, :1640-1641): a routed segment without a qlat / q0 row is a
     # KeyError there, not a segment routed with zeros.  Off-network tail-waters carry no lateral inflow.
-    routed = param_df_sub.index.difference(list(offnetwork_upstreams))
     for name, df in (("qlats", qlats), ("q0", q0)):
-        missing = routed.difference(df.index) if name == "qlats" else param_df_sub.index.difference(df.index)
+        want = routed_index if name == "qlats" else param_df_sub.index
+        if df.index is want or df.index.equals(want):
+            continue
+        missing = want.difference(df.index)
         if len(missing):
             raise KeyError(f"{list(missing[:10])} not in index of {name} ({len(missing)} routed segments without a row)")
-    param_df_sub = param_df_sub.reindex(param_df_sub.index.tolist() + lake_segs).sort_index()   # :1455-1457
     # forcing / state rows follow the parameter index; lake and off-network rows carry no lateral inflow
-    qlat_sub = qlats.reindex(param_df_sub.index)
-    q0_sub = q0.reindex(param_df_sub.index)
+    qlat_sub = qlats if qlats.index.equals(param_df_sub.index) else qlats.reindex(param_df_sub.index)
+    q0_sub = q0 if q0.index.equals(param_df_sub.index) else q0.reindex(param_df_sub.index)
 
     upstream_results = {}
     for us_subn_tw in offnetwork_upstreams:                                    # :1652-1658
@@ -151,10 +195,6 @@ def compute_nhd_routing_v02(
         da_positions_list_byseg, da_positions_list_byreach, da_positions_list_bygage = [], [], []
         lastobs_discharge = np.zeros(0, dtype=np.float32)
         time_since_lastobs = np.zeros(0, dtype=np.float32)
-
-    # the connections of every tail-water, merged (independent_networks[tw] is rconn restricted to that basin)
-    upstream_connections = rconn if rconn is not None else {
-        k: v for net in independent_networks.values() for k, v in net.items()}
 
     e_f = np.zeros(0, dtype=np.float32)
     e_i = np.zeros(0, dtype=np.int32)

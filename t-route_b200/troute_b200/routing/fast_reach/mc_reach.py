@@ -14,8 +14,10 @@ assimilation are host-side, observation-file driven Python in the reference (res
 scope: non-empty inputs for them raise NotImplementedError rather than being silently ignored.
 """
 import hashlib
+import zlib
 from collections import OrderedDict
-from itertools import chain
+from itertools import chain, repeat
+from operator import itemgetter
 
 import numpy as np
 
@@ -116,7 +118,8 @@ REORDER_MIN_ROWS = 200_000
 def _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
     """Cache key of a device network: everything flatten_network reads -- the parameter table, the segment ids of every
     reach in order, the reach types and the upstream list of every reach head (the confluence wiring) -- so that two calls
-    with the same parameters but different connectivity never share a device topology."""
+    with the same parameters but different connectivity never share a device topology.  Iterates at C speed (map /
+    itemgetter / fromiter): ~0.35 s per million segments."""
     h = hashlib.blake2b(digest_size=16)
     h.update(np.ascontiguousarray(data_idx).view(np.uint8))
     h.update(np.ascontiguousarray(data_values).view(np.uint8))
@@ -124,25 +127,62 @@ def _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data
     nreach = len(reaches_wTypes)
     h.update(repr((nreach, device)).encode())
     if nreach:
-        lens = np.fromiter((len(r) for r, _ in reaches_wTypes), dtype=np.int64, count=nreach)
-        types = np.fromiter((t for _, t in reaches_wTypes), dtype=np.int64, count=nreach)
-        segs = np.fromiter(chain.from_iterable(r for r, _ in reaches_wTypes), dtype=np.int64, count=int(lens.sum()))
-        ups = [upstream_connections.get(r[0], ()) for r, _ in reaches_wTypes]
-        up_cnt = np.fromiter((len(u) for u in ups), dtype=np.int64, count=nreach)
+        segs_of = list(map(itemgetter(0), reaches_wTypes))
+        lens = np.fromiter(map(len, segs_of), dtype=np.int64, count=nreach)
+        types = np.fromiter(map(itemgetter(1), reaches_wTypes), dtype=np.int64, count=nreach)
+        segs = np.fromiter(chain.from_iterable(segs_of), dtype=np.int64, count=int(lens.sum()))
+        ups = list(map(upstream_connections.get, map(itemgetter(0), segs_of), repeat(())))
+        up_cnt = np.fromiter(map(len, ups), dtype=np.int64, count=nreach)
         up_ids = np.fromiter(chain.from_iterable(ups), dtype=np.int64, count=int(up_cnt.sum()))
         for a in (lens, types, segs, up_cnt, up_ids):
             h.update(a.view(np.uint8))
     return h.hexdigest()
 
 
+# The full fingerprint walks 2.1 M reaches of a CONUS network: seconds per call, for a routing call of 0.2 s.  A caller that
+# passes THE SAME topology objects again -- what T-Route's loop does: the reach lists of a subnetwork are built once and kept
+# (compute.py:556, :652-656) -- is recognised by a quick key instead: identity and length of the two topology containers, a
+# sample of reaches spread over the list with their upstream lists, a CRC of the id and parameter arrays.  In-place edits of
+# a cached topology between calls are therefore NOT seen unless they touch a sampled reach or change a length; callers that
+# do such edits set VERIFY_TOPOLOGY_EVERY_CALL (or call clear_network_cache()).
+VERIFY_TOPOLOGY_EVERY_CALL = False
+_QUICK_SAMPLES = 256
+_QUICK = {}          # quick key -> full fingerprint
+
+
+def _quick_key(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
+    nreach = len(reaches_wTypes)
+    step = max(1, nreach // _QUICK_SAMPLES)
+    sample = tuple((tuple(r), t, tuple(upstream_connections.get(r[0], ()))) for r, t in reaches_wTypes[::step])
+    return (id(reaches_wTypes), nreach, id(upstream_connections), len(upstream_connections), hash(sample),
+            zlib.crc32(np.ascontiguousarray(data_idx).view(np.uint8)), zlib.crc32(np.ascontiguousarray(data_values).view(np.uint8)),
+            tuple(str(c) for c in data_cols), device)
+
+
+def _network_key(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
+    if VERIFY_TOPOLOGY_EVERY_CALL or not isinstance(reaches_wTypes, list):
+        return _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
+    qk = _quick_key(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
+    full = _QUICK.get(qk)
+    if full is None or full not in _NET_CACHE:
+        full = _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
+        if len(_QUICK) > 64:
+            _QUICK.clear()
+        _QUICK[qk] = full
+    return full
+
+
 def clear_network_cache():
+    _QUICK.clear()
+    if _RESULT_POOL is not None:
+        _RESULT_POOL.clear()
     while _NET_CACHE:
         _, entry = _NET_CACHE.popitem()
         entry["net"].close()
 
 
 def _get_network(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device):
-    key = _fingerprint(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
+    key = _network_key(reaches_wTypes, upstream_connections, data_idx, data_cols, data_values, device)
     entry = _NET_CACHE.get(key)
     if entry is not None:
         _NET_CACHE.move_to_end(key)
@@ -164,6 +204,31 @@ def _get_network(reaches_wTypes, upstream_connections, data_idx, data_cols, data
         _, old = _NET_CACHE.popitem(last=False)
         old["net"].close()
     return entry
+
+
+def _take_rows(a, mask):
+    """a[mask] (:811-813 `flowveldepth[fill_index_mask]`) without the copy when every row is returned -- 9.4 GB for a CONUS day"""
+    return a if mask.all() else a[mask]
+
+
+# The result of a CONUS day is 9.4 GB.  Into a fresh pageable array it costs the page faults of the allocation and a staged
+# copy (2.7 s per call measured); into page-locked memory the copies are DMA at PCIe rate (0.33 s per call).  Results are
+# therefore handed out from a pool of pinned blocks that take an array BACK only when its last reference is gone
+# (network.PinnedPool): a loop that consumes one window before it routes the next keeps re-using one block, a caller that
+# keeps old results makes the pool pin another one, and beyond RESULT_POOL_BYTES the mirror falls back to pageable arrays.
+# Nothing a caller holds is ever overwritten.  0 switches the pool off.
+RESULT_POOL_BYTES = 32 << 30
+_RESULT_POOL = None
+
+
+def _result_buffer(n, nsteps):
+    global _RESULT_POOL
+    if RESULT_POOL_BYTES <= 0:
+        return None
+    if _RESULT_POOL is None:
+        from ...network import PinnedPool
+        _RESULT_POOL = PinnedPool()
+    return _RESULT_POOL.take((int(n), 3 * int(nsteps)), np.float32, RESULT_POOL_BYTES)
 
 
 def _empty(a):
@@ -273,8 +338,14 @@ def compute_network_structured(
     if gages is None:
         nudge, lastobs_times, lastobs_values = placeholders
 
-    fvd, upstream = net.route(nsteps, qts_subdivisions, qlat_values, q0, assume_short_ts=bool(assume_short_ts),
-                              bnd_rows=bnd_rows if bnd_rows.size else None, bnd_fvd=bnd_fvd, want_upstream=True)
+    # One C call (trt_route): the result columns of a time chunk travel home while the next chunk is routed.  The reservoir
+    # inflows come back compact ([n_lp, nsteps]) and are scattered into the reference's upstream_array (zero everywhere else,
+    # :807-813) on the host: the table of zeros never crosses PCIe.
+    fvd, _ = net.route_call(nsteps, qts_subdivisions, qlat_values, q0, assume_short_ts=bool(assume_short_ts),
+                            bnd_rows=bnd_rows if bnd_rows.size else None, bnd_fvd=bnd_fvd, out=_result_buffer(n, nsteps))
+    upstream = np.zeros((n, int(nsteps)), dtype=np.float32)
+    if lp_rows.size:
+        upstream[lp_rows] = net.download_levelpool_inflow(lp_rows.size)
     if gages is not None:
         nudge, lastobs_times, lastobs_values = net.download_gages()
     if not entry["ordered"]:
@@ -297,15 +368,15 @@ def compute_network_structured(
     empty_i = np.zeros(0, dtype=np.int32)
     shift = np.float32(nsteps * dt)                                            # (timestep-1)*dt  (:822-836)
     return (
-        data_idx.astype(np.intp)[fill_index_mask],
-        fvd[fill_index_mask],
+        _take_rows(data_idx.astype(np.intp), fill_index_mask),
+        _take_rows(fvd, fill_index_mask),
         0,
         (np.asarray([data_idx[p] for p in usgs_positions]), lastobs_times, lastobs_values),
         (np.asarray(reservoir_usgs_wbody_idx, dtype=np.int32).reshape(-1), empty_f - shift, empty_f, empty_f,
          empty_f - shift),
         (np.asarray(reservoir_usace_wbody_idx, dtype=np.int32).reshape(-1), empty_f - shift, empty_f, empty_f,
          empty_f - shift),
-        upstream[fill_index_mask],
+        _take_rows(upstream, fill_index_mask),
         (np.asarray(reservoir_rfc_wbody_idx, dtype=np.int32).reshape(-1), empty_f - shift, empty_i),
         nudge,
         (empty_i, empty_f, empty_i, empty_i),

@@ -91,6 +91,41 @@ def test_compute_network_structured_matches_oracle(oracle, short_ts):
     clear_network_cache()
 
 
+def test_mirror_results_come_from_a_pool_of_pinned_blocks(oracle):
+    """mc_reach.RESULT_POOL_BYTES / network.PinnedPool: results live in page-locked memory (DMA copies, no 9.4 GB
+    allocation per CONUS call); a block is re-used only after every reference to its array is gone, so nothing a caller
+    holds is overwritten; beyond the limit the mirror falls back to pageable arrays.  Same bits in every case."""
+    from troute_b200.routing.fast_reach import mc_reach
+    c = _reference_style_case()
+    ref = _call(oracle.compute_network_structured, c)
+    c2 = dict(c); c2["qlat"] = c["qlat"] * np.float32(1.5)
+    ref2 = _call(oracle.compute_network_structured, c2)
+    mc_reach.clear_network_cache()
+    try:
+        a = _call(mc_reach.compute_network_structured, c)
+        H.assert_bit_equal(a[1], ref[1], "flowveldepth (pinned block)")
+        H.assert_bit_equal(a[6], ref[6], "upstream_array")
+        b = _call(mc_reach.compute_network_structured, c2)
+        assert not np.shares_memory(a[1], b[1])                   # `a` is still held: another block
+        H.assert_bit_equal(a[1], ref[1], "first result untouched by the second call")
+        H.assert_bit_equal(b[1], ref2[1], "second result")
+        addr_a = a[1].ctypes.data
+        pinned = mc_reach._RESULT_POOL.pinned_bytes
+        assert pinned >= 2 * a[1].nbytes
+        del a
+        import gc; gc.collect()
+        d = _call(mc_reach.compute_network_structured, c)
+        assert d[1].ctypes.data == addr_a and mc_reach._RESULT_POOL.pinned_bytes == pinned      # the released block, re-used
+        H.assert_bit_equal(d[1], ref[1], "re-used block")
+        H.assert_bit_equal(b[1], ref2[1], "held result still untouched")
+        mc_reach.RESULT_POOL_BYTES = 0                            # pool off: pageable arrays
+        e = _call(mc_reach.compute_network_structured, c)
+        H.assert_bit_equal(e[1], ref[1], "pageable result")
+    finally:
+        mc_reach.RESULT_POOL_BYTES = 32 << 30
+        mc_reach.clear_network_cache()
+
+
 def _gage_inputs(c, n_gages, seed, obs_steps):
     """Gages at the last segment of randomly chosen reaches (T-Route breaks reaches at gages), the four observation
     regimes of simple_da: observations (with gaps), window ended -> decay from the last one, no observation at all,
