@@ -59,6 +59,13 @@ def _frame_crc(df):
     return zlib.crc32(np.ascontiguousarray(v).view(np.uint8), zlib.crc32(np.ascontiguousarray(df.index.values).view(np.uint8)))
 
 
+def _finite_f32(v):
+    """float32 view of a forcing table with NaN -> 0 and +-inf -> the largest finite value (what np.nan_to_num does: rows that
+    the re-indexing added -- lakes, off-network tail-waters -- carry NaN), in one pass when there is nothing to replace"""
+    v = np.asarray(v, dtype=np.float32)
+    return v if np.isfinite(v).all() else np.nan_to_num(v)
+
+
 def _nonempty(df):
     return df is not None and hasattr(df, "empty") and not df.empty
 
@@ -202,7 +209,7 @@ def compute_nhd_routing_v02(
     result = compute_func(
         nts, dt, qts_subdivisions, reaches_list_with_type, upstream_connections,
         param_df_sub.index.values.astype("int64"), param_df_sub.columns.values, param_df_sub.values,
-        np.nan_to_num(q0_sub.values.astype("float32")), np.nan_to_num(qlat_sub.values.astype("float32")),
+        _finite_f32(q0_sub.values), _finite_f32(qlat_sub.values),
         lake_segs, waterbodies_df_sub.values, data_assimilation_parameters,
         waterbody_types_df_sub.values.astype("int32"), waterbody_type_specified,
         t0.strftime("%Y-%m-%d_%H:%M:%S") if hasattr(t0, "strftime") else str(t0),
