@@ -877,8 +877,7 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                 // EVERY unit is not needed -- units are claimed in position order and a segment at level l is busy from
                 // link-time l to l + T -- but the segments that are LIVE at the same time must fit the resident warps,
                 // or the chain stalls behind warps that are still walking an upstream segment through its T steps
-                // (T = 2,016 with one lane per warp: 79 ms instead of ~35, profiles/r02_v6_overlap_onecall).  Live
-                // segments = the largest number of marching segments in any window of T consecutive levels.
+                // (T = 2,016 with one lane per warp: 79 ms instead of ~35, profiles/r02_v6_overlap_onecall).
                 int mg = 0;
                 CU(march_max_grid(&mg));
                 if (net->grid_blocks > 0) mg = std::min(mg, net->grid_blocks);
@@ -888,13 +887,16 @@ static int run_chunk(trt_network* net, int32_t assume_short_ts, int t_off, int T
                     CU(cudaDeviceGetAttribute(&sms_m, cudaDevAttrMultiProcessorCount, net->device));
                     warps = std::max<int64_t>(1, (int64_t)sms_m * 4);
                 }
-                int64_t live = 0;
-                for (int l = Lw; l < net->nlevels; ++l) {
-                    const int hi_l = (int)std::min<int64_t>(net->nlevels, (int64_t)l + std::max(1, T));
-                    live = std::max<int64_t>(live, (int64_t)net->lvl_ptr[(size_t)hi_l] - net->lvl_ptr[(size_t)l]);
-                }
+                // Units are claimed in position order and a warp keeps its unit for all T steps, so the warps work through
+                // the marching segments at (segments / warps) x T links of occupancy while the wave needs `levels` links to
+                // travel down the chain: as long as the first is the smaller number the chain never waits for a warp and one
+                // lane per warp is right, whatever the widest window of levels holds.  Measured on the bench network
+                // (8,192 marching segments, 2,703 levels, 2,368 resident warps): T = 288 -> 996 links of occupancy, one lane
+                // per warp 18.6 ms against 22.4 ms with two (the rule of the largest T-level window asked for two);
+                // T = 2,016 -> 6,974 links, one lane per warp 79 ms against ~35 ms with four.
+                const int64_t n_march = net->n - pos_deep, lv_march = std::max(1, net->nlevels - Lw);
                 G = 1;
-                while (G < 32 && (live + G - 1) / G > warps) G *= 2;
+                while (G < 32 && n_march * std::max(1, T) > (int64_t)G * warps * lv_march) G *= 2;
             }
             if (pos_deep < net->n && (net->march_sched_first != pos_deep || net->march_sched_group != G)) {
                 std::vector<int32_t> start;
