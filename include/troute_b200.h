@@ -239,9 +239,10 @@ int trt_prepare(trt_network* net);
  *                 "deep_lanes" segments (default 8192).  Shards of one network must use the SAME
  *                 deep_level (set it explicitly): a dataflow kernel must never wait for a value that another shard
  *                 produces only in its marching kernel
- *   "march_group" segments per marching warp, 1..32; 0 (default) = 1 up to 16,384 marching segments (shortest
- *                 dependency-chain latency; measured 19.6 instead of 27.9 ms on the bench network), beyond that the
- *                 smallest power of two for which all marching units are resident at once
+ *   "march_group" segments per marching warp, 1..32; 0 (default) = the smallest power of two for which the resident warps
+ *                 get through the marching segments (segments x timesteps / warps links of occupancy) no slower than the
+ *                 wave travels down the chain (levels links): 1 for a day at 300 s on the bench network (shortest link
+ *                 latency; 16.1 ms against 20.0 ms with 2), 4 for a week routed as one call
  *   "gate"        mode 2 run-ahead bound: a unit of stage k starts once stage k - gate is complete; 0 (default) =
  *                 adaptive: max("gate_min" stages, as many stages as hold "gate_lanes" lanes)
  *   "collect_trips", "trip_buckets"  see trt_trip_counts / trt_trip_counts_bucketed
