@@ -1122,8 +1122,12 @@ __device__ __forceinline__ bool march_trip(const McChannel& c, const McIn& in, M
     return mc_iterate(c, in, s, tabs);
 }
 
+// One CTA per SM (8 warps, two per scheduler, up to 255 registers: 159 used, nothing spilled).  The marching kernel is a latency
+// chain: what counts is how fast ONE warp gets through a link, and a warp that shares its scheduler with fewer polling
+// neighbours gets there sooner -- measured 15.3 vs 16.1 ms (T = 288) and 68.7 vs 74.1 ms (T = 2,016) against two CTAs per SM
+// (profiles/r02_v10_final/box_march_one_cta_per_sm.txt); three and four CTAs per SM were slower still (round 1).
 #ifndef TRT_MARCH_MIN_BLOCKS
-#define TRT_MARCH_MIN_BLOCKS 2
+#define TRT_MARCH_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(NetDev net, RunDev run, MarchDev mk, PeerDev peers)
 {
