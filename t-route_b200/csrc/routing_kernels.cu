@@ -1122,12 +1122,14 @@ __device__ __forceinline__ bool march_trip(const McChannel& c, const McIn& in, M
     return mc_iterate(c, in, s, tabs);
 }
 
-// One CTA per SM (8 warps, two per scheduler, up to 255 registers: 159 used, nothing spilled).  The marching kernel is a latency
-// chain: what counts is how fast ONE warp gets through a link, and a warp that shares its scheduler with fewer polling
-// neighbours gets there sooner -- measured 15.3 vs 16.1 ms (T = 288) and 68.7 vs 74.1 ms (T = 2,016) against two CTAs per SM
-// (profiles/r02_v10_final/box_march_one_cta_per_sm.txt); three and four CTAs per SM were slower still (round 1).
+// Two CTAs per SM (128 registers).  One CTA per SM (-DTRT_MARCH_MIN_BLOCKS=1: two warps per scheduler, 159 registers) is ~5 % faster
+// on the chain -- 15.3 vs 16.1 ms (T = 288), 68.7 vs 74.1 ms (T = 2,016), profiles/r02_v10_final/box_march_one_cta_per_sm.txt -- because a
+// marching warp then shares its scheduler with fewer polling neighbours, but it halves the CTAs that can be CO-RESIDENT, and shard
+// handles that share one device (tests/test_gpu_parity.py: three handles x 74 CTAs) rely on all their marching CTAs being resident at
+// once.  It was measured with the last GPU minutes of round 2 and could not be taken through the whole suite, so the default stays;
+// three and four CTAs per SM were slower (round 1).
 #ifndef TRT_MARCH_MIN_BLOCKS
-#define TRT_MARCH_MIN_BLOCKS 1
+#define TRT_MARCH_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(kBlock, TRT_MARCH_MIN_BLOCKS) march_kernel(NetDev net, RunDev run, MarchDev mk, PeerDev peers)
 {
