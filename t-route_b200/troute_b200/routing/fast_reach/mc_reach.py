@@ -59,10 +59,11 @@ def flatten_network(reaches_wTypes, upstream_connections, data_idx):
     Returns (up_ptr, up_rows, kind, seg_rows, reach_len, reach_type)."""
     n = int(data_idx.shape[0])
     nreach = len(reaches_wTypes)
-    reach_len = np.fromiter((len(r) for r, _ in reaches_wTypes), dtype=np.int64, count=nreach)
-    reach_type = np.fromiter((t for _, t in reaches_wTypes), dtype=np.int64, count=nreach)
+    segs_of = list(map(itemgetter(0), reaches_wTypes))                         # iteration at C speed: 2.1 M reaches for CONUS
+    reach_len = np.fromiter(map(len, segs_of), dtype=np.int64, count=nreach)
+    reach_type = np.fromiter(map(itemgetter(1), reaches_wTypes), dtype=np.int64, count=nreach)
     total = int(reach_len.sum())
-    seg_ids = np.fromiter(chain.from_iterable(r for r, _ in reaches_wTypes), dtype=np.int64, count=total)
+    seg_ids = np.fromiter(chain.from_iterable(segs_of), dtype=np.int64, count=total)
     seg_rows = binary_find(data_idx, seg_ids)                                  # ValueError on unknown ids (:65)
     if np.unique(seg_rows).size != total:
         raise ValueError("a segment appears in more than one reach")
@@ -70,9 +71,8 @@ def flatten_network(reaches_wTypes, upstream_connections, data_idx):
     np.cumsum(reach_len, out=starts[1:])
     head_rows = seg_rows[starts[:-1]] if nreach else np.zeros(0, np.int64)
 
-    get = upstream_connections.get
-    head_ups = [get(int(seg_ids[s]), ()) for s in starts[:-1]]
-    head_cnt = np.fromiter((len(u) for u in head_ups), dtype=np.int64, count=nreach)
+    head_ups = list(map(upstream_connections.get, seg_ids[starts[:-1]].tolist(), repeat(())))
+    head_cnt = np.fromiter(map(len, head_ups), dtype=np.int64, count=nreach)
     head_up_ids = np.fromiter(chain.from_iterable(head_ups), dtype=np.int64, count=int(head_cnt.sum()))
     head_up_rows = binary_find(data_idx, head_up_ids)
 
