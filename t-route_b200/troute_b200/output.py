@@ -161,3 +161,41 @@ def flowveldepth_frame(results, nts):
     columns (timestep, 'q' | 'v' | 'd')."""
     cols = pd.MultiIndex.from_product([range(int(nts)), ["q", "v", "d"]]).to_flat_index()
     return pd.concat([pd.DataFrame(r[1], index=r[0], columns=cols) for r in results])
+
+
+# -------------------------------------------------------------------------------------------------
+# lite restart files (checkpoint / resume of the window loop)
+# -------------------------------------------------------------------------------------------------
+def write_lite_restart(q0, waterbodies_df, t0, restart_parameters):
+    """nhd_io.write_lite_restart (nhd_io.py:1458-1505), called after every routing loop (nwm_routing/__main__.py:269-277): the
+    channel state `q0` and, when the domain has waterbodies, their `qd0` / `h0`, each with a `time` column holding `t0`, pickled
+    as `channel_restart_<YYYYmmddHHMM>` / `waterbody_restart_<YYYYmmddHHMM>` under `lite_restart_output_directory`.  Same file
+    names and the same frames as the reference writes (tests/test_output.py); returns the paths written (the reference
+    returns nothing)."""
+    import pathlib
+    output_directory = restart_parameters.get("lite_restart_output_directory", None) if restart_parameters else None
+    if not output_directory:
+        return []
+    output_path = pathlib.Path(output_directory)
+    t0_str = t0.strftime("%Y%m%d%H%M")
+    written = []
+    q0_out = q0.copy()
+    q0_out["time"] = t0
+    path = output_path / ("channel_restart_" + t0_str)
+    q0_out.to_pickle(path)
+    written.append(str(path))
+    if waterbodies_df is not None and not waterbodies_df.empty:
+        wbody_initial_states = waterbodies_df.loc[:, ["qd0", "h0"]].copy()
+        wbody_initial_states["time"] = t0
+        path = output_path / ("waterbody_restart_" + t0_str)
+        wbody_initial_states.to_pickle(path)
+        written.append(str(path))
+    return written
+
+
+def read_lite_restart(file):
+    """nhd_io.read_lite_restart (nhd_io.py:1433-1455): (restart states without the `time` column, restart datetime)"""
+    import pathlib
+    df = pd.read_pickle(pathlib.Path(file))
+    t0 = df["time"].iloc[0].to_pydatetime()
+    return df.drop(columns="time"), t0

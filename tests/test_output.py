@@ -106,3 +106,44 @@ def test_netcdf_stream_output_has_the_reference_variables(tmp_path):
         assert (nc.variables["nudge"][:] == -9999.0).all()
         assert nc.TITLE == b"OUTPUT FROM T-ROUTE" and nc.file_reference_time == b"2023-04-02_00:00:00"
         assert nc.variables["flow"].units == b"m3 s-1" and nc.variables["velocity"].units == b"m/s"
+
+
+def _reference_restart_functions():
+    import logging
+    import pathlib
+    names = ("read_lite_restart", "write_lite_restart")
+    tree = ast.parse(open(NHD_IO).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(fns) == len(names)
+    ns = {"pd": pd, "np": np, "pathlib": pathlib, "LOG": logging.getLogger("ref")}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "reference nhd_io.py", "exec"), ns)
+    return ns
+
+
+@pytest.mark.skipif(not os.path.exists(NHD_IO), reason="pins against the reference tree, present only in the build container")
+@pytest.mark.parametrize("with_lakes", [False, True])
+def test_lite_restart_files_equal_the_reference(tmp_path, with_lakes):
+    """checkpoint / resume of the window loop (nhd_io.py:1433-1505): same file names, same pickled frames, and either
+    implementation reads what the other wrote"""
+    from troute_b200 import output
+    rng = np.random.default_rng(2)
+    ids = np.sort(rng.choice(np.arange(2420000, 2430000), size=40, replace=False)).astype(np.int64)
+    q0 = pd.DataFrame(rng.uniform(0, 30, (40, 3)).astype(np.float32), index=ids, columns=["qu0", "qd0", "h0"])
+    wb = pd.DataFrame(rng.uniform(0, 9, (5, 4)), index=ids[[3, 9, 17, 21, 33]], columns=["LkArea", "qd0", "h0", "ifd"]) if with_lakes \
+        else pd.DataFrame()
+    t0 = datetime.datetime(2023, 4, 2, 6, 0)
+    ours, theirs = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir(); theirs.mkdir()
+    ns = _reference_restart_functions()
+    ns["write_lite_restart"](q0, wb, t0, {"lite_restart_output_directory": str(theirs)})
+    written = output.write_lite_restart(q0, wb, t0, {"lite_restart_output_directory": str(ours)})
+    assert sorted(os.listdir(ours)) == sorted(os.listdir(theirs)) == sorted(os.path.basename(p) for p in written)
+    assert len(written) == (2 if with_lakes else 1)
+    for name in os.listdir(theirs):
+        a, b = pd.read_pickle(ours / name), pd.read_pickle(theirs / name)
+        pd.testing.assert_frame_equal(a, b)
+        for reader, folder in ((output.read_lite_restart, theirs), (ns["read_lite_restart"], ours)):
+            df, t = reader(folder / name)
+            assert t == t0 and "time" not in df.columns
+            pd.testing.assert_frame_equal(df, (q0 if name.startswith("channel") else wb.loc[:, ["qd0", "h0"]]))
+    assert output.write_lite_restart(q0, wb, t0, {}) == []                     # no directory configured: nothing written

@@ -161,3 +161,47 @@ def test_state_handoff_helpers_equal_the_reference_functions():
     ref_update(net)
     got = nwm_routing.update_waterbody_water_elevation(wb.copy(), q0)
     pd.testing.assert_frame_equal(got, net._waterbody_df, check_dtype=False)
+
+
+def test_resume_from_lite_restart_files_on_the_oracle(oracle, tmp_path):
+    """Checkpoint / resume the way T-Route does it (nwm_routing/__main__.py:269-277 writes, AbstractNetwork.py:591,687
+    read): after two of four windows the channel and waterbody states go to lite restart files
+    (output.write_lite_restart), a NEW loop starts from what output.read_lite_restart returns, and the four windows
+    together equal the uninterrupted run bit for bit."""
+    import datetime
+    from troute_b200 import nwm_routing, output
+    c = A._reference_style_case(n=2500, seed=21, n_lp=6, nsteps=48)
+    fn = oracle.compute_network_structured
+    full, _, q0_end = _windowed(fn, c, None, 4)
+
+    # the same loop, cut in two halves of two windows with files in between
+    ids = c["ids"]
+    n_w, qcols = c["nsteps"] // 4, (c["nsteps"] // 4) // c["qts"]
+    wb_cols = ["LkArea", "LkMxE", "OrificeA", "OrificeC", "OrificeE", "WeirC", "WeirE", "WeirL", "ifd", "qd0", "h0"]
+    wb_static = pd.DataFrame(np.array(c["wbody"], dtype=np.float64), index=c["lake_numbers"], columns=wb_cols)
+
+    def route_window(w, q0_df, wb_df, lo_df):
+        part = dict(c)
+        part["nsteps"] = n_w
+        part["qlat"] = c["qlat"][:, w * qcols:(w + 1) * qcols]
+        part["q0"] = q0_df.loc[ids].to_numpy(dtype=np.float32)
+        part["wbody"] = wb_df.loc[c["lake_numbers"]].to_numpy(dtype=np.float64)
+        return [A._call(fn, part)], None
+
+    q0 = pd.DataFrame(c["q0"], index=ids, columns=["qu0", "qd0", "h0"])
+    first, q0_mid, wb_mid, _ = nwm_routing.route_windows(route_window, range(0, 2), q0, wb_static.copy(), pd.DataFrame(), 300.0, n_w)
+    t_mid = datetime.datetime(2023, 4, 2) + datetime.timedelta(seconds=300.0 * n_w * 2)
+    written = output.write_lite_restart(q0_mid, wb_mid, t_mid, {"lite_restart_output_directory": str(tmp_path)})
+    assert len(written) == 2
+    del q0_mid, wb_mid
+
+    q0_r, t_r = output.read_lite_restart(written[0])
+    wb_states, t_w = output.read_lite_restart(written[1])
+    assert t_r == t_w == t_mid
+    wb_r = wb_static.copy()                               # static lake parameters from the hydrofabric, states from the file
+    wb_r.loc[wb_states.index, ["qd0", "h0"]] = wb_states[["qd0", "h0"]]     # (AbstractNetwork.py:591-606)
+    second, q0_fin, _, _ = nwm_routing.route_windows(route_window, range(2, 4), q0_r, wb_r, pd.DataFrame(), 300.0, n_w)
+
+    pieces = [r[0][1][np.argsort(r[0][0])] for r in first + second]
+    H.assert_bit_equal(np.concatenate(pieces, axis=1), full, "resumed run vs uninterrupted run")
+    H.assert_bit_equal(q0_fin.loc[ids].to_numpy(np.float32), q0_end.loc[ids].to_numpy(np.float32), "final state")
