@@ -562,6 +562,8 @@ class PinnedPool:
     of one window before it routes the next (T-Route's does) keeps re-using one block, and a caller that holds on to old
     results simply makes the pool allocate another block (up to `limit_bytes`; beyond that `take` returns None and the caller
     falls back to pageable memory).  No array handed out is ever overwritten behind its owner's back."""
+    _block_type = None           # set below: _PinnedBlock (tests substitute a host-memory stand-in)
+
     def __init__(self):
         self._free = {}          # nbytes -> [blocks]
         self._total = 0
@@ -571,16 +573,27 @@ class PinnedPool:
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         nbytes = max(count * dtype.itemsize, 1)
+        evicted = []
         with self._lock:
             blocks = self._free.get(nbytes)
             block = blocks.pop() if blocks else None
             if block is None:
+                # over the limit: idle blocks of OTHER sizes go first (a caller whose result shape changed)
+                for size in sorted(self._free, reverse=True):
+                    while self._total + nbytes > limit_bytes and self._free[size]:
+                        evicted.append(self._free[size].pop())
+                        self._total -= size
                 if self._total + nbytes > limit_bytes:
-                    return None
-                self._total += nbytes
+                    block = False
+                else:
+                    self._total += nbytes
+        for b in evicted:
+            b.free()
+        if block is False:
+            return None
         if block is None:
             try:
-                block = _PinnedBlock(nbytes)
+                block = self._block_type(nbytes)
             except Exception:      # noqa: BLE001 -- no pinned memory to be had: the caller uses pageable memory
                 with self._lock:
                     self._total -= nbytes
@@ -605,6 +618,9 @@ class PinnedPool:
     @property
     def pinned_bytes(self):
         return self._total
+
+
+PinnedPool._block_type = _PinnedBlock
 
 
 def pinned_empty(shape, dtype=np.float32):

@@ -122,3 +122,52 @@ def test_frames_cache_is_keyed_on_the_tables(monkeypatch):
     call(param_df.copy(), dict(reaches_bytw))
     assert seen[3][0] is not seen[0][0] and np.array_equal(seen[3][1], seen[0][1])
     compute._TOPO_CACHE.clear()
+
+
+class _FakeBlock:
+    """host-memory stand-in for network._PinnedBlock (trt_host_alloc needs a CUDA device)"""
+    live = 0
+
+    def __init__(self, nbytes):
+        import ctypes
+        self._mem = (ctypes.c_uint8 * nbytes)()
+        self.ptr = ctypes.c_void_p(ctypes.addressof(self._mem))
+        self.nbytes = nbytes
+        _FakeBlock.live += 1
+
+    def free(self):
+        if self.ptr:
+            self.ptr = None
+            _FakeBlock.live -= 1
+
+
+def test_pinned_pool_reuses_a_block_only_after_its_array_is_gone(monkeypatch):
+    """network.PinnedPool: the logic behind mc_reach.RESULT_POOL_BYTES, with host memory standing in for pinned blocks"""
+    import gc
+    from troute_b200 import network
+    monkeypatch.setattr(network.PinnedPool, "_block_type", _FakeBlock)
+    _FakeBlock.live = 0
+    pool = network.PinnedPool()
+    a = pool.take((100, 30), np.float32, 30000)
+    a[:] = 1.0
+    b = pool.take((100, 30), np.float32, 30000)               # `a` is held: a second block
+    assert b is not None and not np.shares_memory(a, b) and pool.pinned_bytes == 24000
+    assert pool.take((100, 30), np.float32, 30000) is None     # a third would exceed the limit: the caller goes pageable
+    view = a[10:20]
+    addr = a.ctypes.data
+    del a
+    gc.collect()
+    assert pool.take((100, 30), np.float32, 24000) is None     # a view still holds the block
+    del view
+    gc.collect()
+    c = pool.take((100, 30), np.float32, 24000)
+    assert c is not None and c.ctypes.data == addr and pool.pinned_bytes == 24000      # the released block, nothing new pinned
+    # another shape: the idle block of the old shape is given up to stay under the limit
+    del c
+    gc.collect()
+    d = pool.take((50, 100), np.float32, 36000)
+    assert d is not None and pool.pinned_bytes == 12000 + 20000 and _FakeBlock.live == 2
+    del b, d
+    gc.collect()
+    pool.clear()
+    assert pool.pinned_bytes == 0 and _FakeBlock.live == 0
